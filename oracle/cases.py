@@ -1,0 +1,110 @@
+"""Parity cases shared by oracle/make_golden.py (reference side) and tests/ (oracle + CUDA
+side)  --  TEST INFRASTRUCTURE.  Inputs and weights are regenerated from the deterministic
+recipes in vitlens_b200.synth; only the reference's *outputs* are committed as fixtures."""
+from __future__ import annotations
+
+import os
+import sys
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import torch
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SRC = os.path.join(_ROOT, "vit-lens_b200")
+GOLDEN_DIR = os.path.join(_ROOT, "tests", "golden")
+MODEL_CONFIG_DIR = os.path.join(_SRC, "open_clip", "model_configs")
+
+
+def _synth():
+    # load the recipe module by path: this file must stay importable in a process that has the
+    # *reference's* open_clip on sys.path (make_golden.py), so the product package is not imported.
+    import importlib.util
+
+    name = "_vitlens_synth_recipe"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(_SRC, "vitlens_b200", "synth.py"))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules[name] = m
+    spec.loader.exec_module(m)
+    return m
+
+
+@dataclass
+class Case:
+    name: str
+    model: str  # model_configs/<model>.json
+    kind: str  # "clip" | "tri"
+    batch: int
+    modality: Optional[str] = None  # tri: audio | depth | pc
+    overrides: Dict = field(default_factory=dict)  # fields of the reference's `args`
+    lock: Dict = field(default_factory=dict)  # kwargs of lock_visual_tower for tri models
+    full_grads: bool = True  # store every gradient (tiny) or only norms + a few small ones
+    seed: int = 0
+
+
+_TINY_LENS = dict(perceiver_input_chan=128, perceiver_latent_dim=128, perceiver_latent_heads=2,
+                  perceiver_num_latents=16, perceiver_depth=2, perceiver_self_per_cross_attn=2)
+
+CASES = {c.name: c for c in [
+    Case("tiny_clip", "ViT-tiny-16", "clip", 4),
+    Case("tiny_tri_audio", "ViT-tiny-16", "tri", 4, "audio",
+         dict(_TINY_LENS, audio_mel_bins=32, audio_target_length=48), dict(unlock_cls=True)),
+    Case("tiny_tri_depth", "ViT-tiny-16", "tri", 4, "depth",
+         dict(perceiver_num_latents=16), dict(unlock_cls=True, unlock_trans_first_n_layers=1)),
+    Case("tiny_tri_pc", "ViT-tiny-16", "tri", 3, "pc",
+         dict(_TINY_LENS, perceiver_input_chan=96, perceiver_self_per_cross_attn=1, pc_npoints=256,
+              pc_num_group=16, pc_group_size=8, pc_trans_dim=96, pc_encoder_dims=64), dict(unlock_cls=True)),
+    # BASELINE.json configs[0]: ViT-B/32 image-text ClipLoss, batch 8
+    Case("vitb32_clip_bs8", "ViT-B-32", "clip", 8, full_grads=False),
+    # reduced-batch versions of configs[2..4] (full-size weights, reference runs them in seconds)
+    Case("vitl14_audio128_bs2", "ViT-L-14", "tri", 2, "audio", dict(perceiver_num_latents=128),
+         dict(unlock_cls=True), full_grads=False),
+    Case("vitl14_depth_bs2", "ViT-L-14", "tri", 2, "depth", {}, dict(unlock_cls=True, unlock_trans_first_n_layers=4),
+         full_grads=False),
+    Case("vitl14_pc_bs2", "ViT-L-14", "tri", 2, "pc", {}, dict(unlock_cls=True), full_grads=False),
+]}
+
+
+def model_cfg(case: Case) -> dict:
+    import json
+
+    with open(os.path.join(MODEL_CONFIG_DIR, case.model + ".json")) as f:
+        return json.load(f)
+
+
+def build_inputs(case: Case, args=None) -> Dict[str, torch.Tensor]:
+    """`args`: any object with the modality fields (audio_target_length, audio_mel_bins, pc_npoints);
+    falls back to the vitlensL defaults (mm_vit_lens/model_cfg.py:9-78)."""
+    s = _synth()
+    cfg = model_cfg(case)
+    img = cfg["vision_cfg"]["image_size"]
+    ctx, vocab = cfg["text_cfg"]["context_length"], cfg["text_cfg"]["vocab_size"]
+    B = case.batch
+    out = {
+        "image": s.synth_normal("image", (B, 3, img, img), seed=case.seed + 1),
+        "text": s.synth_text(B, ctx, vocab, seed=case.seed + 1),
+    }
+    ov = case.overrides
+
+    def g(k, d):
+        return ov.get(k, getattr(args, k, d) if args is not None else d)
+
+    if case.modality == "audio":
+        out["visual"] = s.synth_normal("audio", (B, g("audio_target_length", 512), g("audio_mel_bins", 128)), seed=case.seed + 1)
+    elif case.modality == "depth":
+        out["visual"] = s.synth_normal("depth", (B, 1, img, img), seed=case.seed + 1)
+    elif case.modality == "pc":
+        pts, start = s.synth_points(B, g("pc_npoints", 8192), seed=case.seed + 1)
+        out["visual"] = pts
+        out["fps_start"] = start
+    return out
+
+
+def golden_path(case: Case) -> str:
+    return os.path.join(GOLDEN_DIR, case.name + ".pt")
+
+
+def load_golden(name: str) -> Dict[str, torch.Tensor]:
+    return torch.load(golden_path(CASES[name]), map_location="cpu", weights_only=True)

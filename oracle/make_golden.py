@@ -1,0 +1,141 @@
+"""Generate tests/golden/*.pt from the REAL reference and pin the oracle against it.
+
+TEST INFRASTRUCTURE; runs only in the build container (needs /root/reference):
+
+    python oracle/make_golden.py [case ...]
+
+For every case in oracle/cases.py: build the reference model (its own factory / modules,
+unmodified, CPU fp32), load the deterministic synthetic weights, run forward + loss +
+backward, run oracle/vitlens_oracle.py on the same weights + inputs, assert agreement
+(rtol 2e-4 on features, 1e-4 on the loss), and save the REFERENCE's outputs as the fixture.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from oracle import cases as C  # noqa: E402
+from oracle import ref_import  # noqa: E402
+from oracle import vitlens_oracle as O  # noqa: E402
+
+PC_SEED = 1234
+
+
+def _relerr(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+def run_reference(case, open_clip, fetch_model_cfg):
+    from open_clip.factory import add_model_config
+
+    add_model_config(C.MODEL_CONFIG_DIR)
+    args = None
+    if case.kind == "clip":
+        model = open_clip.create_model(case.model, precision="fp32", device="cpu")
+    else:
+        args = ref_import.modality_args(fetch_model_cfg, case.modality, **case.overrides)
+        model = open_clip.factory.tri_create_model(case.model, None, precision="fp32", device="cpu", args=args)
+    synth = C._synth()
+    sd = synth.synth_state_dict(model.state_dict(), seed=case.seed)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    if case.kind == "tri":
+        model.lock_image_tower()
+        model.lock_text_tower()
+        model.lock_visual_tower(**case.lock)
+    inp = C.build_inputs(case, args)
+    if case.kind == "clip":
+        fi, ft, ls = model(inp["image"], inp["text"])
+        loss = open_clip.loss.ClipLoss()(fi, ft, ls)
+        feats = {"image_features": fi, "text_features": ft}
+    else:
+        if case.modality == "pc":  # the reference draws the FPS start with torch.randint (misc.py:60)
+            torch.manual_seed(PC_SEED)
+            start = torch.randint(0, inp["visual"].shape[1], (case.batch,), dtype=torch.long)
+            inp["fps_start"] = start
+            torch.manual_seed(PC_SEED)
+        fi, ft, fv, ls = model(inp["image"], inp["text"], inp["visual"])
+        loss = open_clip.loss.TriClipLoss()(fi, ft, fv, ls)
+        feats = {"image_features": fi, "text_features": ft, "visual_features": fv}
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.requires_grad and p.grad is not None}
+    return model, sd, args, inp, feats, ls.detach(), loss.detach(), grads
+
+
+def run_oracle(case, sd, args, inp, grad_keys):
+    cfg = C.model_cfg(case)
+    vh = cfg["vision_cfg"]["width"] // 64
+    th = cfg["text_cfg"]["heads"]
+    sd = {k: (v.clone().requires_grad_(True) if k in grad_keys else v) for k, v in sd.items()}
+    if case.kind == "clip":
+        fi, ft, ls = O.clip_forward(sd, inp["image"], inp["text"], vh, th)
+        loss = O.clip_loss(fi, ft, ls)
+        feats = {"image_features": fi, "text_features": ft}
+    else:
+        kw = {}
+        if case.modality == "audio":
+            kw = dict(fstride=args.audio_fstride, tstride=args.audio_tstride)
+        if case.modality == "pc":
+            kw = dict(fps_start=inp["fps_start"], num_group=args.pc_num_group, group_size=args.pc_group_size)
+        fi, ft, fv, ls = O.triclip_forward(
+            sd, inp["image"], inp["text"], inp["visual"], case.modality, vh, th,
+            perceiver_as_identity=bool(args.perceiver_as_identity),
+            latent_heads=args.perceiver_latent_heads, cross_heads=args.perceiver_cross_heads, **kw)
+        loss = O.tri_clip_loss(fi, ft, fv, ls)
+        feats = {"image_features": fi, "text_features": ft, "visual_features": fv}
+    loss.backward()
+    grads = {k: sd[k].grad for k in grad_keys}
+    return feats, ls.detach(), loss.detach(), grads
+
+
+def main(names):
+    assert ref_import.available(), "needs /root/reference"
+    open_clip, fetch_model_cfg, _ = ref_import.import_reference()
+    torch.set_num_threads(os.cpu_count())
+    os.makedirs(C.GOLDEN_DIR, exist_ok=True)
+    for name in names:
+        case = C.CASES[name]
+        t0 = time.time()
+        model, sd, args, inp, feats, ls, loss, grads = run_reference(case, open_clip, fetch_model_cfg)
+        t1 = time.time()
+        ofeats, ols, oloss, ograds = run_oracle(case, sd, args, inp, set(grads))
+        t2 = time.time()
+        worst = 0.0
+        for k in feats:
+            e = _relerr(ofeats[k].detach(), feats[k].detach())
+            worst = max(worst, e)
+            assert e < 2e-4, (name, k, e)
+        le = abs(float(oloss) - float(loss)) / abs(float(loss))
+        assert le < 1e-4, (name, "loss", float(oloss), float(loss))
+        gworst = 0.0
+        for k, g in grads.items():
+            e = _relerr(ograds[k], g)
+            gworst = max(gworst, e)
+            assert e < 2e-3, (name, "grad", k, e)
+        fx = {"loss": loss, "logit_scale": ls}
+        fx.update({k: v.detach() for k, v in feats.items()})
+        if "fps_start" in inp:
+            fx["fps_start"] = inp["fps_start"]
+        # recipe drift guards
+        fx["chk_weights"] = torch.tensor(sum(float(v.double().abs().sum()) for v in sd.values() if v.is_floating_point()))
+        fx["chk_inputs"] = torch.tensor(sum(float(v.double().abs().sum()) for v in inp.values()))
+        keys = sorted(grads)
+        fx["grad_norms"] = torch.tensor([float(grads[k].norm()) for k in keys])
+        fx["grad_keys_crc"] = torch.tensor(__import__("zlib").crc32("\n".join(keys).encode()))
+        for k in keys:
+            if grads[k].numel() <= (20000 if case.full_grads else 4096):
+                fx["grad:" + k] = grads[k]
+        torch.save(fx, C.golden_path(case))
+        sz = os.path.getsize(C.golden_path(case))
+        print(f"{name}: loss={float(loss):.6f} feat_relerr={worst:.2e} grad_relerr={gworst:.2e} "
+              f"ngrads={len(keys)} ref={t1 - t0:.1f}s oracle={t2 - t1:.1f}s fixture={sz / 1024:.0f}KiB", flush=True)
+        del model, sd, grads, ograds
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:] or list(C.CASES))
