@@ -1,0 +1,609 @@
+// HBM-bound row kernels of the ViT-Lens hot path: LayerNorm fwd/bwd, bias-gradient column sums,
+// patch gather (conv-as-GEMM A operand), token assembly (cls + positional), embedding lookup,
+// L2 normalisation, GEGLU, casts/transposes and fused AdamW.  All are single-pass, 16-byte
+// vectorised, one warp per row where a row reduction is needed; grids are sized in multiples of
+// the SM count and grid-stride over rows.
+#include "vl_host.h"
+#include "vl_sm100.cuh"
+
+namespace vl {
+
+constexpr int kMaxLnChunks = 8;  // D <= 32 lanes * 8 chunks * 8 elems = 2048
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]); u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+  return u;
+}
+
+// ------------------------------------------------------------------------------------ LayerNorm
+// y[i,:] = (x[r,:] - mean) * rstd * w + b with r = row_index ? row_index[i] : i.
+template <int CH>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                            const long long* __restrict__ row_index,
+                                                            const float* __restrict__ w, const float* __restrict__ b,
+                                                            __nv_bfloat16* __restrict__ y, long long ldy,
+                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                            int T, int D, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int nvec = D >> 3;
+  for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < T; row += (long long)gridDim.x * wpb) {
+    const long long src = row_index ? row_index[row] : row;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + src * ldx);
+    float v[CH][8];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int i = lane + c * 32;
+      if (i < nvec) {
+        unpack8(xr[i], v[c]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[c][j];
+      }
+    }
+    const float mu = warp_sum(s) / D;
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int i = lane + c * 32;
+      if (i < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[c][j] - mu;
+          q += d * d;
+        }
+      }
+    }
+    const float rs = rsqrtf(warp_sum(q) / D + eps);
+    uint4* yr = reinterpret_cast<uint4*>(y + row * ldy);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int i = lane + c * 32;
+      if (i < nvec) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w) + 2 * i), w1 = __ldg(reinterpret_cast<const float4*>(w) + 2 * i + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(b) + 2 * i), b1 = __ldg(reinterpret_cast<const float4*>(b) + 2 * i + 1);
+        float o[8];
+        o[0] = (v[c][0] - mu) * rs * w0.x + b0.x; o[1] = (v[c][1] - mu) * rs * w0.y + b0.y;
+        o[2] = (v[c][2] - mu) * rs * w0.z + b0.z; o[3] = (v[c][3] - mu) * rs * w0.w + b0.w;
+        o[4] = (v[c][4] - mu) * rs * w1.x + b1.x; o[5] = (v[c][5] - mu) * rs * w1.y + b1.y;
+        o[6] = (v[c][6] - mu) * rs * w1.z + b1.z; o[7] = (v[c][7] - mu) * rs * w1.w + b1.w;
+        yr[i] = pack8(o);
+      }
+    }
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mu;
+      if (rstd_out) rstd_out[row] = rs;
+    }
+  }
+}
+
+// dx = rstd * (w*dy - mean(w*dy) - xhat * mean(w*dy*xhat)) [+ dres];  dw += sum_t dy*xhat; db += sum_t dy.
+// Rows may be scattered back through row_index (dx row r = row_index[i]; other rows untouched).
+template <int CH>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy,
+                                                            const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                            const long long* __restrict__ row_index,
+                                                            const float* __restrict__ w, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd,
+                                                            const __nv_bfloat16* __restrict__ dres, long long lddres,
+                                                            __nv_bfloat16* __restrict__ dx, long long lddx,
+                                                            float* __restrict__ dw, float* __restrict__ db, int T, int D) {
+  extern __shared__ float red[];  // [warps][D] reused for dw then db
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  const int nvec = D >> 3;
+  float aw[CH][8], ab[CH][8];
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) aw[c][j] = ab[c][j] = 0.f;
+
+  for (long long row = (long long)blockIdx.x * wpb + warp; row < T; row += (long long)gridDim.x * wpb) {
+    const long long src = row_index ? row_index[row] : row;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + src * ldx);
+    const uint4* gr = reinterpret_cast<const uint4*>(dy + row * lddy);
+    const float mu = mean[row], rs = rstd[row];
+    float xh[CH][8], g[CH][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int i = lane + c * 32;
+      if (i < nvec) {
+        unpack8(xr[i], xh[c]);
+        unpack8(gr[i], g[c]);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w) + 2 * i), w1 = __ldg(reinterpret_cast<const float4*>(w) + 2 * i + 1);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[c][j] = (xh[c][j] - mu) * rs;
+          aw[c][j] += g[c][j] * xh[c][j];
+          ab[c][j] += g[c][j];
+          g[c][j] *= wv[j];  // g now holds w*dy
+          s1 += g[c][j];
+          s2 += g[c][j] * xh[c][j];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / D;
+    s2 = warp_sum(s2) / D;
+    uint4* dr = reinterpret_cast<uint4*>(dx + src * lddx);
+    const uint4* rr = dres ? reinterpret_cast<const uint4*>(dres + src * lddres) : nullptr;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int i = lane + c * 32;
+      if (i < nvec) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rs * (g[c][j] - s1 - xh[c][j] * s2);
+        if (rr) {
+          float r[8];
+          unpack8(rr[i], r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += r[j];
+        }
+        dr[i] = pack8(o);
+      }
+    }
+  }
+  if (dw == nullptr) return;
+  // block reduction of the per-warp partial column sums, then one atomic per column per CTA
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int i = lane + c * 32;
+      if (i < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[warp * D + i * 8 + j] = pass == 0 ? aw[c][j] : ab[c][j];
+      }
+    }
+    __syncthreads();
+    for (int col = threadIdx.x; col < D; col += blockDim.x) {
+      float s = 0.f;
+      for (int ww = 0; ww < wpb; ++ww) s += red[ww * D + col];
+      atomicAdd((pass == 0 ? dw : db) + col, s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ column sums (bias grads)
+// db[n] += sum_t dy[t, n]
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ dy, long long ld, float* __restrict__ db,
+                                                     int T, int N, int rows_per_cta) {
+  __shared__ float red[8][256];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + tx) * 8;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  const long long r1 = min((long long)T, r0 + rows_per_cta);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (col < N) {
+    for (long long r = r0 + ty; r < r1; r += 8) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(dy + r * ld + col), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[ty][tx * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = threadIdx.x;  // 256 columns per CTA
+  float s = 0.f;
+#pragma unroll
+  for (int y = 0; y < 8; ++y) s += red[y][c];
+  const int gc = blockIdx.x * 256 + c;
+  if (gc < N) atomicAdd(db + gc, s);
+}
+
+// ------------------------------------------------------------------------------------ patch gather (im2col)
+// out[(b*OH + oh)*OW + ow, (c*kh + i)*kw + j] = in[b*sb + c*sc + (oh*sth+i)*sh + (ow*stw+j)*sw]; columns >= C*kh*kw are 0.
+template <typename TIn>
+__global__ void __launch_bounds__(256) patchify_kernel(const TIn* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int C,
+                                                       int OH, int OW, int kh, int kw, int sth, int stw, long long sb,
+                                                       long long sc, long long sh, long long sw, int Kpad) {
+  const int kvec = Kpad >> 3;
+  const long long total = (long long)B * OH * OW * kvec;
+  const int K = C * kh * kw;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int kv = (int)(idx % kvec);
+    const long long row = idx / kvec;
+    const int ow = (int)(row % OW);
+    const int oh = (int)((row / OW) % OH);
+    const int b = (int)(row / ((long long)OW * OH));
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kv * 8 + e;
+      float val = 0.f;
+      if (k < K) {
+        const int j = k % kw;
+        const int i = (k / kw) % kh;
+        const int c = k / (kw * kh);
+        val = static_cast<float>(in[b * sb + c * sc + (long long)(oh * sth + i) * sh + (long long)(ow * stw + j) * sw]);
+      }
+      f[e] = val;
+    }
+    *reinterpret_cast<uint4*>(out + row * Kpad + kv * 8) = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------ token assembly
+// out[b, off + l, :] = tok[b, l, :] + pos[off + l, :]  (off = has_cls);  out[b, 0, :] = cls + pos[0] when has_cls.
+// pos may be NULL (treated as 0).
+__global__ void __launch_bounds__(256) assemble_kernel(const __nv_bfloat16* __restrict__ tok, const float* __restrict__ cls,
+                                                       const float* __restrict__ pos, __nv_bfloat16* __restrict__ out, int B, int L,
+                                                       int D, int has_cls) {
+  const int dvec = D >> 3;
+  const int Lo = L + has_cls;
+  const long long total = (long long)B * Lo * dvec;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int dv = (int)(idx % dvec);
+    const long long r = idx / dvec;
+    const int lo = (int)(r % Lo);
+    const long long b = r / Lo;
+    float f[8];
+    if (has_cls && lo == 0) {
+      const float4 c0 = __ldg(reinterpret_cast<const float4*>(cls) + 2 * dv), c1 = __ldg(reinterpret_cast<const float4*>(cls) + 2 * dv + 1);
+      f[0] = c0.x; f[1] = c0.y; f[2] = c0.z; f[3] = c0.w; f[4] = c1.x; f[5] = c1.y; f[6] = c1.z; f[7] = c1.w;
+    } else {
+      unpack8(*reinterpret_cast<const uint4*>(tok + (b * L + (lo - has_cls)) * D + dv * 8), f);
+    }
+    if (pos) {
+      const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos + (long long)lo * D) + 2 * dv);
+      const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos + (long long)lo * D) + 2 * dv + 1);
+      f[0] += p0.x; f[1] += p0.y; f[2] += p0.z; f[3] += p0.w; f[4] += p1.x; f[5] += p1.y; f[6] += p1.z; f[7] += p1.w;
+    }
+    *reinterpret_cast<uint4*>(out + r * D + dv * 8) = pack8(f);
+  }
+}
+
+// Backward of assemble: dtok[b,l,:] = dx[b, off+l, :] (optional);  dpos[lo,:] += sum_b dx[b,lo,:] (optional);
+// dcls[:] += sum_b dx[b,0,:] (optional).  One thread owns (lo, 8 columns) and loops over the batch.
+__global__ void __launch_bounds__(256) assemble_bwd_kernel(const __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dtok,
+                                                           float* __restrict__ dpos, float* __restrict__ dcls, int B, int L, int D,
+                                                           int has_cls, int bchunk) {
+  const int dvec = D >> 3;
+  const int Lo = L + has_cls;
+  const long long total = (long long)Lo * dvec;
+  const int b0 = blockIdx.y * bchunk, b1 = min(B, b0 + bchunk);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int dv = (int)(idx % dvec);
+    const int lo = (int)(idx / dvec);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int b = b0; b < b1; ++b) {
+      const uint4 u = *reinterpret_cast<const uint4*>(dx + ((long long)b * Lo + lo) * D + dv * 8);
+      if (dtok && lo >= has_cls) *reinterpret_cast<uint4*>(dtok + ((long long)b * L + lo - has_cls) * D + dv * 8) = u;
+      float f[8];
+      unpack8(u, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (dpos) atomicAdd(dpos + (long long)lo * D + dv * 8 + j, acc[j]);
+      if (dcls && has_cls && lo == 0) atomicAdd(dcls + dv * 8 + j, acc[j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ text embedding
+// out[b*ctx + t, :] = table[ids[b,t], :] + pos[t, :]
+__global__ void __launch_bounds__(256) embed_kernel(const long long* __restrict__ ids, const float* __restrict__ table,
+                                                    const float* __restrict__ pos, __nv_bfloat16* __restrict__ out, long long rows,
+                                                    int ctx, int D) {
+  const int dvec = D >> 3;
+  const long long total = rows * dvec;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int dv = (int)(idx % dvec);
+    const long long r = idx / dvec;
+    const long long id = ids[r];
+    const int t = (int)(r % ctx);
+    const float4* tr = reinterpret_cast<const float4*>(table + id * D) + 2 * dv;
+    const float4* pr = reinterpret_cast<const float4*>(pos + (long long)t * D) + 2 * dv;
+    const float4 a0 = __ldg(tr), a1 = __ldg(tr + 1), p0 = __ldg(pr), p1 = __ldg(pr + 1);
+    const float f[8] = {a0.x + p0.x, a0.y + p0.y, a0.z + p0.z, a0.w + p0.w, a1.x + p1.x, a1.y + p1.y, a1.z + p1.z, a1.w + p1.w};
+    *reinterpret_cast<uint4*>(out + r * D + dv * 8) = pack8(f);
+  }
+}
+// dtable[ids[r], :] += dx[r, :];  dpos[t, :] += dx[r, :]
+__global__ void __launch_bounds__(256) embed_bwd_kernel(const long long* __restrict__ ids, const __nv_bfloat16* __restrict__ dx,
+                                                        float* __restrict__ dtable, float* __restrict__ dpos, long long rows, int ctx, int D) {
+  const int dvec = D >> 3;
+  const long long total = rows * dvec;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int dv = (int)(idx % dvec);
+    const long long r = idx / dvec;
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(dx + r * D + dv * 8), f);
+    const long long id = ids[r];
+    const int t = (int)(r % ctx);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (dtable) atomicAdd(dtable + id * D + dv * 8 + j, f[j]);
+      if (dpos) atomicAdd(dpos + (long long)t * D + dv * 8 + j, f[j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ L2 normalise (fp32 rows)
+// y = x / max(||x||, eps); inv_norm saved.   bwd: dx = (dy - y * <dy, y>) * inv_norm
+__global__ void __launch_bounds__(256) l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ inv_norm,
+                                                         int B, int E, float eps) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < B; row += gridDim.x * wpb) {
+    float s = 0.f;
+    for (int i = lane; i < E; i += 32) {
+      const float v = x[(long long)row * E + i];
+      s += v * v;
+    }
+    const float inv = 1.0f / fmaxf(sqrtf(warp_sum(s)), eps);
+    for (int i = lane; i < E; i += 32) y[(long long)row * E + i] = x[(long long)row * E + i] * inv;
+    if (lane == 0 && inv_norm) inv_norm[row] = inv;
+  }
+}
+__global__ void __launch_bounds__(256) l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                         const float* __restrict__ inv_norm, float* __restrict__ dx, int B, int E) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < B; row += gridDim.x * wpb) {
+    float s = 0.f;
+    for (int i = lane; i < E; i += 32) s += dy[(long long)row * E + i] * y[(long long)row * E + i];
+    s = warp_sum(s);
+    const float inv = inv_norm[row];
+    for (int i = lane; i < E; i += 32)
+      dx[(long long)row * E + i] = (dy[(long long)row * E + i] - y[(long long)row * E + i] * s) * inv;
+  }
+}
+
+// ------------------------------------------------------------------------------------ GEGLU (Lens FeedForward)
+// h[M, 2F] = [val | gate];  out[M, F] = val * gelu(gate)
+__global__ void __launch_bounds__(256) geglu_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ out, long long M, int F) {
+  const int fvec = F >> 3;
+  const long long total = M * fvec;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int fv = (int)(idx % fvec);
+    const long long r = idx / fvec;
+    float a[8], g[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(h + r * 2 * F + fv * 8), a);
+    unpack8(*reinterpret_cast<const uint4*>(h + r * 2 * F + F + fv * 8), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = a[j] * gelu_fwd(g[j], 0);
+    *reinterpret_cast<uint4*>(out + r * F + fv * 8) = pack8(o);
+  }
+}
+// dh[M, 2F]: dval = dout * gelu(gate); dgate = dout * val * gelu'(gate)
+__global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ dout,
+                                                        __nv_bfloat16* __restrict__ dh, long long M, int F) {
+  const int fvec = F >> 3;
+  const long long total = M * fvec;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int fv = (int)(idx % fvec);
+    const long long r = idx / fvec;
+    float a[8], g[8], d[8], da[8], dg[8];
+    unpack8(*reinterpret_cast<const uint4*>(h + r * 2 * F + fv * 8), a);
+    unpack8(*reinterpret_cast<const uint4*>(h + r * 2 * F + F + fv * 8), g);
+    unpack8(*reinterpret_cast<const uint4*>(dout + r * F + fv * 8), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      da[j] = d[j] * gelu_fwd(g[j], 0);
+      dg[j] = d[j] * a[j] * gelu_grad(g[j], 0);
+    }
+    *reinterpret_cast<uint4*>(dh + r * 2 * F + fv * 8) = pack8(da);
+    *reinterpret_cast<uint4*>(dh + r * 2 * F + F + fv * 8) = pack8(dg);
+  }
+}
+
+// ------------------------------------------------------------------------------------ casts / adds
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  const long long nv = n >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(in)[2 * i], b = reinterpret_cast<const float4*>(in)[2 * i + 1];
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    reinterpret_cast<uint4*>(out)[i] = pack8(f);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = nv << 3; i < n; ++i) out[i] = __float2bfloat16(in[i]);
+}
+// out = a + b  (bf16, n % 8 == 0)
+__global__ void __launch_bounds__(256) add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                                       __nv_bfloat16* __restrict__ out, long long n) {
+  const long long nv = n >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+    float x[8], y[8];
+    unpack8(reinterpret_cast<const uint4*>(a)[i], x);
+    unpack8(reinterpret_cast<const uint4*>(b)[i], y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] += y[j];
+    reinterpret_cast<uint4*>(out)[i] = pack8(x);
+  }
+}
+
+// ------------------------------------------------------------------------------------ fused AdamW (one tensor per launch)
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                                                    float wd, float bc1, float bc2, float grad_scale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    float pi = p[i] * (1.0f - lr * wd);
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    pi -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+    p[i] = pi;
+  }
+}
+
+static inline int grid_for(long long work_items, int threads) {
+  long long g = (work_items + threads - 1) / threads;
+  const long long cap = (long long)num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace vl
+
+using namespace vl;
+
+extern "C" {
+
+int vl_layernorm_fwd(const void* x, int64_t ldx, const int64_t* row_index, const float* w, const float* b, void* y, int64_t ldy,
+                     float* mean, float* rstd, int32_t T, int32_t D, float eps, void* stream) {
+  VL_CHECK_ARG(x && w && b && y, "vl_layernorm_fwd: null pointer");
+  VL_CHECK_ARG(T > 0 && D > 0 && D % 8 == 0 && D <= 256 * kMaxLnChunks, "vl_layernorm_fwd: D=%d must be a multiple of 8 and <= 2048", D);
+  VL_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0, "vl_layernorm_fwd: ld must be a multiple of 8");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = grid_for((long long)T * 32, 256);
+  const int ch = (D / 8 + 31) / 32;
+#define VL_LN_FWD(CH)                                                                                                          \
+  layernorm_fwd_kernel<CH><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, (const long long*)row_index, w, b, \
+                                                reinterpret_cast<__nv_bfloat16*>(y), ldy, mean, rstd, T, D, eps)
+  if (ch <= 1) VL_LN_FWD(1); else if (ch <= 2) VL_LN_FWD(2); else if (ch <= 4) VL_LN_FWD(4); else VL_LN_FWD(8);
+#undef VL_LN_FWD
+  return launch_check("layernorm_fwd");
+}
+
+int vl_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const int64_t* row_index, const float* w,
+                     const float* mean, const float* rstd, const void* dres, int64_t lddres, void* dx, int64_t lddx, float* dw,
+                     float* db, int32_t T, int32_t D, void* stream) {
+  VL_CHECK_ARG(dy && x && w && mean && rstd && dx, "vl_layernorm_bwd: null pointer");
+  VL_CHECK_ARG((dw == nullptr) == (db == nullptr), "vl_layernorm_bwd: dw and db must both be given or both be NULL");
+  VL_CHECK_ARG(T > 0 && D > 0 && D % 8 == 0 && D <= 256 * kMaxLnChunks, "vl_layernorm_bwd: D=%d unsupported", D);
+  VL_CHECK_ARG(ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0 && lddres % 8 == 0, "vl_layernorm_bwd: ld must be a multiple of 8");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int grid = num_sms() * 2;
+  if ((long long)grid * 8 > T) grid = (T + 7) / 8;
+  const size_t smem = dw ? (size_t)8 * D * sizeof(float) : 0;
+  const int ch = (D / 8 + 31) / 32;
+#define VL_LN_BWD(CH)                                                                                                     \
+  do {                                                                                                                    \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    layernorm_bwd_kernel<CH><<<grid, 256, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy,                    \
+        reinterpret_cast<const __nv_bfloat16*>(x), ldx, (const long long*)row_index, w, mean, rstd,                       \
+        reinterpret_cast<const __nv_bfloat16*>(dres), lddres, reinterpret_cast<__nv_bfloat16*>(dx), lddx, dw, db, T, D);  \
+  } while (0)
+  if (ch <= 1) VL_LN_BWD(1); else if (ch <= 2) VL_LN_BWD(2); else if (ch <= 4) VL_LN_BWD(4); else VL_LN_BWD(8);
+#undef VL_LN_BWD
+  return launch_check("layernorm_bwd");
+}
+
+int vl_colsum_bf16(const void* dy, int64_t ld, float* db, int32_t T, int32_t N, void* stream) {
+  VL_CHECK_ARG(dy && db && T > 0 && N > 0 && N % 8 == 0 && ld % 8 == 0, "vl_colsum_bf16: bad arguments");
+  const int gx = (N + 255) / 256;
+  int gy = (num_sms() * 4 + gx - 1) / gx;
+  if (gy > (T + 63) / 64) gy = (T + 63) / 64;
+  if (gy < 1) gy = 1;
+  const int rows_per = (T + gy - 1) / gy;
+  colsum_kernel<<<dim3(gx, gy), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(dy), ld, db, T, N, rows_per);
+  return launch_check("colsum");
+}
+
+int vl_patchify(const void* in, int32_t in_is_bf16, void* out, int32_t B, int32_t C, int32_t OH, int32_t OW, int32_t kh, int32_t kw,
+                int32_t stride_h, int32_t stride_w, int64_t sb, int64_t sc, int64_t sh, int64_t sw, int32_t Kpad, void* stream) {
+  VL_CHECK_ARG(in && out && B > 0 && C > 0 && OH > 0 && OW > 0 && Kpad % 8 == 0 && Kpad >= C * kh * kw, "vl_patchify: bad arguments");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = (long long)B * OH * OW * (Kpad / 8);
+  const int grid = grid_for(total, 256);
+  if (in_is_bf16)
+    patchify_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), B, C, OH, OW, kh, kw, stride_h, stride_w, sb, sc, sh, sw, Kpad);
+  else
+    patchify_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(in), reinterpret_cast<__nv_bfloat16*>(out), B, C, OH, OW, kh, kw, stride_h, stride_w, sb, sc, sh, sw, Kpad);
+  return launch_check("patchify");
+}
+
+int vl_assemble_tokens(const void* tok, const float* cls, const float* pos, void* out, int32_t B, int32_t L, int32_t D, int32_t has_cls,
+                       void* stream) {
+  VL_CHECK_ARG(tok && out && B > 0 && L > 0 && D % 8 == 0 && (!has_cls || cls), "vl_assemble_tokens: bad arguments");
+  const long long total = (long long)B * (L + (has_cls ? 1 : 0)) * (D / 8);
+  assemble_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(tok), cls, pos, reinterpret_cast<__nv_bfloat16*>(out), B, L, D, has_cls ? 1 : 0);
+  return launch_check("assemble_tokens");
+}
+
+int vl_assemble_tokens_bwd(const void* dx, void* dtok, float* dpos, float* dcls, int32_t B, int32_t L, int32_t D, int32_t has_cls,
+                           void* stream) {
+  VL_CHECK_ARG(dx && B > 0 && L > 0 && D % 8 == 0, "vl_assemble_tokens_bwd: bad arguments");
+  const long long total = (long long)(L + (has_cls ? 1 : 0)) * (D / 8);
+  const int gx = (int)((total + 255) / 256);
+  int gy = (num_sms() * 2 + gx - 1) / gx;
+  if (gy > B) gy = B;
+  if (gy < 1) gy = 1;
+  const int bchunk = (B + gy - 1) / gy;
+  assemble_bwd_kernel<<<dim3(gx, gy), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(dtok), dpos, dcls, B, L, D, has_cls ? 1 : 0, bchunk);
+  return launch_check("assemble_tokens_bwd");
+}
+
+int vl_embed_tokens(const int64_t* ids, const float* table, const float* pos, void* out, int64_t rows, int32_t ctx, int32_t D, void* stream) {
+  VL_CHECK_ARG(ids && table && pos && out && rows > 0 && D % 8 == 0, "vl_embed_tokens: bad arguments");
+  embed_kernel<<<grid_for(rows * (D / 8), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const long long*)ids, table, pos, reinterpret_cast<__nv_bfloat16*>(out), rows, ctx, D);
+  return launch_check("embed_tokens");
+}
+
+int vl_embed_tokens_bwd(const int64_t* ids, const void* dx, float* dtable, float* dpos, int64_t rows, int32_t ctx, int32_t D, void* stream) {
+  VL_CHECK_ARG(ids && dx && rows > 0 && D % 8 == 0, "vl_embed_tokens_bwd: bad arguments");
+  embed_bwd_kernel<<<grid_for(rows * (D / 8), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const long long*)ids, reinterpret_cast<const __nv_bfloat16*>(dx), dtable, dpos, rows, ctx, D);
+  return launch_check("embed_tokens_bwd");
+}
+
+int vl_l2norm_fwd(const float* x, float* y, float* inv_norm, int32_t B, int32_t E, float eps, void* stream) {
+  VL_CHECK_ARG(x && y && B > 0 && E > 0, "vl_l2norm_fwd: bad arguments");
+  l2norm_fwd_kernel<<<grid_for((long long)B * 32, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, inv_norm, B, E, eps);
+  return launch_check("l2norm_fwd");
+}
+
+int vl_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, float* dx, int32_t B, int32_t E, void* stream) {
+  VL_CHECK_ARG(dy && y && inv_norm && dx && B > 0 && E > 0, "vl_l2norm_bwd: bad arguments");
+  l2norm_bwd_kernel<<<grid_for((long long)B * 32, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dy, y, inv_norm, dx, B, E);
+  return launch_check("l2norm_bwd");
+}
+
+int vl_geglu_fwd(const void* h, void* out, int64_t M, int32_t F, void* stream) {
+  VL_CHECK_ARG(h && out && M > 0 && F % 8 == 0, "vl_geglu_fwd: bad arguments");
+  geglu_fwd_kernel<<<grid_for(M * (F / 8), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(h), reinterpret_cast<__nv_bfloat16*>(out), M, F);
+  return launch_check("geglu_fwd");
+}
+
+int vl_geglu_bwd(const void* h, const void* dout, void* dh, int64_t M, int32_t F, void* stream) {
+  VL_CHECK_ARG(h && dout && dh && M > 0 && F % 8 == 0, "vl_geglu_bwd: bad arguments");
+  geglu_bwd_kernel<<<grid_for(M * (F / 8), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(h), reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<__nv_bfloat16*>(dh), M, F);
+  return launch_check("geglu_bwd");
+}
+
+int vl_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream) {
+  VL_CHECK_ARG(in && out && n > 0, "vl_cast_f32_bf16: bad arguments");
+  cast_f32_bf16_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, reinterpret_cast<__nv_bfloat16*>(out), n);
+  return launch_check("cast_f32_bf16");
+}
+
+int vl_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream) {
+  VL_CHECK_ARG(a && b && out && n > 0 && n % 8 == 0, "vl_add_bf16: bad arguments");
+  add_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(b), reinterpret_cast<__nv_bfloat16*>(out), n);
+  return launch_check("add_bf16");
+}
+
+int vl_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int32_t step, float grad_scale, void* stream) {
+  VL_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "vl_adamw_step: bad arguments");
+  const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
+  adamw_kernel<<<grid_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale);
+  return launch_check("adamw_step");
+}
+}

@@ -1,0 +1,407 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   D[M,N] = epilogue(alpha * A[M,K] * B[N,K]^T),  bf16 operands, fp32 accumulation in TMEM.
+//
+// Roles (320 threads, 1 CTA / SM, grid = min(#tiles, #SMs)):
+//   warp 0      TMA producer   (one elected lane): global -> 128B-swizzled smem ring, mbarrier tx-count
+//   warp 1      MMA issuer     (one elected lane): tcgen05.mma 128 x BN x 16, accumulators in TMEM,
+//                               tcgen05.commit releases smem stages / publishes accumulators
+//   warps 2..9  epilogue       tcgen05.ld TMEM -> registers -> bias / GELU / residual / GELU' -> global
+// TMEM holds two accumulator buffers (2 x BN columns) so the epilogue of tile i overlaps the
+// main loop of tile i+1.  Operands may be K-major ([rows, K] row-major) or MN-major ([K, rows]
+// row-major, used by the weight-gradient GEMMs where K is the token dimension).
+#include "vl_host.h"
+#include "vl_sm100.cuh"
+
+namespace vl {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int kGemmThreads = 320;
+constexpr int kEpiWarps = 8;
+constexpr int kGroupM = 16;  // m-tiles per L2 reuse group
+
+struct GemmParams {
+  int M, N, K;
+  int a_mn, b_mn;
+  int tiles_m, tiles_n, split_k, kb_total, kb_per_split;
+  int epi, act_quick, d_f32, accumulate;
+  float alpha;
+  void* d;
+  long long ldd;
+  const float* bias;
+  const __nv_bfloat16* aux_in;
+  __nv_bfloat16* aux_out;
+  long long ldaux;
+  uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;  // bytes
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = 2 * BN;
+};
+
+__device__ __forceinline__ void tile_coords(const GemmParams& p, int t, int& m_blk, int& n_blk, int& ks) {
+  int mn = t / p.split_k;
+  ks = t - mn * p.split_k;
+  int group_sz = kGroupM * p.tiles_n;
+  int g = mn / group_sz;
+  int r = mn - g * group_sz;
+  int m_first = g * kGroupM;
+  int gm = min(kGroupM, p.tiles_m - m_first);
+  n_blk = r / gm;
+  m_blk = m_first + (r - n_blk * gm);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_m * p.tiles_n * p.split_k;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int m_blk, n_blk, ks;
+        tile_coords(p, t, m_blk, n_blk, ks);
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          if (!p.a_mn) {
+            tma_load_2d(sa, &tmA, full_bar(stage), kb * kBK, m_blk * kBM);
+          } else {
+#pragma unroll
+            for (int c = 0; c < kBM / 64; ++c)
+              tma_load_2d(sa + c * (kBK * 128), &tmA, full_bar(stage), m_blk * kBM + c * 64, kb * kBK);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(sb, &tmB, full_bar(stage), kb * kBK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(sb + c * (kBK * 128), &tmB, full_bar(stage), n_blk * BN + c * 64, kb * kBK);
+          }
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(kBM, BN, p.a_mn, p.b_mn);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int m_blk, n_blk, ks;
+        tile_coords(p, t, m_blk, n_blk, ks);
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t ad = umma_desc_sw128(sa + k * p.a_kstep, p.a_lbo, p.a_sbo);
+            const uint64_t bd = umma_desc_sw128(sb + k * p.b_kstep, p.b_lbo, p.b_sbo);
+            umma_ss(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int e = warp - 2;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = e >> 2;       // column half of the tile
+    constexpr int kChunks = (BN / 2) / 32;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int m_blk, n_blk, ks;
+      tile_coords(p, t, m_blk, n_blk, ks);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m_blk * kBM + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      const bool lead_split = (ks == 0);  // bias / aux terms are added by split 0 only
+#pragma unroll 1
+      for (int c = 0; c < kChunks; ++c) {
+        const int col0 = n_blk * BN + half * (BN / 2) + c * 32;
+        if (col0 >= p.N) break;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * (BN / 2) + c * 32, v);
+        tc_wait_ld();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+        if (p.bias != nullptr && lead_split && p.epi != VL_EPI_GELU_BWD) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col0 + j < p.N) {  // N % 4 == 0 is enforced on the host
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              f[j] += b4.x;
+              f[j + 1] += b4.y;
+              f[j + 2] += b4.z;
+              f[j + 3] += b4.w;
+            }
+          }
+        }
+        if (row_ok) {
+          const long long aoff = static_cast<long long>(row) * p.ldaux + col0;
+          if (p.epi == VL_EPI_GELU) {
+            if (p.aux_out != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (col0 + j < p.N) {
+                  uint4 u;
+                  u.x = pack_bf16(f[j], f[j + 1]);
+                  u.y = pack_bf16(f[j + 2], f[j + 3]);
+                  u.z = pack_bf16(f[j + 4], f[j + 5]);
+                  u.w = pack_bf16(f[j + 6], f[j + 7]);
+                  *reinterpret_cast<uint4*>(p.aux_out + aoff + j) = u;
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = gelu_fwd(f[j], p.act_quick);
+          } else if (p.epi == VL_EPI_RESIDUAL) {
+            if (lead_split) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (col0 + j < p.N) {
+                  const uint4 u = *reinterpret_cast<const uint4*>(p.aux_in + aoff + j);
+                  f[j] += bf16_lo(u.x);
+                  f[j + 1] += bf16_hi(u.x);
+                  f[j + 2] += bf16_lo(u.y);
+                  f[j + 3] += bf16_hi(u.y);
+                  f[j + 4] += bf16_lo(u.z);
+                  f[j + 5] += bf16_hi(u.z);
+                  f[j + 6] += bf16_lo(u.w);
+                  f[j + 7] += bf16_hi(u.w);
+                }
+              }
+            }
+          } else if (p.epi == VL_EPI_GELU_BWD) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (col0 + j < p.N) {
+                const uint4 u = *reinterpret_cast<const uint4*>(p.aux_in + aoff + j);
+                f[j] *= gelu_grad(bf16_lo(u.x), p.act_quick);
+                f[j + 1] *= gelu_grad(bf16_hi(u.x), p.act_quick);
+                f[j + 2] *= gelu_grad(bf16_lo(u.y), p.act_quick);
+                f[j + 3] *= gelu_grad(bf16_hi(u.y), p.act_quick);
+                f[j + 4] *= gelu_grad(bf16_lo(u.z), p.act_quick);
+                f[j + 5] *= gelu_grad(bf16_hi(u.z), p.act_quick);
+                f[j + 6] *= gelu_grad(bf16_lo(u.w), p.act_quick);
+                f[j + 7] *= gelu_grad(bf16_hi(u.w), p.act_quick);
+              }
+            }
+          }
+          // ---- store
+          const long long doff = static_cast<long long>(row) * p.ldd + col0;
+          if (p.d_f32) {
+            float* dp = reinterpret_cast<float*>(p.d) + doff;
+            if (p.accumulate) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) atomicAdd(dp + j, f[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                if (col0 + j < p.N) *reinterpret_cast<float4*>(dp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            }
+          } else {
+            __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.d) + doff;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (col0 + j < p.N) {
+                uint4 u;
+                u.x = pack_bf16(f[j], f[j + 1]);
+                u.y = pack_bf16(f[j + 2], f[j + 3]);
+                u.z = pack_bf16(f[j + 4], f[j + 5]);
+                u.w = pack_bf16(f[j + 6], f[j + 7]);
+                *reinterpret_cast<uint4*>(dp + j) = u;
+              }
+            }
+          }
+        }
+      }
+      // accumulator drained -> hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN>
+static int launch_gemm(const VlGemmArgs& a, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  GemmParams p;
+  p.M = a.M;
+  p.N = a.N;
+  p.K = a.K;
+  p.a_mn = a.a_mn ? 1 : 0;
+  p.b_mn = a.b_mn ? 1 : 0;
+  p.tiles_m = (a.M + kBM - 1) / kBM;
+  p.tiles_n = (a.N + BN - 1) / BN;
+  p.split_k = a.split_k < 1 ? 1 : a.split_k;
+  p.kb_total = (a.K + kBK - 1) / kBK;
+  if (p.split_k > p.kb_total) p.split_k = p.kb_total;
+  p.kb_per_split = (p.kb_total + p.split_k - 1) / p.split_k;
+  p.split_k = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
+  p.epi = a.epilogue;
+  p.act_quick = a.act_quick;
+  p.d_f32 = a.d_f32;
+  p.accumulate = a.accumulate;
+  p.alpha = a.alpha;
+  p.d = a.d;
+  p.ldd = a.ldd;
+  p.bias = a.bias;
+  p.aux_in = reinterpret_cast<const __nv_bfloat16*>(a.aux_in);
+  p.aux_out = reinterpret_cast<__nv_bfloat16*>(a.aux_out);
+  p.ldaux = a.ldaux;
+  // K-major: 8-row groups 1024 B apart, +32 B per UMMA_K inside the swizzle row.
+  // MN-major: 64-wide chunks kBK*128 B apart (LBO), 8-K groups 1024 B apart (SBO), +2048 B per UMMA_K.
+  p.a_lbo = p.a_mn ? kBK * 128 : 16;
+  p.a_sbo = 1024;
+  p.a_kstep = p.a_mn ? 2048 : 32;
+  p.b_lbo = p.b_mn ? kBK * 128 : 16;
+  p.b_sbo = 1024;
+  p.b_kstep = p.b_mn ? 2048 : 32;
+  if (debug_get(1)) p.a_lbo = debug_get(1);
+  if (debug_get(2)) p.a_sbo = debug_get(2);
+  if (debug_get(3)) p.a_kstep = debug_get(3);
+  if (debug_get(4)) p.b_lbo = debug_get(4);
+  if (debug_get(5)) p.b_sbo = debug_get(5);
+  if (debug_get(6)) p.b_kstep = debug_get(6);
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!p.a_mn)
+    rc = make_tmap_bf16_2d(&tmA, a.a, a.K, a.M, a.lda, kBK, kBM);
+  else
+    rc = make_tmap_bf16_2d(&tmA, a.a, a.M, a.K, a.lda, 64, kBK);
+  if (rc) return rc;
+  if (!p.b_mn)
+    rc = make_tmap_bf16_2d(&tmB, a.b, a.K, a.N, a.ldb, kBK, BN);
+  else
+    rc = make_tmap_bf16_2d(&tmB, a.b, a.N, a.K, a.ldb, 64, kBK);
+  if (rc) return rc;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    VL_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int total = p.tiles_m * p.tiles_n * p.split_k;
+  int grid = total < num_sms() ? total : num_sms();
+  if (debug_get(7) > 0 && debug_get(7) < grid) grid = debug_get(7);
+  gemm_bf16_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  return launch_check("gemm_bf16_kernel");
+}
+
+}  // namespace vl
+
+extern "C" int vl_gemm_bf16(const VlGemmArgs* a, void* stream) {
+  using namespace vl;
+  VL_CHECK_ARG(a != nullptr && a->a && a->b && a->d, "vl_gemm_bf16: null pointer");
+  VL_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "vl_gemm_bf16: non-positive dims M=%d N=%d K=%d", a->M, a->N, a->K);
+  VL_CHECK_ARG(a->N % 8 == 0, "vl_gemm_bf16: N=%d must be a multiple of 8", a->N);
+  VL_CHECK_ARG(a->lda % 8 == 0 && a->ldb % 8 == 0, "vl_gemm_bf16: lda/ldb must be multiples of 8 elements");
+  VL_CHECK_ARG(a->ldd % (a->d_f32 ? 4 : 8) == 0, "vl_gemm_bf16: ldd misaligned");
+  VL_CHECK_ARG(a->lda >= (a->a_mn ? a->M : a->K) && a->ldb >= (a->b_mn ? a->N : a->K) && a->ldd >= a->N,
+               "vl_gemm_bf16: leading dimension smaller than the row length");
+  VL_CHECK_ARG(!(a->accumulate && !a->d_f32), "vl_gemm_bf16: accumulate needs fp32 output");
+  VL_CHECK_ARG(!(a->split_k > 1 && !(a->accumulate && a->d_f32)), "vl_gemm_bf16: split_k needs accumulate fp32 output");
+  VL_CHECK_ARG(!(a->split_k > 1 && a->epilogue != VL_EPI_LINEAR), "vl_gemm_bf16: split_k only with the linear epilogue");
+  if (a->epilogue == VL_EPI_RESIDUAL || a->epilogue == VL_EPI_GELU_BWD)
+    VL_CHECK_ARG(a->aux_in != nullptr && a->ldaux % 8 == 0 && a->ldaux >= a->N, "vl_gemm_bf16: aux_in / ldaux invalid");
+  if (a->epilogue == VL_EPI_GELU && a->aux_out)
+    VL_CHECK_ARG(a->ldaux % 8 == 0 && a->ldaux >= a->N, "vl_gemm_bf16: ldaux invalid");
+  if (a->epilogue < 0 || a->epilogue > VL_EPI_GELU_BWD) {
+    set_error("vl_gemm_bf16: epilogue %d not supported", a->epilogue);
+    return VL_ENOTSUP;
+  }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (a->N <= 128) return launch_gemm<128>(*a, s);
+  return launch_gemm<256>(*a, s);
+}

@@ -1,0 +1,57 @@
+// Host-side helpers shared by the .cu files: error reporting, tensor-map encode (driver entry point
+// resolved at run time so the library loads on a machine without libcuda), device properties.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/vitlens_b200.h"
+
+namespace vl {
+
+void set_error(const char* fmt, ...);
+int num_sms();
+int debug_get(int key);
+
+// 2-D / 3-D bf16 tensor map, row-major global tensor, 128B swizzle (or none), zero OOB fill.
+// dims[0] is the contiguous dimension.  strides_bytes[i] is the stride of dims[i+1].
+int make_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const void* base, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+
+inline int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
+                             uint64_t outer_stride_elems, uint32_t box_inner, uint32_t box_outer,
+                             bool swizzle128 = true) {
+  uint64_t dims[2] = {inner, outer};
+  uint64_t strides[1] = {outer_stride_elems * 2};
+  uint32_t box[2] = {box_inner, box_outer};
+  return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, swizzle128);
+}
+
+#define VL_CHECK_ARG(cond, ...)      \
+  do {                               \
+    if (!(cond)) {                   \
+      vl::set_error(__VA_ARGS__);    \
+      return VL_EINVAL;              \
+    }                                \
+  } while (0)
+
+#define VL_CUDA(expr)                                                           \
+  do {                                                                          \
+    cudaError_t _e = (expr);                                                    \
+    if (_e != cudaSuccess) {                                                    \
+      vl::set_error("%s failed: %s", #expr, cudaGetErrorString(_e));            \
+      return static_cast<int>(_e);                                              \
+    }                                                                           \
+  } while (0)
+
+inline int launch_check(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s launch failed: %s", what, cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  return 0;
+}
+
+}  // namespace vl
