@@ -45,8 +45,15 @@ enum {
   VL_EPI_GELU = 1,     /* u = alpha*acc + bias; aux_out(bf16) = u if given; d = act(u)           */
   VL_EPI_RESIDUAL = 2, /* d = alpha*acc + bias + aux_in                                          */
   VL_EPI_GELU_BWD = 3, /* d = alpha*acc * act'(aux_in)     (dgrad of c_proj fused with GELU bwd) */
-  VL_EPI_GEGLU = 4,    /* weight rows interleaved in 32-column groups (value|gate):
-                          u = alpha*acc + bias; aux_out = u (bf16, [M,N]); d[M,N/2] = val * gelu(gate) */
+  VL_EPI_GEGLU = 4,    /* reserved (fused GEGLU); returns VL_ENOTSUP today                         */
+  /* Contrastive-loss epilogues (replace `logit_scale * x @ y.T` + F.cross_entropy, loss.py:116-163,
+   * 346-385) -- the [rows x cols] logits never reach HBM:                                         */
+  VL_EPI_ROWLSE = 5,   /* z = alpha*acc. Per row and per 128/64-column part p: out_vec0[row*nparts+p] = max z,
+                          out_vec1[row*nparts+p] = sum exp(z - max); out_vec2[row] = z[row, row+iparam].
+                          nparts = ceil(N/BN)*2 is returned through vl_gemm_rowlse_parts(). d unused.     */
+  VL_EPI_CLIPGRAD = 6, /* z = alpha*acc; g = exp(z - row_vec[i]) + (col_vec ? exp(z - col_vec[j]) : 0)
+                          - (col_vec ? 2 : 1) * [j == i + iparam];  d(bf16) = fparam * g;
+                          *scalar_out += sum fparam * g * acc   (d loss / d alpha)                     */
 };
 
 typedef struct {
@@ -66,9 +73,83 @@ typedef struct {
   const void* aux_in; /* bf16 [M,N] (ld = ldaux) or NULL */
   void* aux_out;      /* bf16 [M,N] (ld = ldaux) or NULL */
   int64_t ldaux;
+  /* loss epilogues only */
+  const float* row_vec; /* fp32 [M] */
+  const float* col_vec; /* fp32 [N] or NULL */
+  float* out_vec0;
+  float* out_vec1;
+  float* out_vec2;
+  float* scalar_out;
+  int32_t iparam;
+  float fparam;
 } VlGemmArgs;
 
 int vl_gemm_bf16(const VlGemmArgs* args, void* stream);
+/* number of column parts VL_EPI_ROWLSE writes per row for an N-column problem */
+int vl_gemm_rowlse_parts(int32_t N);
+/* lse[i] = log sum_p out_vec1[i,p]*exp(out_vec0[i,p] - max_p) + max_p;  *loss_sum += sum_i (lse[i] - diag[i]) */
+int vl_lse_combine(const float* part_max, const float* part_sum, const float* diag, int32_t M, int32_t nparts,
+                   float* lse, float* loss_sum, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-head attention core, head_dim = 64 (ViT-L/14, ViT-B/32, CLIP text, Lens self/cross).
+ * Element (b, t, h, d) of q/k/v/o lives at base + (b*n + t)*ld + h*64 + d (bf16), so the packed
+ * in_proj output [T, 3D] is consumed in place (k = qkv + D, v = qkv + 2D, ld = 3D).
+ * softmax(scale * q k^T [+ causal mask]) v, fp32 softmax statistics; lse[b,h,t] (natural log) saved.
+ * Replaces: F.scaled_dot_product_attention inside nn.MultiheadAttention (transformer.py:241-252,
+ * additive causal attn_mask transformer.py:870-876) and the einsum-softmax-einsum of the Lens
+ * (perceiver.py:127-145), plus their autograd backward.
+ */
+int vl_attention_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int32_t B, int32_t H,
+                     int32_t nq, int32_t nk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float scale,
+                     int32_t causal, void* stream);
+int vl_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+                     void* dq, void* dk, void* dv, int32_t B, int32_t H, int32_t nq, int32_t nk, int64_t ldq,
+                     int64_t ldk, int64_t ldv, int64_t ldo, int64_t lddo, int64_t lddq, int64_t lddk, int64_t lddv,
+                     float scale, int32_t causal, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row kernels (HBM-bound, one pass).  x/y/dy/dx are bf16 unless noted; parameters and their
+ * gradients are fp32; gradient outputs named d<param> are ACCUMULATED (+=) with atomics.
+ */
+/* LayerNorm eps affine over the last dim (transformer.py:17-34, perceiver.py:71-72); optional row
+ * gather: y[i] = LN(x[row_index[i]]) (cls pooling transformer.py:653-657,783; EOT pooling model.py:537-540). */
+int vl_layernorm_fwd(const void* x, int64_t ldx, const int64_t* row_index, const float* w, const float* b, void* y,
+                     int64_t ldy, float* mean, float* rstd, int32_t T, int32_t D, float eps, void* stream);
+/* dx[row_index[i] or i] = LN'(dy[i]) (+ dres at the same row); dw += sum dy*xhat; db += sum dy (both or neither). */
+int vl_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const int64_t* row_index, const float* w,
+                     const float* mean, const float* rstd, const void* dres, int64_t lddres, void* dx, int64_t lddx,
+                     float* dw, float* db, int32_t T, int32_t D, void* stream);
+/* db[n] += sum_t dy[t,n]: bias gradients of every nn.Linear on the path. */
+int vl_colsum_bf16(const void* dy, int64_t ld, float* db, int32_t T, int32_t N, void* stream);
+/* Patch gather feeding conv1-as-GEMM (nn.Conv2d bias=False: transformer.py:464-470, AST_tokenizer.py:22-28,
+ * DepthTokenizer.py:22-28): out[(b*OH+oh)*OW+ow, (c*kh+i)*kw+j] = in[b*sb + c*sc + (oh*stride_h+i)*sh + (ow*stride_w+j)*sw],
+ * zero-padded to Kpad columns; `in` is fp32 or bf16 with arbitrary element strides (the audio
+ * unsqueeze/transpose of AST_tokenizer.py:46-47 is just a stride choice). */
+int vl_patchify(const void* in, int32_t in_is_bf16, void* out, int32_t B, int32_t C, int32_t OH, int32_t OW, int32_t kh,
+                int32_t kw, int32_t stride_h, int32_t stride_w, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
+                int32_t Kpad, void* stream);
+/* out[b, c+l] = tok[b,l] + pos[c+l]; out[b,0] = cls + pos[0] when has_cls (transformer.py:743,756-768). */
+int vl_assemble_tokens(const void* tok, const float* cls, const float* pos, void* out, int32_t B, int32_t L, int32_t D,
+                       int32_t has_cls, void* stream);
+int vl_assemble_tokens_bwd(const void* dx, void* dtok, float* dpos, float* dcls, int32_t B, int32_t L, int32_t D,
+                           int32_t has_cls, void* stream);
+/* out[r] = table[ids[r]] + pos[r % ctx] (model.py:530-532) and its backward. */
+int vl_embed_tokens(const int64_t* ids, const float* table, const float* pos, void* out, int64_t rows, int32_t ctx,
+                    int32_t D, void* stream);
+int vl_embed_tokens_bwd(const int64_t* ids, const void* dx, float* dtable, float* dpos, int64_t rows, int32_t ctx,
+                        int32_t D, void* stream);
+/* F.normalize(dim=-1, eps=1e-12) on fp32 [B,E] rows (model.py:522,526,540) and backward. */
+int vl_l2norm_fwd(const float* x, float* y, float* inv_norm, int32_t B, int32_t E, float eps, void* stream);
+int vl_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, float* dx, int32_t B, int32_t E, void* stream);
+/* GEGLU of the Lens FeedForward (perceiver.py:85-88): h[M,2F] = [val|gate] -> out[M,F] = val*gelu(gate). */
+int vl_geglu_fwd(const void* h, void* out, int64_t M, int32_t F, void* stream);
+int vl_geglu_bwd(const void* h, const void* dout, void* dh, int64_t M, int32_t F, void* stream);
+int vl_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream);
+int vl_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
+/* Decoupled-weight-decay Adam step on one fp32 tensor (optim.AdamW, training/point_cloud/pc_tri_main.py:394-419). */
+int vl_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

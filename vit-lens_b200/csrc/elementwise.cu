@@ -445,6 +445,35 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
   }
 }
 
+// ------------------------------------------------------------------------------------ contrastive loss: combine per-part LSEs
+__global__ void __launch_bounds__(256) lse_combine_kernel(const float* __restrict__ pm, const float* __restrict__ ps,
+                                                          const float* __restrict__ diag, int M, int nparts, float* __restrict__ lse,
+                                                          float* __restrict__ loss_sum) {
+  __shared__ float red[8];
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  float contrib = 0.f;
+  if (row < M) {
+    float mx = -INFINITY;
+    for (int q = 0; q < nparts; ++q) mx = fmaxf(mx, pm[(long long)row * nparts + q]);
+    float sum = 0.f;
+    for (int q = 0; q < nparts; ++q) {
+      const float m = pm[(long long)row * nparts + q];
+      if (m > -INFINITY) sum += ps[(long long)row * nparts + q] * __expf(m - mx);
+    }
+    const float l = mx + __logf(sum);
+    lse[row] = l;
+    contrib = l - diag[row];
+  }
+  contrib = warp_sum(contrib);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = contrib;
+  __syncthreads();
+  if (threadIdx.x == 0 && loss_sum) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(loss_sum, t);
+  }
+}
+
 static inline int grid_for(long long work_items, int threads) {
   long long g = (work_items + threads - 1) / threads;
   const long long cap = (long long)num_sms() * 16;
@@ -605,5 +634,12 @@ int vl_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float
   const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
   adamw_kernel<<<grid_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale);
   return launch_check("adamw_step");
+}
+
+int vl_lse_combine(const float* part_max, const float* part_sum, const float* diag, int32_t M, int32_t nparts, float* lse,
+                   float* loss_sum, void* stream) {
+  VL_CHECK_ARG(part_max && part_sum && diag && lse && M > 0 && nparts > 0, "vl_lse_combine: bad arguments");
+  lse_combine_kernel<<<(M + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(part_max, part_sum, diag, M, nparts, lse, loss_sum);
+  return launch_check("lse_combine");
 }
 }

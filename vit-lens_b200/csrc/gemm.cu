@@ -33,6 +33,14 @@ struct GemmParams {
   const __nv_bfloat16* aux_in;
   __nv_bfloat16* aux_out;
   long long ldaux;
+  const float* row_vec;
+  const float* col_vec;
+  float* out_vec0;
+  float* out_vec1;
+  float* out_vec2;
+  float* scalar_out;
+  int iparam;
+  float fparam;
   uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;  // bytes
 };
 
@@ -191,6 +199,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row = m_blk * kBM + quarter * 32 + lane;
       const bool row_ok = row < p.M;
       const bool lead_split = (ks == 0);  // bias / aux terms are added by split 0 only
+      float lse_m = -INFINITY, lse_s = 0.f, clip_ds = 0.f;
 #pragma unroll 1
       for (int c = 0; c < kChunks; ++c) {
         const int col0 = n_blk * BN + half * (BN / 2) + c * 32;
@@ -212,6 +221,58 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               f[j + 3] += b4.w;
             }
           }
+        }
+        if (p.epi == VL_EPI_ROWLSE) {
+          // online (max, sum-exp) over this thread's columns of the tile; one part per (n tile, half)
+          if (c == 0) {
+            lse_m = -INFINITY;
+            lse_s = 0.f;
+          }
+          float cm = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) cm = fmaxf(cm, f[j]);
+          const float nm = fmaxf(lse_m, cm);
+          float add = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) add += __expf(f[j] - nm);
+          lse_s = lse_s * __expf(lse_m - nm) + add;
+          lse_m = nm;
+          if (row_ok) {
+            const int dj = row + p.iparam - col0;
+            if (dj >= 0 && dj < 32) {
+              float dv = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j == dj) dv = f[j];
+              p.out_vec2[row] = dv;
+            }
+            const bool last = (c == kChunks - 1) || (col0 + 32 >= p.N);
+            if (last) {
+              const long long po = static_cast<long long>(row) * (p.tiles_n * 2) + n_blk * 2 + half;
+              p.out_vec0[po] = lse_m;
+              p.out_vec1[po] = lse_s;
+            }
+          }
+          continue;
+        }
+        if (p.epi == VL_EPI_CLIPGRAD) {
+          const float rl = row_ok ? __ldg(p.row_vec + row) : 0.f;
+          float dsum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float g = 0.f;
+            if (row_ok && col0 + j < p.N) {
+              g = __expf(f[j] - rl);
+              if (p.col_vec) g += __expf(f[j] - __ldg(p.col_vec + col0 + j));
+              if (col0 + j == row + p.iparam) g -= p.col_vec ? 2.f : 1.f;
+              g *= p.fparam;
+              dsum += g * __uint_as_float(v[j]);
+            }
+            f[j] = g;
+          }
+          clip_ds += dsum;
         }
         if (row_ok) {
           const long long aoff = static_cast<long long>(row) * p.ldaux + col0;
@@ -293,6 +354,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      if (p.epi == VL_EPI_CLIPGRAD && p.scalar_out != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) clip_ds += __shfl_xor_sync(0xffffffffu, clip_ds, o);
+        if (lane == 0) atomicAdd(p.scalar_out, clip_ds);
+      }
       // accumulator drained -> hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -339,6 +405,14 @@ static int launch_gemm(const VlGemmArgs& a, cudaStream_t stream) {
   p.aux_in = reinterpret_cast<const __nv_bfloat16*>(a.aux_in);
   p.aux_out = reinterpret_cast<__nv_bfloat16*>(a.aux_out);
   p.ldaux = a.ldaux;
+  p.row_vec = a.row_vec;
+  p.col_vec = a.col_vec;
+  p.out_vec0 = a.out_vec0;
+  p.out_vec1 = a.out_vec1;
+  p.out_vec2 = a.out_vec2;
+  p.scalar_out = a.scalar_out;
+  p.iparam = a.iparam;
+  p.fparam = a.fparam;
   // K-major: 8-row groups 1024 B apart, +32 B per UMMA_K inside the swizzle row.
   // MN-major: 64-wide chunks kBK*128 B apart (LBO), 8-K groups 1024 B apart (SBO), +2048 B per UMMA_K.
   p.a_lbo = p.a_mn ? kBK * 128 : 16;
@@ -383,7 +457,7 @@ static int launch_gemm(const VlGemmArgs& a, cudaStream_t stream) {
 
 extern "C" int vl_gemm_bf16(const VlGemmArgs* a, void* stream) {
   using namespace vl;
-  VL_CHECK_ARG(a != nullptr && a->a && a->b && a->d, "vl_gemm_bf16: null pointer");
+  VL_CHECK_ARG(a != nullptr && a->a && a->b && (a->d || a->epilogue == VL_EPI_ROWLSE), "vl_gemm_bf16: null pointer");
   VL_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "vl_gemm_bf16: non-positive dims M=%d N=%d K=%d", a->M, a->N, a->K);
   VL_CHECK_ARG(a->N % 8 == 0, "vl_gemm_bf16: N=%d must be a multiple of 8", a->N);
   VL_CHECK_ARG(a->lda % 8 == 0 && a->ldb % 8 == 0, "vl_gemm_bf16: lda/ldb must be multiples of 8 elements");
@@ -397,11 +471,18 @@ extern "C" int vl_gemm_bf16(const VlGemmArgs* a, void* stream) {
     VL_CHECK_ARG(a->aux_in != nullptr && a->ldaux % 8 == 0 && a->ldaux >= a->N, "vl_gemm_bf16: aux_in / ldaux invalid");
   if (a->epilogue == VL_EPI_GELU && a->aux_out)
     VL_CHECK_ARG(a->ldaux % 8 == 0 && a->ldaux >= a->N, "vl_gemm_bf16: ldaux invalid");
-  if (a->epilogue < 0 || a->epilogue > VL_EPI_GELU_BWD) {
+  if (a->epilogue < 0 || a->epilogue > VL_EPI_CLIPGRAD || a->epilogue == VL_EPI_GEGLU) {
     set_error("vl_gemm_bf16: epilogue %d not supported", a->epilogue);
     return VL_ENOTSUP;
   }
+  if (a->epilogue == VL_EPI_ROWLSE)
+    VL_CHECK_ARG(a->out_vec0 && a->out_vec1 && a->out_vec2 && a->split_k <= 1, "vl_gemm_bf16: ROWLSE needs out_vec0/1/2 and split_k == 1");
+  if (a->epilogue == VL_EPI_CLIPGRAD)
+    VL_CHECK_ARG(a->row_vec && !a->d_f32 && a->split_k <= 1, "vl_gemm_bf16: CLIPGRAD needs row_vec, bf16 output, split_k == 1");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (a->epilogue == VL_EPI_ROWLSE || a->epilogue == VL_EPI_CLIPGRAD) return launch_gemm<256>(*a, s);  // fixed part geometry
   if (a->N <= 128) return launch_gemm<128>(*a, s);
   return launch_gemm<256>(*a, s);
 }
+
+extern "C" int vl_gemm_rowlse_parts(int32_t N) { return ((N + 255) / 256) * 2; }

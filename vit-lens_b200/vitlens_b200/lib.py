@@ -31,10 +31,12 @@ class GemmArgs(C.Structure):
         ("d_f32", C.c_int32), ("accumulate", C.c_int32), ("split_k", C.c_int32),
         ("epilogue", C.c_int32), ("act_quick", C.c_int32), ("alpha", C.c_float),
         ("bias", C.c_void_p), ("aux_in", C.c_void_p), ("aux_out", C.c_void_p), ("ldaux", C.c_int64),
+        ("row_vec", C.c_void_p), ("col_vec", C.c_void_p), ("out_vec0", C.c_void_p), ("out_vec1", C.c_void_p),
+        ("out_vec2", C.c_void_p), ("scalar_out", C.c_void_p), ("iparam", C.c_int32), ("fparam", C.c_float),
     ]
 
 
-EPI_LINEAR, EPI_GELU, EPI_RESIDUAL, EPI_GELU_BWD, EPI_GEGLU = 0, 1, 2, 3, 4
+EPI_LINEAR, EPI_GELU, EPI_RESIDUAL, EPI_GELU_BWD, EPI_GEGLU, EPI_ROWLSE, EPI_CLIPGRAD = 0, 1, 2, 3, 4, 5, 6
 
 
 def lib_path() -> str:
@@ -87,14 +89,146 @@ def _count():
 
 
 def gemm(a, b, d, *, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, epilogue=EPI_LINEAR, bias=None,
-         aux_in=None, aux_out=None, ldaux=0, alpha=1.0, accumulate=False, split_k=1, act_quick=False):
+         aux_in=None, aux_out=None, ldaux=0, alpha=1.0, accumulate=False, split_k=1, act_quick=False,
+         row_vec=None, col_vec=None, out_vec0=None, out_vec1=None, out_vec2=None, scalar_out=None, iparam=0, fparam=0.0):
     """Raw GEMM call; see include/vitlens_b200.h.  a, b bf16; d bf16 or fp32; bias fp32."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
-    assert d.dtype in (torch.bfloat16, torch.float32)
+    assert d is None or d.dtype in (torch.bfloat16, torch.float32)
     assert bias is None or bias.dtype == torch.float32
     args = GemmArgs(
         _ptr(a), _ptr(b), _ptr(d), M, N, K, lda, ldb, ldd, int(a_mn), int(b_mn),
-        int(d.dtype == torch.float32), int(accumulate), int(split_k), int(epilogue), int(act_quick), float(alpha),
-        _ptr(bias), _ptr(aux_in), _ptr(aux_out), ldaux)
+        int(d is not None and d.dtype == torch.float32), int(accumulate), int(split_k), int(epilogue), int(act_quick), float(alpha),
+        _ptr(bias), _ptr(aux_in), _ptr(aux_out), ldaux,
+        _ptr(row_vec), _ptr(col_vec), _ptr(out_vec0), _ptr(out_vec1), _ptr(out_vec2), _ptr(scalar_out), int(iparam), float(fparam))
     _count()
-    _check(load().vl_gemm_bf16(C.byref(args), _stream()), "vl_gemm_bf16")
+    _check(_fn("vl_gemm_bf16")(C.cast(C.pointer(args), C.c_void_p), _stream()), "vl_gemm_bf16")
+
+
+# ----------------------------------------------------------------------------- prototypes
+_P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+_PROTOS = {
+    "vl_gemm_bf16": [_P, _P],
+    "vl_attention_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _L, _F, _I, _P],
+    "vl_attention_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _L, _L, _F, _I, _P],
+    "vl_layernorm_fwd": [_P, _L, _P, _P, _P, _P, _L, _P, _P, _I, _I, _F, _P],
+    "vl_layernorm_bwd": [_P, _L, _P, _L, _P, _P, _P, _P, _P, _L, _P, _L, _P, _P, _I, _I, _P],
+    "vl_colsum_bf16": [_P, _L, _P, _I, _I, _P],
+    "vl_patchify": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _L, _L, _I, _P],
+    "vl_assemble_tokens": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "vl_assemble_tokens_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "vl_embed_tokens": [_P, _P, _P, _P, _L, _I, _I, _P],
+    "vl_embed_tokens_bwd": [_P, _P, _P, _P, _L, _I, _I, _P],
+    "vl_l2norm_fwd": [_P, _P, _P, _I, _I, _F, _P],
+    "vl_l2norm_bwd": [_P, _P, _P, _P, _I, _I, _P],
+    "vl_geglu_fwd": [_P, _P, _L, _I, _P],
+    "vl_geglu_bwd": [_P, _P, _P, _L, _I, _P],
+    "vl_cast_f32_bf16": [_P, _P, _L, _P],
+    "vl_add_bf16": [_P, _P, _P, _L, _P],
+    "vl_adamw_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
+    "vl_lse_combine": [_P, _P, _P, _I, _I, _P, _P, _P],
+}
+
+
+def _fn(name):
+    lib = load()
+    f = getattr(lib, name)
+    if not getattr(f, "_vl_ready", False):
+        f.argtypes = _PROTOS[name]
+        f.restype = C.c_int
+        f._vl_ready = True
+    return f
+
+
+def _call(name, *args):
+    _count()
+    rc = _fn(name)(*args, _stream())
+    if rc != 0:
+        _check(rc, name)
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def attention_fwd(q, k, v, o, lse, *, B, H, nq, nk, ldq, ldk, ldv, ldo, scale, causal=False):
+    _call("vl_attention_fwd", _p(q), _p(k), _p(v), _p(o), _p(lse), B, H, nq, nk, ldq, ldk, ldv, ldo, float(scale), int(causal))
+
+
+def attention_bwd(q, k, v, o, dout, lse, dq, dk, dv, *, B, H, nq, nk, ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, scale, causal=False):
+    _call("vl_attention_bwd", _p(q), _p(k), _p(v), _p(o), _p(dout), _p(lse), _p(dq), _p(dk), _p(dv), B, H, nq, nk,
+          ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, float(scale), int(causal))
+
+
+def layernorm_fwd(x, w, b, y, mean, rstd, *, T, D, ldx, ldy, row_index=None, eps=1e-5):
+    _call("vl_layernorm_fwd", _p(x), ldx, _p(row_index), _p(w), _p(b), _p(y), ldy, _p(mean), _p(rstd), T, D, float(eps))
+
+
+def layernorm_bwd(dy, x, w, mean, rstd, dx, dw, db, *, T, D, lddy, ldx, lddx, dres=None, lddres=0, row_index=None):
+    _call("vl_layernorm_bwd", _p(dy), lddy, _p(x), ldx, _p(row_index), _p(w), _p(mean), _p(rstd), _p(dres), lddres,
+          _p(dx), lddx, _p(dw), _p(db), T, D)
+
+
+def colsum(dy, db, *, T, N, ld):
+    _call("vl_colsum_bf16", _p(dy), ld, _p(db), T, N)
+
+
+def patchify(inp, out, *, B, C, OH, OW, kh, kw, stride_h, stride_w, sb, sc, sh, sw, Kpad):
+    assert inp.dtype in (F32, BF16)
+    _call("vl_patchify", _p(inp), int(inp.dtype == BF16), _p(out), B, C, OH, OW, kh, kw, stride_h, stride_w, sb, sc, sh, sw, Kpad)
+
+
+def assemble_tokens(tok, cls, pos, out, *, B, L, D, has_cls):
+    _call("vl_assemble_tokens", _p(tok), _p(cls), _p(pos), _p(out), B, L, D, int(has_cls))
+
+
+def assemble_tokens_bwd(dx, dtok, dpos, dcls, *, B, L, D, has_cls):
+    _call("vl_assemble_tokens_bwd", _p(dx), _p(dtok), _p(dpos), _p(dcls), B, L, D, int(has_cls))
+
+
+def embed_tokens(ids, table, pos, out, *, rows, ctx, D):
+    _call("vl_embed_tokens", _p(ids), _p(table), _p(pos), _p(out), rows, ctx, D)
+
+
+def embed_tokens_bwd(ids, dx, dtable, dpos, *, rows, ctx, D):
+    _call("vl_embed_tokens_bwd", _p(ids), _p(dx), _p(dtable), _p(dpos), rows, ctx, D)
+
+
+def l2norm_fwd(x, y, inv_norm, *, B, E, eps=1e-12):
+    _call("vl_l2norm_fwd", _p(x), _p(y), _p(inv_norm), B, E, float(eps))
+
+
+def l2norm_bwd(dy, y, inv_norm, dx, *, B, E):
+    _call("vl_l2norm_bwd", _p(dy), _p(y), _p(inv_norm), _p(dx), B, E)
+
+
+def geglu_fwd(h, out, *, M, F):
+    _call("vl_geglu_fwd", _p(h), _p(out), M, F)
+
+
+def geglu_bwd(h, dout, dh, *, M, F):
+    _call("vl_geglu_bwd", _p(h), _p(dout), _p(dh), M, F)
+
+
+def cast_f32_bf16(inp, out):
+    _call("vl_cast_f32_bf16", _p(inp), _p(out), inp.numel())
+
+
+def add_bf16(a, b, out):
+    _call("vl_add_bf16", _p(a), _p(b), _p(out), a.numel())
+
+
+def adamw_step(p, g, m, v, *, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    _call("vl_adamw_step", _p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay, step, grad_scale)
+
+
+def rowlse_parts(N: int) -> int:
+    f = load().vl_gemm_rowlse_parts
+    f.argtypes, f.restype = [C.c_int32], C.c_int
+    return f(N)
+
+
+def lse_combine(part_max, part_sum, diag, lse, loss_sum, *, M, nparts):
+    _call("vl_lse_combine", _p(part_max), _p(part_sum), _p(diag), M, nparts, _p(lse), _p(loss_sum))

@@ -1,0 +1,201 @@
+"""Tensor-level front end of the C ABI: derives (M, N, K, ld...) from torch views, allocates
+outputs, and calls vitlens_b200.lib (the ctypes binding of libvitlens_b200.so).
+
+Every function here launches hand-written sm_100a kernels; torch only provides memory.
+2-D arguments are row-major views with unit inner stride (``t.stride(-1) == 1``); the row
+stride is the leading dimension.  ``tests/emu_ops.py`` mirrors this module's signatures in
+plain torch so the host logic (engine.py) can be exercised on a CPU-only box -- that emulation
+lives in tests/ and is never importable from the product package.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import lib as L
+
+BF16, F32 = torch.bfloat16, torch.float32
+EPI_LINEAR, EPI_GELU, EPI_RESIDUAL, EPI_GELU_BWD = L.EPI_LINEAR, L.EPI_GELU, L.EPI_RESIDUAL, L.EPI_GELU_BWD
+
+
+def _v2(t: torch.Tensor, dtype=None) -> torch.Tensor:
+    assert t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] == 1), f"need a row-major 2-D view, got {tuple(t.shape)} {t.stride()}"
+    assert dtype is None or t.dtype == dtype, f"expected {dtype}, got {t.dtype}"
+    assert t.is_cuda, "vitlens_b200 kernels need CUDA tensors (there is no CPU path)"
+    return t
+
+
+def _ld(t: torch.Tensor) -> int:
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def pick_split_k(M: int, N: int, K: int) -> int:
+    """Split the reduction when an (M, N) grid alone cannot fill the 148 SMs (weight gradients)."""
+    tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 128 else 1)
+    kb = (K + 63) // 64
+    if tiles >= 120 or kb < 8:
+        return 1
+    return max(1, min(kb // 4, (296 + tiles - 1) // tiles))
+
+
+def gemm(a, b, *, a_t=False, b_t=False, bias=None, epilogue=EPI_LINEAR, aux_in=None, want_aux_out=False, out=None,
+         out_dtype=BF16, alpha=1.0, accumulate=False, split_k=None, act_quick=False):
+    """out[M,N] = epilogue(alpha * A @ B^T); A = a ([M,K]) or a^T when a_t (a is [K,M]); B = b ([N,K]) or b^T when b_t."""
+    _v2(a, BF16), _v2(b, BF16)
+    M, K = (a.shape[1], a.shape[0]) if a_t else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if b_t else (b.shape[0], b.shape[1])
+    assert K == Kb, f"K mismatch {K} vs {Kb}"
+    if out is None:
+        out = (torch.zeros if accumulate else torch.empty)((M, N), device=a.device, dtype=out_dtype)
+    _v2(out)
+    assert tuple(out.shape) == (M, N)
+    aux_out = torch.empty((M, N), device=a.device, dtype=BF16) if want_aux_out else None
+    if aux_in is not None:
+        _v2(aux_in, BF16)
+        assert tuple(aux_in.shape) == (M, N)
+    ldaux = _ld(aux_in) if aux_in is not None else (N if want_aux_out else 0)
+    if split_k is None:
+        split_k = pick_split_k(M, N, K) if (accumulate and out.dtype == F32 and epilogue == EPI_LINEAR) else 1
+    L.gemm(a, b, out, M=M, N=N, K=K, lda=_ld(a), ldb=_ld(b), ldd=_ld(out), a_mn=a_t, b_mn=b_t, epilogue=epilogue, bias=bias,
+           aux_in=aux_in, aux_out=aux_out, ldaux=ldaux, alpha=alpha, accumulate=accumulate, split_k=split_k, act_quick=act_quick)
+    return (out, aux_out) if want_aux_out else out
+
+
+def attention_fwd(q, k, v, *, B, H, nq, nk, causal=False, scale=None):
+    _v2(q, BF16), _v2(k, BF16), _v2(v, BF16)
+    assert q.shape == (B * nq, H * 64) and k.shape == (B * nk, H * 64) and v.shape == (B * nk, H * 64)
+    scale = 64 ** -0.5 if scale is None else scale
+    o = torch.empty((B * nq, H * 64), device=q.device, dtype=BF16)
+    lse = torch.empty((B, H, nq), device=q.device, dtype=F32)
+    L.attention_fwd(q, k, v, o, lse, B=B, H=H, nq=nq, nk=nk, ldq=_ld(q), ldk=_ld(k), ldv=_ld(v), ldo=H * 64, scale=scale, causal=causal)
+    return o, lse
+
+
+def attention_bwd(q, k, v, o, dout, lse, dq, dk, dv, *, B, H, nq, nk, causal=False, scale=None):
+    for t in (q, k, v, o, dout, dq, dk, dv):
+        _v2(t, BF16)
+    scale = 64 ** -0.5 if scale is None else scale
+    L.attention_bwd(q, k, v, o, dout, lse, dq, dk, dv, B=B, H=H, nq=nq, nk=nk, ldq=_ld(q), ldk=_ld(k), ldv=_ld(v), ldo=_ld(o),
+                    lddo=_ld(dout), lddq=_ld(dq), lddk=_ld(dk), lddv=_ld(dv), scale=scale, causal=causal)
+
+
+def layernorm_fwd(x, w, b, *, row_index=None, eps=1e-5, want_stats=True):
+    _v2(x, BF16)
+    T = x.shape[0] if row_index is None else row_index.numel()
+    D = x.shape[1]
+    y = torch.empty((T, D), device=x.device, dtype=BF16)
+    mean = torch.empty((T,), device=x.device, dtype=F32) if want_stats else None
+    rstd = torch.empty((T,), device=x.device, dtype=F32) if want_stats else None
+    L.layernorm_fwd(x, w, b, y, mean, rstd, T=T, D=D, ldx=_ld(x), ldy=D, row_index=row_index, eps=eps)
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, w, mean, rstd, *, dres=None, row_index=None, want_wgrad=True):
+    """Returns (dx, dw, db).  With row_index, dx has x's full row count and is zero outside the gathered rows."""
+    _v2(dy, BF16), _v2(x, BF16)
+    T, D = dy.shape
+    if row_index is None:
+        dx = torch.empty((x.shape[0], D), device=x.device, dtype=BF16)
+    else:
+        dx = torch.zeros((x.shape[0], D), device=x.device, dtype=BF16)
+    dw = torch.zeros((D,), device=x.device, dtype=F32) if want_wgrad else None
+    db = torch.zeros((D,), device=x.device, dtype=F32) if want_wgrad else None
+    if dres is not None:
+        _v2(dres, BF16)
+    L.layernorm_bwd(dy, x, w, mean, rstd, dx, dw, db, T=T, D=D, lddy=_ld(dy), ldx=_ld(x), lddx=D, dres=dres,
+                    lddres=_ld(dres) if dres is not None else 0, row_index=row_index)
+    return dx, dw, db
+
+
+def colsum(dy):
+    _v2(dy, BF16)
+    T, N = dy.shape
+    db = torch.zeros((N,), device=dy.device, dtype=F32)
+    L.colsum(dy, db, T=T, N=N, ld=_ld(dy))
+    return db
+
+
+def patchify(inp, *, B, C, OH, OW, kh, kw, stride_h, stride_w, sb, sc, sh, sw, Kpad):
+    out = torch.empty((B * OH * OW, Kpad), device=inp.device, dtype=BF16)
+    L.patchify(inp, out, B=B, C=C, OH=OH, OW=OW, kh=kh, kw=kw, stride_h=stride_h, stride_w=stride_w, sb=sb, sc=sc, sh=sh, sw=sw, Kpad=Kpad)
+    return out
+
+
+def assemble_tokens(tok, cls, pos, *, B, L_, D):
+    """tok: contiguous [B*L_, D] bf16 -> [B*(L_+has_cls), D]"""
+    has_cls = cls is not None
+    out = torch.empty((B * (L_ + int(has_cls)), D), device=tok.device, dtype=BF16)
+    L.assemble_tokens(tok, cls, pos, out, B=B, L=L_, D=D, has_cls=has_cls)
+    return out
+
+
+def assemble_tokens_bwd(dx, *, B, L_, D, has_cls, want_tok=True, want_pos=True, want_cls=True):
+    dev = dx.device
+    dtok = torch.empty((B * L_, D), device=dev, dtype=BF16) if want_tok else None
+    dpos = torch.zeros((L_ + int(has_cls), D), device=dev, dtype=F32) if want_pos else None
+    dcls = torch.zeros((D,), device=dev, dtype=F32) if (want_cls and has_cls) else None
+    L.assemble_tokens_bwd(dx, dtok, dpos, dcls, B=B, L=L_, D=D, has_cls=has_cls)
+    return dtok, dpos, dcls
+
+
+def embed_tokens(ids, table, pos):
+    rows, ctx, D = ids.numel(), ids.shape[-1], table.shape[1]
+    out = torch.empty((rows, D), device=table.device, dtype=BF16)
+    L.embed_tokens(ids.contiguous(), table, pos, out, rows=rows, ctx=ctx, D=D)
+    return out
+
+
+def embed_tokens_bwd(ids, dx, *, vocab, want_table=True, want_pos=True):
+    rows, ctx, D = ids.numel(), ids.shape[-1], dx.shape[1]
+    dtable = torch.zeros((vocab, D), device=dx.device, dtype=F32) if want_table else None
+    dpos = torch.zeros((ctx, D), device=dx.device, dtype=F32) if want_pos else None
+    L.embed_tokens_bwd(ids.contiguous(), dx, dtable, dpos, rows=rows, ctx=ctx, D=D)
+    return dtable, dpos
+
+
+def l2norm_fwd(x, eps=1e-12):
+    B, E = x.shape
+    y = torch.empty_like(x)
+    inv = torch.empty((B,), device=x.device, dtype=F32)
+    L.l2norm_fwd(x, y, inv, B=B, E=E, eps=eps)
+    return y, inv
+
+
+def l2norm_bwd(dy, y, inv):
+    dx = torch.empty_like(y)
+    L.l2norm_bwd(dy.contiguous(), y, inv, dx, B=y.shape[0], E=y.shape[1])
+    return dx
+
+
+def geglu_fwd(h):
+    M, F2 = h.shape
+    out = torch.empty((M, F2 // 2), device=h.device, dtype=BF16)
+    L.geglu_fwd(h, out, M=M, F=F2 // 2)
+    return out
+
+
+def geglu_bwd(h, dout):
+    dh = torch.empty_like(h)
+    L.geglu_bwd(h, dout, dh, M=h.shape[0], F=h.shape[1] // 2)
+    return dh
+
+
+def cast_bf16(x):
+    """fp32 -> bf16 copy (weights for the tensor cores, dfeatures for the head GEMMs)."""
+    x = x.contiguous()
+    out = torch.empty(x.shape, device=x.device, dtype=BF16)
+    L.cast_f32_bf16(x, out)
+    return out
+
+
+def add_bf16(a, b):
+    out = torch.empty_like(a)
+    L.add_bf16(a, b, out)
+    return out
+
+
+def clip_loss_fwd_bwd(*args, **kw):
+    from . import loss_ops
+
+    return loss_ops.clip_loss_fwd_bwd(*args, **kw)
