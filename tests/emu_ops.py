@@ -1,0 +1,241 @@
+"""Torch-CPU emulation of vitlens_b200.ops (same function signatures)  --  TEST INFRASTRUCTURE ONLY.
+
+Lets the CPU-only test tier exercise the host logic of vitlens_b200.engine / open_clip.* (which
+kernel is called with which operands, what is saved for backward, how gradients are assembled)
+against the oracle.  It mimics the kernels' numerics contract: bf16 storage of activations, fp32
+accumulation / statistics.  It is never imported by the product package.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+BF16, F32 = torch.bfloat16, torch.float32
+EPI_LINEAR, EPI_GELU, EPI_RESIDUAL, EPI_GELU_BWD = 0, 1, 2, 3
+launches = 0
+
+
+def _n():
+    global launches
+    launches += 1
+
+
+def _act(x, quick):
+    return x * torch.sigmoid(1.702 * x) if quick else F.gelu(x)
+
+
+def _act_grad(x, quick):
+    if quick:
+        s = torch.sigmoid(1.702 * x)
+        return s * (1 + 1.702 * x * (1 - s))
+    return 0.5 * (1 + torch.erf(x / math.sqrt(2))) + x * torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi)
+
+
+def gemm(a, b, *, a_t=False, b_t=False, bias=None, epilogue=EPI_LINEAR, aux_in=None, want_aux_out=False, out=None,
+         out_dtype=BF16, alpha=1.0, accumulate=False, split_k=None, act_quick=False):
+    _n()
+    assert a.dtype == BF16 and b.dtype == BF16
+    A = a.float().t() if a_t else a.float()
+    B = b.float() if b_t else b.float().t()
+    acc = (A @ B) * alpha
+    aux_out = None
+    if epilogue == EPI_GELU_BWD:
+        res = acc * _act_grad(aux_in.float(), act_quick)
+    else:
+        if bias is not None:
+            acc = acc + bias
+        if epilogue == EPI_GELU:
+            if want_aux_out:
+                aux_out = acc.to(BF16)
+            res = _act(acc, act_quick)
+        elif epilogue == EPI_RESIDUAL:
+            res = acc + aux_in.float()
+        else:
+            res = acc
+    if out is None:
+        out = torch.zeros(res.shape, dtype=out_dtype)
+        accumulate = False
+    if accumulate:
+        out += res.to(out.dtype)
+    else:
+        out.copy_(res.to(out.dtype))
+    return (out, aux_out) if want_aux_out else out
+
+
+def _split(t, B, n, H):
+    return t.float().reshape(B, n, H, 64).permute(0, 2, 1, 3)
+
+
+def attention_fwd(q, k, v, *, B, H, nq, nk, causal=False, scale=None):
+    _n()
+    scale = 64 ** -0.5 if scale is None else scale
+    s = (_split(q, B, nq, H) @ _split(k, B, nk, H).transpose(-1, -2)) * scale
+    if causal:
+        s = s + torch.full((nq, nk), float("-inf")).triu_(1)
+    lse = torch.logsumexp(s, dim=-1)
+    p = torch.exp(s - lse.unsqueeze(-1)).to(BF16).float()  # P is rounded to bf16 before P@V on the tensor cores
+    o = (p @ _split(v, B, nk, H)).permute(0, 2, 1, 3).reshape(B * nq, H * 64).to(BF16)
+    return o, lse
+
+
+def attention_bwd(q, k, v, o, dout, lse, dq, dk, dv, *, B, H, nq, nk, causal=False, scale=None):
+    _n()
+    scale = 64 ** -0.5 if scale is None else scale
+    Q, K, V = _split(q, B, nq, H), _split(k, B, nk, H), _split(v, B, nk, H)
+    dO, O = _split(dout, B, nq, H), _split(o, B, nq, H)
+    s = (Q @ K.transpose(-1, -2)) * scale
+    if causal:
+        s = s + torch.full((nq, nk), float("-inf")).triu_(1)
+    p = torch.exp(s - lse.unsqueeze(-1))
+    D = (dO * O).sum(-1, keepdim=True)
+    dP = dO @ V.transpose(-1, -2)
+    dS = (p * (dP - D) * scale).to(BF16).float()
+    pb = p.to(BF16).float()
+
+    def merge(t, n):
+        return t.permute(0, 2, 1, 3).reshape(B * n, H * 64).to(BF16)
+
+    dv.copy_(merge(pb.transpose(-1, -2) @ dO, nk))
+    dk.copy_(merge(dS.transpose(-1, -2) @ Q, nk))
+    dq.copy_(merge(dS @ K, nq))
+
+
+def layernorm_fwd(x, w, b, *, row_index=None, eps=1e-5, want_stats=True):
+    _n()
+    xs = x.float() if row_index is None else x.float()[row_index]
+    mean = xs.mean(-1)
+    var = ((xs - mean[:, None]) ** 2).mean(-1)
+    rstd = torch.rsqrt(var + eps)
+    y = ((xs - mean[:, None]) * rstd[:, None] * w + b).to(BF16)
+    return y, (mean if want_stats else None), (rstd if want_stats else None)
+
+
+def layernorm_bwd(dy, x, w, mean, rstd, *, dres=None, row_index=None, want_wgrad=True):
+    _n()
+    xs = x.float() if row_index is None else x.float()[row_index]
+    g = dy.float()
+    xh = (xs - mean[:, None]) * rstd[:, None]
+    wg = g * w
+    dxs = rstd[:, None] * (wg - wg.mean(-1, keepdim=True) - xh * (wg * xh).mean(-1, keepdim=True))
+    if row_index is None:
+        if dres is not None:
+            dxs = dxs + dres.float()
+        dx = dxs.to(BF16)
+    else:
+        dx = torch.zeros(x.shape, dtype=BF16)
+        if dres is not None:
+            dxs = dxs + dres.float()[row_index]
+        dx[row_index] = dxs.to(BF16)
+    if want_wgrad:
+        return dx, (g * xh).sum(0), g.sum(0)
+    return dx, None, None
+
+
+def colsum(dy):
+    _n()
+    return dy.float().sum(0)
+
+
+def patchify(inp, *, B, C, OH, OW, kh, kw, stride_h, stride_w, sb, sc, sh, sw, Kpad):
+    _n()
+    flat = inp.reshape(-1) if inp.is_contiguous() else None
+    base = inp.as_strided((B, C, (OH - 1) * stride_h + kh, (OW - 1) * stride_w + kw), (sb, sc, sh, sw))
+    cols = F.unfold(base.float(), (kh, kw), stride=(stride_h, stride_w)).transpose(1, 2).reshape(B * OH * OW, C * kh * kw)
+    out = torch.zeros((B * OH * OW, Kpad), dtype=BF16)
+    out[:, : C * kh * kw] = cols.to(BF16)
+    return out
+
+
+def assemble_tokens(tok, cls, pos, *, B, L_, D):
+    _n()
+    t = tok.float().reshape(B, L_, D)
+    if cls is not None:
+        t = torch.cat([cls.float().view(1, 1, D).expand(B, 1, D), t], 1)
+    if pos is not None:
+        t = t + pos.float()
+    return t.reshape(-1, D).to(BF16)
+
+
+def assemble_tokens_bwd(dx, *, B, L_, D, has_cls, want_tok=True, want_pos=True, want_cls=True):
+    _n()
+    Lo = L_ + int(has_cls)
+    d = dx.float().reshape(B, Lo, D)
+    dtok = d[:, int(has_cls):].reshape(B * L_, D).to(BF16) if want_tok else None
+    dpos = d.sum(0) if want_pos else None
+    dcls = d[:, 0].sum(0) if (want_cls and has_cls) else None
+    return dtok, dpos, dcls
+
+
+def embed_tokens(ids, table, pos):
+    _n()
+    return (table[ids] + pos).reshape(-1, table.shape[1]).to(BF16)
+
+
+def embed_tokens_bwd(ids, dx, *, vocab, want_table=True, want_pos=True):
+    _n()
+    ctx, D = ids.shape[-1], dx.shape[1]
+    d = dx.float()
+    dt = torch.zeros(vocab, D).index_add_(0, ids.reshape(-1), d) if want_table else None
+    dp = d.reshape(-1, ctx, D).sum(0) if want_pos else None
+    return dt, dp
+
+
+def l2norm_fwd(x, eps=1e-12):
+    _n()
+    inv = 1.0 / x.norm(dim=-1).clamp_min(eps)
+    return x * inv[:, None], inv
+
+
+def l2norm_bwd(dy, y, inv):
+    _n()
+    return (dy - y * (dy * y).sum(-1, keepdim=True)) * inv[:, None]
+
+
+def geglu_fwd(h):
+    _n()
+    a, g = h.float().chunk(2, -1)
+    return (a * F.gelu(g)).to(BF16)
+
+
+def geglu_bwd(h, dout):
+    _n()
+    a, g = h.float().chunk(2, -1)
+    d = dout.float()
+    return torch.cat([d * F.gelu(g), d * a * _act_grad(g, False)], -1).to(BF16)
+
+
+def cast_bf16(x):
+    _n()
+    return x.contiguous().to(BF16)
+
+
+def add_bf16(a, b):
+    _n()
+    return (a.float() + b.float()).to(BF16)
+
+
+def rowlse(p16, q16, *, alpha, label_off=0):
+    _n()
+    z = alpha * (p16.float() @ q16.float().t())
+    lse = torch.logsumexp(z, -1)
+    M = z.shape[0]
+    diag = z[torch.arange(M), torch.arange(M) + label_off]
+    return lse, (lse - diag).sum().reshape(1)
+
+
+def clipgrad(p16, q16, *, alpha, row_lse, col_lse, label_off, gscale):
+    _n()
+    acc = p16.float() @ q16.float().t()
+    z = alpha * acc
+    M, N = z.shape
+    g = torch.exp(z - row_lse[:, None])
+    k = 1.0
+    if col_lse is not None:
+        g = g + torch.exp(z - col_lse[None, :])
+        k = 2.0
+    onehot = torch.zeros(M, N)
+    onehot[torch.arange(M), torch.arange(M) + label_off] = 1.0
+    g = gscale * (g - k * onehot)
+    return g.to(BF16), (g * acc).sum().reshape(1)

@@ -1,0 +1,46 @@
+"""Host logic (open_clip modules + vitlens_b200.engine autograd stages) on CPU with the kernel gateway
+swapped for tests/emu_ops.py, against the reference's golden outputs.  Tolerances are the bf16 ones."""
+import pytest
+import torch
+
+from tests.common import C, build_model, cosine, relerr, run_model
+
+CASES = ["tiny_clip", "tiny_tri_audio", "tiny_tri_depth"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_backward_vs_reference(name, emu):
+    case = C.CASES[name]
+    gold = C.load_golden(name)
+    model, sd, args = build_model(case)
+    inp = C.build_inputs(case, args)
+    feats, ls, loss = run_model(case, model, inp)
+    for k, v in feats.items():
+        assert cosine(v, gold[k]) > 0.999, (k, cosine(v, gold[k]))
+    assert abs(float(loss.detach()) - float(gold["loss"])) < 2e-2 * abs(float(gold["loss"]))
+    loss.backward()
+    got = {k: p.grad for k, p in model.named_parameters() if p.requires_grad}
+    assert all(g is not None for g in got.values()), [k for k, g in got.items() if g is None]
+    keys = sorted(got)
+    norms = torch.tensor([float(got[k].norm()) for k in keys])
+    assert norms.numel() == gold["grad_norms"].numel()
+    bad = []
+    for i, k in enumerate(keys):
+        gk = "grad:" + k
+        if gk in gold and float(gold[gk].abs().max()) > 0:
+            c = cosine(got[k], gold[gk])
+            if c < 0.98:
+                bad.append((k, c))
+        rn = abs(float(norms[i]) - float(gold["grad_norms"][i])) / max(float(gold["grad_norms"][i]), 1e-6)
+        if rn > 0.1 and float(gold["grad_norms"][i]) > 1e-4:
+            bad.append((k, "norm", float(norms[i]), float(gold["grad_norms"][i])))
+    assert not bad, bad
+
+
+def test_frozen_towers_save_nothing(emu):
+    case = C.CASES["tiny_tri_audio"]
+    model, sd, args = build_model(case)
+    inp = C.build_inputs(case, args)
+    with torch.no_grad():
+        f = model.encode_image(inp["image"], normalize=True)
+    assert not f.requires_grad

@@ -1,0 +1,48 @@
+"""The CPU oracle reproduces the REFERENCE's outputs (fixtures written by oracle/make_golden.py from the
+real reference) on every case: features, loss and gradients."""
+import zlib
+
+import pytest
+import torch
+
+from tests.common import C, build_model, relerr, run_oracle
+
+FAST = ["tiny_clip", "tiny_tri_audio", "tiny_tri_depth", "tiny_tri_pc", "vitb32_clip_bs8"]
+SLOW = ["vitl14_audio128_bs2", "vitl14_depth_bs2", "vitl14_pc_bs2"]
+
+
+def _check(name, with_grads):
+    case = C.CASES[name]
+    gold = C.load_golden(name)
+    model, sd, args = build_model(case)
+    # recipe / schema drift guards: same weights and inputs as the reference saw
+    chk_w = sum(float(v.double().abs().sum()) for v in sd.values() if v.is_floating_point())
+    assert abs(chk_w - float(gold["chk_weights"])) <= 1e-6 * abs(chk_w)
+    inp = C.build_inputs(case, args)
+    if "fps_start" in gold:
+        inp["fps_start"] = gold["fps_start"]
+    assert abs(sum(float(v.double().abs().sum()) for v in inp.values()) - float(gold["chk_inputs"])) <= 1e-5 * float(gold["chk_inputs"])
+    keys = sorted(k for k, p in model.named_parameters() if p.requires_grad) if with_grads else []
+    if with_grads and case.kind == "tri" and case.modality != "pc":
+        assert zlib.crc32("\n".join(keys).encode()) == int(gold["grad_keys_crc"])
+    feats, ls, loss, grads = run_oracle(case, sd, args, inp, set(keys))
+    for k, v in feats.items():
+        assert relerr(v.detach(), gold[k]) < 2e-4, k
+    assert abs(float(loss) - float(gold["loss"])) < 1e-4 * abs(float(gold["loss"]))
+    if with_grads:
+        norms = torch.tensor([float(grads[k].norm()) for k in keys])
+        if norms.numel() == gold["grad_norms"].numel():
+            assert relerr(norms, gold["grad_norms"]) < 2e-3
+        for k in keys:
+            if "grad:" + k in gold:
+                assert relerr(grads[k], gold["grad:" + k]) < 2e-3, k
+
+
+@pytest.mark.parametrize("name", FAST)
+def test_oracle_matches_reference_fixture(name):
+    _check(name, with_grads=True)
+
+
+@pytest.mark.parametrize("name", SLOW)
+def test_oracle_matches_reference_fixture_vitl(name):
+    _check(name, with_grads=False)

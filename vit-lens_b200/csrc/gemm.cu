@@ -459,11 +459,13 @@ extern "C" int vl_gemm_bf16(const VlGemmArgs* a, void* stream) {
   using namespace vl;
   VL_CHECK_ARG(a != nullptr && a->a && a->b && (a->d || a->epilogue == VL_EPI_ROWLSE), "vl_gemm_bf16: null pointer");
   VL_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "vl_gemm_bf16: non-positive dims M=%d N=%d K=%d", a->M, a->N, a->K);
-  VL_CHECK_ARG(a->N % 8 == 0, "vl_gemm_bf16: N=%d must be a multiple of 8", a->N);
+  const bool loss_epi = a->epilogue == VL_EPI_ROWLSE || a->epilogue == VL_EPI_CLIPGRAD;
+  VL_CHECK_ARG(a->N % 8 == 0 || loss_epi, "vl_gemm_bf16: N=%d must be a multiple of 8", a->N);
   VL_CHECK_ARG(a->lda % 8 == 0 && a->ldb % 8 == 0, "vl_gemm_bf16: lda/ldb must be multiples of 8 elements");
   VL_CHECK_ARG(a->ldd % (a->d_f32 ? 4 : 8) == 0, "vl_gemm_bf16: ldd misaligned");
-  VL_CHECK_ARG(a->lda >= (a->a_mn ? a->M : a->K) && a->ldb >= (a->b_mn ? a->N : a->K) && a->ldd >= a->N,
-               "vl_gemm_bf16: leading dimension smaller than the row length");
+  VL_CHECK_ARG(a->lda >= (a->a_mn ? a->M : a->K) && a->ldb >= (a->b_mn ? a->N : a->K) &&
+                   (a->epilogue == VL_EPI_ROWLSE || a->ldd >= ((a->N + 7) / 8) * 8),
+               "vl_gemm_bf16: leading dimension smaller than the (8-padded) row length");
   VL_CHECK_ARG(!(a->accumulate && !a->d_f32), "vl_gemm_bf16: accumulate needs fp32 output");
   VL_CHECK_ARG(!(a->split_k > 1 && !(a->accumulate && a->d_f32)), "vl_gemm_bf16: split_k needs accumulate fp32 output");
   VL_CHECK_ARG(!(a->split_k > 1 && a->epilogue != VL_EPI_LINEAR), "vl_gemm_bf16: split_k only with the linear epilogue");

@@ -1,0 +1,140 @@
+"""Contrastive losses of the ViT-Lens hot path with the reference's constructors / forward signatures
+(reference open_clip/loss.py:20-165, 234-385), computed by the fused tcgen05 row-LSE / gradient
+epilogues (vitlens_b200.engine.ContrastiveFn): the [B x B_all] logits never reach HBM in forward.
+
+Distributed semantics (loss.py:20-78) are reproduced for all four (local_loss, gather_with_grad)
+combinations, but with ONE packed all-gather of the feature block per step instead of one per
+tensor, and without every rank recomputing the full [Bg x Bg] matrix: each rank evaluates only its
+[B_loc x Bg] row blocks and the ranks exchange the [B_loc] row-LSE vectors (see engine.ContrastiveFn).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from vitlens_b200 import engine as E
+
+try:
+    import torch.distributed.nn  # noqa: F401
+    from torch import distributed as dist
+
+    has_distributed = True
+except ImportError:  # pragma: no cover
+    dist = None
+    has_distributed = False
+
+
+def gather_features(image_features, text_features, local_loss=False, gather_with_grad=False, rank=0, world_size=1, use_horovod=False):
+    """API-compatible feature all-gather (loss.py:20-78).  The loss modules below do not use it on their
+    hot path (they gather one packed block); it is kept for callers that want the gathered tensors."""
+    assert has_distributed, "torch.distributed did not import correctly"
+    if use_horovod:
+        raise NotImplementedError("horovod is not part of the B200 path; use torch.distributed (NCCL)")
+    if gather_with_grad:
+        all_image_features = torch.cat(torch.distributed.nn.all_gather(image_features), dim=0)
+        all_text_features = torch.cat(torch.distributed.nn.all_gather(text_features), dim=0)
+    else:
+        gi = [torch.zeros_like(image_features) for _ in range(world_size)]
+        gt = [torch.zeros_like(text_features) for _ in range(world_size)]
+        dist.all_gather(gi, image_features)
+        dist.all_gather(gt, text_features)
+        if not local_loss:
+            gi[rank] = image_features
+            gt[rank] = text_features
+        all_image_features = torch.cat(gi, dim=0)
+        all_text_features = torch.cat(gt, dim=0)
+    return all_image_features, all_text_features
+
+
+class _ContrastiveBase(nn.Module):
+    def __init__(self, local_loss=False, gather_with_grad=False, cache_labels=False, rank=0, world_size=1, use_horovod=False):
+        super().__init__()
+        if use_horovod:
+            raise NotImplementedError("horovod is not part of the B200 path; use torch.distributed (NCCL)")
+        self.local_loss = local_loss
+        self.gather_with_grad = gather_with_grad
+        self.cache_labels = cache_labels
+        self.rank = rank
+        self.world_size = world_size
+        self.use_horovod = use_horovod
+        self.prev_num_logits = 0
+        self.labels = {}
+
+    def get_ground_truth(self, device, num_logits) -> torch.Tensor:
+        labels = torch.arange(num_logits, device=device, dtype=torch.long)
+        if self.world_size > 1 and self.local_loss:
+            labels = labels + num_logits * self.rank
+        return labels
+
+    # ---- distributed plumbing
+    def _gather_packed(self, feats):
+        """One all-gather of the packed [k, B_loc, E] block -> list of k tensors [Bg, E] (rank-major rows)."""
+        W = self.world_size
+        packed = torch.stack([f.detach().float() for f in feats], 0).contiguous()  # [k, B_loc, E]
+        out = torch.empty((W,) + tuple(packed.shape), device=packed.device, dtype=packed.dtype)
+        dist.all_gather_into_tensor(out, packed)
+        k, Bl, Ed = packed.shape
+        return [out[:, i].reshape(W * Bl, Ed) for i in range(k)]
+
+    def _gather_vec(self, v):
+        out = torch.empty((self.world_size * v.numel(),), device=v.device, dtype=v.dtype)
+        dist.all_gather_into_tensor(out, v.contiguous())
+        return out
+
+    def _pair(self, x, y, all_x, all_y, logit_scale):
+        """Loss of one (x, y) feature pair for this rank's rows; value follows the reference's definition."""
+        W = self.world_size
+        Bl = x.shape[0]
+        if W == 1:
+            return E.ContrastiveFn.apply(x, y, None, None, logit_scale, 0, Bl, Bl, True, None, None)
+        Bg = W * Bl
+        off = self.rank * Bl
+        if self.local_loss:
+            col = bool(self.gather_with_grad)
+            return E.ContrastiveFn.apply(x, y, all_x, all_y, logit_scale, off, Bl, Bl, col, self._gather_vec if col else None, None)
+        # full-matrix loss on every rank in the reference: value / d(scale) need cross-rank sums
+        grad_rows = Bl if self.gather_with_grad else Bg
+
+        def ds_post(ds):
+            ds = ds.clone()
+            dist.all_reduce(ds)
+            return ds / W if self.gather_with_grad else ds
+
+        part = E.ContrastiveFn.apply(x, y, all_x, all_y, logit_scale, off, Bg, grad_rows, True, self._gather_vec, ds_post)
+        total = part.detach().clone()
+        dist.all_reduce(total)
+        return part + (total - part.detach())
+
+
+class ClipLoss(_ContrastiveBase):
+    """loss.py:311-385."""
+
+    def forward(self, image_features, text_features, logit_scale, output_dict=False):
+        all_i = all_t = None
+        if self.world_size > 1:
+            all_i, all_t = self._gather_packed([image_features, text_features])
+        total_loss = self._pair(image_features, text_features, all_i, all_t, logit_scale)
+        return {"contrastive_loss": total_loss} if output_dict else total_loss
+
+
+class ClipLossGeneral(_ContrastiveBase):
+    """loss.py:234-308."""
+
+    def forward(self, x, y, logit_scale, output_dict=False, key="contrastive_loss"):
+        all_x = all_y = None
+        if self.world_size > 1:
+            all_x, all_y = self._gather_packed([x, y])
+        total_loss = self._pair(x, y, all_x, all_y, logit_scale)
+        return {key: total_loss} if output_dict else total_loss
+
+
+class TriClipLoss(_ContrastiveBase):
+    """loss.py:81-165: pairs (image, visual) and (text, visual); four CE terms / 2."""
+
+    def forward(self, image_features, text_features, visual_features, logit_scale, output_dict=False):
+        all_i = all_t = all_v = None
+        if self.world_size > 1:
+            all_i, all_t, all_v = self._gather_packed([image_features, text_features, visual_features])
+        total_loss = self._pair(image_features, visual_features, all_i, all_v, logit_scale) + \
+            self._pair(text_features, visual_features, all_t, all_v, logit_scale)
+        return {"contrastive_loss": total_loss} if output_dict else total_loss

@@ -1,0 +1,493 @@
+"""Autograd glue between the reference-compatible nn.Modules (open_clip/*) and the sm_100a kernels.
+
+Each ``torch.autograd.Function`` below covers one fused stage of the hot path, runs only
+vitlens_b200 kernels (through ``ops``) in forward and backward, owns exactly the activations
+it needs, and skips weight-gradient work for frozen parameters (the ViT-Lens recipes freeze
+the ViT and train the Lens: transformer.py:553-627).  Activations and the residual stream are
+bf16, LayerNorm/softmax statistics and parameter gradients fp32.
+
+`_ops` is the only gateway to arithmetic; tests may swap it for a torch emulation to exercise
+this file on a CPU-only box (tests/emu_ops.py).  There is no fallback in the product.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops as _ops
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+# ----------------------------------------------------------------------------- bf16 weight cache
+class _WeightCache:
+    """bf16 copies of fp32 master weights, refreshed when the parameter changes (its autograd
+    version counter moves on every in-place optimizer update)."""
+
+    def __init__(self):
+        self._c = {}
+
+    def get(self, p: torch.Tensor, tag: str = "", make=None) -> torch.Tensor:
+        key = (id(p), tag)
+        ver = (p._version, p.data_ptr(), tuple(p.shape))
+        hit = self._c.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        with torch.no_grad():
+            t = make(p) if make is not None else _ops.cast_bf16(p.detach().reshape(p.shape[0], -1) if p.dim() > 1 else p.detach())
+        self._c[key] = (ver, t)
+        return t
+
+    def clear(self):
+        self._c.clear()
+
+
+WEIGHTS = _WeightCache()
+
+
+def w16(p):
+    return WEIGHTS.get(p)
+
+
+def _cat16(tag, *ps):
+    """bf16 concat of several weights along dim 0 (Lens to_q | to_kv -> one QKV GEMM)."""
+    key = (tuple(id(p) for p in ps), tag)
+    ver = tuple((p._version, p.data_ptr()) for p in ps)
+    hit = WEIGHTS._c.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    with torch.no_grad():
+        t = torch.cat([w16(p) for p in ps], dim=0).contiguous()
+    WEIGHTS._c[key] = (ver, t)
+    return t
+
+
+def _conv_w16(p, kpad):
+    def make(w):
+        o = w.shape[0]
+        flat = w.detach().reshape(o, -1)
+        if flat.shape[1] != kpad:
+            pad = torch.zeros((o, kpad), device=w.device, dtype=F32)
+            pad[:, : flat.shape[1]] = flat
+            flat = pad
+        return _ops.cast_bf16(flat)
+
+    return WEIGHTS.get(p, f"conv{kpad}", make)
+
+
+def _wgrad(dy, x):
+    """dW[out, in] = dy^T x  (both operands MN-major: the reduction runs over tokens)."""
+    return _ops.gemm(dy, x, a_t=True, b_t=True, out_dtype=F32, accumulate=True)
+
+
+def _dgrad(dy, w, **kw):
+    """dx[T, in] = dy[T, out] @ W[out, in]  (W consumed in place as an MN-major B operand)."""
+    return _ops.gemm(dy, w, b_t=True, **kw)
+
+
+def _need(ctx, i):
+    return ctx.needs_input_grad[i]
+
+
+# ----------------------------------------------------------------------------- ResidualAttentionBlock
+class VitBlockFn(torch.autograd.Function):
+    """ResidualAttentionBlock.forward (transformer.py:254-272):
+    x + out_proj(MHSA(ln_1(x))) then + c_proj(act(c_fc(ln_2(.)))), as 4 GEMMs with fused
+    bias / residual / GELU epilogues, 2 LayerNorm kernels and 1 attention kernel."""
+
+    @staticmethod
+    def forward(ctx, x, ln1w, ln1b, inw, inb, outw, outb, ln2w, ln2b, fcw, fcb, pjw, pjb, B, N, H, causal, quick):
+        D = x.shape[1]
+        train_w = any(ctx.needs_input_grad[1:13])
+        need_bwd = train_w or ctx.needs_input_grad[0]
+        xn1, m1, r1 = _ops.layernorm_fwd(x, ln1w, ln1b, want_stats=need_bwd)
+        qkv = _ops.gemm(xn1, w16(inw), bias=inb)
+        o, lse = _ops.attention_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B=B, H=H, nq=N, nk=N, causal=causal)
+        x1 = _ops.gemm(o, w16(outw), bias=outb, epilogue=_ops.EPI_RESIDUAL, aux_in=x)
+        xn2, m2, r2 = _ops.layernorm_fwd(x1, ln2w, ln2b, want_stats=need_bwd)
+        h, u = _ops.gemm(xn2, w16(fcw), bias=fcb, epilogue=_ops.EPI_GELU, want_aux_out=True, act_quick=quick)
+        y = _ops.gemm(h, w16(pjw), bias=pjb, epilogue=_ops.EPI_RESIDUAL, aux_in=x1)
+        if need_bwd:
+            ctx.cfg = (B, N, H, causal, quick, train_w)
+            keep_w = (xn1, xn2, h) if train_w else (None, None, None)
+            ctx.save_for_backward(x, m1, r1, qkv, o, lse, x1, m2, r2, u, ln1w, inw, outw, ln2w, fcw, pjw, *keep_w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, N, H, causal, quick, train_w = ctx.cfg
+        x, m1, r1, qkv, o, lse, x1, m2, r2, u, ln1w, inw, outw, ln2w, fcw, pjw, xn1, xn2, h = ctx.saved_tensors
+        D = x.shape[1]
+        dy = dy.contiguous()
+        g = [None] * 18
+        # ---- MLP
+        if _need(ctx, 11):
+            g[11] = _wgrad(dy, h)
+        if _need(ctx, 12):
+            g[12] = _ops.colsum(dy)
+        du = _dgrad(dy, w16(pjw), epilogue=_ops.EPI_GELU_BWD, aux_in=u, act_quick=quick)
+        if _need(ctx, 9):
+            g[9] = _wgrad(du, xn2)
+        if _need(ctx, 10):
+            g[10] = _ops.colsum(du)
+        dxn2 = _dgrad(du, w16(fcw))
+        want_ln2 = _need(ctx, 7) or _need(ctx, 8)
+        dx1, g7, g8 = _ops.layernorm_bwd(dxn2, x1, ln2w, m2, r2, dres=dy, want_wgrad=want_ln2)
+        g[7], g[8] = (g7, g8) if want_ln2 else (None, None)
+        # ---- attention
+        if _need(ctx, 5):
+            g[5] = _wgrad(dx1, o)
+        if _need(ctx, 6):
+            g[6] = _ops.colsum(dx1)
+        do = _dgrad(dx1, w16(outw))
+        dqkv = torch.empty_like(qkv)
+        _ops.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], o, do, lse, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
+                           B=B, H=H, nq=N, nk=N, causal=causal)
+        if _need(ctx, 3):
+            g[3] = _wgrad(dqkv, xn1)
+        if _need(ctx, 4):
+            g[4] = _ops.colsum(dqkv)
+        if _need(ctx, 0) or _need(ctx, 1) or _need(ctx, 2):
+            dxn1 = _dgrad(dqkv, w16(inw))
+            want_ln1 = _need(ctx, 1) or _need(ctx, 2)
+            dx, g1, g2 = _ops.layernorm_bwd(dxn1, x, ln1w, m1, r1, dres=dx1, want_wgrad=want_ln1)
+            g[0] = dx
+            g[1], g[2] = (g1, g2) if want_ln1 else (None, None)
+        return tuple(g)
+
+
+# ----------------------------------------------------------------------------- stand-alone LayerNorm (ln_pre / ln_post / ln_final / gathers)
+class LayerNormFn(torch.autograd.Function):
+    """F.layer_norm on bf16 rows; with row_index it is the fused `ln(x[rows])` used for cls / EOT
+    pooling (transformer.py:653-657,783; model.py:537-540)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, row_index):
+        need = any(ctx.needs_input_grad[:3])
+        y, m, r = _ops.layernorm_fwd(x, w, b, row_index=row_index, want_stats=need)
+        if need:
+            ctx.save_for_backward(x, w, m, r, row_index if row_index is not None else torch.empty(0))
+            ctx.has_index = row_index is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, m, r, idx = ctx.saved_tensors
+        want_w = _need(ctx, 1) or _need(ctx, 2)
+        dx, dw, db = _ops.layernorm_bwd(dy.contiguous(), x, w, m, r, row_index=idx if ctx.has_index else None, want_wgrad=want_w)
+        return (dx if _need(ctx, 0) else None), (dw if _need(ctx, 1) else None), (db if _need(ctx, 2) else None), None
+
+
+# ----------------------------------------------------------------------------- patch embed (conv1 as GEMM)
+class PatchEmbedFn(torch.autograd.Function):
+    """Bias-free strided Conv2d -> [B*L, width] tokens (transformer.py:464-470,674-676;
+    AST_tokenizer.py:44-52; DepthTokenizer.py:50-53): a gather kernel builds the bf16 patch matrix,
+    the tcgen05 GEMM multiplies it with the flattened kernel.  `geom` = dict of vl_patchify args."""
+
+    @staticmethod
+    def forward(ctx, inp, weight, geom):
+        K = weight[0].numel()
+        kpad = (K + 7) // 8 * 8
+        cols = _ops.patchify(inp, Kpad=kpad, **geom)
+        tok = _ops.gemm(cols, _conv_w16(weight, kpad))
+        if ctx.needs_input_grad[1]:
+            ctx.save_for_backward(cols)
+            ctx.wshape = tuple(weight.shape)
+        return tok
+
+    @staticmethod
+    def backward(ctx, dtok):
+        (cols,) = ctx.saved_tensors
+        dw = _wgrad(dtok.contiguous(), cols)  # [width, Kpad]
+        O = ctx.wshape[0]
+        K = 1
+        for s in ctx.wshape[1:]:
+            K *= s
+        return None, dw[:, :K].reshape(ctx.wshape), None
+
+
+class PatchEmbedBiasFn(torch.autograd.Function):
+    """Conv1d-with-bias patch embed of the EEG tokenizer (modal_eeg/models/EEG_tokenizer.py:16-21,35-36)."""
+
+    @staticmethod
+    def forward(ctx, inp, weight, bias, geom):
+        K = weight[0].numel()
+        kpad = (K + 7) // 8 * 8
+        cols = _ops.patchify(inp, Kpad=kpad, **geom)
+        tok = _ops.gemm(cols, _conv_w16(weight, kpad), bias=bias)
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            ctx.save_for_backward(cols)
+            ctx.wshape = tuple(weight.shape)
+        return tok
+
+    @staticmethod
+    def backward(ctx, dtok):
+        (cols,) = ctx.saved_tensors
+        dtok = dtok.contiguous()
+        K = 1
+        for s in ctx.wshape[1:]:
+            K *= s
+        dw = _wgrad(dtok, cols)[:, :K].reshape(ctx.wshape) if _need(ctx, 1) else None
+        db = _ops.colsum(dtok) if _need(ctx, 2) else None
+        return None, dw, db, None
+
+
+# ----------------------------------------------------------------------------- cls / positional assembly
+class AssembleFn(torch.autograd.Function):
+    """cat(cls, tokens) + positional_embedding (transformer.py:756-768) or tokens + pos
+    (adapter output, transformer.py:743) in one pass.  tok: [B*L, D] bf16 -> [B*(L+has_cls), D]."""
+
+    @staticmethod
+    def forward(ctx, tok, cls, pos, B, L):
+        D = tok.shape[1]
+        ctx.cfg = (B, L, D, cls is not None)
+        return _ops.assemble_tokens(tok.contiguous(), cls, pos, B=B, L_=L, D=D)
+
+    @staticmethod
+    def backward(ctx, dx):
+        B, L, D, has_cls = ctx.cfg
+        dtok, dpos, dcls = _ops.assemble_tokens_bwd(dx.contiguous(), B=B, L_=L, D=D, has_cls=has_cls, want_tok=_need(ctx, 0),
+                                                    want_pos=_need(ctx, 2), want_cls=_need(ctx, 1))
+        return dtok, dcls, dpos, None, None
+
+
+class BroadcastRowsFn(torch.autograd.Function):
+    """repeat(latents, 'n d -> b n d') (perceiver.py:316) as a bf16 broadcast; backward sums over the batch."""
+
+    @staticmethod
+    def forward(ctx, latents, B):
+        n, D = latents.shape
+        ctx.cfg = (B, n, D)
+        zero = torch.zeros((B * n, D), device=latents.device, dtype=BF16)
+        return _ops.assemble_tokens(zero, None, latents, B=B, L_=n, D=D)
+
+    @staticmethod
+    def backward(ctx, dx):
+        B, n, D = ctx.cfg
+        _, dpos, _ = _ops.assemble_tokens_bwd(dx.contiguous(), B=B, L_=n, D=D, has_cls=False, want_tok=False, want_pos=True, want_cls=False)
+        return dpos, None
+
+
+# ----------------------------------------------------------------------------- projection head
+class ProjFn(torch.autograd.Function):
+    """`pooled @ proj` (transformer.py:786-787; text_projection model.py:540): bf16 rows x fp32 [D, E]
+    parameter -> fp32 features."""
+
+    @staticmethod
+    def forward(ctx, pooled, proj):
+        ctx.save_for_backward(pooled, proj)
+        return _ops.gemm(pooled, w16(proj), b_t=True, out_dtype=F32)
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        pooled, proj = ctx.saved_tensors
+        d16 = _ops.cast_bf16(dfeat)
+        dpooled = _ops.gemm(d16, w16(proj)) if _need(ctx, 0) else None
+        dproj = _ops.gemm(pooled, d16, a_t=True, b_t=True, out_dtype=F32, accumulate=True) if _need(ctx, 1) else None
+        return dpooled, dproj
+
+
+class L2NormFn(torch.autograd.Function):
+    """F.normalize(dim=-1) on fp32 features (model.py:295,307,522,526,540)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        y, inv = _ops.l2norm_fwd(x.contiguous())
+        ctx.save_for_backward(y, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, inv = ctx.saved_tensors
+        return _ops.l2norm_bwd(dy.contiguous(), y, inv)
+
+
+class TextEmbedFn(torch.autograd.Function):
+    """token_embedding(text) + positional_embedding (model.py:530-532)."""
+
+    @staticmethod
+    def forward(ctx, ids, table, pos):
+        ctx.save_for_backward(ids)
+        ctx.vocab = table.shape[0]
+        return _ops.embed_tokens(ids, table, pos)
+
+    @staticmethod
+    def backward(ctx, dx):
+        (ids,) = ctx.saved_tensors
+        dt, dp = _ops.embed_tokens_bwd(ids, dx.contiguous(), vocab=ctx.vocab, want_table=_need(ctx, 1), want_pos=_need(ctx, 2))
+        return None, dt, dp
+
+
+# ----------------------------------------------------------------------------- the Lens (Perceiver) stages
+class LensAttnFn(torch.autograd.Function):
+    """PreNorm(Attention) + residual (perceiver.py:67-82,105-154,319/323).  `ctx_rows is None` ->
+    latent self-attention (context = normed x); otherwise cross-attention over `data` with its own
+    norm_context.  to_q / to_kv are bias-free, to_out has a bias."""
+
+    @staticmethod
+    def forward(ctx, x, data, nw, nb, cw, cb, wq, wkv, wo, bo, B, n, M, heads):
+        cross = data is not None
+        inner = wq.shape[0]
+        need = any(ctx.needs_input_grad)
+        xn, mx, rx = _ops.layernorm_fwd(x, nw, nb, want_stats=need)
+        if cross:
+            cn, mc, rc = _ops.layernorm_fwd(data, cw, cb, want_stats=need)
+            q = _ops.gemm(xn, w16(wq))
+            kv = _ops.gemm(cn, w16(wkv))
+            k, v = kv[:, :inner], kv[:, inner:]
+        else:
+            cn = mc = rc = None
+            qkv = _ops.gemm(xn, _cat16("qkv", wq, wkv))
+            q, k, v = qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:]
+            kv = qkv
+        o, lse = _ops.attention_fwd(q, k, v, B=B, H=heads, nq=n, nk=M if cross else n)
+        y = _ops.gemm(o, w16(wo), bias=bo, epilogue=_ops.EPI_RESIDUAL, aux_in=x)
+        if need:
+            ctx.cfg = (cross, B, n, M, heads, inner)
+            dummy = torch.empty(0, device=x.device)
+            ctx.save_for_backward(x, xn, mx, rx, q if cross else dummy, kv, o, lse, nw, wq, wkv, wo,
+                                  *( (data, cn, mc, rc, cw) if cross else (dummy,) * 5))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        cross, B, n, M, heads, inner = ctx.cfg
+        x, xn, mx, rx, q, kv, o, lse, nw, wq, wkv, wo, data, cn, mc, rc, cw = ctx.saved_tensors
+        dy = dy.contiguous()
+        g = [None] * 14
+        if _need(ctx, 8):
+            g[8] = _wgrad(dy, o)
+        if _need(ctx, 9):
+            g[9] = _ops.colsum(dy)
+        do = _dgrad(dy, w16(wo))
+        if cross:
+            dq = torch.empty_like(q)
+            dkv = torch.empty_like(kv)
+            _ops.attention_bwd(q, kv[:, :inner], kv[:, inner:], o, do, lse, dq, dkv[:, :inner], dkv[:, inner:], B=B, H=heads, nq=n, nk=M)
+            if _need(ctx, 6):
+                g[6] = _wgrad(dq, xn)
+            if _need(ctx, 7):
+                g[7] = _wgrad(dkv, cn)
+            dxn = _dgrad(dq, w16(wq))
+            if _need(ctx, 1) or _need(ctx, 4) or _need(ctx, 5):
+                dcn = _dgrad(dkv, w16(wkv))
+                want = _need(ctx, 4) or _need(ctx, 5)
+                ddata, g4, g5 = _ops.layernorm_bwd(dcn, data, cw, mc, rc, want_wgrad=want)
+                g[1] = ddata if _need(ctx, 1) else None
+                g[4], g[5] = (g4, g5) if want else (None, None)
+        else:
+            qkv = kv
+            dqkv = torch.empty_like(qkv)
+            _ops.attention_bwd(qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:], o, do, lse, dqkv[:, :inner],
+                               dqkv[:, inner:2 * inner], dqkv[:, 2 * inner:], B=B, H=heads, nq=n, nk=n)
+            if _need(ctx, 6) or _need(ctx, 7):
+                dw = _wgrad(dqkv, xn)  # [3*inner, D]
+                g[6], g[7] = dw[:inner], dw[inner:]
+            dxn = _dgrad(dqkv, _cat16("qkv", wq, wkv))
+        want = _need(ctx, 2) or _need(ctx, 3)
+        dx, g2, g3 = _ops.layernorm_bwd(dxn, x, nw, mx, rx, dres=dy, want_wgrad=want)
+        g[0] = dx if _need(ctx, 0) else None
+        g[2], g[3] = (g2, g3) if want else (None, None)
+        return tuple(g)
+
+
+class LensFFFn(torch.autograd.Function):
+    """PreNorm(FeedForward) + residual (perceiver.py:85-102,320/324): Linear(d, 8d) -> GEGLU -> Linear(4d, d)."""
+
+    @staticmethod
+    def forward(ctx, x, nw, nb, w0, b0, w2, b2):
+        need = any(ctx.needs_input_grad)
+        xn, m, r = _ops.layernorm_fwd(x, nw, nb, want_stats=need)
+        h = _ops.gemm(xn, w16(w0), bias=b0)
+        gg = _ops.geglu_fwd(h)
+        y = _ops.gemm(gg, w16(w2), bias=b2, epilogue=_ops.EPI_RESIDUAL, aux_in=x)
+        if need:
+            ctx.save_for_backward(x, xn, m, r, h, gg, nw, w0, w2)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, xn, m, r, h, gg, nw, w0, w2 = ctx.saved_tensors
+        dy = dy.contiguous()
+        g = [None] * 7
+        if _need(ctx, 5):
+            g[5] = _wgrad(dy, gg)
+        if _need(ctx, 6):
+            g[6] = _ops.colsum(dy)
+        dg = _dgrad(dy, w16(w2))
+        dh = _ops.geglu_bwd(h, dg)
+        if _need(ctx, 3):
+            g[3] = _wgrad(dh, xn)
+        if _need(ctx, 4):
+            g[4] = _ops.colsum(dh)
+        dxn = _dgrad(dh, w16(w0))
+        want = _need(ctx, 1) or _need(ctx, 2)
+        dx, g1, g2 = _ops.layernorm_bwd(dxn, x, nw, m, r, dres=dy, want_wgrad=want)
+        g[0] = dx if _need(ctx, 0) else None
+        g[1], g[2] = (g1, g2) if want else (None, None)
+        return tuple(g)
+
+
+# ----------------------------------------------------------------------------- contrastive loss
+class ContrastiveFn(torch.autograd.Function):
+    """One feature pair of ClipLoss / TriClipLoss (loss.py:116-163, 346-385), local rows only:
+
+        value = [ sum_i CE_i(s * X_loc @ all_Y^T) + sum_i CE_i(s * Y_loc @ all_X^T) ] / (2 * val_rows)
+
+    with labels = arange + label_off.  Two tcgen05 GEMMs with the row-LSE epilogue produce it
+    without writing logits to HBM.  Backward re-runs the GEMMs with the gradient epilogue
+        g = gscale * (softmax_row + [col_term] softmax_col - k * onehot)     (bf16 [B_loc x B_all] scratch)
+    followed by dX = s * g @ all_Y.  softmax_col needs the LSE of every *column*, i.e. the row LSEs
+    of the opposite direction from all ranks: `gather_lse` all-gathers a [B_loc] vector when
+    world_size > 1.  col_term=False is the `local_loss=True, gather_with_grad=False` gradient.
+    `ds_post` post-processes d(loss)/d(scale) (cross-rank sum where the reference computes the
+    full matrix on every rank)."""
+
+    @staticmethod
+    def forward(ctx, x, y, all_x, all_y, scale, label_off, val_rows, grad_rows, col_term, gather_lse, ds_post):
+        x16, y16 = _ops.cast_bf16(x.detach()), _ops.cast_bf16(y.detach())
+        ax16 = x16 if all_x is None else _ops.cast_bf16(all_x.detach())
+        ay16 = y16 if all_y is None else _ops.cast_bf16(all_y.detach())
+        s = float(scale.detach())
+        lse_x, sum_x = _ops.rowlse(x16, ay16, alpha=s, label_off=label_off)
+        lse_y, sum_y = _ops.rowlse(y16, ax16, alpha=s, label_off=label_off)
+        loss = (sum_x + sum_y) / (2.0 * val_rows)
+        empty = torch.empty(0, device=x.device)
+        col_x = col_y = empty
+        if col_term:
+            col_x = gather_lse(lse_y) if gather_lse is not None else lse_y  # columns of the x-direction = rows of the y-direction
+            col_y = gather_lse(lse_x) if gather_lse is not None else lse_x
+        ctx.save_for_backward(x16, y16, ax16, ay16, lse_x, lse_y, col_x, col_y)
+        ctx.cfg = (s, label_off, grad_rows, col_term, ds_post)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        x16, y16, ax16, ay16, lse_x, lse_y, col_x, col_y = ctx.saved_tensors
+        s, label_off, grad_rows, col_term, ds_post = ctx.cfg
+        gs = float(dloss) / (2.0 * grad_rows)
+        gx, ds_x = _ops.clipgrad(x16, ay16, alpha=s, row_lse=lse_x, col_lse=col_x if col_term else None, label_off=label_off, gscale=gs)
+        gy, ds_y = _ops.clipgrad(y16, ax16, alpha=s, row_lse=lse_y, col_lse=col_y if col_term else None, label_off=label_off, gscale=gs)
+        dx = _ops.gemm(gx, ay16, b_t=True, out_dtype=F32, alpha=s) if _need(ctx, 0) else None
+        dy = _ops.gemm(gy, ax16, b_t=True, out_dtype=F32, alpha=s) if _need(ctx, 1) else None
+        dscale = None
+        if _need(ctx, 4):
+            # with the column term every logit's gradient appears in both directions
+            dscale = (ds_x + ds_y) * (0.5 if col_term else 1.0)
+            if ds_post is not None:
+                dscale = ds_post(dscale)
+            dscale = dscale.reshape(())
+        return dx, dy, None, None, dscale, None, None, None, None, None, None
+
+
+class AddFn(torch.autograd.Function):
+    """bf16 a + b (token features + per-sample positional tokens, transformer.py:743)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        return _ops.add_bf16(a.contiguous(), b.contiguous())
+
+    @staticmethod
+    def backward(ctx, d):
+        return d, d

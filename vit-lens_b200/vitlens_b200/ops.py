@@ -195,7 +195,34 @@ def add_bf16(a, b):
     return out
 
 
-def clip_loss_fwd_bwd(*args, **kw):
-    from . import loss_ops
+def rowlse(p16, q16, *, alpha, label_off=0):
+    """Row-wise log-sum-exp of alpha * P @ Q^T without materialising the logits.
+    Returns (lse [M] fp32, sum_i(lse_i - z[i, i + label_off]) as a 1-element fp32 tensor)."""
+    _v2(p16, BF16), _v2(q16, BF16)
+    M, E = p16.shape
+    N = q16.shape[0]
+    nparts = L.rowlse_parts(N)
+    dev = p16.device
+    pm = torch.full((M, nparts), float("-inf"), device=dev, dtype=F32)
+    ps = torch.zeros((M, nparts), device=dev, dtype=F32)
+    diag = torch.zeros((M,), device=dev, dtype=F32)
+    L.gemm(p16, q16, None, M=M, N=N, K=E, lda=_ld(p16), ldb=_ld(q16), ldd=0, epilogue=L.EPI_ROWLSE, alpha=alpha,
+           out_vec0=pm, out_vec1=ps, out_vec2=diag, iparam=label_off)
+    lse = torch.empty((M,), device=dev, dtype=F32)
+    loss_sum = torch.zeros((1,), device=dev, dtype=F32)
+    L.lse_combine(pm, ps, diag, lse, loss_sum, M=M, nparts=nparts)
+    return lse, loss_sum
 
-    return loss_ops.clip_loss_fwd_bwd(*args, **kw)
+
+def clipgrad(p16, q16, *, alpha, row_lse, col_lse, label_off, gscale):
+    """g[M,N] (bf16) = gscale * (exp(z - row_lse_i) + [col_lse] exp(z - col_lse_j) - k * onehot(j == i + label_off)),
+    z = alpha * P @ Q^T;  also returns sum(g * P@Q^T) (d loss / d alpha) as a 1-element fp32 tensor."""
+    _v2(p16, BF16), _v2(q16, BF16)
+    M, E = p16.shape
+    N = q16.shape[0]
+    N8 = (N + 7) // 8 * 8
+    g = torch.zeros((M, N8), device=p16.device, dtype=BF16)
+    ds = torch.zeros((1,), device=p16.device, dtype=F32)
+    L.gemm(p16, q16, g, M=M, N=N, K=E, lda=_ld(p16), ldb=_ld(q16), ldd=N8, epilogue=L.EPI_CLIPGRAD, alpha=alpha,
+           row_vec=row_lse, col_vec=col_lse, iparam=label_off, fparam=gscale, scalar_out=ds)
+    return g[:, :N], ds
