@@ -1,0 +1,208 @@
+"""Kernel parity on the B200, through the C ABI (vitlens_b200.lib -> libvitlens_b200.so), against plain fp32 torch
+references of the same ops.  Tolerances: bf16 outputs 2e-2 of the tensor's max (8 mantissa bits + fp32 accumulate)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from vitlens_b200 import ops as o
+
+    torch.manual_seed(0)
+    return o
+
+
+def close(got, ref, tol=2e-2, atol=1e-3):
+    err = (got.float() - ref.float()).abs().max().item()
+    sc = ref.float().abs().max().item()
+    assert math.isfinite(err) and err <= tol * sc + atol, (err, sc)
+
+
+def _gelu(x, quick):
+    return x * torch.sigmoid(1.702 * x) if quick else F.gelu(x)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (1000, 384, 1024), (304, 72, 200), (257 * 8, 3072, 1024), (72, 128, 128)])
+@pytest.mark.parametrize("a_t,b_t", [(False, False), (False, True), (True, True)])
+def test_gemm_layouts(ops, M, N, K, a_t, b_t):
+    A = torch.randn(M, K, device="cuda").to(BF)
+    B = torch.randn(N, K, device="cuda").to(BF)
+    out = ops.gemm(A.t().contiguous() if a_t else A, B.t().contiguous() if b_t else B, a_t=a_t, b_t=b_t, out_dtype=torch.float32)
+    close(out, A.float() @ B.float().t(), tol=1e-3)
+
+
+@pytest.mark.parametrize("quick", [False, True])
+def test_gemm_epilogues(ops, quick):
+    M, N, K = 520, 1024, 256
+    A = torch.randn(M, K, device="cuda").to(BF)
+    B = torch.randn(N, K, device="cuda").to(BF) * 0.1
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda").to(BF)
+    acc = A.float() @ B.float().t()
+    close(ops.gemm(A, B, bias=bias), acc + bias)
+    h, u = ops.gemm(A, B, bias=bias, epilogue=ops.EPI_GELU, want_aux_out=True, act_quick=quick)
+    close(u, acc + bias)
+    close(h, _gelu(acc + bias, quick))
+    close(ops.gemm(A, B, bias=bias, epilogue=ops.EPI_RESIDUAL, aux_in=res), acc + bias + res.float())
+    xr = res.float().requires_grad_(True)
+    g = torch.autograd.grad(_gelu(xr, quick).sum(), xr)[0]
+    close(ops.gemm(A, B, epilogue=ops.EPI_GELU_BWD, aux_in=res, act_quick=quick), acc * g)
+
+
+def test_gemm_splitk_accumulate(ops):
+    M, N, K = 384, 512, 8192
+    A = torch.randn(K, M, device="cuda").to(BF)
+    B = torch.randn(K, N, device="cuda").to(BF)
+    out = ops.gemm(A, B, a_t=True, b_t=True, out_dtype=torch.float32, accumulate=True)
+    close(out, A.float().t() @ B.float(), tol=1e-3)
+
+
+def _ref_attn(q, k, v, causal):
+    s = torch.einsum("bqhd,bkhd->bhqk", q, k) * 0.125
+    if causal:
+        n = q.shape[1]
+        s = s + torch.full((n, n), float("-inf"), device=q.device).triu_(1)
+    return torch.einsum("bhqk,bkhd->bqhd", torch.softmax(s, -1), v), torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("B,H,nq,nk,causal,packed", [
+    (2, 2, 257, 257, False, True), (3, 2, 77, 77, True, True), (2, 16, 256, 256, False, True), (2, 1, 256, 600, False, False),
+    (2, 2, 17, 17, False, True), (4, 12, 50, 50, False, True), (2, 1, 128, 512, False, False), (1, 1, 1, 1, False, True)])
+def test_attention_fwd_bwd(ops, B, H, nq, nk, causal, packed):
+    D = H * 64
+    if packed:
+        qkv = torch.randn(B * nq, 3 * D, device="cuda").to(BF)
+        q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+        dqkv = torch.zeros_like(qkv)
+        dq, dk, dv = dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:]
+    else:
+        q = torch.randn(B * nq, D, device="cuda").to(BF)
+        kv = torch.randn(B * nk, 2 * D, device="cuda").to(BF)
+        k, v = kv[:, :D], kv[:, D:]
+        dq = torch.zeros_like(q)
+        dkv = torch.zeros_like(kv)
+        dk, dv = dkv[:, :D], dkv[:, D:]
+    o, lse = ops.attention_fwd(q, k, v, B=B, H=H, nq=nq, nk=nk, causal=causal)
+    qf = q.float().reshape(B, nq, H, 64).requires_grad_(True)
+    kf = k.float().reshape(B, nk, H, 64).requires_grad_(True)
+    vf = v.float().reshape(B, nk, H, 64).requires_grad_(True)
+    oref, lref = _ref_attn(qf, kf, vf, causal)
+    close(o.reshape(B, nq, H, 64), oref.detach(), tol=3e-2)
+    close(lse, lref.detach(), tol=1e-3, atol=1e-3)
+    do = torch.randn(B * nq, D, device="cuda").to(BF)
+    ops.attention_bwd(q, k, v, o, do, lse, dq, dk, dv, B=B, H=H, nq=nq, nk=nk, causal=causal)
+    gq, gk, gv = torch.autograd.grad(oref, (qf, kf, vf), do.float().reshape(B, nq, H, 64))
+    close(dq.reshape(B, nq, H, 64), gq, tol=3e-2)
+    close(dk.reshape(B, nk, H, 64), gk, tol=3e-2)
+    close(dv.reshape(B, nk, H, 64), gv, tol=3e-2)
+
+
+@pytest.mark.parametrize("T,D,gather", [(1000, 1024, False), (77, 128, False), (513, 768, True), (300, 512, False)])
+def test_layernorm(ops, T, D, gather):
+    x = (torch.randn(T, D, device="cuda") * 2 + 0.5).to(BF)
+    w = torch.randn(D, device="cuda") * 0.1 + 1
+    b = torch.randn(D, device="cuda") * 0.1
+    idx = torch.randperm(T, device="cuda")[: T // 3].contiguous() if gather else None
+    y, mean, rstd = ops.layernorm_fwd(x, w, b, row_index=idx)
+    xs = x.float()[idx] if gather else x.float()
+    xr, wr, br = xs.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.layer_norm(xr, (D,), wr, br, 1e-5)
+    close(y, yr.detach())
+    dy = torch.randn_like(yr).to(BF)
+    yr.backward(dy.float())
+    dres = torch.randn(T, D, device="cuda").to(BF)
+    dx, dw, db = ops.layernorm_bwd(dy, x, w, mean, rstd, dres=dres, row_index=idx)
+    close(dx[idx] if gather else dx, xr.grad + (dres.float()[idx] if gather else dres.float()))
+    close(dw, wr.grad, tol=1e-3, atol=0.05)
+    close(db, br.grad, tol=1e-3, atol=0.05)
+    if gather:
+        mask = torch.ones(T, dtype=torch.bool, device="cuda")
+        mask[idx] = False
+        assert float(dx[mask].abs().max()) == 0.0
+
+
+def test_row_kernels(ops):
+    dy = torch.randn(5000, 3072, device="cuda").to(BF)
+    close(ops.colsum(dy), dy.float().sum(0), tol=1e-3, atol=0.05)
+    img = torch.randn(3, 3, 224, 224, device="cuda")
+    cols = ops.patchify(img, B=3, C=3, OH=16, OW=16, kh=14, kw=14, stride_h=14, stride_w=14, sb=3 * 224 * 224, sc=224 * 224, sh=224, sw=1, Kpad=592)
+    close(cols[:, :588], F.unfold(img, 14, stride=14).transpose(1, 2).reshape(-1, 588), tol=1e-2)
+    assert float(cols[:, 588:].abs().max()) == 0.0
+    x = torch.randn(3, 512, 128, device="cuda")
+    cols = ops.patchify(x, B=3, C=1, OH=12, OW=50, kh=14, kw=14, stride_h=10, stride_w=10, sb=512 * 128, sc=0, sh=1, sw=128, Kpad=200)
+    close(cols[:, :196], F.unfold(x.unsqueeze(1).transpose(2, 3), 14, stride=10).transpose(1, 2).reshape(-1, 196), tol=1e-2)
+    tok = torch.randn(5 * 16, 128, device="cuda").to(BF)
+    cls, pos = torch.randn(128, device="cuda"), torch.randn(17, 128, device="cuda")
+    out = ops.assemble_tokens(tok, cls, pos, B=5, L_=16, D=128)
+    ref = torch.cat([cls.view(1, 1, 128).expand(5, 1, 128), tok.float().reshape(5, 16, 128)], 1) + pos
+    close(out.reshape(5, 17, 128), ref)
+    dx = torch.randn(5 * 17, 128, device="cuda").to(BF)
+    dtok, dpos, dcls = ops.assemble_tokens_bwd(dx, B=5, L_=16, D=128, has_cls=True)
+    d3 = dx.float().reshape(5, 17, 128)
+    close(dtok.reshape(5, 16, 128), d3[:, 1:])
+    close(dpos, d3.sum(0), atol=0.02)
+    close(dcls, d3[:, 0].sum(0), atol=0.02)
+    xx = torch.randn(37, 768, device="cuda")
+    yy, inv = ops.l2norm_fwd(xx)
+    xr = xx.clone().requires_grad_(True)
+    yr = F.normalize(xr, dim=-1)
+    close(yy, yr.detach(), tol=1e-5, atol=1e-6)
+    g = torch.randn_like(xx)
+    yr.backward(g)
+    close(ops.l2norm_bwd(g, yy, inv), xr.grad, tol=1e-4, atol=1e-6)
+    h = torch.randn(300, 1024, device="cuda").to(BF)
+    hr = h.float().requires_grad_(True)
+    a, gt = hr.chunk(2, -1)
+    r = a * F.gelu(gt)
+    close(ops.geglu_fwd(h), r.detach())
+    dout = torch.randn(300, 512, device="cuda").to(BF)
+    r.backward(dout.float())
+    close(ops.geglu_bwd(h, dout), hr.grad)
+
+
+@pytest.mark.parametrize("Bl,Ball,off", [(8, 8, 0), (4, 4, 0), (512, 512, 0), (64, 256, 128), (100, 300, 100)])
+def test_contrastive_epilogues(ops, Bl, Ball, off):
+    E = 768
+    x = F.normalize(torch.randn(Bl, E, device="cuda"), dim=-1).to(BF)
+    y = F.normalize(torch.randn(Ball, E, device="cuda"), dim=-1).to(BF)
+    s = 14.3
+    lse, tot = ops.rowlse(x, y, alpha=s, label_off=off)
+    z = s * (x.float() @ y.float().t())
+    ref = torch.logsumexp(z, -1)
+    close(lse, ref, tol=1e-4, atol=1e-3)
+    diag = z[torch.arange(Bl), torch.arange(Bl) + off]
+    assert abs(float(tot) - float((ref - diag).sum())) < 1e-3 * Bl
+    col = torch.randn(Ball, device="cuda") + 3
+    for cl in (None, col):
+        g, ds = ops.clipgrad(x, y, alpha=s, row_lse=lse, col_lse=cl, label_off=off, gscale=0.01)
+        gr = torch.exp(z - lse[:, None])
+        k = 1.0
+        if cl is not None:
+            gr = gr + torch.exp(z - cl[None, :])
+            k = 2.0
+        oh = torch.zeros_like(z)
+        oh[torch.arange(Bl), torch.arange(Bl) + off] = 1
+        gr = 0.01 * (gr - k * oh)
+        close(g, gr, tol=1e-2, atol=1e-5)
+        assert abs(float(ds) - float((gr * (z / s)).sum())) < 2e-2 * float((gr * (z / s)).abs().sum()) + 1e-4
+
+
+def test_adamw(ops):
+    from vitlens_b200 import lib as L
+
+    p = torch.randn(10000, device="cuda")
+    gr = torch.randn(10000, device="cuda")
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pr], lr=1e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.2)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in (1, 2, 3):
+        pr.grad = gr.clone()
+        opt.step()
+        L.adamw_step(p, gr, m, v, lr=1e-3, beta1=0.9, beta2=0.98, eps=1e-6, weight_decay=0.2, step=step)
+    close(p, pr.detach(), tol=1e-5, atol=1e-6)

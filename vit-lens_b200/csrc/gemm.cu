@@ -50,7 +50,8 @@ struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = kEpiWarps * 4096;  // per epilogue warp: 32 rows x 128 B transpose buffer
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = 2 * BN;
 };
 
@@ -66,13 +67,63 @@ __device__ __forceinline__ void tile_coords(const GemmParams& p, int t, int& m_b
   m_blk = m_first + (r - n_blk * gm);
 }
 
+// ---- coalesced epilogue I/O: a warp owns 32 rows x 64 bf16 columns (one 128-byte line per row).
+// Thread t computes row t; global traffic is issued with lane l -> (row (l>>3)+4i, 16-byte segment l&7), i.e.
+// four complete 128-byte lines per instruction, going through a swizzled 4 KB smem transpose buffer.
+__device__ __forceinline__ uint32_t stg_off(int row, int seg) { return static_cast<uint32_t>(row * 128 + ((seg ^ (row & 7)) << 4)); }
+
+__device__ __forceinline__ void store_tile_bf16(uint8_t* stg, const float (&f)[64], __nv_bfloat16* g, long long ld, int rows_valid,
+                                                int cols_valid, int lane) {
+#pragma unroll
+  for (int sgm = 0; sgm < 8; ++sgm) {
+    uint4 u;
+    u.x = pack_bf16(f[8 * sgm], f[8 * sgm + 1]);
+    u.y = pack_bf16(f[8 * sgm + 2], f[8 * sgm + 3]);
+    u.z = pack_bf16(f[8 * sgm + 4], f[8 * sgm + 5]);
+    u.w = pack_bf16(f[8 * sgm + 6], f[8 * sgm + 7]);
+    *reinterpret_cast<uint4*>(stg + stg_off(lane, sgm)) = u;
+  }
+  __syncwarp();
+  const int seg = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = (lane >> 3) + 4 * i;
+    const uint4 u = *reinterpret_cast<const uint4*>(stg + stg_off(row, seg));
+    if (row < rows_valid && seg * 8 < cols_valid) *reinterpret_cast<uint4*>(g + static_cast<long long>(row) * ld + seg * 8) = u;
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void load_tile_bf16(uint8_t* stg, uint32_t (&a)[32], const __nv_bfloat16* g, long long ld, int rows_valid,
+                                               int cols_valid, int lane) {
+  const int seg = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = (lane >> 3) + 4 * i;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (row < rows_valid && seg * 8 < cols_valid) u = *reinterpret_cast<const uint4*>(g + static_cast<long long>(row) * ld + seg * 8);
+    *reinterpret_cast<uint4*>(stg + stg_off(row, seg)) = u;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int sgm = 0; sgm < 8; ++sgm) {
+    const uint4 u = *reinterpret_cast<const uint4*>(stg + stg_off(lane, sgm));
+    a[4 * sgm] = u.x;
+    a[4 * sgm + 1] = u.y;
+    a[4 * sgm + 2] = u.z;
+    a[4 * sgm + 3] = u.w;
+  }
+  __syncwarp();
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t stg_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t bar_base = stg_base + Cfg::kStagingBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
@@ -200,8 +251,90 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool row_ok = row < p.M;
       const bool lead_split = (ks == 0);  // bias / aux terms are added by split 0 only
       float lse_m = -INFINITY, lse_s = 0.f, clip_ds = 0.f;
+      const bool fast = !p.d_f32 && p.epi != VL_EPI_ROWLSE;
+      if (fast) {
+        // ---------------- bf16 outputs: 64-column groups, fully coalesced global traffic
+        uint8_t* stg = smem_raw + (stg_base - smem_u32(smem_raw)) + e * 4096;
+        const int row0 = m_blk * kBM + quarter * 32;
+        const int rows_valid = min(32, p.M - row0);
 #pragma unroll 1
-      for (int c = 0; c < kChunks; ++c) {
+        for (int gidx = 0; gidx < kChunks / 2; ++gidx) {
+          const int col0 = n_blk * BN + half * (BN / 2) + gidx * 64;
+          if (col0 >= p.N) break;
+          const int cols_valid = min(64, p.N - col0);
+          uint32_t ax[32];
+          const bool need_aux = (p.epi == VL_EPI_RESIDUAL && lead_split) || p.epi == VL_EPI_GELU_BWD;
+          if (need_aux)
+            load_tile_bf16(stg, ax, p.aux_in + static_cast<long long>(row0) * p.ldaux + col0, p.ldaux, rows_valid, cols_valid, lane);
+          float f[64];
+#pragma unroll
+          for (int hc = 0; hc < 2; ++hc) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * (BN / 2) + gidx * 64 + hc * 32, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[hc * 32 + j] = __uint_as_float(v[j]);
+          }
+          if (p.epi == VL_EPI_CLIPGRAD) {
+            const float rl = row_ok ? __ldg(p.row_vec + row) : 0.f;
+            float dsum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+              const float accv = f[j];
+              const float z = accv * p.alpha;
+              float gval = 0.f;
+              if (row_ok && col0 + j < p.N) {
+                gval = __expf(z - rl);
+                if (p.col_vec) gval += __expf(z - __ldg(p.col_vec + col0 + j));
+                if (col0 + j == row + p.iparam) gval -= p.col_vec ? 2.f : 1.f;
+                gval *= p.fparam;
+                dsum += gval * accv;
+              }
+              f[j] = gval;
+            }
+            clip_ds += dsum;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) f[j] *= p.alpha;
+            if (p.bias != nullptr && lead_split && p.epi != VL_EPI_GELU_BWD) {
+#pragma unroll
+              for (int j = 0; j < 64; j += 4) {
+                if (col0 + j < p.N) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                  f[j] += b4.x;
+                  f[j + 1] += b4.y;
+                  f[j + 2] += b4.z;
+                  f[j + 3] += b4.w;
+                }
+              }
+            }
+            if (p.epi == VL_EPI_GELU) {
+              if (p.aux_out != nullptr)
+                store_tile_bf16(stg, f, p.aux_out + static_cast<long long>(row0) * p.ldaux + col0, p.ldaux, rows_valid, cols_valid, lane);
+#pragma unroll
+              for (int j = 0; j < 64; ++j) f[j] = gelu_fwd(f[j], p.act_quick);
+            } else if (need_aux) {
+              if (p.epi == VL_EPI_RESIDUAL) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  f[2 * j] += bf16_lo(ax[j]);
+                  f[2 * j + 1] += bf16_hi(ax[j]);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  f[2 * j] *= gelu_grad(bf16_lo(ax[j]), p.act_quick);
+                  f[2 * j + 1] *= gelu_grad(bf16_hi(ax[j]), p.act_quick);
+                }
+              }
+            }
+          }
+          store_tile_bf16(stg, f, reinterpret_cast<__nv_bfloat16*>(p.d) + static_cast<long long>(row0) * p.ldd + col0, p.ldd, rows_valid,
+                          cols_valid, lane);
+        }
+      }
+#pragma unroll 1
+      for (int c = 0; c < (fast ? 0 : kChunks); ++c) {
         const int col0 = n_blk * BN + half * (BN / 2) + c * 32;
         if (col0 >= p.N) break;
         uint32_t v[32];

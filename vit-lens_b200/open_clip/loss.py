@@ -71,9 +71,10 @@ class _ContrastiveBase(nn.Module):
         """One all-gather of the packed [k, B_loc, E] block -> list of k tensors [Bg, E] (rank-major rows)."""
         W = self.world_size
         packed = torch.stack([f.detach().float() for f in feats], 0).contiguous()  # [k, B_loc, E]
-        out = torch.empty((W,) + tuple(packed.shape), device=packed.device, dtype=packed.dtype)
-        dist.all_gather_into_tensor(out, packed)
         k, Bl, Ed = packed.shape
+        out = torch.empty((W * k, Bl, Ed), device=packed.device, dtype=packed.dtype)
+        dist.all_gather_into_tensor(out, packed)  # rank-major concat along dim 0
+        out = out.view(W, k, Bl, Ed)
         return [out[:, i].reshape(W * Bl, Ed) for i in range(k)]
 
     def _gather_vec(self, v):

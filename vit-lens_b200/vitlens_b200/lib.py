@@ -16,6 +16,20 @@ from . import build as _build
 _lock = threading.Lock()
 _lib = None
 launch_count = 0  # number of vl_* kernel-launching calls issued (bench.py reports it)
+# bench.py roofline instrumentation: when a list, every GEMM / attention launch is bracketed by CUDA events on
+# the launching stream and (start, end, algorithmic flops | kind, bytes) is appended.
+GEMM_TIMING = None
+ATTN_TIMING = None
+
+
+def _timed(store, payload, fn):
+    if store is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    store.append((e0, e1) + payload)
 
 
 class VlError(RuntimeError):
@@ -101,7 +115,8 @@ def gemm(a, b, d, *, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, epilogue=EP
         _ptr(bias), _ptr(aux_in), _ptr(aux_out), ldaux,
         _ptr(row_vec), _ptr(col_vec), _ptr(out_vec0), _ptr(out_vec1), _ptr(out_vec2), _ptr(scalar_out), int(iparam), float(fparam))
     _count()
-    _check(_fn("vl_gemm_bf16")(C.cast(C.pointer(args), C.c_void_p), _stream()), "vl_gemm_bf16")
+    _timed(GEMM_TIMING, (2.0 * M * N * K,),
+           lambda: _check(_fn("vl_gemm_bf16")(C.cast(C.pointer(args), C.c_void_p), _stream()), "vl_gemm_bf16"))
 
 
 # ----------------------------------------------------------------------------- prototypes
@@ -154,12 +169,16 @@ BF16, F32 = torch.bfloat16, torch.float32
 
 
 def attention_fwd(q, k, v, o, lse, *, B, H, nq, nk, ldq, ldk, ldv, ldo, scale, causal=False):
-    _call("vl_attention_fwd", _p(q), _p(k), _p(v), _p(o), _p(lse), B, H, nq, nk, ldq, ldk, ldv, ldo, float(scale), int(causal))
+    byts = 2.0 * B * H * 64 * (2 * nq + 2 * nk)  # read Q,K,V + write O (bf16)
+    _timed(ATTN_TIMING, ("fwd", byts),
+           lambda: _call("vl_attention_fwd", _p(q), _p(k), _p(v), _p(o), _p(lse), B, H, nq, nk, ldq, ldk, ldv, ldo, float(scale), int(causal)))
 
 
 def attention_bwd(q, k, v, o, dout, lse, dq, dk, dv, *, B, H, nq, nk, ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, scale, causal=False):
-    _call("vl_attention_bwd", _p(q), _p(k), _p(v), _p(o), _p(dout), _p(lse), _p(dq), _p(dk), _p(dv), B, H, nq, nk,
-          ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, float(scale), int(causal))
+    byts = 2.0 * B * H * 64 * (4 * nq + 4 * nk)  # read Q,K,V,O,dO + write dQ,dK,dV (bf16)
+    _timed(ATTN_TIMING, ("bwd", byts),
+           lambda: _call("vl_attention_bwd", _p(q), _p(k), _p(v), _p(o), _p(dout), _p(lse), _p(dq), _p(dk), _p(dv), B, H, nq, nk,
+                         ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, float(scale), int(causal)))
 
 
 def layernorm_fwd(x, w, b, y, mean, rstd, *, T, D, ldx, ldy, row_index=None, eps=1e-5):
