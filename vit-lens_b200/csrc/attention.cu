@@ -24,6 +24,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 
 struct AttnParams {
   int B, H, nq, nk;
+  int nq_main;  // query rows handled by the tensor-core tiles (nq minus a short tail done on CUDA cores)
   int q_rows_per_batch, kv_rows_per_batch;
   int causal;
   float scale;
@@ -58,7 +59,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + 16384 + 65536 + 32768 + 64);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nqt = (p.nq + kTQ - 1) / kTQ;
+  const int nqt = (p.nq_main + kTQ - 1) / kTQ;
   const int qt = blockIdx.x % nqt;
   const int bh = blockIdx.x / nqt;
   const int h = bh % p.H, b = bh / p.H;
@@ -203,7 +204,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(bar_odone, (nblk - 1) & 1);
     tc_fence_after();
     const float inv = 1.0f / l;
-    const bool ok = qrow < p.nq;
+    const bool ok = qrow < p.nq_main;
     __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * p.q_rows_per_batch + qrow) * p.ldo + h * kHD;
 #pragma unroll
     for (int c = 0; c < kHD; c += 32) {
@@ -234,14 +235,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
+// dot(row `row` of a [rows x 64] bf16 128B-swizzled tile, fp32 vector in smem)
+__device__ __forceinline__ float dot_row_sw128(const uint8_t* tile, int row, const float* vec) {
+  float acc = 0.f;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const uint4 w = *reinterpret_cast<const uint4*>(tile + sw128_off(row, u * 8));
+    const float4 a = *reinterpret_cast<const float4*>(vec + u * 8), c = *reinterpret_cast<const float4*>(vec + u * 8 + 4);
+    acc += bf16_lo(w.x) * a.x + bf16_hi(w.x) * a.y + bf16_lo(w.y) * a.z + bf16_hi(w.y) * a.w + bf16_lo(w.z) * c.x + bf16_hi(w.z) * c.y +
+           bf16_lo(w.w) * c.z + bf16_hi(w.w) * c.w;
+  }
+  return acc;
+}
+
 // ============================================================================================ backward
 constexpr int kBwdThreads = 192;
 constexpr int kBwdMaxQT = 3;  // nq <= 384
 // Q tiles | dO tiles | K | V | P | dS | lse,D | barriers
-constexpr int kBwdSmem = 2 * kBwdMaxQT * 16384 + 2 * 16384 + 2 * 32768 + 2 * kBwdMaxQT * kTQ * 4 + 1024 + 128;
+constexpr int kMaxTail = 4;  // tail rows / keys (n % 128) folded in on CUDA cores when 1..kMaxTail
+constexpr int kTailFloats = 2 * kMaxTail * 2 * kHD + 2 * kMaxTail;  // q|dO, k|v vectors + (lse2, D) per tail query
+constexpr int kBwdSmem = 2 * kBwdMaxQT * 16384 + 2 * 16384 + 2 * 32768 + 2 * kBwdMaxQT * kTQ * 4 + kTailFloats * 4 + 1024 + 128;
 
 struct AttnBwdParams {
   int B, H, nq, nk;
+  int nq_main, nk_main;  // rows / keys covered by the tensor-core tiles; the short tails [n_main, n) are
+  int tq, tk;            // folded in on CUDA cores (epilogue corrections here + attn_bwd_tail_kernel)
+  const __nv_bfloat16 *q, *k, *v;
+  long long ldq, ldk, ldv;
   int q_rows_per_batch, kv_rows_per_batch;
   int causal;
   float scale;
@@ -269,7 +289,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sDS_ptr = base_ptr + (sDS - base);
   float* s_lse = reinterpret_cast<float*>(base_ptr + (sDS - base) + 32768);  // [kBwdMaxQT*128] (lse * log2e)
   float* s_D = s_lse + kBwdMaxQT * kTQ;
-  const uint32_t bars = sDS + 32768 + 2 * kBwdMaxQT * kTQ * 4;
+  float* s_tail = s_D + kBwdMaxQT * kTQ;               // [(tq + tk) * 2][64] fp32
+  float* s_tail_stat = s_tail + 2 * kMaxTail * 2 * kHD;  // [tq][2]
+  uint8_t* sQ_ptr = base_ptr;
+  uint8_t* sDO_ptr = base_ptr + (sDO - base);
+  uint8_t* sK_ptr = base_ptr + (sK - base);
+  uint8_t* sV_ptr = base_ptr + (sV - base);
+  const uint32_t bars = sDS + 32768 + 2 * kBwdMaxQT * kTQ * 4 + kTailFloats * 4;
   const uint32_t bar_qdo = bars, bar_kvfull = bars + 8, bar_kvempty = bars + 16, bar_sfull = bars + 24,
                  bar_pfull = bars + 32, bar_dpfull = bars + 40, bar_dsfull = bars + 48, bar_pairdone = bars + 56,
                  bar_dkvfull = bars + 64, bar_dkvfree = bars + 72, bar_dqfull = bars + 80, tmem_slot = bars + 88;
@@ -277,8 +303,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x % p.H, b = blockIdx.x / p.H;
-  const int nqt = (p.nq + kTQ - 1) / kTQ;
-  const int nkblk = (p.nk + kTK - 1) / kTK;
+  const int nqt = (p.nq_main + kTQ - 1) / kTQ;
+  const int nkblk = (p.nk_main + kTK - 1) / kTK;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -287,7 +313,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmDO);
     mbar_init(bar_qdo, 1);
     mbar_init(bar_kvfull, 1);
-    mbar_init(bar_kvempty, 1);
+    mbar_init(bar_kvempty, 1 + 128);  // MMA commit + the compute warps (they read K/V rows for the tail corrections)
     mbar_init(bar_sfull, 1);
     mbar_init(bar_pfull, 128);
     mbar_init(bar_dpfull, 1);
@@ -331,7 +357,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       uint32_t pair = 0;
       uint32_t dq_started = 0;  // bit i set once dQ_i has been written (accumulate afterwards)
       for (int j = 0; j < nkblk; ++j) {
-        const int nkb = min(kTK, ((p.nk - j * kTK) + 15) & ~15);
+        const int nkb = min(kTK, ((p.nk_main - j * kTK) + 15) & ~15);
         mbar_wait(bar_kvfull, j & 1);
         mbar_wait(bar_dkvfree, (j & 1) ^ 1);  // previous block's dK/dV drained by the compute warps
         tc_fence_after();
@@ -388,7 +414,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int i = 0; i < nqt; ++i) {
       const int qrow = i * kTQ + r;
       float lse2 = 0.f, dsum = 0.f;
-      if (qrow < p.nq) {
+      if (qrow < p.nq_main) {
         lse2 = p.lse[(static_cast<long long>(b) * p.H + h) * p.nq + qrow] * kLog2e;
         const long long grow = static_cast<long long>(b) * p.q_rows_per_batch + qrow;
         const uint4* orow = reinterpret_cast<const uint4*>(p.o + grow * p.ldo + h * kHD);
@@ -403,13 +429,41 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       s_lse[i * kTQ + r] = lse2;
       s_D[i * kTQ + r] = dsum;
     }
+    // tail rows (CUDA-core corrections): stage q/dO of the tail queries and k/v of the tail keys as fp32 in smem
+    if (p.tq + p.tk > 0) {
+      const int nvec = (p.tq * 2 + p.tk * 2) * kHD;  // [tq][q|dO][64] then [tk][k|v][64]
+      for (int idx = r; idx < nvec; idx += 128) {
+        const int d = idx % kHD;
+        const int which = (idx / kHD) & 1;
+        const int t = idx / (2 * kHD);
+        float val;
+        if (t < p.tq) {
+          const long long grow = static_cast<long long>(b) * p.q_rows_per_batch + p.nq_main + t;
+          val = which == 0 ? __bfloat162float(p.q[grow * p.ldq + h * kHD + d]) : __bfloat162float(p.dout[grow * p.lddo + h * kHD + d]);
+        } else {
+          const long long grow = static_cast<long long>(b) * p.kv_rows_per_batch + p.nk_main + (t - p.tq);
+          val = which == 0 ? __bfloat162float(p.k[grow * p.ldk + h * kHD + d]) : __bfloat162float(p.v[grow * p.ldv + h * kHD + d]);
+        }
+        s_tail[idx] = val;
+      }
+      if (r < p.tq) {  // lse (log2 domain) and D of the tail queries
+        const int qrow = p.nq_main + r;
+        const long long grow = static_cast<long long>(b) * p.q_rows_per_batch + qrow;
+        float dsum = 0.f;
+        for (int d = 0; d < kHD; ++d)
+          dsum += __bfloat162float(p.o[grow * p.ldo + h * kHD + d]) * __bfloat162float(p.dout[grow * p.lddo + h * kHD + d]);
+        s_tail_stat[2 * r] = p.lse[(static_cast<long long>(b) * p.H + h) * p.nq + qrow] * kLog2e;
+        s_tail_stat[2 * r + 1] = dsum;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four compute warps only
+    }
     uint32_t pair = 0;
     for (int j = 0; j < nkblk; ++j) {
-      const int nkb = min(kTK, ((p.nk - j * kTK) + 15) & ~15);
+      const int nkb = min(kTK, ((p.nk_main - j * kTK) + 15) & ~15);
       for (int i = first_qt(j); i < nqt; ++i, ++pair) {
         const int qrow = i * kTQ + r;
-        const bool row_ok = qrow < p.nq;
-        const int kmax = p.causal ? min(p.nk, qrow + 1) : p.nk;
+        const bool row_ok = qrow < p.nq_main;
+        const int kmax = p.causal ? min(p.nk_main, qrow + 1) : p.nk_main;
         const float lse2 = s_lse[i * kTQ + r], Di = s_D[i * kTQ + r];
         mbar_wait(bar_sfull, pair & 1);
         tc_fence_after();
@@ -479,8 +533,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_after();
       {
         const int krow = j * kTK + r;
-        const bool ok = krow < p.nk;
+        const bool ok = krow < p.nk_main;
         const long long grow = static_cast<long long>(b) * p.kv_rows_per_batch + krow;
+        // tail queries' contributions to this key row: dV_j += p_tj dO_t ; dK_j += ds_tj q_t
+        float pt[kMaxTail], dst_[kMaxTail];
+        for (int t = 0; t < p.tq; ++t) {
+          const float* qv = s_tail + (2 * t) * kHD;
+          const float* gv = qv + kHD;
+          const float sdot = dot_row_sw128(sK_ptr, r, qv);
+          const float dpv = dot_row_sw128(sV_ptr, r, gv);
+          const float pv = ok ? exp2f(fmaf(sdot, sl2, -s_tail_stat[2 * t])) : 0.f;
+          pt[t] = pv;
+          dst_[t] = pv * (dpv - s_tail_stat[2 * t + 1]) * p.scale;
+        }
 #pragma unroll
         for (int which = 0; which < 2; ++which) {
           __nv_bfloat16* dst = which == 0 ? p.dv + grow * p.lddv + h * kHD : p.dk + grow * p.lddk + h * kHD;
@@ -490,6 +555,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             uint32_t v[32];
             tmem_ld32(t0 + lane_off + c, v);
             tc_wait_ld();
+            for (int t = 0; t < p.tq; ++t) {
+              const float coef = which == 0 ? pt[t] : dst_[t];
+              const float* vec = s_tail + (2 * t + (which == 0 ? 1 : 0)) * kHD + c;
+#pragma unroll
+              for (int e2 = 0; e2 < 32; ++e2) v[e2] = __float_as_uint(fmaf(coef, vec[e2], __uint_as_float(v[e2])));
+            }
             if (ok) {
 #pragma unroll
               for (int t = 0; t < 32; t += 8) {
@@ -506,19 +577,34 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       tc_fence_before();
       mbar_arrive(bar_dkvfree);
+      mbar_arrive(bar_kvempty);
     }
     // dQ tiles -> global
     mbar_wait(bar_dqfull, 0);
     tc_fence_after();
     for (int i = 0; i < nqt; ++i) {
       const int qrow = i * kTQ + r;
-      const bool ok = qrow < p.nq;
+      const bool ok = qrow < p.nq_main;
       __nv_bfloat16* dst = p.dq + (static_cast<long long>(b) * p.q_rows_per_batch + qrow) * p.lddq + h * kHD;
+      // tail keys' contribution to this query row: dQ_i += ds_it k_t
+      float dsk[kMaxTail];
+      for (int t = 0; t < p.tk; ++t) {
+        const float* kv = s_tail + (2 * (p.tq + t)) * kHD;
+        const float sdot = dot_row_sw128(sQ_ptr + i * 16384, r, kv);
+        const float dpv = dot_row_sw128(sDO_ptr + i * 16384, r, kv + kHD);
+        const float pv = ok ? exp2f(fmaf(sdot, sl2, -s_lse[i * kTQ + r])) : 0.f;
+        dsk[t] = pv * (dpv - s_D[i * kTQ + r]) * p.scale;
+      }
 #pragma unroll
       for (int c = 0; c < kHD; c += 32) {
         uint32_t v[32];
         tmem_ld32(tDQ + 64 * i + lane_off + c, v);
         tc_wait_ld();
+        for (int t = 0; t < p.tk; ++t) {
+          const float* vec = s_tail + (2 * (p.tq + t)) * kHD + c;
+#pragma unroll
+          for (int e2 = 0; e2 < 32; ++e2) v[e2] = __float_as_uint(fmaf(dsk[t], vec[e2], __uint_as_float(v[e2])));
+        }
         if (ok) {
 #pragma unroll
           for (int t = 0; t < 32; t += 8) {
@@ -541,6 +627,186 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     __syncwarp();
     tmem_dealloc(tmem, 512);
   }
+}
+
+// ============================================================================================ tail rows on CUDA cores
+// N = 257 (ViT-L/14: 256 patches + cls) leaves one query row / key past the last full 128-tile.  Padding it to a
+// whole tensor-core tile wastes 1/3 (fwd) to 5/9 (bwd) of the MMA work, so rows [n_main, n) are handled by these
+// small warp-per-head kernels (O(N * 64) work each) plus the epilogue corrections inside attn_bwd_kernel.
+constexpr int kTailMaxIter = 10;  // keys (queries) per lane: n <= 320 (covers N = 257); longer rows use the padded tiles
+
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void load_row64(const __nv_bfloat16* p, float (&f)[64]) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const uint4 w = reinterpret_cast<const uint4*>(p)[u];
+    f[8 * u] = bf16_lo(w.x); f[8 * u + 1] = bf16_hi(w.x); f[8 * u + 2] = bf16_lo(w.y); f[8 * u + 3] = bf16_hi(w.y);
+    f[8 * u + 4] = bf16_lo(w.z); f[8 * u + 5] = bf16_hi(w.z); f[8 * u + 6] = bf16_lo(w.w); f[8 * u + 7] = bf16_hi(w.w);
+  }
+}
+__device__ __forceinline__ float dot_row64(const __nv_bfloat16* p, const float (&f)[64]) {
+  float acc = 0.f;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const uint4 w = reinterpret_cast<const uint4*>(p)[u];
+    acc += bf16_lo(w.x) * f[8 * u] + bf16_hi(w.x) * f[8 * u + 1] + bf16_lo(w.y) * f[8 * u + 2] + bf16_hi(w.y) * f[8 * u + 3] +
+           bf16_lo(w.z) * f[8 * u + 4] + bf16_hi(w.z) * f[8 * u + 5] + bf16_lo(w.w) * f[8 * u + 6] + bf16_hi(w.w) * f[8 * u + 7];
+  }
+  return acc;
+}
+
+struct AttnTailParams {
+  const __nv_bfloat16 *q, *k, *v, *o, *dout;
+  __nv_bfloat16 *out_o, *dq, *dk, *dv;
+  float* lse;
+  long long ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv;
+  int B, H, nq, nk, tq, tk;
+  float scale;
+};
+
+// forward: one warp per (b, h, tail query): full-row softmax over all nk keys, lane-strided over keys.
+constexpr int kTailMaxN = 32 * kTailMaxIter;
+
+__global__ void __launch_bounds__(128) attn_fwd_tail_kernel(const AttnTailParams p) {
+  __shared__ float sh[4][kTailMaxN];
+  const int lane = threadIdx.x & 31;
+  float* sc = sh[threadIdx.x >> 5];
+  const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (w >= static_cast<long long>(p.B) * p.H * p.tq) return;
+  const int t = static_cast<int>(w % p.tq);
+  const int h = static_cast<int>((w / p.tq) % p.H);
+  const int b = static_cast<int>(w / (static_cast<long long>(p.tq) * p.H));
+  const int qrow = p.nq - p.tq + t;
+  const float sl2 = p.scale * kLog2e;
+  float qf[64];
+  load_row64(p.q + (static_cast<long long>(b) * p.nq + qrow) * p.ldq + h * kHD, qf);
+  const __nv_bfloat16* kb = p.k + static_cast<long long>(b) * p.nk * p.ldk + h * kHD;
+  const __nv_bfloat16* vb = p.v + static_cast<long long>(b) * p.nk * p.ldv + h * kHD;
+  float m = -INFINITY;
+  for (int j = lane; j < p.nk; j += 32) {
+    const float sv = dot_row64(kb + static_cast<long long>(j) * p.ldk, qf) * sl2;
+    sc[j] = sv;
+    m = fmaxf(m, sv);
+  }
+  m = warp_max_f(m);
+  float l = 0.f;
+  for (int j = lane; j < p.nk; j += 32) {
+    const float e = exp2f(sc[j] - m);
+    sc[j] = e;
+    l += e;
+  }
+  l = warp_sum_f(l);
+  __syncwarp();
+  // O[d] = sum_j p_j V[j, d]: lane owns dims (2*lane, 2*lane+1); p_j is a broadcast smem read
+  float o0 = 0.f, o1 = 0.f;
+  for (int j = 0; j < p.nk; ++j) {
+    const float pj = sc[j];
+    const uint32_t vv = *reinterpret_cast<const uint32_t*>(vb + static_cast<long long>(j) * p.ldv + 2 * lane);
+    o0 = fmaf(pj, bf16_lo(vv), o0);
+    o1 = fmaf(pj, bf16_hi(vv), o1);
+  }
+  const float inv = 1.0f / l;
+  *reinterpret_cast<uint32_t*>(p.out_o + (static_cast<long long>(b) * p.nq + qrow) * p.ldo + h * kHD + 2 * lane) = pack_bf16(o0 * inv, o1 * inv);
+  if (lane == 0 && p.lse) p.lse[(static_cast<long long>(b) * p.H + h) * p.nq + qrow] = (m + log2f(l)) * 0.6931471805599453f;
+}
+
+// backward: one warp per (b, h).  Part A: dQ of every tail query (sum over all keys).
+// Part B: dK, dV of every tail key (sum over all queries).
+__global__ void __launch_bounds__(128) attn_bwd_tail_kernel(const AttnTailParams p) {
+  __shared__ float sh[4][2][kTailMaxN];
+  const int lane = threadIdx.x & 31;
+  float* s_ds = sh[threadIdx.x >> 5][0];
+  float* s_p = sh[threadIdx.x >> 5][1];
+  const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (w >= static_cast<long long>(p.B) * p.H) return;
+  const int h = static_cast<int>(w % p.H);
+  const int b = static_cast<int>(w / p.H);
+  const float sl2 = p.scale * kLog2e;
+  const __nv_bfloat16* qb = p.q + static_cast<long long>(b) * p.nq * p.ldq + h * kHD;
+  const __nv_bfloat16* kb = p.k + static_cast<long long>(b) * p.nk * p.ldk + h * kHD;
+  const __nv_bfloat16* vb = p.v + static_cast<long long>(b) * p.nk * p.ldv + h * kHD;
+  const __nv_bfloat16* ob = p.o + static_cast<long long>(b) * p.nq * p.ldo + h * kHD;
+  const __nv_bfloat16* gb = p.dout + static_cast<long long>(b) * p.nq * p.lddo + h * kHD;
+  const float* lse = p.lse + (static_cast<long long>(b) * p.H + h) * p.nq;
+  // ---------------- Part A
+  for (int t = 0; t < p.tq; ++t) {
+    const int qrow = p.nq - p.tq + t;
+    {
+      float qf[64], gf[64];
+      load_row64(qb + static_cast<long long>(qrow) * p.ldq, qf);
+      load_row64(gb + static_cast<long long>(qrow) * p.lddo, gf);
+      const float Dq = dot_row64(ob + static_cast<long long>(qrow) * p.ldo, gf);
+      const float lse2 = lse[qrow] * kLog2e;
+      for (int j = lane; j < p.nk; j += 32) {
+        const float sdot = dot_row64(kb + static_cast<long long>(j) * p.ldk, qf);
+        const float dpv = dot_row64(vb + static_cast<long long>(j) * p.ldv, gf);
+        s_ds[j] = exp2f(fmaf(sdot, sl2, -lse2)) * (dpv - Dq) * p.scale;
+      }
+    }
+    __syncwarp();
+    float a0 = 0.f, a1 = 0.f;
+    for (int j = 0; j < p.nk; ++j) {
+      const float dsj = s_ds[j];
+      const uint32_t kk = *reinterpret_cast<const uint32_t*>(kb + static_cast<long long>(j) * p.ldk + 2 * lane);
+      a0 = fmaf(dsj, bf16_lo(kk), a0);
+      a1 = fmaf(dsj, bf16_hi(kk), a1);
+    }
+    *reinterpret_cast<uint32_t*>(p.dq + (static_cast<long long>(b) * p.nq + qrow) * p.lddq + h * kHD + 2 * lane) = pack_bf16(a0, a1);
+    __syncwarp();
+  }
+  // ---------------- Part B
+  for (int t = 0; t < p.tk; ++t) {
+    const int krow = p.nk - p.tk + t;
+    {
+      float kf[64], vf[64];
+      load_row64(kb + static_cast<long long>(krow) * p.ldk, kf);
+      load_row64(vb + static_cast<long long>(krow) * p.ldv, vf);
+      for (int i = lane; i < p.nq; i += 32) {
+        const float sdot = dot_row64(qb + static_cast<long long>(i) * p.ldq, kf);
+        const float dpv = dot_row64(gb + static_cast<long long>(i) * p.lddo, vf);
+        float Di = 0.f;  // D_i = dO_i . O_i
+        const uint4* orow = reinterpret_cast<const uint4*>(ob + static_cast<long long>(i) * p.ldo);
+        const uint4* grow = reinterpret_cast<const uint4*>(gb + static_cast<long long>(i) * p.lddo);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint4 a = orow[u], g = grow[u];
+          Di += bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) + bf16_hi(a.y) * bf16_hi(g.y) +
+                bf16_lo(a.z) * bf16_lo(g.z) + bf16_hi(a.z) * bf16_hi(g.z) + bf16_lo(a.w) * bf16_lo(g.w) + bf16_hi(a.w) * bf16_hi(g.w);
+        }
+        const float pi = exp2f(fmaf(sdot, sl2, -lse[i] * kLog2e));
+        s_p[i] = pi;
+        s_ds[i] = pi * (dpv - Di) * p.scale;
+      }
+    }
+    __syncwarp();
+    float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
+    for (int i = 0; i < p.nq; ++i) {
+      const float dsi = s_ds[i], pi = s_p[i];
+      const uint32_t qq = *reinterpret_cast<const uint32_t*>(qb + static_cast<long long>(i) * p.ldq + 2 * lane);
+      const uint32_t gg = *reinterpret_cast<const uint32_t*>(gb + static_cast<long long>(i) * p.lddo + 2 * lane);
+      k0 = fmaf(dsi, bf16_lo(qq), k0);
+      k1 = fmaf(dsi, bf16_hi(qq), k1);
+      v0 = fmaf(pi, bf16_lo(gg), v0);
+      v1 = fmaf(pi, bf16_hi(gg), v1);
+    }
+    *reinterpret_cast<uint32_t*>(p.dk + (static_cast<long long>(b) * p.nk + krow) * p.lddk + h * kHD + 2 * lane) = pack_bf16(k0, k1);
+    *reinterpret_cast<uint32_t*>(p.dv + (static_cast<long long>(b) * p.nk + krow) * p.lddv + h * kHD + 2 * lane) = pack_bf16(v0, v1);
+    __syncwarp();
+  }
+}
+
+static int tail_rows(int n, int causal) {
+  const int t = n % kTQ;
+  return (!causal && n > kTQ && t > 0 && t <= kMaxTail && n <= 32 * kTailMaxIter) ? t : 0;
 }
 
 static int check_common(const char* who, int B, int H, int nq, int nk, int64_t ldq, int64_t ldk, int64_t ldv) {
@@ -569,6 +835,8 @@ int vl_attention_fwd(const void* q, const void* k, const void* v, void* o, float
   if ((rc = make_tmap_bf16_2d(&tmV, v, (uint64_t)H * kHD, (uint64_t)B * nk, ldv, kHD, kTK))) return rc;
   AttnParams p;
   p.B = B; p.H = H; p.nq = nq; p.nk = nk;
+  const int tq = tail_rows(nq, causal);
+  p.nq_main = nq - tq;
   p.q_rows_per_batch = nq; p.kv_rows_per_batch = nk;
   p.causal = causal; p.scale = scale;
   p.o = reinterpret_cast<__nv_bfloat16*>(o); p.ldo = ldo; p.lse = lse;
@@ -577,11 +845,22 @@ int vl_attention_fwd(const void* q, const void* k, const void* v, void* o, float
     VL_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
     attr = true;
   }
-  const int nqt = (nq + kTQ - 1) / kTQ;
+  const int nqt = (p.nq_main + kTQ - 1) / kTQ;
   const long long grid = (long long)B * H * nqt;
   VL_CHECK_ARG(grid < (1ll << 31), "vl_attention_fwd: grid too large");
   attn_fwd_kernel<<<(unsigned)grid, kFwdThreads, kFwdSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
-  return launch_check("attn_fwd_kernel");
+  if (int rc2 = launch_check("attn_fwd_kernel")) return rc2;
+  if (tq > 0) {
+    AttnTailParams t{};
+    t.q = reinterpret_cast<const __nv_bfloat16*>(q); t.k = reinterpret_cast<const __nv_bfloat16*>(k); t.v = reinterpret_cast<const __nv_bfloat16*>(v);
+    t.out_o = reinterpret_cast<__nv_bfloat16*>(o); t.lse = lse;
+    t.ldq = ldq; t.ldk = ldk; t.ldv = ldv; t.ldo = ldo;
+    t.B = B; t.H = H; t.nq = nq; t.nk = nk; t.tq = tq; t.tk = 0; t.scale = scale;
+    const long long warps = (long long)B * H * tq;
+    attn_fwd_tail_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(t);
+    return launch_check("attn_fwd_tail_kernel");
+  }
+  return 0;
 }
 
 int vl_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, void* dq, void* dk,
@@ -591,7 +870,8 @@ int vl_attention_bwd(const void* q, const void* k, const void* v, const void* o,
   if (int rc = check_common("vl_attention_bwd", B, H, nq, nk, ldq, ldk, ldv)) return rc;
   VL_CHECK_ARG(ldo % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0, "vl_attention_bwd: bad leading dims");
   VL_CHECK_ARG(!causal || nq == nk, "vl_attention_bwd: causal requires nq == nk");
-  if (nq > kBwdMaxQT * kTQ) {
+  const int tq = tail_rows(nq, causal), tk = tail_rows(nk, causal);
+  if (nq - tq > kBwdMaxQT * kTQ) {
     set_error("vl_attention_bwd: nq=%d > %d not supported", nq, kBwdMaxQT * kTQ);
     return VL_ENOTSUP;
   }
@@ -603,6 +883,9 @@ int vl_attention_bwd(const void* q, const void* k, const void* v, const void* o,
   if ((rc = make_tmap_bf16_2d(&tmDO, dout, (uint64_t)H * kHD, (uint64_t)B * nq, lddo, kHD, kTQ))) return rc;
   AttnBwdParams p;
   p.B = B; p.H = H; p.nq = nq; p.nk = nk;
+  p.nq_main = nq - tq; p.nk_main = nk - tk; p.tq = tq; p.tk = tk;
+  p.q = reinterpret_cast<const __nv_bfloat16*>(q); p.k = reinterpret_cast<const __nv_bfloat16*>(k); p.v = reinterpret_cast<const __nv_bfloat16*>(v);
+  p.ldq = ldq; p.ldk = ldk; p.ldv = ldv;
   p.q_rows_per_batch = nq; p.kv_rows_per_batch = nk;
   p.causal = causal; p.scale = scale;
   p.o = reinterpret_cast<const __nv_bfloat16*>(o); p.dout = reinterpret_cast<const __nv_bfloat16*>(dout);
@@ -615,6 +898,17 @@ int vl_attention_bwd(const void* q, const void* k, const void* v, const void* o,
     attr = true;
   }
   attn_bwd_kernel<<<(unsigned)(B * H), kBwdThreads, kBwdSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmDO, p);
-  return launch_check("attn_bwd_kernel");
+  if (int rc2 = launch_check("attn_bwd_kernel")) return rc2;
+  if (tq + tk > 0) {
+    AttnTailParams t{};
+    t.q = p.q; t.k = p.k; t.v = p.v; t.o = p.o; t.dout = p.dout;
+    t.dq = p.dq; t.dk = p.dk; t.dv = p.dv; t.lse = const_cast<float*>(lse);
+    t.ldq = ldq; t.ldk = ldk; t.ldv = ldv; t.ldo = ldo; t.lddo = lddo; t.lddq = lddq; t.lddk = lddk; t.lddv = lddv;
+    t.B = B; t.H = H; t.nq = nq; t.nk = nk; t.tq = tq; t.tk = tk; t.scale = scale;
+    const long long warps = (long long)B * H;
+    attn_bwd_tail_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(t);
+    return launch_check("attn_bwd_tail_kernel");
+  }
+  return 0;
 }
 }

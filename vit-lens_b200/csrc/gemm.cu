@@ -297,22 +297,38 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 64; ++j) f[j] *= p.alpha;
             if (p.bias != nullptr && lead_split && p.epi != VL_EPI_GELU_BWD) {
+              if (cols_valid == 64) {
 #pragma unroll
-              for (int j = 0; j < 64; j += 4) {
-                if (col0 + j < p.N) {
+                for (int j = 0; j < 64; j += 4) {
                   const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
                   f[j] += b4.x;
                   f[j + 1] += b4.y;
                   f[j + 2] += b4.z;
                   f[j + 3] += b4.w;
                 }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 64; j += 4) {
+                  if (col0 + j < p.N) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                    f[j] += b4.x;
+                    f[j + 1] += b4.y;
+                    f[j + 2] += b4.z;
+                    f[j + 3] += b4.w;
+                  }
+                }
               }
             }
             if (p.epi == VL_EPI_GELU) {
               if (p.aux_out != nullptr)
                 store_tile_bf16(stg, f, p.aux_out + static_cast<long long>(row0) * p.ldaux + col0, p.ldaux, rows_valid, cols_valid, lane);
+              if (p.act_quick) {
 #pragma unroll
-              for (int j = 0; j < 64; ++j) f[j] = gelu_fwd(f[j], p.act_quick);
+                for (int j = 0; j < 64; ++j) f[j] = gelu_quick_fwd(f[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) f[j] = gelu_erf_fwd(f[j]);
+              }
             } else if (need_aux) {
               if (p.epi == VL_EPI_RESIDUAL) {
 #pragma unroll
@@ -320,11 +336,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   f[2 * j] += bf16_lo(ax[j]);
                   f[2 * j + 1] += bf16_hi(ax[j]);
                 }
+              } else if (p.act_quick) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  f[2 * j] *= gelu_quick_grad(bf16_lo(ax[j]));
+                  f[2 * j + 1] *= gelu_quick_grad(bf16_hi(ax[j]));
+                }
               } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                  f[2 * j] *= gelu_grad(bf16_lo(ax[j]), p.act_quick);
-                  f[2 * j + 1] *= gelu_grad(bf16_hi(ax[j]), p.act_quick);
+                  f[2 * j] *= gelu_erf_grad(bf16_lo(ax[j]));
+                  f[2 * j + 1] *= gelu_erf_grad(bf16_hi(ax[j]));
                 }
               }
             }

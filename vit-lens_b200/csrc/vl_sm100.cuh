@@ -199,29 +199,36 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 // erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): one EX2 + one RCP
 __device__ __forceinline__ float erf_fast(float x) {
   float ax = fabsf(x);
-  float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
   float poly = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t,
                     0.254829592f) * t;
   float e = __expf(-ax * ax);
   float r = fmaf(-poly, e, 1.0f);
   return copysignf(r, x);
 }
-// act: 0 = erf-GELU (nn.GELU), 1 = QuickGELU x*sigmoid(1.702x)
-__device__ __forceinline__ float gelu_fwd(float x, int quick) {
-  if (quick) return x * __frcp_rn(1.0f + __expf(-1.702f * x));
-  return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f));
-}
-__device__ __forceinline__ float gelu_grad(float x, int quick) {
-  if (quick) {
-    float s = __frcp_rn(1.0f + __expf(-1.702f * x));
-    return s * fmaf(1.702f * x, 1.0f - s, 1.0f);
-  }
-  float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752f));
-  float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+// Branch-free activation bodies (callers pick the variant once per loop, never per element, so the
+// unrolled element streams interleave for ILP).
+__device__ __forceinline__ float gelu_erf_fwd(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_quick_fwd(float x) { return x * rcp_approx(1.0f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
   return fmaf(x, pdf, cdf);
 }
+__device__ __forceinline__ float gelu_quick_grad(float x) {
+  const float s = rcp_approx(1.0f + __expf(-1.702f * x));
+  return s * fmaf(1.702f * x, 1.0f - s, 1.0f);
+}
+// act: 0 = erf-GELU (nn.GELU), 1 = QuickGELU x*sigmoid(1.702x)
+__device__ __forceinline__ float gelu_fwd(float x, int quick) { return quick ? gelu_quick_fwd(x) : gelu_erf_fwd(x); }
+__device__ __forceinline__ float gelu_grad(float x, int quick) { return quick ? gelu_quick_grad(x) : gelu_erf_grad(x); }
 
 }  // namespace vl
