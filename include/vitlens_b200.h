@@ -82,6 +82,13 @@ typedef struct {
   float* scalar_out;
   int32_t iparam;
   float fparam;
+  /* optional device scalars (no host sync): effective alpha = alpha * (*alpha_dev), fparam = fparam * (*fparam_dev) */
+  const float* alpha_dev;
+  const float* fparam_dev;
+  /* LINEAR / RESIDUAL extras (grouped PointNet, dvae.py:196-212): aux_in row = output row / aux_row_div (0 or 1 = same row:
+   * the per-group "global feature" term is broadcast over the group's points); relu != 0 clamps the result at 0. */
+  int32_t aux_row_div;
+  int32_t relu;
 } VlGemmArgs;
 
 int vl_gemm_bf16(const VlGemmArgs* args, void* stream);
@@ -116,10 +123,11 @@ int vl_attention_bwd(const void* q, const void* k, const void* v, const void* o,
  * gather: y[i] = LN(x[row_index[i]]) (cls pooling transformer.py:653-657,783; EOT pooling model.py:537-540). */
 int vl_layernorm_fwd(const void* x, int64_t ldx, const int64_t* row_index, const float* w, const float* b, void* y,
                      int64_t ldy, float* mean, float* rstd, int32_t T, int32_t D, float eps, void* stream);
-/* dx[row_index[i] or i] = LN'(dy[i]) (+ dres at the same row); dw += sum dy*xhat; db += sum dy (both or neither). */
+/* dx[row_index[i] or i] = LN'(dy[i]) (+ dres at the same row); dw += sum dy*xhat; db += sum dy (both or neither);
+ * dres_sum[d] += sum_i dres[i, d] (optional: the bias gradient of the Linear that produced the residual branch). */
 int vl_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const int64_t* row_index, const float* w,
                      const float* mean, const float* rstd, const void* dres, int64_t lddres, void* dx, int64_t lddx,
-                     float* dw, float* db, int32_t T, int32_t D, void* stream);
+                     float* dw, float* db, float* dres_sum, int32_t T, int32_t D, void* stream);
 /* db[n] += sum_t dy[t,n]: bias gradients of every nn.Linear on the path. */
 int vl_colsum_bf16(const void* dy, int64_t ld, float* db, int32_t T, int32_t N, void* stream);
 /* Patch gather feeding conv1-as-GEMM (nn.Conv2d bias=False: transformer.py:464-470, AST_tokenizer.py:22-28,
@@ -150,6 +158,19 @@ int vl_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream
 /* Decoupled-weight-decay Adam step on one fp32 tensor (optim.AdamW, training/point_cloud/pc_tri_main.py:394-419). */
 int vl_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Point-cloud tokenizer (reference modal_3d/models/pointbert): farthest point sampling with explicit start indices
+ * (misc.py:48-68; the reference draws them with torch.randint at :60), kNN grouping minus centre (dvae.py:107-176),
+ * K=3 linear + folded BatchNorm + ReLU / GELU (dvae.py:200-203, point_encoder.py:325-327), per-group max (dvae.py:205,210).
+ */
+int vl_fps(const float* xyz, const int64_t* start, int32_t B, int32_t N, int32_t npoint, int64_t* idx_out, float* centers,
+           void* stream);
+int vl_knn_group(const float* xyz, const float* centers, int32_t B, int32_t N, int32_t G, int32_t k, float* nb_out,
+                 int64_t* idx_out, void* stream);
+int vl_linear3(const float* x, const float* w, const float* scale, const float* shift, void* out, int64_t R, int32_t C,
+               int32_t act, void* stream);
+int vl_group_max(const void* x, void* out, int32_t* arg, int64_t groups, int32_t G, int32_t C, void* stream);
 
 #ifdef __cplusplus
 }

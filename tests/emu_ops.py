@@ -34,8 +34,10 @@ def _act_grad(x, quick):
 
 
 def gemm(a, b, *, a_t=False, b_t=False, bias=None, epilogue=EPI_LINEAR, aux_in=None, want_aux_out=False, out=None,
-         out_dtype=BF16, alpha=1.0, accumulate=False, split_k=None, act_quick=False):
+         out_dtype=BF16, alpha=1.0, accumulate=False, split_k=None, act_quick=False, alpha_dev=None):
     _n()
+    if alpha_dev is not None:
+        alpha = alpha * float(alpha_dev)
     assert a.dtype == BF16 and b.dtype == BF16
     A = a.float().t() if a_t else a.float()
     B = b.float() if b_t else b.float().t()
@@ -112,7 +114,7 @@ def layernorm_fwd(x, w, b, *, row_index=None, eps=1e-5, want_stats=True):
     return y, (mean if want_stats else None), (rstd if want_stats else None)
 
 
-def layernorm_bwd(dy, x, w, mean, rstd, *, dres=None, row_index=None, want_wgrad=True):
+def layernorm_bwd(dy, x, w, mean, rstd, *, dres=None, row_index=None, want_wgrad=True, want_dres_sum=False):
     _n()
     xs = x.float() if row_index is None else x.float()[row_index]
     g = dy.float()
@@ -128,9 +130,11 @@ def layernorm_bwd(dy, x, w, mean, rstd, *, dres=None, row_index=None, want_wgrad
         if dres is not None:
             dxs = dxs + dres.float()[row_index]
         dx[row_index] = dxs.to(BF16)
-    if want_wgrad:
-        return dx, (g * xh).sum(0), g.sum(0)
-    return dx, None, None
+    out = (dx, (g * xh).sum(0), g.sum(0)) if want_wgrad else (dx, None, None)
+    if want_dres_sum:
+        rs = dres.float() if row_index is None else dres.float()[row_index]
+        out = out + (rs.sum(0),)
+    return out
 
 
 def colsum(dy):
@@ -218,6 +222,7 @@ def add_bf16(a, b):
 
 def rowlse(p16, q16, *, alpha, label_off=0):
     _n()
+    alpha = float(alpha)
     z = alpha * (p16.float() @ q16.float().t())
     lse = torch.logsumexp(z, -1)
     M = z.shape[0]
@@ -225,8 +230,11 @@ def rowlse(p16, q16, *, alpha, label_off=0):
     return lse, (lse - diag).sum().reshape(1)
 
 
-def clipgrad(p16, q16, *, alpha, row_lse, col_lse, label_off, gscale):
+def clipgrad(p16, q16, *, alpha, row_lse, col_lse, label_off, gscale, gscale_dev=None):
     _n()
+    alpha = float(alpha)
+    if gscale_dev is not None:
+        gscale = gscale * float(gscale_dev)
     acc = p16.float() @ q16.float().t()
     z = alpha * acc
     M, N = z.shape
@@ -239,3 +247,57 @@ def clipgrad(p16, q16, *, alpha, row_lse, col_lse, label_off, gscale):
     onehot[torch.arange(M), torch.arange(M) + label_off] = 1.0
     g = gscale * (g - k * onehot)
     return g.to(BF16), (g * acc).sum().reshape(1)
+
+
+# ----------------------------------------------------------------------------- point-cloud tokenizer
+def fps(pts, start, npoint):
+    _n()
+    B, N, _ = pts.shape
+    idx = torch.zeros(B, npoint, dtype=torch.long)
+    dist = torch.full((B, N), 1e10)
+    far = start.clone()
+    bi = torch.arange(B)
+    for i in range(npoint):
+        idx[:, i] = far
+        c = pts[bi, far].view(B, 1, 3)
+        dist = torch.minimum(dist, ((pts - c) ** 2).sum(-1))
+        far = dist.max(-1)[1]
+    centers = torch.gather(pts, 1, idx.unsqueeze(-1).expand(-1, -1, 3)).reshape(B * npoint, 3)
+    return idx, centers
+
+
+def knn_group(pts, centers, G, k, want_idx=False):
+    _n()
+    B, N, _ = pts.shape
+    c = centers.reshape(B, G, 3)
+    d = -2 * c @ pts.transpose(1, 2) + (c ** 2).sum(-1, keepdim=True) + (pts ** 2).sum(-1).unsqueeze(1)
+    idx = torch.topk(d, k, dim=-1, largest=False)[1]
+    nb = torch.gather(pts.unsqueeze(1).expand(-1, G, -1, -1), 2, idx.unsqueeze(-1).expand(-1, -1, -1, 3)) - c.unsqueeze(2)
+    nb = nb.reshape(B * G * k, 3)
+    return (nb, idx.reshape(-1)) if want_idx else nb
+
+
+def linear3(x, w, scale, shift, act):
+    _n()
+    v = (x @ w.t()) * scale + shift
+    if act == 1:
+        v = torch.relu(v)
+    elif act == 2:
+        v = F.gelu(v)
+    return v.to(BF16)
+
+
+def group_max(x, G, want_arg=False):
+    _n()
+    rows, C = x.shape
+    v, a = x.float().reshape(rows // G, G, C).max(dim=1)
+    return (v.to(BF16), a.to(torch.int32)) if want_arg else v.to(BF16)
+
+
+def gemm_grouped_residual_relu(a, b, gp, group, *, bias=None):
+    _n()
+    acc = a.float() @ b.float().t()
+    if bias is not None:
+        acc = acc + bias
+    acc = acc + gp.float().repeat_interleave(group, dim=0)
+    return torch.relu(acc).to(BF16)

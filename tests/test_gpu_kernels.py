@@ -117,7 +117,8 @@ def test_layernorm(ops, T, D, gather):
     dy = torch.randn_like(yr).to(BF)
     yr.backward(dy.float())
     dres = torch.randn(T, D, device="cuda").to(BF)
-    dx, dw, db = ops.layernorm_bwd(dy, x, w, mean, rstd, dres=dres, row_index=idx)
+    dx, dw, db, rsum = ops.layernorm_bwd(dy, x, w, mean, rstd, dres=dres, row_index=idx, want_dres_sum=True)
+    close(rsum, (dres.float()[idx] if gather else dres.float()).sum(0), tol=1e-3, atol=0.05)
     close(dx[idx] if gather else dx, xr.grad + (dres.float()[idx] if gather else dres.float()))
     close(dw, wr.grad, tol=1e-3, atol=0.05)
     close(db, br.grad, tol=1e-3, atol=0.05)
@@ -172,7 +173,8 @@ def test_contrastive_epilogues(ops, Bl, Ball, off):
     x = F.normalize(torch.randn(Bl, E, device="cuda"), dim=-1).to(BF)
     y = F.normalize(torch.randn(Ball, E, device="cuda"), dim=-1).to(BF)
     s = 14.3
-    lse, tot = ops.rowlse(x, y, alpha=s, label_off=off)
+    s_dev = torch.tensor([s], device="cuda")
+    lse, tot = ops.rowlse(x, y, alpha=s_dev, label_off=off)
     z = s * (x.float() @ y.float().t())
     ref = torch.logsumexp(z, -1)
     close(lse, ref, tol=1e-4, atol=1e-3)
@@ -180,7 +182,7 @@ def test_contrastive_epilogues(ops, Bl, Ball, off):
     assert abs(float(tot) - float((ref - diag).sum())) < 1e-3 * Bl
     col = torch.randn(Ball, device="cuda") + 3
     for cl in (None, col):
-        g, ds = ops.clipgrad(x, y, alpha=s, row_lse=lse, col_lse=cl, label_off=off, gscale=0.01)
+        g, ds = ops.clipgrad(x, y, alpha=s_dev, row_lse=lse, col_lse=cl, label_off=off, gscale=0.02, gscale_dev=torch.tensor([0.5], device="cuda"))
         gr = torch.exp(z - lse[:, None])
         k = 1.0
         if cl is not None:
@@ -206,3 +208,43 @@ def test_adamw(ops):
         opt.step()
         L.adamw_step(p, gr, m, v, lr=1e-3, beta1=0.9, beta2=0.98, eps=1e-6, weight_decay=0.2, step=step)
     close(p, pr.detach(), tol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,N,G,k", [(3, 256, 16, 8), (2, 8192, 512, 32), (2, 1000, 64, 32)])
+def test_point_cloud_sampling_and_grouping(ops, B, N, G, k):
+    """FPS indices are bit-exact against the oracle's restatement of misc.fps; kNN neighbourhoods equal the exact
+    k-nearest sets (compared as sorted distance lists: ties / fp re-association may swap equidistant points)."""
+    from oracle import vitlens_oracle as O
+    from vitlens_b200 import synth
+
+    pts, start = synth.synth_points(B, N, seed=3)
+    idx, centers = ops.fps(pts.cuda(), start.cuda(), G)
+    ref_idx = O.fps_indices(pts, G, start)
+    assert torch.equal(idx.cpu(), ref_idx)
+    ref_c = torch.gather(pts, 1, ref_idx.unsqueeze(-1).expand(-1, -1, 3)).reshape(B * G, 3)
+    assert torch.equal(centers.cpu(), ref_c)
+    nb, nidx = ops.knn_group(pts.cuda(), centers, G, k, want_idx=True)
+    d = ((pts.unsqueeze(1) - ref_c.reshape(B, G, 1, 3)) ** 2).sum(-1)           # [B,G,N] exact form
+    ref_sorted = torch.topk(d, k, dim=-1, largest=False, sorted=True)[0]
+    got_d = torch.gather(d, 2, nidx.cpu().reshape(B, G, k)).sort(dim=-1)[0]
+    assert float((got_d - ref_sorted).abs().max()) < 1e-5
+    sel = torch.gather(pts.unsqueeze(1).expand(-1, G, -1, -1), 2, nidx.cpu().reshape(B, G, k, 1).expand(-1, -1, -1, 3))
+    assert torch.equal(nb.cpu().reshape(B, G, k, 3), sel - ref_c.reshape(B, G, 1, 3))
+
+
+def test_point_cloud_row_kernels(ops):
+    x = torch.randn(1000, 3, device="cuda")
+    w = torch.randn(128, 3, device="cuda")
+    sc, sh = torch.rand(128, device="cuda") + 0.5, torch.randn(128, device="cuda")
+    close(ops.linear3(x, w, sc, sh, 1), torch.relu((x @ w.t()) * sc + sh))
+    close(ops.linear3(x, w, sc, sh, 2), F.gelu((x @ w.t()) * sc + sh))
+    f = torch.randn(64 * 32, 256, device="cuda").to(BF)
+    mx, arg = ops.group_max(f, 32, want_arg=True)
+    rv, ra = f.float().reshape(64, 32, 256).max(dim=1)
+    assert torch.equal(mx.float(), rv)
+    assert torch.equal(torch.gather(f.float().reshape(64, 32, 256), 1, arg.long().unsqueeze(1)).squeeze(1), rv)
+    a = torch.randn(64 * 32, 256, device="cuda").to(BF)
+    b = (torch.randn(512, 256, device="cuda") * 0.1).to(BF)
+    gp = torch.randn(64, 512, device="cuda").to(BF)
+    out = ops.gemm_grouped_residual_relu(a, b, gp, 32)
+    close(out, torch.relu(a.float() @ b.float().t() + gp.float().repeat_interleave(32, 0)))

@@ -112,3 +112,15 @@ def test_vitlens_encode_api():
         out = m.encode({ModalityType.IMAGE: torch.randn(2, 3, 224, 224), ModalityType.DEPTH: torch.randn(2, 1, 224, 224)})
     assert out["image"].shape == (2, 768) and out["depth"].shape == (2, 768)
     assert float((out["depth"].norm(dim=-1) - 1).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["tiny_tri_pc", "vitl14_pc_bs2"])
+def test_point_cloud_tower_forward_vs_reference_fixture(name):
+    """FPS + kNN + grouped PointNet + point Lens + ViT, frozen tokenizer, against the reference's features."""
+    case = C.CASES[name]
+    gold = C.load_golden(name)
+    model, sd, args = build_model(case, device="cuda")
+    inp = C.build_inputs(case, args)
+    with torch.no_grad():
+        fv = model.encode_visual(inp["visual"].cuda(), normalize=True, fps_start=gold["fps_start"].cuda())
+    assert cosine(fv.cpu(), gold["visual_features"]) > 0.999

@@ -44,3 +44,14 @@ def test_frozen_towers_save_nothing(emu):
     with torch.no_grad():
         f = model.encode_image(inp["image"], normalize=True)
     assert not f.requires_grad
+
+
+def test_point_cloud_tower_forward_vs_reference(emu):
+    """tiny_tri_pc: FPS / kNN / grouped PointNet host logic (frozen tokenizer) against the reference's features."""
+    case = C.CASES["tiny_tri_pc"]
+    gold = C.load_golden("tiny_tri_pc")
+    model, sd, args = build_model(case)
+    inp = C.build_inputs(case, args)
+    with torch.no_grad():
+        fv = model.encode_visual(inp["visual"], normalize=True, fps_start=gold["fps_start"])
+    assert cosine(fv, gold["visual_features"]) > 0.999

@@ -122,6 +122,9 @@ def timeit(M, N, K, a_mn=False, b_mn=False, epi=L.EPI_LINEAR, f32=False, split_k
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), flush=True)
+    if "--pair" in sys.argv:
+        L.debug_set(8, 2)
+        print("### CTA-pair (cta_group::2) kernel forced", flush=True)
     t0 = time.time()
     ok = run(128, 128, 64, f32=True, tag="smallest")
     ok &= run(256, 256, 128, tag="small")

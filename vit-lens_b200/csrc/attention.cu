@@ -673,63 +673,117 @@ struct AttnTailParams {
   float scale;
 };
 
-// forward: one warp per (b, h, tail query): full-row softmax over all nk keys, lane-strided over keys.
-constexpr int kTailMaxN = 32 * kTailMaxIter;
+// dot(bf16 row in global memory, fp32 vector in shared memory)
+__device__ __forceinline__ float dot_row64_sm(const __nv_bfloat16* p, const float* vec) {
+  float acc = 0.f;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const uint4 w = reinterpret_cast<const uint4*>(p)[u];
+    const float4 a = *reinterpret_cast<const float4*>(vec + 8 * u), c = *reinterpret_cast<const float4*>(vec + 8 * u + 4);
+    acc += bf16_lo(w.x) * a.x + bf16_hi(w.x) * a.y + bf16_lo(w.y) * a.z + bf16_hi(w.y) * a.w + bf16_lo(w.z) * c.x + bf16_hi(w.z) * c.y +
+           bf16_lo(w.w) * c.z + bf16_hi(w.w) * c.w;
+  }
+  return acc;
+}
 
-__global__ void __launch_bounds__(128) attn_fwd_tail_kernel(const AttnTailParams p) {
-  __shared__ float sh[4][kTailMaxN];
-  const int lane = threadIdx.x & 31;
-  float* sc = sh[threadIdx.x >> 5];
-  const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  if (w >= static_cast<long long>(p.B) * p.H * p.tq) return;
-  const int t = static_cast<int>(w % p.tq);
-  const int h = static_cast<int>((w / p.tq) % p.H);
-  const int b = static_cast<int>(w / (static_cast<long long>(p.tq) * p.H));
+constexpr int kTailMaxN = 32 * kTailMaxIter;
+constexpr int kTailThreads = 128;
+constexpr int kTailSegs = kTailThreads / 8;  // 16 key segments x 8 dim groups (8 dims = one 16-byte load each)
+
+// acc[e] += sum over this thread's key segment of w[j] * row_j[dv*8 + e]   (rows of 64 bf16, stride ld)
+__device__ __forceinline__ void weighted_rows_segment(const float* w, const __nv_bfloat16* rows, long long ld, int n, float (&acc)[8]) {
+  const int dv = threadIdx.x & 7, seg = threadIdx.x >> 3;
+  const int per = (n + kTailSegs - 1) / kTailSegs;
+  const int j0 = seg * per, j1 = min(n, j0 + per);
+#pragma unroll 4
+  for (int j = j0; j < j1; ++j) {
+    const uint4 u = *reinterpret_cast<const uint4*>(rows + static_cast<long long>(j) * ld + dv * 8);
+    const float wj = w[j];
+    acc[0] = fmaf(wj, bf16_lo(u.x), acc[0]); acc[1] = fmaf(wj, bf16_hi(u.x), acc[1]);
+    acc[2] = fmaf(wj, bf16_lo(u.y), acc[2]); acc[3] = fmaf(wj, bf16_hi(u.y), acc[3]);
+    acc[4] = fmaf(wj, bf16_lo(u.z), acc[4]); acc[5] = fmaf(wj, bf16_hi(u.z), acc[5]);
+    acc[6] = fmaf(wj, bf16_lo(u.w), acc[6]); acc[7] = fmaf(wj, bf16_hi(u.w), acc[7]);
+  }
+}
+// part[seg][64] <- acc ; then threads < 64 reduce over the segments
+__device__ __forceinline__ float reduce_segments(float (*part)[kHD], const float (&acc)[8]) {
+  const int dv = threadIdx.x & 7, seg = threadIdx.x >> 3;
+  __syncthreads();
+#pragma unroll
+  for (int e2 = 0; e2 < 8; ++e2) part[seg][dv * 8 + e2] = acc[e2];
+  __syncthreads();
+  float r = 0.f;
+  if (threadIdx.x < kHD) {
+#pragma unroll
+    for (int sg = 0; sg < kTailSegs; ++sg) r += part[sg][threadIdx.x];
+  }
+  return r;
+}
+
+__device__ __forceinline__ float block_reduce_128(float v, float* red, bool is_max) {
+  v = is_max ? warp_max_f(v) : warp_sum_f(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int w = 1; w < kTailThreads / 32; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+  return r;
+}
+
+// forward: one 128-thread CTA per (b, h, tail query): thread-per-key scores, then 64 dims x 2 key halves for P @ V.
+__global__ void __launch_bounds__(kTailThreads, 4) attn_fwd_tail_kernel(const AttnTailParams p) {
+  __shared__ float sc[kTailMaxN];
+  __shared__ __align__(16) float qv[kHD];
+  __shared__ float red[4];
+  __shared__ float part[kTailSegs][kHD];
+  const int tid = threadIdx.x;
+  const int t = blockIdx.x % p.tq;
+  const int h = (blockIdx.x / p.tq) % p.H;
+  const int b = blockIdx.x / (p.tq * p.H);
   const int qrow = p.nq - p.tq + t;
   const float sl2 = p.scale * kLog2e;
-  float qf[64];
-  load_row64(p.q + (static_cast<long long>(b) * p.nq + qrow) * p.ldq + h * kHD, qf);
+  if (tid < kHD) qv[tid] = __bfloat162float(p.q[(static_cast<long long>(b) * p.nq + qrow) * p.ldq + h * kHD + tid]);
+  __syncthreads();
   const __nv_bfloat16* kb = p.k + static_cast<long long>(b) * p.nk * p.ldk + h * kHD;
   const __nv_bfloat16* vb = p.v + static_cast<long long>(b) * p.nk * p.ldv + h * kHD;
   float m = -INFINITY;
-  for (int j = lane; j < p.nk; j += 32) {
-    const float sv = dot_row64(kb + static_cast<long long>(j) * p.ldk, qf) * sl2;
+  for (int j = tid; j < p.nk; j += kTailThreads) {
+    const float sv = dot_row64_sm(kb + static_cast<long long>(j) * p.ldk, qv) * sl2;
     sc[j] = sv;
     m = fmaxf(m, sv);
   }
-  m = warp_max_f(m);
+  m = block_reduce_128(m, red, true);
   float l = 0.f;
-  for (int j = lane; j < p.nk; j += 32) {
+  for (int j = tid; j < p.nk; j += kTailThreads) {
     const float e = exp2f(sc[j] - m);
     sc[j] = e;
     l += e;
   }
-  l = warp_sum_f(l);
-  __syncwarp();
-  // O[d] = sum_j p_j V[j, d]: lane owns dims (2*lane, 2*lane+1); p_j is a broadcast smem read
-  float o0 = 0.f, o1 = 0.f;
-  for (int j = 0; j < p.nk; ++j) {
-    const float pj = sc[j];
-    const uint32_t vv = *reinterpret_cast<const uint32_t*>(vb + static_cast<long long>(j) * p.ldv + 2 * lane);
-    o0 = fmaf(pj, bf16_lo(vv), o0);
-    o1 = fmaf(pj, bf16_hi(vv), o1);
+  l = block_reduce_128(l, red, false);  // also orders the sc[] writes before the reads below
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  weighted_rows_segment(sc, vb, p.ldv, p.nk, acc);
+  const float osum = reduce_segments(part, acc);
+  if (tid < kHD) {
+    p.out_o[(static_cast<long long>(b) * p.nq + qrow) * p.ldo + h * kHD + tid] = __float2bfloat16(osum / l);
+    if (tid == 0 && p.lse) p.lse[(static_cast<long long>(b) * p.H + h) * p.nq + qrow] = (m + log2f(l)) * 0.6931471805599453f;
   }
-  const float inv = 1.0f / l;
-  *reinterpret_cast<uint32_t*>(p.out_o + (static_cast<long long>(b) * p.nq + qrow) * p.ldo + h * kHD + 2 * lane) = pack_bf16(o0 * inv, o1 * inv);
-  if (lane == 0 && p.lse) p.lse[(static_cast<long long>(b) * p.H + h) * p.nq + qrow] = (m + log2f(l)) * 0.6931471805599453f;
 }
 
-// backward: one warp per (b, h).  Part A: dQ of every tail query (sum over all keys).
-// Part B: dK, dV of every tail key (sum over all queries).
-__global__ void __launch_bounds__(128) attn_bwd_tail_kernel(const AttnTailParams p) {
-  __shared__ float sh[4][2][kTailMaxN];
-  const int lane = threadIdx.x & 31;
-  float* s_ds = sh[threadIdx.x >> 5][0];
-  float* s_p = sh[threadIdx.x >> 5][1];
-  const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  if (w >= static_cast<long long>(p.B) * p.H) return;
-  const int h = static_cast<int>(w % p.H);
-  const int b = static_cast<int>(w / p.H);
+// backward: one 128-thread CTA per (b, h, part, t).  part 0: dQ of tail query t (sum over all keys);
+// part 1: dK, dV of tail key t (sum over all queries).
+__global__ void __launch_bounds__(kTailThreads, 3) attn_bwd_tail_kernel(const AttnTailParams p) {
+  __shared__ float s_ds[kTailMaxN];
+  __shared__ float s_p[kTailMaxN];
+  __shared__ __align__(16) float va[kHD];
+  __shared__ __align__(16) float vb_[kHD];
+  __shared__ float part[kTailSegs][kHD];
+  __shared__ float stat[2];
+  const int tid = threadIdx.x;
+  const int nper = p.tq + p.tk;
+  const int unit = blockIdx.x % nper;
+  const int h = (blockIdx.x / nper) % p.H;
+  const int b = blockIdx.x / (nper * p.H);
   const float sl2 = p.scale * kLog2e;
   const __nv_bfloat16* qb = p.q + static_cast<long long>(b) * p.nq * p.ldq + h * kHD;
   const __nv_bfloat16* kb = p.k + static_cast<long long>(b) * p.nk * p.ldk + h * kHD;
@@ -737,70 +791,64 @@ __global__ void __launch_bounds__(128) attn_bwd_tail_kernel(const AttnTailParams
   const __nv_bfloat16* ob = p.o + static_cast<long long>(b) * p.nq * p.ldo + h * kHD;
   const __nv_bfloat16* gb = p.dout + static_cast<long long>(b) * p.nq * p.lddo + h * kHD;
   const float* lse = p.lse + (static_cast<long long>(b) * p.H + h) * p.nq;
-  // ---------------- Part A
-  for (int t = 0; t < p.tq; ++t) {
-    const int qrow = p.nq - p.tq + t;
-    {
-      float qf[64], gf[64];
-      load_row64(qb + static_cast<long long>(qrow) * p.ldq, qf);
-      load_row64(gb + static_cast<long long>(qrow) * p.lddo, gf);
-      const float Dq = dot_row64(ob + static_cast<long long>(qrow) * p.ldo, gf);
-      const float lse2 = lse[qrow] * kLog2e;
-      for (int j = lane; j < p.nk; j += 32) {
-        const float sdot = dot_row64(kb + static_cast<long long>(j) * p.ldk, qf);
-        const float dpv = dot_row64(vb + static_cast<long long>(j) * p.ldv, gf);
-        s_ds[j] = exp2f(fmaf(sdot, sl2, -lse2)) * (dpv - Dq) * p.scale;
-      }
+  if (unit < p.tq) {
+    // ---------------- part 0: tail query
+    const int qrow = p.nq - p.tq + unit;
+    if (tid < kHD) {
+      va[tid] = __bfloat162float(qb[static_cast<long long>(qrow) * p.ldq + tid]);
+      vb_[tid] = __bfloat162float(gb[static_cast<long long>(qrow) * p.lddo + tid]);
     }
-    __syncwarp();
-    float a0 = 0.f, a1 = 0.f;
-    for (int j = 0; j < p.nk; ++j) {
-      const float dsj = s_ds[j];
-      const uint32_t kk = *reinterpret_cast<const uint32_t*>(kb + static_cast<long long>(j) * p.ldk + 2 * lane);
-      a0 = fmaf(dsj, bf16_lo(kk), a0);
-      a1 = fmaf(dsj, bf16_hi(kk), a1);
+    __syncthreads();
+    if (tid == 0) {
+      stat[0] = lse[qrow] * kLog2e;
+      stat[1] = dot_row64_sm(ob + static_cast<long long>(qrow) * p.ldo, vb_);
     }
-    *reinterpret_cast<uint32_t*>(p.dq + (static_cast<long long>(b) * p.nq + qrow) * p.lddq + h * kHD + 2 * lane) = pack_bf16(a0, a1);
-    __syncwarp();
-  }
-  // ---------------- Part B
-  for (int t = 0; t < p.tk; ++t) {
-    const int krow = p.nk - p.tk + t;
-    {
-      float kf[64], vf[64];
-      load_row64(kb + static_cast<long long>(krow) * p.ldk, kf);
-      load_row64(vb + static_cast<long long>(krow) * p.ldv, vf);
-      for (int i = lane; i < p.nq; i += 32) {
-        const float sdot = dot_row64(qb + static_cast<long long>(i) * p.ldq, kf);
-        const float dpv = dot_row64(gb + static_cast<long long>(i) * p.lddo, vf);
-        float Di = 0.f;  // D_i = dO_i . O_i
-        const uint4* orow = reinterpret_cast<const uint4*>(ob + static_cast<long long>(i) * p.ldo);
-        const uint4* grow = reinterpret_cast<const uint4*>(gb + static_cast<long long>(i) * p.lddo);
+    __syncthreads();
+    const float lse2 = stat[0], Dq = stat[1];
+    for (int j = tid; j < p.nk; j += kTailThreads) {
+      const float sdot = dot_row64_sm(kb + static_cast<long long>(j) * p.ldk, va);
+      const float dpv = dot_row64_sm(vb + static_cast<long long>(j) * p.ldv, vb_);
+      s_ds[j] = exp2f(fmaf(sdot, sl2, -lse2)) * (dpv - Dq) * p.scale;
+    }
+    __syncthreads();
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    weighted_rows_segment(s_ds, kb, p.ldk, p.nk, acc);
+    const float r = reduce_segments(part, acc);
+    if (tid < kHD) p.dq[(static_cast<long long>(b) * p.nq + qrow) * p.lddq + h * kHD + tid] = __float2bfloat16(r);
+  } else {
+    // ---------------- part 1: tail key
+    const int krow = p.nk - p.tk + (unit - p.tq);
+    if (tid < kHD) {
+      va[tid] = __bfloat162float(kb[static_cast<long long>(krow) * p.ldk + tid]);
+      vb_[tid] = __bfloat162float(vb[static_cast<long long>(krow) * p.ldv + tid]);
+    }
+    __syncthreads();
+    for (int i = tid; i < p.nq; i += kTailThreads) {
+      const float sdot = dot_row64_sm(qb + static_cast<long long>(i) * p.ldq, va);
+      const float dpv = dot_row64_sm(gb + static_cast<long long>(i) * p.lddo, vb_);
+      float Di = 0.f;  // D_i = dO_i . O_i
+      const uint4* orow = reinterpret_cast<const uint4*>(ob + static_cast<long long>(i) * p.ldo);
+      const uint4* grow = reinterpret_cast<const uint4*>(gb + static_cast<long long>(i) * p.lddo);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const uint4 a = orow[u], g = grow[u];
-          Di += bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) + bf16_hi(a.y) * bf16_hi(g.y) +
-                bf16_lo(a.z) * bf16_lo(g.z) + bf16_hi(a.z) * bf16_hi(g.z) + bf16_lo(a.w) * bf16_lo(g.w) + bf16_hi(a.w) * bf16_hi(g.w);
-        }
-        const float pi = exp2f(fmaf(sdot, sl2, -lse[i] * kLog2e));
-        s_p[i] = pi;
-        s_ds[i] = pi * (dpv - Di) * p.scale;
+      for (int u = 0; u < 8; ++u) {
+        const uint4 x = orow[u], g = grow[u];
+        Di += bf16_lo(x.x) * bf16_lo(g.x) + bf16_hi(x.x) * bf16_hi(g.x) + bf16_lo(x.y) * bf16_lo(g.y) + bf16_hi(x.y) * bf16_hi(g.y) +
+              bf16_lo(x.z) * bf16_lo(g.z) + bf16_hi(x.z) * bf16_hi(g.z) + bf16_lo(x.w) * bf16_lo(g.w) + bf16_hi(x.w) * bf16_hi(g.w);
       }
+      const float pi = exp2f(fmaf(sdot, sl2, -lse[i] * kLog2e));
+      s_p[i] = pi;
+      s_ds[i] = pi * (dpv - Di) * p.scale;
     }
-    __syncwarp();
-    float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
-    for (int i = 0; i < p.nq; ++i) {
-      const float dsi = s_ds[i], pi = s_p[i];
-      const uint32_t qq = *reinterpret_cast<const uint32_t*>(qb + static_cast<long long>(i) * p.ldq + 2 * lane);
-      const uint32_t gg = *reinterpret_cast<const uint32_t*>(gb + static_cast<long long>(i) * p.lddo + 2 * lane);
-      k0 = fmaf(dsi, bf16_lo(qq), k0);
-      k1 = fmaf(dsi, bf16_hi(qq), k1);
-      v0 = fmaf(pi, bf16_lo(gg), v0);
-      v1 = fmaf(pi, bf16_hi(gg), v1);
+    __syncthreads();
+    float acck[8] = {0, 0, 0, 0, 0, 0, 0, 0}, accv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    weighted_rows_segment(s_ds, qb, p.ldq, p.nq, acck);
+    weighted_rows_segment(s_p, gb, p.lddo, p.nq, accv);
+    const float rk = reduce_segments(part, acck);
+    const float rv = reduce_segments(part, accv);
+    if (tid < kHD) {
+      p.dk[(static_cast<long long>(b) * p.nk + krow) * p.lddk + h * kHD + tid] = __float2bfloat16(rk);
+      p.dv[(static_cast<long long>(b) * p.nk + krow) * p.lddv + h * kHD + tid] = __float2bfloat16(rv);
     }
-    *reinterpret_cast<uint32_t*>(p.dk + (static_cast<long long>(b) * p.nk + krow) * p.lddk + h * kHD + 2 * lane) = pack_bf16(k0, k1);
-    *reinterpret_cast<uint32_t*>(p.dv + (static_cast<long long>(b) * p.nk + krow) * p.lddv + h * kHD + 2 * lane) = pack_bf16(v0, v1);
-    __syncwarp();
   }
 }
 
@@ -856,8 +904,7 @@ int vl_attention_fwd(const void* q, const void* k, const void* v, void* o, float
     t.out_o = reinterpret_cast<__nv_bfloat16*>(o); t.lse = lse;
     t.ldq = ldq; t.ldk = ldk; t.ldv = ldv; t.ldo = ldo;
     t.B = B; t.H = H; t.nq = nq; t.nk = nk; t.tq = tq; t.tk = 0; t.scale = scale;
-    const long long warps = (long long)B * H * tq;
-    attn_fwd_tail_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(t);
+    attn_fwd_tail_kernel<<<(unsigned)(B * H * tq), kTailThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(t);
     return launch_check("attn_fwd_tail_kernel");
   }
   return 0;
@@ -905,8 +952,7 @@ int vl_attention_bwd(const void* q, const void* k, const void* v, const void* o,
     t.dq = p.dq; t.dk = p.dk; t.dv = p.dv; t.lse = const_cast<float*>(lse);
     t.ldq = ldq; t.ldk = ldk; t.ldv = ldv; t.ldo = ldo; t.lddo = lddo; t.lddq = lddq; t.lddk = lddk; t.lddv = lddv;
     t.B = B; t.H = H; t.nq = nq; t.nk = nk; t.tq = tq; t.tk = tk; t.scale = scale;
-    const long long warps = (long long)B * H;
-    attn_bwd_tail_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(t);
+    attn_bwd_tail_kernel<<<(unsigned)(B * H * (tq + tk)), kTailThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(t);
     return launch_check("attn_bwd_tail_kernel");
   }
   return 0;

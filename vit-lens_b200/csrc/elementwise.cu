@@ -98,17 +98,18 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
                                                             const float* __restrict__ rstd,
                                                             const __nv_bfloat16* __restrict__ dres, long long lddres,
                                                             __nv_bfloat16* __restrict__ dx, long long lddx,
-                                                            float* __restrict__ dw, float* __restrict__ db, int T, int D) {
-  extern __shared__ float red[];  // [warps][D] reused for dw then db
+                                                            float* __restrict__ dw, float* __restrict__ db,
+                                                            float* __restrict__ dres_sum, int T, int D) {
+  extern __shared__ float red[];  // [warps][D] reused for dw, db, dres_sum
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
   const int nvec = D >> 3;
-  float aw[CH][8], ab[CH][8];
+  float aw[CH][8], ab[CH][8], ar[CH][8];
 #pragma unroll
   for (int c = 0; c < CH; ++c)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) aw[c][j] = ab[c][j] = 0.f;
+    for (int j = 0; j < 8; ++j) aw[c][j] = ab[c][j] = ar[c][j] = 0.f;
 
   for (long long row = (long long)blockIdx.x * wpb + warp; row < T; row += (long long)gridDim.x * wpb) {
     const long long src = row_index ? row_index[row] : row;
@@ -151,29 +152,34 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
           float r[8];
           unpack8(rr[i], r);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += r[j];
+          for (int j = 0; j < 8; ++j) {
+            o[j] += r[j];
+            ar[c][j] += r[j];
+          }
         }
         dr[i] = pack8(o);
       }
     }
   }
-  if (dw == nullptr) return;
+  if (dw == nullptr && dres_sum == nullptr) return;
   // block reduction of the per-warp partial column sums, then one atomic per column per CTA
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < 3; ++pass) {
+    float* dst = pass == 0 ? dw : (pass == 1 ? db : dres_sum);
+    if (dst == nullptr) continue;
     __syncthreads();
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int i = lane + c * 32;
       if (i < nvec) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) red[warp * D + i * 8 + j] = pass == 0 ? aw[c][j] : ab[c][j];
+        for (int j = 0; j < 8; ++j) red[warp * D + i * 8 + j] = pass == 0 ? aw[c][j] : (pass == 1 ? ab[c][j] : ar[c][j]);
       }
     }
     __syncthreads();
     for (int col = threadIdx.x; col < D; col += blockDim.x) {
       float s = 0.f;
       for (int ww = 0; ww < wpb; ++ww) s += red[ww * D + col];
-      atomicAdd((pass == 0 ? dw : db) + col, s);
+      atomicAdd(dst + col, s);
     }
   }
 }
@@ -506,22 +512,23 @@ int vl_layernorm_fwd(const void* x, int64_t ldx, const int64_t* row_index, const
 
 int vl_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const int64_t* row_index, const float* w,
                      const float* mean, const float* rstd, const void* dres, int64_t lddres, void* dx, int64_t lddx, float* dw,
-                     float* db, int32_t T, int32_t D, void* stream) {
+                     float* db, float* dres_sum, int32_t T, int32_t D, void* stream) {
   VL_CHECK_ARG(dy && x && w && mean && rstd && dx, "vl_layernorm_bwd: null pointer");
   VL_CHECK_ARG((dw == nullptr) == (db == nullptr), "vl_layernorm_bwd: dw and db must both be given or both be NULL");
+  VL_CHECK_ARG(dres_sum == nullptr || dres != nullptr, "vl_layernorm_bwd: dres_sum needs dres");
   VL_CHECK_ARG(T > 0 && D > 0 && D % 8 == 0 && D <= 256 * kMaxLnChunks, "vl_layernorm_bwd: D=%d unsupported", D);
   VL_CHECK_ARG(ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0 && lddres % 8 == 0, "vl_layernorm_bwd: ld must be a multiple of 8");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int grid = num_sms() * 2;
   if ((long long)grid * 8 > T) grid = (T + 7) / 8;
-  const size_t smem = dw ? (size_t)8 * D * sizeof(float) : 0;
+  const size_t smem = (dw || dres_sum) ? (size_t)8 * D * sizeof(float) : 0;
   const int ch = (D / 8 + 31) / 32;
 #define VL_LN_BWD(CH)                                                                                                     \
   do {                                                                                                                    \
     if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     layernorm_bwd_kernel<CH><<<grid, 256, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy,                    \
         reinterpret_cast<const __nv_bfloat16*>(x), ldx, (const long long*)row_index, w, mean, rstd,                       \
-        reinterpret_cast<const __nv_bfloat16*>(dres), lddres, reinterpret_cast<__nv_bfloat16*>(dx), lddx, dw, db, T, D);  \
+        reinterpret_cast<const __nv_bfloat16*>(dres), lddres, reinterpret_cast<__nv_bfloat16*>(dx), lddx, dw, db, dres_sum, T, D); \
   } while (0)
   if (ch <= 1) VL_LN_BWD(1); else if (ch <= 2) VL_LN_BWD(2); else if (ch <= 4) VL_LN_BWD(4); else VL_LN_BWD(8);
 #undef VL_LN_BWD

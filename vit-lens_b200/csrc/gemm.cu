@@ -41,6 +41,9 @@ struct GemmParams {
   float* scalar_out;
   int iparam;
   float fparam;
+  const float* alpha_dev;
+  const float* fparam_dev;
+  int aux_row_div, relu;
   uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;  // bytes
 };
 
@@ -94,14 +97,17 @@ __device__ __forceinline__ void store_tile_bf16(uint8_t* stg, const float (&f)[6
   __syncwarp();
 }
 
-__device__ __forceinline__ void load_tile_bf16(uint8_t* stg, uint32_t (&a)[32], const __nv_bfloat16* g, long long ld, int rows_valid,
-                                               int cols_valid, int lane) {
+// `g` points at (row 0 of the matrix, col0); rows are addressed as (row0 + row) / row_div (row_div > 1: one aux row is
+// shared by row_div consecutive output rows)
+__device__ __forceinline__ void load_tile_bf16(uint8_t* stg, uint32_t (&a)[32], const __nv_bfloat16* g, long long ld, int row0, int row_div,
+                                               int rows_valid, int cols_valid, int lane) {
   const int seg = lane & 7;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int row = (lane >> 3) + 4 * i;
     uint4 u = make_uint4(0, 0, 0, 0);
-    if (row < rows_valid && seg * 8 < cols_valid) u = *reinterpret_cast<const uint4*>(g + static_cast<long long>(row) * ld + seg * 8);
+    if (row < rows_valid && seg * 8 < cols_valid)
+      u = *reinterpret_cast<const uint4*>(g + static_cast<long long>((row0 + row) / row_div) * ld + seg * 8);
     *reinterpret_cast<uint4*>(stg + stg_off(row, seg)) = u;
   }
   __syncwarp();
@@ -114,6 +120,284 @@ __device__ __forceinline__ void load_tile_bf16(uint8_t* stg, uint32_t (&a)[32], 
     a[4 * sgm + 3] = u.w;
   }
   __syncwarp();
+}
+
+// One output tile's epilogue for the calling epilogue warp: rows [row_base + quarter*32, +32) of the tile whose
+// accumulator starts at TMEM column `tmem_acc` (lane offset added here), columns of n-tile n_blk (this warp's half).
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_base, uint32_t acc_col, int row_base, int n_blk, int ks,
+                                              int e, int quarter, int lane, uint8_t* stg_warp) {
+  const int half = e >> 2;
+  constexpr int kChunks = (BN / 2) / 32;
+  const float alpha_eff = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f);
+  const float fparam_eff = p.fparam * (p.fparam_dev ? __ldg(p.fparam_dev) : 1.0f);
+  const int row = row_base + quarter * 32 + lane;
+  const bool row_ok = row < p.M;
+  const bool lead_split = (ks == 0);  // bias / aux terms are added by split 0 only
+  float lse_m = -INFINITY, lse_s = 0.f, clip_ds = 0.f;
+  const bool fast = !p.d_f32 && p.epi != VL_EPI_ROWLSE;
+  if (fast) {
+    // ---------------- bf16 outputs: 64-column groups, fully coalesced global traffic
+    uint8_t* stg = stg_warp;
+    const int row0 = row_base + quarter * 32;
+    const int rows_valid = min(32, p.M - row0);
+#pragma unroll 1
+    for (int gidx = 0; gidx < kChunks / 2; ++gidx) {
+      const int col0 = n_blk * BN + half * (BN / 2) + gidx * 64;
+      if (col0 >= p.N) break;
+      const int cols_valid = min(64, p.N - col0);
+      uint32_t ax[32];
+      const bool need_aux = (p.epi == VL_EPI_RESIDUAL && lead_split) || p.epi == VL_EPI_GELU_BWD;
+      if (need_aux)
+        load_tile_bf16(stg, ax, p.aux_in + col0, p.ldaux, row0, p.aux_row_div, rows_valid, cols_valid, lane);
+      float f[64];
+#pragma unroll
+      for (int hc = 0; hc < 2; ++hc) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc_col + half * (BN / 2) + gidx * 64 + hc * 32, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[hc * 32 + j] = __uint_as_float(v[j]);
+      }
+      if (p.epi == VL_EPI_CLIPGRAD) {
+        const float rl = row_ok ? __ldg(p.row_vec + row) : 0.f;
+        float dsum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          const float accv = f[j];
+          const float z = accv * alpha_eff;
+          float gval = 0.f;
+          if (row_ok && col0 + j < p.N) {
+            gval = __expf(z - rl);
+            if (p.col_vec) gval += __expf(z - __ldg(p.col_vec + col0 + j));
+            if (col0 + j == row + p.iparam) gval -= p.col_vec ? 2.f : 1.f;
+            gval *= fparam_eff;
+            dsum += gval * accv;
+          }
+          f[j] = gval;
+        }
+        clip_ds += dsum;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) f[j] *= alpha_eff;
+        if (p.bias != nullptr && lead_split && p.epi != VL_EPI_GELU_BWD) {
+          if (cols_valid == 64) {
+#pragma unroll
+            for (int j = 0; j < 64; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              f[j] += b4.x;
+              f[j + 1] += b4.y;
+              f[j + 2] += b4.z;
+              f[j + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 64; j += 4) {
+              if (col0 + j < p.N) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                f[j] += b4.x;
+                f[j + 1] += b4.y;
+                f[j + 2] += b4.z;
+                f[j + 3] += b4.w;
+              }
+            }
+          }
+        }
+        if (p.epi == VL_EPI_GELU) {
+          if (p.aux_out != nullptr)
+            store_tile_bf16(stg, f, p.aux_out + static_cast<long long>(row0) * p.ldaux + col0, p.ldaux, rows_valid, cols_valid, lane);
+          if (p.act_quick) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) f[j] = gelu_quick_fwd(f[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) f[j] = gelu_erf_fwd(f[j]);
+          }
+        } else if (need_aux) {
+          if (p.epi == VL_EPI_RESIDUAL) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              f[2 * j] += bf16_lo(ax[j]);
+              f[2 * j + 1] += bf16_hi(ax[j]);
+            }
+          } else if (p.act_quick) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              f[2 * j] *= gelu_quick_grad(bf16_lo(ax[j]));
+              f[2 * j + 1] *= gelu_quick_grad(bf16_hi(ax[j]));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              f[2 * j] *= gelu_erf_grad(bf16_lo(ax[j]));
+              f[2 * j + 1] *= gelu_erf_grad(bf16_hi(ax[j]));
+            }
+          }
+        }
+      }
+      store_tile_bf16(stg, f, reinterpret_cast<__nv_bfloat16*>(p.d) + static_cast<long long>(row0) * p.ldd + col0, p.ldd, rows_valid,
+                      cols_valid, lane);
+    }
+  }
+#pragma unroll 1
+  for (int c = 0; c < (fast ? 0 : kChunks); ++c) {
+    const int col0 = n_blk * BN + half * (BN / 2) + c * 32;
+    if (col0 >= p.N) break;
+    uint32_t v[32];
+    tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc_col + half * (BN / 2) + c * 32, v);
+    tc_wait_ld();
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * alpha_eff;
+    if (p.bias != nullptr && lead_split && p.epi != VL_EPI_GELU_BWD) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        if (col0 + j < p.N) {  // N % 4 == 0 is enforced on the host
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+          f[j] += b4.x;
+          f[j + 1] += b4.y;
+          f[j + 2] += b4.z;
+          f[j + 3] += b4.w;
+        }
+      }
+    }
+    if (p.epi == VL_EPI_ROWLSE) {
+      // online (max, sum-exp) over this thread's columns of the tile; one part per (n tile, half)
+      if (c == 0) {
+        lse_m = -INFINITY;
+        lse_s = 0.f;
+      }
+      float cm = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) cm = fmaxf(cm, f[j]);
+      const float nm = fmaxf(lse_m, cm);
+      float add = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) add += __expf(f[j] - nm);
+      lse_s = lse_s * __expf(lse_m - nm) + add;
+      lse_m = nm;
+      if (row_ok) {
+        const int dj = row + p.iparam - col0;
+        if (dj >= 0 && dj < 32) {
+          float dv = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j == dj) dv = f[j];
+          p.out_vec2[row] = dv;
+        }
+        const bool last = (c == kChunks - 1) || (col0 + 32 >= p.N);
+        if (last) {
+          const long long po = static_cast<long long>(row) * (p.tiles_n * 2) + n_blk * 2 + half;
+          p.out_vec0[po] = lse_m;
+          p.out_vec1[po] = lse_s;
+        }
+      }
+      continue;
+    }
+    if (p.epi == VL_EPI_CLIPGRAD) {
+      const float rl = row_ok ? __ldg(p.row_vec + row) : 0.f;
+      float dsum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float g = 0.f;
+        if (row_ok && col0 + j < p.N) {
+          g = __expf(f[j] - rl);
+          if (p.col_vec) g += __expf(f[j] - __ldg(p.col_vec + col0 + j));
+          if (col0 + j == row + p.iparam) g -= p.col_vec ? 2.f : 1.f;
+          g *= fparam_eff;
+          dsum += g * __uint_as_float(v[j]);
+        }
+        f[j] = g;
+      }
+      clip_ds += dsum;
+    }
+    if (row_ok) {
+      const long long aoff = static_cast<long long>(row) * p.ldaux + col0;
+      if (p.epi == VL_EPI_GELU) {
+        if (p.aux_out != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (col0 + j < p.N) {
+              uint4 u;
+              u.x = pack_bf16(f[j], f[j + 1]);
+              u.y = pack_bf16(f[j + 2], f[j + 3]);
+              u.z = pack_bf16(f[j + 4], f[j + 5]);
+              u.w = pack_bf16(f[j + 6], f[j + 7]);
+              *reinterpret_cast<uint4*>(p.aux_out + aoff + j) = u;
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = gelu_fwd(f[j], p.act_quick);
+      } else if (p.epi == VL_EPI_RESIDUAL) {
+        if (lead_split) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (col0 + j < p.N) {
+              const uint4 u = *reinterpret_cast<const uint4*>(p.aux_in + aoff + j);
+              f[j] += bf16_lo(u.x);
+              f[j + 1] += bf16_hi(u.x);
+              f[j + 2] += bf16_lo(u.y);
+              f[j + 3] += bf16_hi(u.y);
+              f[j + 4] += bf16_lo(u.z);
+              f[j + 5] += bf16_hi(u.z);
+              f[j + 6] += bf16_lo(u.w);
+              f[j + 7] += bf16_hi(u.w);
+            }
+          }
+        }
+      } else if (p.epi == VL_EPI_GELU_BWD) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          if (col0 + j < p.N) {
+            const uint4 u = *reinterpret_cast<const uint4*>(p.aux_in + aoff + j);
+            f[j] *= gelu_grad(bf16_lo(u.x), p.act_quick);
+            f[j + 1] *= gelu_grad(bf16_hi(u.x), p.act_quick);
+            f[j + 2] *= gelu_grad(bf16_lo(u.y), p.act_quick);
+            f[j + 3] *= gelu_grad(bf16_hi(u.y), p.act_quick);
+            f[j + 4] *= gelu_grad(bf16_lo(u.z), p.act_quick);
+            f[j + 5] *= gelu_grad(bf16_hi(u.z), p.act_quick);
+            f[j + 6] *= gelu_grad(bf16_lo(u.w), p.act_quick);
+            f[j + 7] *= gelu_grad(bf16_hi(u.w), p.act_quick);
+          }
+        }
+      }
+      // ---- store
+      const long long doff = static_cast<long long>(row) * p.ldd + col0;
+      if (p.d_f32) {
+        float* dp = reinterpret_cast<float*>(p.d) + doff;
+        if (p.accumulate) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) atomicAdd(dp + j, f[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (col0 + j < p.N) *reinterpret_cast<float4*>(dp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        }
+      } else {
+        __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.d) + doff;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          if (col0 + j < p.N) {
+            uint4 u;
+            u.x = pack_bf16(f[j], f[j + 1]);
+            u.y = pack_bf16(f[j + 2], f[j + 3]);
+            u.z = pack_bf16(f[j + 4], f[j + 5]);
+            u.w = pack_bf16(f[j + 6], f[j + 7]);
+            *reinterpret_cast<uint4*>(dp + j) = u;
+          }
+        }
+      }
+    }
+  }
+  if (p.epi == VL_EPI_CLIPGRAD && p.scalar_out != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) clip_ds += __shfl_xor_sync(0xffffffffu, clip_ds, o);
+    if (lane == 0) atomicAdd(p.scalar_out, clip_ds);
+  }
 }
 
 template <int BN>
@@ -238,8 +522,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------------------------------------------ epilogue warps
     const int e = warp - 2;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int half = e >> 2;       // column half of the tile
-    constexpr int kChunks = (BN / 2) / 32;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -247,273 +529,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tile_coords(p, t, m_blk, n_blk, ks);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row = m_blk * kBM + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
-      const bool lead_split = (ks == 0);  // bias / aux terms are added by split 0 only
-      float lse_m = -INFINITY, lse_s = 0.f, clip_ds = 0.f;
-      const bool fast = !p.d_f32 && p.epi != VL_EPI_ROWLSE;
-      if (fast) {
-        // ---------------- bf16 outputs: 64-column groups, fully coalesced global traffic
-        uint8_t* stg = smem_raw + (stg_base - smem_u32(smem_raw)) + e * 4096;
-        const int row0 = m_blk * kBM + quarter * 32;
-        const int rows_valid = min(32, p.M - row0);
-#pragma unroll 1
-        for (int gidx = 0; gidx < kChunks / 2; ++gidx) {
-          const int col0 = n_blk * BN + half * (BN / 2) + gidx * 64;
-          if (col0 >= p.N) break;
-          const int cols_valid = min(64, p.N - col0);
-          uint32_t ax[32];
-          const bool need_aux = (p.epi == VL_EPI_RESIDUAL && lead_split) || p.epi == VL_EPI_GELU_BWD;
-          if (need_aux)
-            load_tile_bf16(stg, ax, p.aux_in + static_cast<long long>(row0) * p.ldaux + col0, p.ldaux, rows_valid, cols_valid, lane);
-          float f[64];
-#pragma unroll
-          for (int hc = 0; hc < 2; ++hc) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * (BN / 2) + gidx * 64 + hc * 32, v);
-            tc_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[hc * 32 + j] = __uint_as_float(v[j]);
-          }
-          if (p.epi == VL_EPI_CLIPGRAD) {
-            const float rl = row_ok ? __ldg(p.row_vec + row) : 0.f;
-            float dsum = 0.f;
-#pragma unroll
-            for (int j = 0; j < 64; ++j) {
-              const float accv = f[j];
-              const float z = accv * p.alpha;
-              float gval = 0.f;
-              if (row_ok && col0 + j < p.N) {
-                gval = __expf(z - rl);
-                if (p.col_vec) gval += __expf(z - __ldg(p.col_vec + col0 + j));
-                if (col0 + j == row + p.iparam) gval -= p.col_vec ? 2.f : 1.f;
-                gval *= p.fparam;
-                dsum += gval * accv;
-              }
-              f[j] = gval;
-            }
-            clip_ds += dsum;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 64; ++j) f[j] *= p.alpha;
-            if (p.bias != nullptr && lead_split && p.epi != VL_EPI_GELU_BWD) {
-              if (cols_valid == 64) {
-#pragma unroll
-                for (int j = 0; j < 64; j += 4) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                  f[j] += b4.x;
-                  f[j + 1] += b4.y;
-                  f[j + 2] += b4.z;
-                  f[j + 3] += b4.w;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 64; j += 4) {
-                  if (col0 + j < p.N) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                    f[j] += b4.x;
-                    f[j + 1] += b4.y;
-                    f[j + 2] += b4.z;
-                    f[j + 3] += b4.w;
-                  }
-                }
-              }
-            }
-            if (p.epi == VL_EPI_GELU) {
-              if (p.aux_out != nullptr)
-                store_tile_bf16(stg, f, p.aux_out + static_cast<long long>(row0) * p.ldaux + col0, p.ldaux, rows_valid, cols_valid, lane);
-              if (p.act_quick) {
-#pragma unroll
-                for (int j = 0; j < 64; ++j) f[j] = gelu_quick_fwd(f[j]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 64; ++j) f[j] = gelu_erf_fwd(f[j]);
-              }
-            } else if (need_aux) {
-              if (p.epi == VL_EPI_RESIDUAL) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  f[2 * j] += bf16_lo(ax[j]);
-                  f[2 * j + 1] += bf16_hi(ax[j]);
-                }
-              } else if (p.act_quick) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  f[2 * j] *= gelu_quick_grad(bf16_lo(ax[j]));
-                  f[2 * j + 1] *= gelu_quick_grad(bf16_hi(ax[j]));
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  f[2 * j] *= gelu_erf_grad(bf16_lo(ax[j]));
-                  f[2 * j + 1] *= gelu_erf_grad(bf16_hi(ax[j]));
-                }
-              }
-            }
-          }
-          store_tile_bf16(stg, f, reinterpret_cast<__nv_bfloat16*>(p.d) + static_cast<long long>(row0) * p.ldd + col0, p.ldd, rows_valid,
-                          cols_valid, lane);
-        }
-      }
-#pragma unroll 1
-      for (int c = 0; c < (fast ? 0 : kChunks); ++c) {
-        const int col0 = n_blk * BN + half * (BN / 2) + c * 32;
-        if (col0 >= p.N) break;
-        uint32_t v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * (BN / 2) + c * 32, v);
-        tc_wait_ld();
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
-        if (p.bias != nullptr && lead_split && p.epi != VL_EPI_GELU_BWD) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (col0 + j < p.N) {  // N % 4 == 0 is enforced on the host
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-              f[j] += b4.x;
-              f[j + 1] += b4.y;
-              f[j + 2] += b4.z;
-              f[j + 3] += b4.w;
-            }
-          }
-        }
-        if (p.epi == VL_EPI_ROWLSE) {
-          // online (max, sum-exp) over this thread's columns of the tile; one part per (n tile, half)
-          if (c == 0) {
-            lse_m = -INFINITY;
-            lse_s = 0.f;
-          }
-          float cm = -INFINITY;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) cm = fmaxf(cm, f[j]);
-          const float nm = fmaxf(lse_m, cm);
-          float add = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) add += __expf(f[j] - nm);
-          lse_s = lse_s * __expf(lse_m - nm) + add;
-          lse_m = nm;
-          if (row_ok) {
-            const int dj = row + p.iparam - col0;
-            if (dj >= 0 && dj < 32) {
-              float dv = 0.f;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j == dj) dv = f[j];
-              p.out_vec2[row] = dv;
-            }
-            const bool last = (c == kChunks - 1) || (col0 + 32 >= p.N);
-            if (last) {
-              const long long po = static_cast<long long>(row) * (p.tiles_n * 2) + n_blk * 2 + half;
-              p.out_vec0[po] = lse_m;
-              p.out_vec1[po] = lse_s;
-            }
-          }
-          continue;
-        }
-        if (p.epi == VL_EPI_CLIPGRAD) {
-          const float rl = row_ok ? __ldg(p.row_vec + row) : 0.f;
-          float dsum = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float g = 0.f;
-            if (row_ok && col0 + j < p.N) {
-              g = __expf(f[j] - rl);
-              if (p.col_vec) g += __expf(f[j] - __ldg(p.col_vec + col0 + j));
-              if (col0 + j == row + p.iparam) g -= p.col_vec ? 2.f : 1.f;
-              g *= p.fparam;
-              dsum += g * __uint_as_float(v[j]);
-            }
-            f[j] = g;
-          }
-          clip_ds += dsum;
-        }
-        if (row_ok) {
-          const long long aoff = static_cast<long long>(row) * p.ldaux + col0;
-          if (p.epi == VL_EPI_GELU) {
-            if (p.aux_out != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                if (col0 + j < p.N) {
-                  uint4 u;
-                  u.x = pack_bf16(f[j], f[j + 1]);
-                  u.y = pack_bf16(f[j + 2], f[j + 3]);
-                  u.z = pack_bf16(f[j + 4], f[j + 5]);
-                  u.w = pack_bf16(f[j + 6], f[j + 7]);
-                  *reinterpret_cast<uint4*>(p.aux_out + aoff + j) = u;
-                }
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_fwd(f[j], p.act_quick);
-          } else if (p.epi == VL_EPI_RESIDUAL) {
-            if (lead_split) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                if (col0 + j < p.N) {
-                  const uint4 u = *reinterpret_cast<const uint4*>(p.aux_in + aoff + j);
-                  f[j] += bf16_lo(u.x);
-                  f[j + 1] += bf16_hi(u.x);
-                  f[j + 2] += bf16_lo(u.y);
-                  f[j + 3] += bf16_hi(u.y);
-                  f[j + 4] += bf16_lo(u.z);
-                  f[j + 5] += bf16_hi(u.z);
-                  f[j + 6] += bf16_lo(u.w);
-                  f[j + 7] += bf16_hi(u.w);
-                }
-              }
-            }
-          } else if (p.epi == VL_EPI_GELU_BWD) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (col0 + j < p.N) {
-                const uint4 u = *reinterpret_cast<const uint4*>(p.aux_in + aoff + j);
-                f[j] *= gelu_grad(bf16_lo(u.x), p.act_quick);
-                f[j + 1] *= gelu_grad(bf16_hi(u.x), p.act_quick);
-                f[j + 2] *= gelu_grad(bf16_lo(u.y), p.act_quick);
-                f[j + 3] *= gelu_grad(bf16_hi(u.y), p.act_quick);
-                f[j + 4] *= gelu_grad(bf16_lo(u.z), p.act_quick);
-                f[j + 5] *= gelu_grad(bf16_hi(u.z), p.act_quick);
-                f[j + 6] *= gelu_grad(bf16_lo(u.w), p.act_quick);
-                f[j + 7] *= gelu_grad(bf16_hi(u.w), p.act_quick);
-              }
-            }
-          }
-          // ---- store
-          const long long doff = static_cast<long long>(row) * p.ldd + col0;
-          if (p.d_f32) {
-            float* dp = reinterpret_cast<float*>(p.d) + doff;
-            if (p.accumulate) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) atomicAdd(dp + j, f[j]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                if (col0 + j < p.N) *reinterpret_cast<float4*>(dp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            }
-          } else {
-            __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.d) + doff;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (col0 + j < p.N) {
-                uint4 u;
-                u.x = pack_bf16(f[j], f[j + 1]);
-                u.y = pack_bf16(f[j + 2], f[j + 3]);
-                u.z = pack_bf16(f[j + 4], f[j + 5]);
-                u.w = pack_bf16(f[j + 6], f[j + 7]);
-                *reinterpret_cast<uint4*>(dp + j) = u;
-              }
-            }
-          }
-        }
-      }
-      if (p.epi == VL_EPI_CLIPGRAD && p.scalar_out != nullptr) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) clip_ds += __shfl_xor_sync(0xffffffffu, clip_ds, o);
-        if (lane == 0) atomicAdd(p.scalar_out, clip_ds);
-      }
+      epilogue_tile<BN>(p, tmem_base, acc * BN, m_blk * kBM, n_blk, ks, e, quarter, lane, smem_raw + (stg_base - smem_u32(smem_raw)) + e * 4096);
       // accumulator drained -> hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -532,6 +548,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
+
+template <int BN>
+static int launch_gemm2(const VlGemmArgs& a, GemmParams p, cudaStream_t stream);
+
+// debug knob 8: 0 = default kernel choice, 1 = force the single-CTA kernel, 2 = force the CTA-pair kernel.
+// Measured on B200 (profiles/r01_probe_gemm_pair_vs_single.log): the pair kernel equals the single-CTA kernel on the
+// K-major shapes and is 8-10 % faster on the MN-major weight-gradient shapes, so it is the default only there.
 
 template <int BN>
 static int launch_gemm(const VlGemmArgs& a, cudaStream_t stream) {
@@ -568,6 +591,10 @@ static int launch_gemm(const VlGemmArgs& a, cudaStream_t stream) {
   p.scalar_out = a.scalar_out;
   p.iparam = a.iparam;
   p.fparam = a.fparam;
+  p.alpha_dev = a.alpha_dev;
+  p.fparam_dev = a.fparam_dev;
+  p.aux_row_div = a.aux_row_div > 1 ? a.aux_row_div : 1;
+  p.relu = a.relu;
   // K-major: 8-row groups 1024 B apart, +32 B per UMMA_K inside the swizzle row.
   // MN-major: 64-wide chunks kBK*128 B apart (LBO), 8-K groups 1024 B apart (SBO), +2048 B per UMMA_K.
   p.a_lbo = p.a_mn ? kBK * 128 : 16;
@@ -583,6 +610,12 @@ static int launch_gemm(const VlGemmArgs& a, cudaStream_t stream) {
   if (debug_get(5)) p.b_sbo = debug_get(5);
   if (debug_get(6)) p.b_kstep = debug_get(6);
 
+  {
+    const int mode = debug_get(8);
+    const bool pair_ok = a.M >= 4 * kBM && BN == 256;
+    const bool pair_default = p.a_mn && p.b_mn;
+    if (mode == 2 || (mode == 0 && pair_default && pair_ok)) return launch_gemm2<BN>(a, p, stream);
+  }
   CUtensorMap tmA, tmB;
   int rc;
   if (!p.a_mn)
@@ -606,6 +639,240 @@ static int launch_gemm(const VlGemmArgs& a, cudaStream_t stream) {
   if (debug_get(7) > 0 && debug_get(7) < grid) grid = debug_get(7);
   gemm_bf16_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
   return launch_check("gemm_bf16_kernel");
+}
+
+
+// =============================================================================================== CTA-pair variant
+// Same roles, but two CTAs of a cluster (one per SM of a TPC) share a 256 x BN tile: each loads its own 128 rows of A
+// and only HALF of B (BN/2 rows); the leader issues tcgen05.mma.cta_group::2 (M = 256) which reads both halves and
+// writes 128 accumulator rows into each CTA's TMEM.  Per-SM operand traffic (smem fill + MMA reads) drops by 1/3, which
+// is what lets the tensor pipe run closer to its peak.  mbarrier protocol:
+//   full[s]   (leader's, 1 arrival + tx bytes of both CTAs)   <- leader's producer arms it, both CTAs' TMA complete it
+//   empty[s]  (one per CTA)                                   <- leader's tcgen05.commit, multicast to both CTAs
+//   tfull[a]  (one per CTA)                                   <- leader's tcgen05.commit, multicast
+//   tempty[a] (leader's, 2 x 8 arrivals)                      <- epilogue warps of both CTAs
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int kStages = (BN == 256) ? 6 : 8;
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = (BN / 2) * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingBytes = kEpiWarps * 4096;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 256;
+  static constexpr int kTmemCols = 2 * BN;
+};
+
+__device__ __forceinline__ void mbar_wait_guarded(uint32_t bar, uint32_t parity) {
+  // bring-up guard: a protocol bug must fail the launch instead of hanging the GPU
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0 && clock64() - t0 > 8000000000ll) __trap();
+  }
+}
+
+__device__ __forceinline__ void tile_coords2(const GemmParams& p, int tiles_m2, int t, int& m_blk, int& n_blk, int& ks) {
+  int mn = t / p.split_k;
+  ks = t - mn * p.split_k;
+  constexpr int kGroup = kGroupM / 2;
+  int group_sz = kGroup * p.tiles_n;
+  int g = mn / group_sz;
+  int r = mn - g * group_sz;
+  int m_first = g * kGroup;
+  int gm = min(kGroup, tiles_m2 - m_first);
+  n_blk = r / gm;
+  m_blk = m_first + (r - n_blk * gm);
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = Gemm2Cfg<BN>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();  // both CTAs must use identical offsets (the MMA addresses the peer by offset)
+  const uint32_t stg_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t bar_base = stg_base + Cfg::kStagingBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int tiles_m2 = (p.M + 2 * kBM - 1) / (2 * kBM);
+  const int total_tiles = tiles_m2 * p.tiles_n * p.split_k;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar(s), 1);  // the leader's arrive.expect_tx; the peer only contributes transaction bytes
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 2 * kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+        int m_blk, n_blk, ks;
+        tile_coords2(p, tiles_m2, t, m_blk, n_blk, ks);
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int row_a = m_blk * 2 * kBM + rank * kBM;
+        const int row_b = n_blk * BN + rank * (BN / 2);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait_guarded(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+          const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
+          // No arrival from the peer: a cluster-scope release per stage would serialise its producer.  The peer can
+          // only refill stage s after the leader's MMA consumed it (empty[s] is signalled by the leader's commit), so
+          // its bytes always land in the phase the leader is arming.
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+          if (!p.a_mn) {
+            tma_load_2d_pair(sa, &tmA, lead_full, kb * kBK, row_a);
+          } else {
+#pragma unroll
+            for (int c = 0; c < kBM / 64; ++c) tma_load_2d_pair(sa + c * (kBK * 128), &tmA, lead_full, row_a + c * 64, kb * kBK);
+          }
+          if (!p.b_mn) {
+            tma_load_2d_pair(sb, &tmB, lead_full, kb * kBK, row_b);
+          } else {
+#pragma unroll
+            for (int c = 0; c < (BN / 2) / 64; ++c) tma_load_2d_pair(sb + c * (kBK * 128), &tmB, lead_full, row_b + c * 64, kb * kBK);
+          }
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(2 * kBM, BN, p.a_mn, p.b_mn);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+        int m_blk, n_blk, ks;
+        tile_coords2(p, tiles_m2, t, m_blk, n_blk, ks);
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait_guarded(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait_guarded(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t ad = umma_desc_sw128(sa + k * p.a_kstep, p.a_lbo, p.a_sbo);
+            const uint64_t bd = umma_desc_sw128(sb + k * p.b_kstep, p.b_lbo, p.b_sbo);
+            umma_ss_pair(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_pair_mc(empty_bar(stage), 3);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_pair_mc(tfull_bar(acc), 3);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (both CTAs, own 128 rows)
+    const int e = warp - 2;
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+      int m_blk, n_blk, ks;
+      tile_coords2(p, tiles_m2, t, m_blk, n_blk, ks);
+      mbar_wait_guarded(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      epilogue_tile<BN>(p, tmem_base, acc * BN, m_blk * 2 * kBM + static_cast<int>(rank) * kBM, n_blk, ks, e, quarter, lane,
+                        smem_raw + (stg_base - smem_base) + e * 4096);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer may still be signalling barriers / reading operands in this CTA's smem
+  if (warp == 1) {
+    tc_fence_after();
+    __syncwarp();
+    tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN>
+static int launch_gemm2(const VlGemmArgs& a, GemmParams p, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN>;
+  // MN-major chunk strides are the same; only B's per-CTA row count halves
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!p.a_mn)
+    rc = make_tmap_bf16_2d(&tmA, a.a, a.K, a.M, a.lda, kBK, kBM);
+  else
+    rc = make_tmap_bf16_2d(&tmA, a.a, a.M, a.K, a.lda, 64, kBK);
+  if (rc) return rc;
+  if (!p.b_mn)
+    rc = make_tmap_bf16_2d(&tmB, a.b, a.K, a.N, a.ldb, kBK, BN / 2);
+  else
+    rc = make_tmap_bf16_2d(&tmB, a.b, a.N, a.K, a.ldb, 64, kBK);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VL_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles_m2 = (a.M + 2 * kBM - 1) / (2 * kBM);
+  const int total = tiles_m2 * p.tiles_n * p.split_k;
+  int clusters = num_sms() / 2;
+  if (total < clusters) clusters = total;
+  if (debug_get(7) > 0 && debug_get(7) < clusters) clusters = debug_get(7);
+  gemm2_bf16_kernel<BN><<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  return launch_check("gemm2_bf16_kernel");
 }
 
 }  // namespace vl
@@ -632,6 +899,8 @@ extern "C" int vl_gemm_bf16(const VlGemmArgs* a, void* stream) {
     set_error("vl_gemm_bf16: epilogue %d not supported", a->epilogue);
     return VL_ENOTSUP;
   }
+  VL_CHECK_ARG(!((a->relu || a->aux_row_div > 1) && (a->d_f32 || (a->epilogue != VL_EPI_LINEAR && a->epilogue != VL_EPI_RESIDUAL))),
+               "vl_gemm_bf16: relu / aux_row_div need a bf16 LINEAR or RESIDUAL epilogue");
   if (a->epilogue == VL_EPI_ROWLSE)
     VL_CHECK_ARG(a->out_vec0 && a->out_vec1 && a->out_vec2 && a->split_k <= 1, "vl_gemm_bf16: ROWLSE needs out_vec0/1/2 and split_k == 1");
   if (a->epilogue == VL_EPI_CLIPGRAD)

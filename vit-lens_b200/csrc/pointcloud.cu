@@ -1,0 +1,264 @@
+// Point-cloud tokenizer kernels (reference modal_3d/models/pointbert: misc.py:48-68 fps, dvae.py:107-176 knn + grouping,
+// dvae.py:196-212 mini-PointNet).  Index work (FPS order, kNN sets) is exact integer/compare logic on fp32 distances
+// computed without FMA contraction, in the reference's operation order, so the selected indices match the CPU oracle.
+#include "vl_host.h"
+#include "vl_sm100.cuh"
+
+namespace vl {
+
+// ------------------------------------------------------------------------------------ farthest point sampling
+// One CTA per sample, 1024 threads, points in registers (<= 16 per thread).  Each of the `npoint` iterations: update the
+// running min-distance to the chosen set, block-wide arg-max (first index wins ties), broadcast the winner.
+constexpr int kFpsThreads = 1024;
+constexpr int kFpsMaxPer = 8;  // N <= 8192 (vitlensL point clouds)
+
+__device__ __forceinline__ void argmax_combine(float& v, int& i, float v2, int i2) {
+  if (v2 > v || (v2 == v && i2 < i)) {
+    v = v2;
+    i = i2;
+  }
+}
+
+__global__ void __launch_bounds__(kFpsThreads) fps_kernel(const float* __restrict__ xyz, const long long* __restrict__ start, int N, int npoint,
+                                                          long long* __restrict__ idx_out, float* __restrict__ centers) {
+  __shared__ float s_val[32];
+  __shared__ int s_idx[32];
+  __shared__ float s_c[3];
+  __shared__ int s_far;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* p = xyz + static_cast<long long>(b) * N * 3;
+  float px[kFpsMaxPer], py[kFpsMaxPer], pz[kFpsMaxPer], dist[kFpsMaxPer];
+#pragma unroll
+  for (int k = 0; k < kFpsMaxPer; ++k) {
+    const int i = tid + k * kFpsThreads;
+    if (i < N) {
+      px[k] = p[3 * i];
+      py[k] = p[3 * i + 1];
+      pz[k] = p[3 * i + 2];
+    } else {
+      px[k] = py[k] = pz[k] = 0.f;
+    }
+    dist[k] = 1e10f;
+  }
+  int far = static_cast<int>(start[b]);
+  for (int it = 0; it < npoint; ++it) {
+    if (tid == 0) {
+      idx_out[static_cast<long long>(b) * npoint + it] = far;
+      s_c[0] = p[3 * far];
+      s_c[1] = p[3 * far + 1];
+      s_c[2] = p[3 * far + 2];
+      centers[(static_cast<long long>(b) * npoint + it) * 3] = s_c[0];
+      centers[(static_cast<long long>(b) * npoint + it) * 3 + 1] = s_c[1];
+      centers[(static_cast<long long>(b) * npoint + it) * 3 + 2] = s_c[2];
+    }
+    __syncthreads();
+    const float cx = s_c[0], cy = s_c[1], cz = s_c[2];
+    float bv = -1.f;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < kFpsMaxPer; ++k) {
+      const int i = tid + k * kFpsThreads;
+      if (i < N) {
+        const float dx = __fsub_rn(px[k], cx), dy = __fsub_rn(py[k], cy), dz = __fsub_rn(pz[k], cz);
+        const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        dist[k] = fminf(dist[k], d);
+        argmax_combine(bv, bi, dist[k], i);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float v2 = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+      argmax_combine(bv, bi, v2, i2);
+    }
+    if (lane == 0) {
+      s_val[warp] = bv;
+      s_idx[warp] = bi;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      bv = s_val[lane];
+      bi = s_idx[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float v2 = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+        argmax_combine(bv, bi, v2, i2);
+      }
+      if (lane == 0) s_far = bi;
+    }
+    __syncthreads();
+    far = s_far;
+  }
+}
+
+// ------------------------------------------------------------------------------------ kNN grouping
+// One warp per centre: keeps the `k` (<= 32) smallest squared distances, one per lane; scans the points 32 at a time
+// and replaces the current worst entry whenever a closer point shows up.  Writes neighbours minus the centre
+// (dvae.py:162-176) as [B*G*k, 3] fp32 and, padded with zeros to 8 columns, as bf16 rows for the first GEMM.
+__global__ void __launch_bounds__(256) knn_group_kernel(const float* __restrict__ xyz, const float* __restrict__ centers, int N, int G, int k,
+                                                        long long total_centers, float* __restrict__ nb_out, long long* __restrict__ idx_out) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (w >= total_centers) return;
+  const long long b = w / G;
+  const float* p = xyz + b * N * 3;
+  const float cx = centers[w * 3], cy = centers[w * 3 + 1], cz = centers[w * 3 + 2];
+  const float c2 = __fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz));
+  float best = (lane < k) ? INFINITY : -INFINITY;  // lanes >= k never hold candidates
+  int best_i = -1;
+  float worst = INFINITY;
+  int worst_lane = 0;
+  for (int base = 0; base < N; base += 32) {
+    const int i = base + lane;
+    float d = INFINITY;
+    if (i < N) {
+      const float x = p[3 * i], y = p[3 * i + 1], z = p[3 * i + 2];
+      // square_distance (dvae.py:121-140): -2 * <c, x> + |c|^2 + |x|^2
+      const float dot = __fadd_rn(__fadd_rn(__fmul_rn(cx, x), __fmul_rn(cy, y)), __fmul_rn(cz, z));
+      const float x2 = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+      d = __fadd_rn(__fadd_rn(__fmul_rn(-2.f, dot), c2), x2);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, d < worst);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const float dv = __shfl_sync(0xffffffffu, d, src);
+      if (dv < worst) {  // worst may have tightened since the ballot
+        if (lane == worst_lane) {
+          best = dv;
+          best_i = base + src;
+        }
+        // recompute the worst entry among the k candidate lanes
+        float wv = (lane < k) ? best : -INFINITY;
+        int wl = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float v2 = __shfl_xor_sync(0xffffffffu, wv, o);
+          const int l2 = __shfl_xor_sync(0xffffffffu, wl, o);
+          if (v2 > wv || (v2 == wv && l2 < wl)) {
+            wv = v2;
+            wl = l2;
+          }
+        }
+        worst = wv;
+        worst_lane = wl;
+      }
+    }
+  }
+  if (lane < k) {
+    const long long o = (w * k + lane);
+    nb_out[o * 3] = p[3 * best_i] - cx;
+    nb_out[o * 3 + 1] = p[3 * best_i + 1] - cy;
+    nb_out[o * 3 + 2] = p[3 * best_i + 2] - cz;
+    if (idx_out) idx_out[o] = best_i;
+  }
+}
+
+// ------------------------------------------------------------------------------------ tiny-K linear: out = act(x[R,3] @ W[C,3]^T * scale + shift)
+// first_conv.0 (+ folded BatchNorm + ReLU, dvae.py:200-203) and pos_embed.0 (+ GELU, point_encoder.py:325-327).
+// act: 0 none, 1 relu, 2 gelu(erf).  scale/shift are per-output-channel fp32 (bias and BN already folded in).
+__global__ void __launch_bounds__(256) linear3_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
+                                                      const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, long long R, int C, int act) {
+  const int cvec = C >> 3;
+  const long long total = R * cvec;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(idx % cvec);
+    const long long r = idx / cvec;
+    const float x0 = x[3 * r], x1 = x[3 * r + 1], x2 = x[3 * r + 2];
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = cv * 8 + e;
+      float v = x0 * __ldg(w + 3 * c) + x1 * __ldg(w + 3 * c + 1) + x2 * __ldg(w + 3 * c + 2);
+      v = v * __ldg(scale + c) + __ldg(shift + c);
+      if (act == 1) v = fmaxf(v, 0.f);
+      if (act == 2) v = gelu_erf_fwd(v);
+      f[e] = v;
+    }
+    uint4 u;
+    u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]); u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+    *reinterpret_cast<uint4*>(out + r * C + cv * 8) = u;
+  }
+}
+
+// ------------------------------------------------------------------------------------ max over groups of G consecutive rows
+// out[g, c] = max_{r in group g} x[g*G + r, c]  (torch.max(feature, dim=2), dvae.py:205,210); optional arg-max rows.
+__global__ void __launch_bounds__(256) group_max_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int* __restrict__ arg,
+                                                        long long groups, int G, int C) {
+  const int cvec = C >> 3;
+  const long long total = groups * cvec;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(idx % cvec);
+    const long long g = idx / cvec;
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      best[e] = -INFINITY;
+      bi[e] = 0;
+    }
+    for (int r = 0; r < G; ++r) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + (g * G + r) * C + cv * 8);
+      const float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y), bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (f[e] > best[e]) {
+          best[e] = f[e];
+          bi[e] = r;
+        }
+    }
+    uint4 o;
+    o.x = pack_bf16(best[0], best[1]); o.y = pack_bf16(best[2], best[3]); o.z = pack_bf16(best[4], best[5]); o.w = pack_bf16(best[6], best[7]);
+    *reinterpret_cast<uint4*>(out + g * C + cv * 8) = o;
+    if (arg) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) arg[g * C + cv * 8 + e] = bi[e];
+    }
+  }
+}
+
+}  // namespace vl
+
+using namespace vl;
+
+extern "C" {
+
+int vl_fps(const float* xyz, const int64_t* start, int32_t B, int32_t N, int32_t npoint, int64_t* idx_out, float* centers, void* stream) {
+  VL_CHECK_ARG(xyz && start && idx_out && centers && B > 0 && N > 0 && npoint > 0, "vl_fps: bad arguments");
+  if (N > kFpsThreads * kFpsMaxPer) {
+    set_error("vl_fps: N=%d > %d not supported", N, kFpsThreads * kFpsMaxPer);
+    return VL_ENOTSUP;
+  }
+  fps_kernel<<<B, kFpsThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(xyz, (const long long*)start, N, npoint, (long long*)idx_out, centers);
+  return launch_check("fps");
+}
+
+int vl_knn_group(const float* xyz, const float* centers, int32_t B, int32_t N, int32_t G, int32_t k, float* nb_out, int64_t* idx_out,
+                 void* stream) {
+  VL_CHECK_ARG(xyz && centers && nb_out && B > 0 && N > 0 && G > 0 && k > 0 && k <= 32 && k <= N, "vl_knn_group: bad arguments (k must be <= 32)");
+  const long long total = static_cast<long long>(B) * G;
+  const long long blocks = (total * 32 + 255) / 256;
+  knn_group_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(xyz, centers, N, G, k, total, nb_out, (long long*)idx_out);
+  return launch_check("knn_group");
+}
+
+int vl_linear3(const float* x, const float* w, const float* scale, const float* shift, void* out, int64_t R, int32_t C, int32_t act, void* stream) {
+  VL_CHECK_ARG(x && w && scale && shift && out && R > 0 && C > 0 && C % 8 == 0 && act >= 0 && act <= 2, "vl_linear3: bad arguments");
+  long long g = (R * (C / 8) + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (g > cap) g = cap;
+  linear3_kernel<<<(unsigned)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, w, scale, shift, reinterpret_cast<__nv_bfloat16*>(out), R, C, act);
+  return launch_check("linear3");
+}
+
+int vl_group_max(const void* x, void* out, int32_t* arg, int64_t groups, int32_t G, int32_t C, void* stream) {
+  VL_CHECK_ARG(x && out && groups > 0 && G > 0 && C > 0 && C % 8 == 0, "vl_group_max: bad arguments");
+  long long g = (groups * (C / 8) + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (g > cap) g = cap;
+  group_max_kernel<<<(unsigned)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                                                     reinterpret_cast<__nv_bfloat16*>(out), arg, groups, G, C);
+  return launch_check("group_max");
+}
+}

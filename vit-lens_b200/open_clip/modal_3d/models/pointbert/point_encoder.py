@@ -1,11 +1,17 @@
 """Point-cloud tokenizer (reference modal_3d/models/pointbert/point_encoder.py:299-362, dvae.py:107-212,
 misc.py:48-68): FPS -> kNN grouping -> mini-PointNet -> Linear, pos = MLP(centres).
 
-Parameter tree and state_dict keys match the reference.  The FPS / kNN / grouped-PointNet kernels
-are the next row of the coverage table (BASELINE config 5); until they land the
-forward raises instead of silently running a non-native path."""
+Parameter tree and state_dict keys match the reference.  The forward runs vl_fps / vl_knn_group / vl_linear3 /
+vl_group_max and the tcgen05 GEMM (BatchNorm folded into the neighbouring 1x1 convs).  BatchNorm uses its running
+statistics (eval semantics, what ViTLens.encode needs); batch-statistics BatchNorm and the tokenizer backward are the
+next step of this coverage row."""
 import torch
 import torch.nn as nn
+
+from vitlens_b200 import engine as E
+
+from ....transformer import TokenMat
+from ....util.Sample import Sample
 
 
 class Encoder(nn.Module):
@@ -37,6 +43,14 @@ class PointTokenizer(nn.Module):
         self.pos_embed = nn.Sequential(nn.Linear(3, 128), nn.GELU(), nn.Linear(128, self.trans_dim))
 
     def forward(self, pts, fps_start=None):
-        raise NotImplementedError(
-            "PointTokenizer.forward: FPS / kNN / grouped-PointNet sm_100a kernels are not built yet "
-            "(next coverage row, DESIGN.md); there is deliberately no PyTorch fallback.")
+        """pts [B, N, 3] fp32.  `fps_start` [B] int64: first FPS index per sample (the reference draws it with
+        torch.randint, misc.py:60); drawn the same way when omitted."""
+        if any(p.requires_grad for p in self.parameters()) and torch.is_grad_enabled():
+            raise NotImplementedError("PointTokenizer backward (training BASELINE config 5) is not built yet; run it frozen / under no_grad")
+        if self.group_size > 32:
+            raise NotImplementedError("group_size > 32")
+        B, N, _ = pts.shape
+        if fps_start is None:
+            fps_start = torch.randint(0, N, (B,), dtype=torch.long, device=pts.device)
+        tok, pos = E.point_tokenizer_forward(self, pts.float(), fps_start.to(pts.device))
+        return Sample({"x": TokenMat(tok, B, self.num_group), "pos": TokenMat(pos, B, self.num_group)})

@@ -124,8 +124,6 @@ class VitBlockFn(torch.autograd.Function):
         # ---- MLP
         if _need(ctx, 11):
             g[11] = _wgrad(dy, h)
-        if _need(ctx, 12):
-            g[12] = _ops.colsum(dy)
         du = _dgrad(dy, w16(pjw), epilogue=_ops.EPI_GELU_BWD, aux_in=u, act_quick=quick)
         if _need(ctx, 9):
             g[9] = _wgrad(du, xn2)
@@ -133,13 +131,13 @@ class VitBlockFn(torch.autograd.Function):
             g[10] = _ops.colsum(du)
         dxn2 = _dgrad(du, w16(fcw))
         want_ln2 = _need(ctx, 7) or _need(ctx, 8)
-        dx1, g7, g8 = _ops.layernorm_bwd(dxn2, x1, ln2w, m2, r2, dres=dy, want_wgrad=want_ln2)
+        # the column sums of the residual-branch gradient (= c_proj bias gradient) ride along in the LN backward pass
+        dx1, g7, g8, g12 = _ops.layernorm_bwd(dxn2, x1, ln2w, m2, r2, dres=dy, want_wgrad=want_ln2, want_dres_sum=True)
         g[7], g[8] = (g7, g8) if want_ln2 else (None, None)
+        g[12] = g12 if _need(ctx, 12) else None
         # ---- attention
         if _need(ctx, 5):
             g[5] = _wgrad(dx1, o)
-        if _need(ctx, 6):
-            g[6] = _ops.colsum(dx1)
         do = _dgrad(dx1, w16(outw))
         dqkv = torch.empty_like(qkv)
         _ops.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], o, do, lse, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
@@ -151,9 +149,12 @@ class VitBlockFn(torch.autograd.Function):
         if _need(ctx, 0) or _need(ctx, 1) or _need(ctx, 2):
             dxn1 = _dgrad(dqkv, w16(inw))
             want_ln1 = _need(ctx, 1) or _need(ctx, 2)
-            dx, g1, g2 = _ops.layernorm_bwd(dxn1, x, ln1w, m1, r1, dres=dx1, want_wgrad=want_ln1)
+            dx, g1, g2, g6 = _ops.layernorm_bwd(dxn1, x, ln1w, m1, r1, dres=dx1, want_wgrad=want_ln1, want_dres_sum=True)
             g[0] = dx
             g[1], g[2] = (g1, g2) if want_ln1 else (None, None)
+            g[6] = g6 if _need(ctx, 6) else None
+        elif _need(ctx, 6):
+            g[6] = _ops.colsum(dx1)
         return tuple(g)
 
 
@@ -449,7 +450,7 @@ class ContrastiveFn(torch.autograd.Function):
         x16, y16 = _ops.cast_bf16(x.detach()), _ops.cast_bf16(y.detach())
         ax16 = x16 if all_x is None else _ops.cast_bf16(all_x.detach())
         ay16 = y16 if all_y is None else _ops.cast_bf16(all_y.detach())
-        s = float(scale.detach())
+        s = scale.detach().float().reshape(1).contiguous()  # stays on the device: no host sync in the step
         lse_x, sum_x = _ops.rowlse(x16, ay16, alpha=s, label_off=label_off)
         lse_y, sum_y = _ops.rowlse(y16, ax16, alpha=s, label_off=label_off)
         loss = (sum_x + sum_y) / (2.0 * val_rows)
@@ -458,19 +459,20 @@ class ContrastiveFn(torch.autograd.Function):
         if col_term:
             col_x = gather_lse(lse_y) if gather_lse is not None else lse_y  # columns of the x-direction = rows of the y-direction
             col_y = gather_lse(lse_x) if gather_lse is not None else lse_x
-        ctx.save_for_backward(x16, y16, ax16, ay16, lse_x, lse_y, col_x, col_y)
-        ctx.cfg = (s, label_off, grad_rows, col_term, ds_post)
+        ctx.save_for_backward(x16, y16, ax16, ay16, lse_x, lse_y, col_x, col_y, s)
+        ctx.cfg = (label_off, grad_rows, col_term, ds_post)
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, dloss):
-        x16, y16, ax16, ay16, lse_x, lse_y, col_x, col_y = ctx.saved_tensors
-        s, label_off, grad_rows, col_term, ds_post = ctx.cfg
-        gs = float(dloss) / (2.0 * grad_rows)
-        gx, ds_x = _ops.clipgrad(x16, ay16, alpha=s, row_lse=lse_x, col_lse=col_x if col_term else None, label_off=label_off, gscale=gs)
-        gy, ds_y = _ops.clipgrad(y16, ax16, alpha=s, row_lse=lse_y, col_lse=col_y if col_term else None, label_off=label_off, gscale=gs)
-        dx = _ops.gemm(gx, ay16, b_t=True, out_dtype=F32, alpha=s) if _need(ctx, 0) else None
-        dy = _ops.gemm(gy, ax16, b_t=True, out_dtype=F32, alpha=s) if _need(ctx, 1) else None
+        x16, y16, ax16, ay16, lse_x, lse_y, col_x, col_y, s = ctx.saved_tensors
+        label_off, grad_rows, col_term, ds_post = ctx.cfg
+        gs = 1.0 / (2.0 * grad_rows)
+        dl = dloss.detach().float().reshape(1).contiguous()  # upstream gradient stays on the device too
+        gx, ds_x = _ops.clipgrad(x16, ay16, alpha=s, row_lse=lse_x, col_lse=col_x if col_term else None, label_off=label_off, gscale=gs, gscale_dev=dl)
+        gy, ds_y = _ops.clipgrad(y16, ax16, alpha=s, row_lse=lse_y, col_lse=col_y if col_term else None, label_off=label_off, gscale=gs, gscale_dev=dl)
+        dx = _ops.gemm(gx, ay16, b_t=True, out_dtype=F32, alpha_dev=s) if _need(ctx, 0) else None
+        dy = _ops.gemm(gy, ax16, b_t=True, out_dtype=F32, alpha_dev=s) if _need(ctx, 1) else None
         dscale = None
         if _need(ctx, 4):
             # with the column term every logit's gradient appears in both directions
@@ -491,3 +493,39 @@ class AddFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d):
         return d, d
+
+
+# ----------------------------------------------------------------------------- point-cloud tokenizer (forward)
+def _bn_fold(conv, bn):
+    """Conv1d(k=1) followed by eval-mode BatchNorm1d -> (W [out,in] fp32, per-channel scale, shift) with
+    y = (W x) * scale + shift."""
+    w = conv.weight.detach().squeeze(-1)
+    inv = torch.rsqrt(bn.running_var.detach() + bn.eps) * bn.weight.detach()
+    shift = (conv.bias.detach() - bn.running_mean.detach()) * inv + bn.bias.detach()
+    return w, inv, shift
+
+
+def point_tokenizer_forward(tk, pts, fps_start):
+    """PointTokenizer.forward (point_encoder.py:350-362) -> (tokens [B*G, trans_dim] bf16, pos [B*G, trans_dim] bf16)."""
+    G, k = tk.num_group, tk.group_size
+    with torch.no_grad():
+        _, centers = _ops.fps(pts, fps_start, G)
+        nb = _ops.knn_group(pts, centers, G, k)
+        enc = tk.encoder
+        w0, s0, t0 = _bn_fold(enc.first_conv[0], enc.first_conv[1])
+        f1 = _ops.linear3(nb, w0, s0, t0, 1)                                            # [R,128]  conv + BN + ReLU
+        f2 = _ops.gemm(f1, w16(enc.first_conv[3].weight), bias=enc.first_conv[3].bias)  # [R,256]
+        g1 = _ops.group_max(f2, k)                                                      # [BG,256]
+        w1, s1, t1 = _bn_fold(enc.second_conv[0], enc.second_conv[1])
+        w1 = w1 * s1[:, None]                                                           # BN scale folded into the conv rows
+        half = w1.shape[1] // 2
+        wg, wl = _ops.cast_bf16(w1[:, :half].contiguous()), _ops.cast_bf16(w1[:, half:].contiguous())
+        gp = _ops.gemm(g1, wg, bias=t1)                                                 # global-feature half + shift, per group
+        f3 = _ops.gemm_grouped_residual_relu(f2, wl, gp, k)                             # [R,512]
+        f4 = _ops.gemm(f3, w16(enc.second_conv[3].weight), bias=enc.second_conv[3].bias)
+        tokf = _ops.group_max(f4, k)                                                    # [BG,enc]
+        tok = _ops.gemm(tokf, w16(tk.reduce_dim.weight), bias=tk.reduce_dim.bias)
+        ones = torch.ones_like(tk.pos_embed[0].bias)
+        p1 = _ops.linear3(centers, tk.pos_embed[0].weight.detach(), ones, tk.pos_embed[0].bias.detach(), 2)
+        pos = _ops.gemm(p1, w16(tk.pos_embed[2].weight), bias=tk.pos_embed[2].bias)
+    return tok, pos

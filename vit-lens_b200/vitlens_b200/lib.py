@@ -47,6 +47,7 @@ class GemmArgs(C.Structure):
         ("bias", C.c_void_p), ("aux_in", C.c_void_p), ("aux_out", C.c_void_p), ("ldaux", C.c_int64),
         ("row_vec", C.c_void_p), ("col_vec", C.c_void_p), ("out_vec0", C.c_void_p), ("out_vec1", C.c_void_p),
         ("out_vec2", C.c_void_p), ("scalar_out", C.c_void_p), ("iparam", C.c_int32), ("fparam", C.c_float),
+        ("alpha_dev", C.c_void_p), ("fparam_dev", C.c_void_p), ("aux_row_div", C.c_int32), ("relu", C.c_int32),
     ]
 
 
@@ -104,7 +105,8 @@ def _count():
 
 def gemm(a, b, d, *, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, epilogue=EPI_LINEAR, bias=None,
          aux_in=None, aux_out=None, ldaux=0, alpha=1.0, accumulate=False, split_k=1, act_quick=False,
-         row_vec=None, col_vec=None, out_vec0=None, out_vec1=None, out_vec2=None, scalar_out=None, iparam=0, fparam=0.0):
+         row_vec=None, col_vec=None, out_vec0=None, out_vec1=None, out_vec2=None, scalar_out=None, iparam=0, fparam=0.0,
+         alpha_dev=None, fparam_dev=None, aux_row_div=0, relu=False):
     """Raw GEMM call; see include/vitlens_b200.h.  a, b bf16; d bf16 or fp32; bias fp32."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     assert d is None or d.dtype in (torch.bfloat16, torch.float32)
@@ -113,7 +115,8 @@ def gemm(a, b, d, *, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, epilogue=EP
         _ptr(a), _ptr(b), _ptr(d), M, N, K, lda, ldb, ldd, int(a_mn), int(b_mn),
         int(d is not None and d.dtype == torch.float32), int(accumulate), int(split_k), int(epilogue), int(act_quick), float(alpha),
         _ptr(bias), _ptr(aux_in), _ptr(aux_out), ldaux,
-        _ptr(row_vec), _ptr(col_vec), _ptr(out_vec0), _ptr(out_vec1), _ptr(out_vec2), _ptr(scalar_out), int(iparam), float(fparam))
+        _ptr(row_vec), _ptr(col_vec), _ptr(out_vec0), _ptr(out_vec1), _ptr(out_vec2), _ptr(scalar_out), int(iparam), float(fparam),
+        _ptr(alpha_dev), _ptr(fparam_dev), int(aux_row_div), int(relu))
     _count()
     _timed(GEMM_TIMING, (2.0 * M * N * K,),
            lambda: _check(_fn("vl_gemm_bf16")(C.cast(C.pointer(args), C.c_void_p), _stream()), "vl_gemm_bf16"))
@@ -126,7 +129,7 @@ _PROTOS = {
     "vl_attention_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _L, _F, _I, _P],
     "vl_attention_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _L, _L, _F, _I, _P],
     "vl_layernorm_fwd": [_P, _L, _P, _P, _P, _P, _L, _P, _P, _I, _I, _F, _P],
-    "vl_layernorm_bwd": [_P, _L, _P, _L, _P, _P, _P, _P, _P, _L, _P, _L, _P, _P, _I, _I, _P],
+    "vl_layernorm_bwd": [_P, _L, _P, _L, _P, _P, _P, _P, _P, _L, _P, _L, _P, _P, _P, _I, _I, _P],
     "vl_colsum_bf16": [_P, _L, _P, _I, _I, _P],
     "vl_patchify": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _L, _L, _I, _P],
     "vl_assemble_tokens": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
@@ -141,6 +144,10 @@ _PROTOS = {
     "vl_add_bf16": [_P, _P, _P, _L, _P],
     "vl_adamw_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
     "vl_lse_combine": [_P, _P, _P, _I, _I, _P, _P, _P],
+    "vl_fps": [_P, _P, _I, _I, _I, _P, _P, _P],
+    "vl_knn_group": [_P, _P, _I, _I, _I, _I, _P, _P, _P],
+    "vl_linear3": [_P, _P, _P, _P, _P, _L, _I, _I, _P],
+    "vl_group_max": [_P, _P, _P, _L, _I, _I, _P],
 }
 
 
@@ -185,9 +192,9 @@ def layernorm_fwd(x, w, b, y, mean, rstd, *, T, D, ldx, ldy, row_index=None, eps
     _call("vl_layernorm_fwd", _p(x), ldx, _p(row_index), _p(w), _p(b), _p(y), ldy, _p(mean), _p(rstd), T, D, float(eps))
 
 
-def layernorm_bwd(dy, x, w, mean, rstd, dx, dw, db, *, T, D, lddy, ldx, lddx, dres=None, lddres=0, row_index=None):
+def layernorm_bwd(dy, x, w, mean, rstd, dx, dw, db, *, T, D, lddy, ldx, lddx, dres=None, lddres=0, row_index=None, dres_sum=None):
     _call("vl_layernorm_bwd", _p(dy), lddy, _p(x), ldx, _p(row_index), _p(w), _p(mean), _p(rstd), _p(dres), lddres,
-          _p(dx), lddx, _p(dw), _p(db), T, D)
+          _p(dx), lddx, _p(dw), _p(db), _p(dres_sum), T, D)
 
 
 def colsum(dy, db, *, T, N, ld):
@@ -251,3 +258,19 @@ def rowlse_parts(N: int) -> int:
 
 def lse_combine(part_max, part_sum, diag, lse, loss_sum, *, M, nparts):
     _call("vl_lse_combine", _p(part_max), _p(part_sum), _p(diag), M, nparts, _p(lse), _p(loss_sum))
+
+
+def fps(xyz, start, idx_out, centers, *, B, N, npoint):
+    _call("vl_fps", _p(xyz), _p(start), B, N, npoint, _p(idx_out), _p(centers))
+
+
+def knn_group(xyz, centers, nb_out, idx_out, *, B, N, G, k):
+    _call("vl_knn_group", _p(xyz), _p(centers), B, N, G, k, _p(nb_out), _p(idx_out))
+
+
+def linear3(x, w, scale, shift, out, *, R, C, act):
+    _call("vl_linear3", _p(x), _p(w), _p(scale), _p(shift), _p(out), R, C, act)
+
+
+def group_max(x, out, arg, *, groups, G, C):
+    _call("vl_group_max", _p(x), _p(out), _p(arg), groups, G, C)

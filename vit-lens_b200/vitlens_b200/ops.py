@@ -40,7 +40,7 @@ def pick_split_k(M: int, N: int, K: int) -> int:
 
 
 def gemm(a, b, *, a_t=False, b_t=False, bias=None, epilogue=EPI_LINEAR, aux_in=None, want_aux_out=False, out=None,
-         out_dtype=BF16, alpha=1.0, accumulate=False, split_k=None, act_quick=False):
+         out_dtype=BF16, alpha=1.0, accumulate=False, split_k=None, act_quick=False, alpha_dev=None):
     """out[M,N] = epilogue(alpha * A @ B^T); A = a ([M,K]) or a^T when a_t (a is [K,M]); B = b ([N,K]) or b^T when b_t."""
     _v2(a, BF16), _v2(b, BF16)
     M, K = (a.shape[1], a.shape[0]) if a_t else (a.shape[0], a.shape[1])
@@ -58,7 +58,8 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, epilogue=EPI_LINEAR, aux_in=N
     if split_k is None:
         split_k = pick_split_k(M, N, K) if (accumulate and out.dtype == F32 and epilogue == EPI_LINEAR) else 1
     L.gemm(a, b, out, M=M, N=N, K=K, lda=_ld(a), ldb=_ld(b), ldd=_ld(out), a_mn=a_t, b_mn=b_t, epilogue=epilogue, bias=bias,
-           aux_in=aux_in, aux_out=aux_out, ldaux=ldaux, alpha=alpha, accumulate=accumulate, split_k=split_k, act_quick=act_quick)
+           aux_in=aux_in, aux_out=aux_out, ldaux=ldaux, alpha=alpha, accumulate=accumulate, split_k=split_k, act_quick=act_quick,
+           alpha_dev=alpha_dev)
     return (out, aux_out) if want_aux_out else out
 
 
@@ -91,8 +92,9 @@ def layernorm_fwd(x, w, b, *, row_index=None, eps=1e-5, want_stats=True):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, w, mean, rstd, *, dres=None, row_index=None, want_wgrad=True):
-    """Returns (dx, dw, db).  With row_index, dx has x's full row count and is zero outside the gathered rows."""
+def layernorm_bwd(dy, x, w, mean, rstd, *, dres=None, row_index=None, want_wgrad=True, want_dres_sum=False):
+    """Returns (dx, dw, db) or (dx, dw, db, colsum(dres)) with want_dres_sum.  With row_index, dx has x's full row
+    count and is zero outside the gathered rows."""
     _v2(dy, BF16), _v2(x, BF16)
     T, D = dy.shape
     if row_index is None:
@@ -103,9 +105,10 @@ def layernorm_bwd(dy, x, w, mean, rstd, *, dres=None, row_index=None, want_wgrad
     db = torch.zeros((D,), device=x.device, dtype=F32) if want_wgrad else None
     if dres is not None:
         _v2(dres, BF16)
+    rsum = torch.zeros((D,), device=x.device, dtype=F32) if want_dres_sum else None
     L.layernorm_bwd(dy, x, w, mean, rstd, dx, dw, db, T=T, D=D, lddy=_ld(dy), ldx=_ld(x), lddx=D, dres=dres,
-                    lddres=_ld(dres) if dres is not None else 0, row_index=row_index)
-    return dx, dw, db
+                    lddres=_ld(dres) if dres is not None else 0, row_index=row_index, dres_sum=rsum)
+    return (dx, dw, db, rsum) if want_dres_sum else (dx, dw, db)
 
 
 def colsum(dy):
@@ -196,7 +199,7 @@ def add_bf16(a, b):
 
 
 def rowlse(p16, q16, *, alpha, label_off=0):
-    """Row-wise log-sum-exp of alpha * P @ Q^T without materialising the logits.
+    """Row-wise log-sum-exp of alpha * P @ Q^T without materialising the logits (alpha: 1-element fp32 device tensor).
     Returns (lse [M] fp32, sum_i(lse_i - z[i, i + label_off]) as a 1-element fp32 tensor)."""
     _v2(p16, BF16), _v2(q16, BF16)
     M, E = p16.shape
@@ -206,7 +209,7 @@ def rowlse(p16, q16, *, alpha, label_off=0):
     pm = torch.full((M, nparts), float("-inf"), device=dev, dtype=F32)
     ps = torch.zeros((M, nparts), device=dev, dtype=F32)
     diag = torch.zeros((M,), device=dev, dtype=F32)
-    L.gemm(p16, q16, None, M=M, N=N, K=E, lda=_ld(p16), ldb=_ld(q16), ldd=0, epilogue=L.EPI_ROWLSE, alpha=alpha,
+    L.gemm(p16, q16, None, M=M, N=N, K=E, lda=_ld(p16), ldb=_ld(q16), ldd=0, epilogue=L.EPI_ROWLSE, alpha=1.0, alpha_dev=alpha,
            out_vec0=pm, out_vec1=ps, out_vec2=diag, iparam=label_off)
     lse = torch.empty((M,), device=dev, dtype=F32)
     loss_sum = torch.zeros((1,), device=dev, dtype=F32)
@@ -214,7 +217,7 @@ def rowlse(p16, q16, *, alpha, label_off=0):
     return lse, loss_sum
 
 
-def clipgrad(p16, q16, *, alpha, row_lse, col_lse, label_off, gscale):
+def clipgrad(p16, q16, *, alpha, row_lse, col_lse, label_off, gscale, gscale_dev=None):
     """g[M,N] (bf16) = gscale * (exp(z - row_lse_i) + [col_lse] exp(z - col_lse_j) - k * onehot(j == i + label_off)),
     z = alpha * P @ Q^T;  also returns sum(g * P@Q^T) (d loss / d alpha) as a 1-element fp32 tensor."""
     _v2(p16, BF16), _v2(q16, BF16)
@@ -223,6 +226,54 @@ def clipgrad(p16, q16, *, alpha, row_lse, col_lse, label_off, gscale):
     N8 = (N + 7) // 8 * 8
     g = torch.zeros((M, N8), device=p16.device, dtype=BF16)
     ds = torch.zeros((1,), device=p16.device, dtype=F32)
-    L.gemm(p16, q16, g, M=M, N=N, K=E, lda=_ld(p16), ldb=_ld(q16), ldd=N8, epilogue=L.EPI_CLIPGRAD, alpha=alpha,
-           row_vec=row_lse, col_vec=col_lse, iparam=label_off, fparam=gscale, scalar_out=ds)
+    L.gemm(p16, q16, g, M=M, N=N, K=E, lda=_ld(p16), ldb=_ld(q16), ldd=N8, epilogue=L.EPI_CLIPGRAD, alpha=1.0, alpha_dev=alpha,
+           row_vec=row_lse, col_vec=col_lse, iparam=label_off, fparam=gscale, fparam_dev=gscale_dev, scalar_out=ds)
     return g[:, :N], ds
+
+
+# ----------------------------------------------------------------------------- point-cloud tokenizer
+def fps(pts, start, npoint):
+    """pts [B,N,3] fp32, start [B] int64 -> (idx [B,npoint] int64, centers [B*npoint, 3] fp32)"""
+    B, N, _ = pts.shape
+    pts = pts.contiguous()
+    idx = torch.empty((B, npoint), device=pts.device, dtype=torch.int64)
+    centers = torch.empty((B * npoint, 3), device=pts.device, dtype=F32)
+    L.fps(pts, start.contiguous(), idx, centers, B=B, N=N, npoint=npoint)
+    return idx, centers
+
+
+def knn_group(pts, centers, G, k, want_idx=False):
+    """-> neighbourhoods minus centre [B*G*k, 3] fp32 (and the point indices [B*G*k] int64)"""
+    B, N, _ = pts.shape
+    nb = torch.empty((B * G * k, 3), device=pts.device, dtype=F32)
+    idx = torch.empty((B * G * k,), device=pts.device, dtype=torch.int64) if want_idx else None
+    L.knn_group(pts.contiguous(), centers, nb, idx, B=B, N=N, G=G, k=k)
+    return (nb, idx) if want_idx else nb
+
+
+def linear3(x, w, scale, shift, act):
+    """act(x[R,3] @ w[C,3]^T * scale + shift) -> bf16 [R,C]; act: 0 none, 1 relu, 2 gelu"""
+    R, C = x.shape[0], w.shape[0]
+    out = torch.empty((R, C), device=x.device, dtype=BF16)
+    L.linear3(x.contiguous(), w.contiguous(), scale.contiguous(), shift.contiguous(), out, R=R, C=C, act=act)
+    return out
+
+
+def group_max(x, G, want_arg=False):
+    _v2(x, BF16)
+    rows, C = x.shape
+    out = torch.empty((rows // G, C), device=x.device, dtype=BF16)
+    arg = torch.empty((rows // G, C), device=x.device, dtype=torch.int32) if want_arg else None
+    L.group_max(x, out, arg, groups=rows // G, G=G, C=C)
+    return (out, arg) if want_arg else out
+
+
+def gemm_grouped_residual_relu(a, b, gp, group, *, bias=None):
+    """relu(a @ b^T + gp[row // group]) -- second_conv.0 on cat(global, local) with folded BatchNorm (dvae.py:206-208)."""
+    _v2(a, BF16), _v2(b, BF16), _v2(gp, BF16)
+    M, K = a.shape
+    N = b.shape[0]
+    out = torch.empty((M, N), device=a.device, dtype=BF16)
+    L.gemm(a, b, out, M=M, N=N, K=K, lda=_ld(a), ldb=_ld(b), ldd=N, epilogue=L.EPI_RESIDUAL, bias=bias, aux_in=gp, ldaux=_ld(gp),
+           aux_row_div=group, relu=True)
+    return out
