@@ -296,8 +296,16 @@ def run_cuda(args):
             "kernel": "gemm_bf16_kernel (tcgen05, all linear layers fwd/dgrad/wgrad)", "peak_source": f"{pk['src']} bf16_tflops_sustained"}
     if gemm_t:
         torch.cuda.synchronize()
-        tot_ms = sum(a.elapsed_time(b) for a, b, _ in gemm_t)
-        tot_fl = sum(f for _, _, f in gemm_t)
+        tot_ms = sum(a.elapsed_time(b) for a, b, _, _ in gemm_t)
+        tot_fl = sum(f for _, _, f, _ in gemm_t)
+        by_shape = {}
+        for a, b, f, key in gemm_t:
+            d = by_shape.setdefault(key, [0.0, 0.0, 0])
+            d[0] += a.elapsed_time(b)
+            d[1] += f
+            d[2] += 1
+        roof["by_shape"] = [{"MNK_epi_amn_bmn": list(k), "launches": v[2], "ms": round(v[0], 3), "tflops": round(v[1] / v[0] / 1e9, 1)}
+                            for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][0])[:14]]
         roof["achieved"] = tot_fl / tot_ms / 1e9
         roof["frac"] = roof["achieved"] / pk["tf"]
         roof["launches_timed"] = len(gemm_t)

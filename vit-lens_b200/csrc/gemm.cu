@@ -17,8 +17,6 @@ namespace vl {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int kGemmThreads = 320;
-constexpr int kEpiWarps = 8;
 constexpr int kGroupM = 16;  // m-tiles per L2 reuse group
 
 struct GemmParams {
@@ -53,8 +51,8 @@ struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = kEpiWarps * 4096;  // per epilogue warp: 32 rows x 128 B transpose buffer
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = 0;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = 2 * BN;
 };
 
@@ -70,226 +68,88 @@ __device__ __forceinline__ void tile_coords(const GemmParams& p, int t, int& m_b
   m_blk = m_first + (r - n_blk * gm);
 }
 
-// ---- coalesced epilogue I/O: a warp owns 32 rows x 64 bf16 columns (one 128-byte line per row).
-// Thread t computes row t; global traffic is issued with lane l -> (row (l>>3)+4i, 16-byte segment l&7), i.e.
-// four complete 128-byte lines per instruction, going through a swizzled 4 KB smem transpose buffer.
-__device__ __forceinline__ uint32_t stg_off(int row, int seg) { return static_cast<uint32_t>(row * 128 + ((seg ^ (row & 7)) << 4)); }
-
-__device__ __forceinline__ void store_tile_bf16(uint8_t* stg, const float (&f)[64], __nv_bfloat16* g, long long ld, int rows_valid,
-                                                int cols_valid, int lane) {
-#pragma unroll
-  for (int sgm = 0; sgm < 8; ++sgm) {
-    uint4 u;
-    u.x = pack_bf16(f[8 * sgm], f[8 * sgm + 1]);
-    u.y = pack_bf16(f[8 * sgm + 2], f[8 * sgm + 3]);
-    u.z = pack_bf16(f[8 * sgm + 4], f[8 * sgm + 5]);
-    u.w = pack_bf16(f[8 * sgm + 6], f[8 * sgm + 7]);
-    *reinterpret_cast<uint4*>(stg + stg_off(lane, sgm)) = u;
-  }
-  __syncwarp();
-  const int seg = lane & 7;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = (lane >> 3) + 4 * i;
-    const uint4 u = *reinterpret_cast<const uint4*>(stg + stg_off(row, seg));
-    if (row < rows_valid && seg * 8 < cols_valid) *reinterpret_cast<uint4*>(g + static_cast<long long>(row) * ld + seg * 8) = u;
-  }
-  __syncwarp();
-}
-
-// `g` points at (row 0 of the matrix, col0); rows are addressed as (row0 + row) / row_div (row_div > 1: one aux row is
-// shared by row_div consecutive output rows)
-__device__ __forceinline__ void load_tile_bf16(uint8_t* stg, uint32_t (&a)[32], const __nv_bfloat16* g, long long ld, int row0, int row_div,
-                                               int rows_valid, int cols_valid, int lane) {
-  const int seg = lane & 7;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = (lane >> 3) + 4 * i;
-    uint4 u = make_uint4(0, 0, 0, 0);
-    if (row < rows_valid && seg * 8 < cols_valid)
-      u = *reinterpret_cast<const uint4*>(g + static_cast<long long>((row0 + row) / row_div) * ld + seg * 8);
-    *reinterpret_cast<uint4*>(stg + stg_off(row, seg)) = u;
-  }
-  __syncwarp();
-#pragma unroll
-  for (int sgm = 0; sgm < 8; ++sgm) {
-    const uint4 u = *reinterpret_cast<const uint4*>(stg + stg_off(lane, sgm));
-    a[4 * sgm] = u.x;
-    a[4 * sgm + 1] = u.y;
-    a[4 * sgm + 2] = u.z;
-    a[4 * sgm + 3] = u.w;
-  }
-  __syncwarp();
-}
-
-// One output tile's epilogue for the calling epilogue warp: rows [row_base + quarter*32, +32) of the tile whose
-// accumulator starts at TMEM column `tmem_acc` (lane offset added here), columns of n-tile n_blk (this warp's half).
+// Epilogue geometry: 4 TMEM lane quarters x kSlices column slices of 64 accumulator columns each.  BN = 256 -> 16
+// epilogue warps (4 per SM sub-partition: the GELU / GELU' math is issue-latency bound, more resident warps hide it),
+// BN = 128 -> 8 warps.
 template <int BN>
+struct EpiCfg {
+  static constexpr int kSlices = BN / 64;
+  static constexpr int kWarps = 4 * kSlices;
+  static constexpr int kThreads = 64 + 32 * kWarps;
+  static constexpr int kChunk = (kWarps > 8) ? 16 : 32;  // accumulator columns per step (register budget: 65536 / kThreads)
+};
+
+// One output tile's epilogue for the calling warp: rows [row_base + quarter*32, +32), columns of slice (e >> 2) of n-tile
+// n_blk; thread t owns row quarter*32 + t and processes it 32 accumulator columns at a time.
+template <int BN, int CW>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_base, uint32_t acc_col, int row_base, int n_blk, int ks,
-                                              int e, int quarter, int lane, uint8_t* stg_warp) {
-  const int half = e >> 2;
-  constexpr int kChunks = (BN / 2) / 32;
+                                              int e, int quarter, int lane) {
+  const int slice = e >> 2;
   const float alpha_eff = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f);
   const float fparam_eff = p.fparam * (p.fparam_dev ? __ldg(p.fparam_dev) : 1.0f);
   const int row = row_base + quarter * 32 + lane;
   const bool row_ok = row < p.M;
   const bool lead_split = (ks == 0);  // bias / aux terms are added by split 0 only
   float lse_m = -INFINITY, lse_s = 0.f, clip_ds = 0.f;
-  const bool fast = !p.d_f32 && p.epi != VL_EPI_ROWLSE;
-  if (fast) {
-    // ---------------- bf16 outputs: 64-column groups, fully coalesced global traffic
-    uint8_t* stg = stg_warp;
-    const int row0 = row_base + quarter * 32;
-    const int rows_valid = min(32, p.M - row0);
+  const long long arow = p.aux_row_div > 1 ? row / p.aux_row_div : row;
 #pragma unroll 1
-    for (int gidx = 0; gidx < kChunks / 2; ++gidx) {
-      const int col0 = n_blk * BN + half * (BN / 2) + gidx * 64;
-      if (col0 >= p.N) break;
-      const int cols_valid = min(64, p.N - col0);
-      uint32_t ax[32];
-      const bool need_aux = (p.epi == VL_EPI_RESIDUAL && lead_split) || p.epi == VL_EPI_GELU_BWD;
-      if (need_aux)
-        load_tile_bf16(stg, ax, p.aux_in + col0, p.ldaux, row0, p.aux_row_div, rows_valid, cols_valid, lane);
-      float f[64];
-#pragma unroll
-      for (int hc = 0; hc < 2; ++hc) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc_col + half * (BN / 2) + gidx * 64 + hc * 32, v);
-        tc_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[hc * 32 + j] = __uint_as_float(v[j]);
-      }
-      if (p.epi == VL_EPI_CLIPGRAD) {
-        const float rl = row_ok ? __ldg(p.row_vec + row) : 0.f;
-        float dsum = 0.f;
-#pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          const float accv = f[j];
-          const float z = accv * alpha_eff;
-          float gval = 0.f;
-          if (row_ok && col0 + j < p.N) {
-            gval = __expf(z - rl);
-            if (p.col_vec) gval += __expf(z - __ldg(p.col_vec + col0 + j));
-            if (col0 + j == row + p.iparam) gval -= p.col_vec ? 2.f : 1.f;
-            gval *= fparam_eff;
-            dsum += gval * accv;
-          }
-          f[j] = gval;
-        }
-        clip_ds += dsum;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 64; ++j) f[j] *= alpha_eff;
-        if (p.bias != nullptr && lead_split && p.epi != VL_EPI_GELU_BWD) {
-          if (cols_valid == 64) {
-#pragma unroll
-            for (int j = 0; j < 64; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-              f[j] += b4.x;
-              f[j + 1] += b4.y;
-              f[j + 2] += b4.z;
-              f[j + 3] += b4.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 64; j += 4) {
-              if (col0 + j < p.N) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                f[j] += b4.x;
-                f[j + 1] += b4.y;
-                f[j + 2] += b4.z;
-                f[j + 3] += b4.w;
-              }
-            }
-          }
-        }
-        if (p.epi == VL_EPI_GELU) {
-          if (p.aux_out != nullptr)
-            store_tile_bf16(stg, f, p.aux_out + static_cast<long long>(row0) * p.ldaux + col0, p.ldaux, rows_valid, cols_valid, lane);
-          if (p.act_quick) {
-#pragma unroll
-            for (int j = 0; j < 64; ++j) f[j] = gelu_quick_fwd(f[j]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 64; ++j) f[j] = gelu_erf_fwd(f[j]);
-          }
-        } else if (need_aux) {
-          if (p.epi == VL_EPI_RESIDUAL) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              f[2 * j] += bf16_lo(ax[j]);
-              f[2 * j + 1] += bf16_hi(ax[j]);
-            }
-          } else if (p.act_quick) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              f[2 * j] *= gelu_quick_grad(bf16_lo(ax[j]));
-              f[2 * j + 1] *= gelu_quick_grad(bf16_hi(ax[j]));
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              f[2 * j] *= gelu_erf_grad(bf16_lo(ax[j]));
-              f[2 * j + 1] *= gelu_erf_grad(bf16_hi(ax[j]));
-            }
-          }
-        }
-      }
-      store_tile_bf16(stg, f, reinterpret_cast<__nv_bfloat16*>(p.d) + static_cast<long long>(row0) * p.ldd + col0, p.ldd, rows_valid,
-                      cols_valid, lane);
-    }
-  }
-#pragma unroll 1
-  for (int c = 0; c < (fast ? 0 : kChunks); ++c) {
-    const int col0 = n_blk * BN + half * (BN / 2) + c * 32;
+  for (int c = 0; c < 64 / CW; ++c) {
+    const int col0 = n_blk * BN + slice * 64 + c * CW;
     if (col0 >= p.N) break;
-    uint32_t v[32];
-    tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc_col + half * (BN / 2) + c * 32, v);
-    tc_wait_ld();
-    float f[32];
+    const bool full = col0 + CW <= p.N;
+    uint32_t v[CW];
+    if constexpr (CW == 32)
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc_col + slice * 64 + c * CW, v);
+    else
+      tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc_col + slice * 64 + c * CW, v);
+    // issue the independent global loads (bias, residual / pre-activation row) before waiting on the TMEM read
+    uint4 ax[CW / 8];
+    const bool need_aux = row_ok && ((p.epi == VL_EPI_RESIDUAL && lead_split) || p.epi == VL_EPI_GELU_BWD);
+    if (need_aux) {
+      const uint4* ap = reinterpret_cast<const uint4*>(p.aux_in + arow * p.ldaux + col0);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * alpha_eff;
-    if (p.bias != nullptr && lead_split && p.epi != VL_EPI_GELU_BWD) {
+      for (int j = 0; j < CW / 8; ++j) ax[j] = (col0 + 8 * j < p.N) ? ap[j] : make_uint4(0, 0, 0, 0);
+    }
+    float bv[CW];
+    const bool need_bias = p.bias != nullptr && lead_split && p.epi != VL_EPI_GELU_BWD && p.epi != VL_EPI_ROWLSE && p.epi != VL_EPI_CLIPGRAD;
+    if (need_bias) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        if (col0 + j < p.N) {  // N % 4 == 0 is enforced on the host
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-          f[j] += b4.x;
-          f[j + 1] += b4.y;
-          f[j + 2] += b4.z;
-          f[j + 3] += b4.w;
-        }
+      for (int j = 0; j < CW; j += 4) {
+        const float4 b4 = (col0 + j < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j)) : make_float4(0, 0, 0, 0);
+        bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
       }
     }
+    tc_wait_ld();
+    float f[CW];
     if (p.epi == VL_EPI_ROWLSE) {
-      // online (max, sum-exp) over this thread's columns of the tile; one part per (n tile, half)
+#pragma unroll
+      for (int j = 0; j < CW; ++j) f[j] = __uint_as_float(v[j]) * alpha_eff;
       if (c == 0) {
         lse_m = -INFINITY;
         lse_s = 0.f;
       }
       float cm = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
+      for (int j = 0; j < CW; ++j)
         if (col0 + j < p.N) cm = fmaxf(cm, f[j]);
       const float nm = fmaxf(lse_m, cm);
       float add = 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
+      for (int j = 0; j < CW; ++j)
         if (col0 + j < p.N) add += __expf(f[j] - nm);
       lse_s = lse_s * __expf(lse_m - nm) + add;
       lse_m = nm;
       if (row_ok) {
         const int dj = row + p.iparam - col0;
-        if (dj >= 0 && dj < 32) {
+        if (dj >= 0 && dj < CW) {
           float dv = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
+          for (int j = 0; j < CW; ++j)
             if (j == dj) dv = f[j];
           p.out_vec2[row] = dv;
         }
-        const bool last = (c == kChunks - 1) || (col0 + 32 >= p.N);
-        if (last) {
-          const long long po = static_cast<long long>(row) * (p.tiles_n * 2) + n_blk * 2 + half;
+        if (c == 64 / CW - 1 || col0 + CW >= p.N) {
+          const long long po = static_cast<long long>(row) * (p.tiles_n * (BN / 64)) + n_blk * (BN / 64) + slice;
           p.out_vec0[po] = lse_m;
           p.out_vec1[po] = lse_s;
         }
@@ -300,96 +160,91 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
       const float rl = row_ok ? __ldg(p.row_vec + row) : 0.f;
       float dsum = 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float g = 0.f;
+      for (int j = 0; j < CW; ++j) {
+        const float accv = __uint_as_float(v[j]);
+        const float z = accv * alpha_eff;
+        float gval = 0.f;
         if (row_ok && col0 + j < p.N) {
-          g = __expf(f[j] - rl);
-          if (p.col_vec) g += __expf(f[j] - __ldg(p.col_vec + col0 + j));
-          if (col0 + j == row + p.iparam) g -= p.col_vec ? 2.f : 1.f;
-          g *= fparam_eff;
-          dsum += g * __uint_as_float(v[j]);
+          gval = __expf(z - rl);
+          if (p.col_vec) gval += __expf(z - __ldg(p.col_vec + col0 + j));
+          if (col0 + j == row + p.iparam) gval -= p.col_vec ? 2.f : 1.f;
+          gval *= fparam_eff;
+          dsum += gval * accv;
         }
-        f[j] = g;
+        f[j] = gval;
       }
       clip_ds += dsum;
-    }
-    if (row_ok) {
-      const long long aoff = static_cast<long long>(row) * p.ldaux + col0;
+    } else {
+#pragma unroll
+      for (int j = 0; j < CW; ++j) f[j] = __uint_as_float(v[j]) * alpha_eff;
+      if (need_bias) {
+#pragma unroll
+        for (int j = 0; j < CW; ++j) f[j] += bv[j];
+      }
       if (p.epi == VL_EPI_GELU) {
-        if (p.aux_out != nullptr) {
+        if (p.aux_out != nullptr && row_ok) {
+          uint4* up = reinterpret_cast<uint4*>(p.aux_out + static_cast<long long>(row) * p.ldaux + col0);
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (col0 + j < p.N) {
-              uint4 u;
-              u.x = pack_bf16(f[j], f[j + 1]);
-              u.y = pack_bf16(f[j + 2], f[j + 3]);
-              u.z = pack_bf16(f[j + 4], f[j + 5]);
-              u.w = pack_bf16(f[j + 6], f[j + 7]);
-              *reinterpret_cast<uint4*>(p.aux_out + aoff + j) = u;
-            }
-          }
+          for (int j = 0; j < CW / 8; ++j)
+            if (full || col0 + 8 * j < p.N)
+              up[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]), pack_bf16(f[8 * j + 4], f[8 * j + 5]),
+                                 pack_bf16(f[8 * j + 6], f[8 * j + 7]));
         }
+        if (p.act_quick) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = gelu_fwd(f[j], p.act_quick);
-      } else if (p.epi == VL_EPI_RESIDUAL) {
-        if (lead_split) {
+          for (int j = 0; j < CW; ++j) f[j] = gelu_quick_fwd(f[j]);
+        } else {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (col0 + j < p.N) {
-              const uint4 u = *reinterpret_cast<const uint4*>(p.aux_in + aoff + j);
-              f[j] += bf16_lo(u.x);
-              f[j + 1] += bf16_hi(u.x);
-              f[j + 2] += bf16_lo(u.y);
-              f[j + 3] += bf16_hi(u.y);
-              f[j + 4] += bf16_lo(u.z);
-              f[j + 5] += bf16_hi(u.z);
-              f[j + 6] += bf16_lo(u.w);
-              f[j + 7] += bf16_hi(u.w);
-            }
-          }
+          for (int j = 0; j < CW; ++j) f[j] = gelu_erf_fwd(f[j]);
         }
-      } else if (p.epi == VL_EPI_GELU_BWD) {
+      } else if (need_aux) {
+        const uint32_t* aw = reinterpret_cast<const uint32_t*>(ax);
+        if (p.epi == VL_EPI_RESIDUAL) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          if (col0 + j < p.N) {
-            const uint4 u = *reinterpret_cast<const uint4*>(p.aux_in + aoff + j);
-            f[j] *= gelu_grad(bf16_lo(u.x), p.act_quick);
-            f[j + 1] *= gelu_grad(bf16_hi(u.x), p.act_quick);
-            f[j + 2] *= gelu_grad(bf16_lo(u.y), p.act_quick);
-            f[j + 3] *= gelu_grad(bf16_hi(u.y), p.act_quick);
-            f[j + 4] *= gelu_grad(bf16_lo(u.z), p.act_quick);
-            f[j + 5] *= gelu_grad(bf16_hi(u.z), p.act_quick);
-            f[j + 6] *= gelu_grad(bf16_lo(u.w), p.act_quick);
-            f[j + 7] *= gelu_grad(bf16_hi(u.w), p.act_quick);
+          for (int j = 0; j < CW / 2; ++j) {
+            f[2 * j] += bf16_lo(aw[j]);
+            f[2 * j + 1] += bf16_hi(aw[j]);
+          }
+        } else if (p.act_quick) {
+#pragma unroll
+          for (int j = 0; j < CW / 2; ++j) {
+            f[2 * j] *= gelu_quick_grad(bf16_lo(aw[j]));
+            f[2 * j + 1] *= gelu_quick_grad(bf16_hi(aw[j]));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < CW / 2; ++j) {
+            f[2 * j] *= gelu_erf_grad(bf16_lo(aw[j]));
+            f[2 * j + 1] *= gelu_erf_grad(bf16_hi(aw[j]));
           }
         }
       }
-      // ---- store
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < CW; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+    }
+    // ---- store
+    if (row_ok) {
       const long long doff = static_cast<long long>(row) * p.ldd + col0;
       if (p.d_f32) {
         float* dp = reinterpret_cast<float*>(p.d) + doff;
         if (p.accumulate) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
+          for (int j = 0; j < CW; ++j)
             if (col0 + j < p.N) atomicAdd(dp + j, f[j]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
+          for (int j = 0; j < CW; j += 4)
             if (col0 + j < p.N) *reinterpret_cast<float4*>(dp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
         }
       } else {
-        __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.d) + doff;
+        uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.d) + doff);
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          if (col0 + j < p.N) {
-            uint4 u;
-            u.x = pack_bf16(f[j], f[j + 1]);
-            u.y = pack_bf16(f[j + 2], f[j + 3]);
-            u.z = pack_bf16(f[j + 4], f[j + 5]);
-            u.w = pack_bf16(f[j + 6], f[j + 7]);
-            *reinterpret_cast<uint4*>(dp + j) = u;
-          }
-        }
+        for (int j = 0; j < CW / 8; ++j)
+          if (full || col0 + 8 * j < p.N)
+            dp[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]), pack_bf16(f[8 * j + 4], f[8 * j + 5]),
+                               pack_bf16(f[8 * j + 6], f[8 * j + 7]));
       }
     }
   }
@@ -401,7 +256,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
 }
 
 template <int BN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(EpiCfg<BN>::kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -429,7 +284,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kEpiWarps);
+      mbar_init(tempty_bar(a), EpiCfg<BN>::kWarps);
     }
     fence_mbar_init();
   }
@@ -529,7 +384,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tile_coords(p, t, m_blk, n_blk, ks);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      epilogue_tile<BN>(p, tmem_base, acc * BN, m_blk * kBM, n_blk, ks, e, quarter, lane, smem_raw + (stg_base - smem_u32(smem_raw)) + e * 4096);
+      epilogue_tile<BN, EpiCfg<BN>::kChunk>(p, tmem_base, acc * BN, m_blk * kBM, n_blk, ks, e, quarter, lane);
       // accumulator drained -> hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -637,7 +492,7 @@ static int launch_gemm(const VlGemmArgs& a, cudaStream_t stream) {
   const int total = p.tiles_m * p.tiles_n * p.split_k;
   int grid = total < num_sms() ? total : num_sms();
   if (debug_get(7) > 0 && debug_get(7) < grid) grid = debug_get(7);
-  gemm_bf16_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  gemm_bf16_kernel<BN><<<grid, EpiCfg<BN>::kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
   return launch_check("gemm_bf16_kernel");
 }
 
@@ -657,8 +512,8 @@ struct Gemm2Cfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = (BN / 2) * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = kEpiWarps * 4096;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 256;
+  static constexpr int kStagingBytes = 0;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
   static constexpr int kTmemCols = 2 * BN;
 };
 
@@ -685,7 +540,7 @@ __device__ __forceinline__ void tile_coords2(const GemmParams& p, int tiles_m2, 
 }
 
 template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<BN>::kThreads, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = Gemm2Cfg<BN>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -718,7 +573,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 2 * kEpiWarps);
+      mbar_init(tempty_bar(a), 2 * EpiCfg<BN>::kWarps);
     }
     fence_mbar_init();
   }
@@ -823,8 +678,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tile_coords2(p, tiles_m2, t, m_blk, n_blk, ks);
       mbar_wait_guarded(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      epilogue_tile<BN>(p, tmem_base, acc * BN, m_blk * 2 * kBM + static_cast<int>(rank) * kBM, n_blk, ks, e, quarter, lane,
-                        smem_raw + (stg_base - smem_base) + e * 4096);
+      epilogue_tile<BN, EpiCfg<BN>::kChunk>(p, tmem_base, acc * BN, m_blk * 2 * kBM + static_cast<int>(rank) * kBM, n_blk, ks, e, quarter, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
@@ -871,7 +725,7 @@ static int launch_gemm2(const VlGemmArgs& a, GemmParams p, cudaStream_t stream) 
   int clusters = num_sms() / 2;
   if (total < clusters) clusters = total;
   if (debug_get(7) > 0 && debug_get(7) < clusters) clusters = debug_get(7);
-  gemm2_bf16_kernel<BN><<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  gemm2_bf16_kernel<BN><<<2 * clusters, EpiCfg<BN>::kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
   return launch_check("gemm2_bf16_kernel");
 }
 
@@ -911,4 +765,4 @@ extern "C" int vl_gemm_bf16(const VlGemmArgs* a, void* stream) {
   return launch_gemm<256>(*a, s);
 }
 
-extern "C" int vl_gemm_rowlse_parts(int32_t N) { return ((N + 255) / 256) * 2; }
+extern "C" int vl_gemm_rowlse_parts(int32_t N) { return ((N + 255) / 256) * 4; }  // one part per 64-column slice

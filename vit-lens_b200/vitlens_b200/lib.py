@@ -118,7 +118,7 @@ def gemm(a, b, d, *, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, epilogue=EP
         _ptr(row_vec), _ptr(col_vec), _ptr(out_vec0), _ptr(out_vec1), _ptr(out_vec2), _ptr(scalar_out), int(iparam), float(fparam),
         _ptr(alpha_dev), _ptr(fparam_dev), int(aux_row_div), int(relu))
     _count()
-    _timed(GEMM_TIMING, (2.0 * M * N * K,),
+    _timed(GEMM_TIMING, (2.0 * M * N * K, (M, N, K, int(epilogue), int(a_mn), int(b_mn))),
            lambda: _check(_fn("vl_gemm_bf16")(C.cast(C.pointer(args), C.c_void_p), _stream()), "vl_gemm_bf16"))
 
 
