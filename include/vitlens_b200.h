@@ -29,6 +29,8 @@ int vl_abi_version(void);
 const char* vl_last_error(void);
 /* debug/bring-up knobs (descriptor overrides etc.); key/value are kernel-specific, 0 resets. */
 int vl_debug_set(int key, int value);
+/* bring-up: device buffer (>= 64 KiB) that instrumented kernels fill with clock64 timelines; NULL disables. */
+int vl_debug_buffer(void* dev_ptr);
 
 /* ---------------------------------------------------------------------------------------------
  * GEMM (tcgen05 / TMEM / TMA, bf16 x bf16 -> fp32 accumulate):
@@ -67,7 +69,8 @@ typedef struct {
   int32_t accumulate; /* fp32 output only: D += result (atomic; required when split_k > 1) */
   int32_t split_k;    /* >= 1 */
   int32_t epilogue;   /* VL_EPI_* */
-  int32_t act_quick;  /* 0 = erf GELU (nn.GELU), 1 = QuickGELU (transformer.py:37-40) */
+  int32_t act_quick;  /* activation of VL_EPI_GELU / VL_EPI_GELU_BWD: 0 = erf GELU (nn.GELU), 1 = QuickGELU
+                         (transformer.py:37-40), 2 = ReLU (grouped PointNet, dvae.py:200-208) */
   float alpha;
   const float* bias;  /* fp32 [N] or NULL */
   const void* aux_in; /* bf16 [M,N] (ld = ldaux) or NULL */
@@ -168,9 +171,14 @@ int vl_fps(const float* xyz, const int64_t* start, int32_t B, int32_t N, int32_t
            void* stream);
 int vl_knn_group(const float* xyz, const float* centers, int32_t B, int32_t N, int32_t G, int32_t k, float* nb_out,
                  int64_t* idx_out, void* stream);
-int vl_linear3(const float* x, const float* w, const float* scale, const float* shift, void* out, int64_t R, int32_t C,
-               int32_t act, void* stream);
+int vl_linear3(const float* x, const float* w, const float* scale, const float* shift, void* out, void* pre_out, int64_t R,
+               int32_t C, int32_t act, void* stream);
 int vl_group_max(const void* x, void* out, int32_t* arg, int64_t groups, int32_t G, int32_t C, void* stream);
+/* backward pieces of the tokenizer: max scatter, per-group sums, (sum a, sum a*b) column sums, 3-input weight gradient */
+int vl_group_max_bwd(const void* dout, const int32_t* arg, void* dx, int64_t groups, int32_t G, int32_t C, void* stream);
+int vl_group_sum(const void* x, void* out, int64_t groups, int32_t G, int32_t C, void* stream);
+int vl_colsum2_bf16(const void* a, const void* b, float* s1, float* s2, int64_t T, int32_t N, void* stream);
+int vl_wgrad3(const void* dy, const float* x, float* dw, int64_t R, int32_t C, void* stream);
 
 #ifdef __cplusplus
 }

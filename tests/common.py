@@ -50,7 +50,13 @@ def run_model(case, model, inp, loss_mod=None):
         loss = (loss_mod or open_clip.ClipLoss())(fi, ft, ls)
         feats = {"image_features": fi, "text_features": ft}
     else:
-        fi, ft, fv, ls = model(inp["image"], inp["text"], inp["visual"])
+        if "fps_start" in inp:  # point clouds: the FPS start indices are an explicit input (misc.py:60 draws them at random)
+            fi = model.encode_image(inp["image"], normalize=True)
+            ft = model.encode_text(inp["text"], normalize=True)
+            fv = model.encode_visual(inp["visual"], normalize=True, fps_start=inp["fps_start"])
+            ls = model.logit_scale.exp()
+        else:
+            fi, ft, fv, ls = model(inp["image"], inp["text"], inp["visual"])
         loss = (loss_mod or open_clip.TriClipLoss())(fi, ft, fv, ls)
         feats = {"image_features": fi, "text_features": ft, "visual_features": fv}
     return feats, ls, loss

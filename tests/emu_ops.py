@@ -23,10 +23,14 @@ def _n():
 
 
 def _act(x, quick):
+    if quick == 2:
+        return torch.relu(x)
     return x * torch.sigmoid(1.702 * x) if quick else F.gelu(x)
 
 
 def _act_grad(x, quick):
+    if quick == 2:
+        return (x > 0).float()
     if quick:
         s = torch.sigmoid(1.702 * x)
         return s * (1 + 1.702 * x * (1 - s))
@@ -277,14 +281,39 @@ def knn_group(pts, centers, G, k, want_idx=False):
     return (nb, idx.reshape(-1)) if want_idx else nb
 
 
-def linear3(x, w, scale, shift, act):
+def linear3(x, w, scale, shift, act, want_pre=False):
     _n()
-    v = (x @ w.t()) * scale + shift
+    pre = (x @ w.t()) * scale + shift
+    v = pre
     if act == 1:
         v = torch.relu(v)
     elif act == 2:
         v = F.gelu(v)
-    return v.to(BF16)
+    return (v.to(BF16), pre.to(BF16)) if want_pre else v.to(BF16)
+
+
+def group_max_bwd(dout, arg, G):
+    _n()
+    groups, C = dout.shape
+    dx = torch.zeros(groups, G, C)
+    dx.scatter_(1, arg.long().unsqueeze(1), dout.float().unsqueeze(1))
+    return dx.reshape(groups * G, C).to(BF16)
+
+
+def group_sum(x, G):
+    _n()
+    rows, C = x.shape
+    return x.float().reshape(rows // G, G, C).sum(1).to(BF16)
+
+
+def colsum2(a, b):
+    _n()
+    return a.float().sum(0), (a.float() * b.float()).sum(0)
+
+
+def wgrad3(dy, x):
+    _n()
+    return dy.float().t() @ x
 
 
 def group_max(x, G, want_arg=False):

@@ -248,3 +248,28 @@ def test_point_cloud_row_kernels(ops):
     gp = torch.randn(64, 512, device="cuda").to(BF)
     out = ops.gemm_grouped_residual_relu(a, b, gp, 32)
     close(out, torch.relu(a.float() @ b.float().t() + gp.float().repeat_interleave(32, 0)))
+
+
+def test_point_cloud_backward_kernels(ops):
+    d = torch.randn(64, 256, device="cuda").to(BF)
+    arg = torch.randint(0, 32, (64, 256), device="cuda", dtype=torch.int32)
+    dx = ops.group_max_bwd(d, arg, 32)
+    ref = torch.zeros(64, 32, 256, device="cuda").scatter_(1, arg.long().unsqueeze(1), d.float().unsqueeze(1))
+    assert torch.equal(dx.float().reshape(64, 32, 256), ref)
+    x = torch.randn(64 * 32, 512, device="cuda").to(BF)
+    close(ops.group_sum(x, 32), x.float().reshape(64, 32, 512).sum(1))
+    a, b = torch.randn(3000, 512, device="cuda").to(BF), torch.randn(3000, 512, device="cuda").to(BF)
+    s1, s2 = ops.colsum2(a, b)
+    close(s1, a.float().sum(0), tol=1e-3, atol=0.05)
+    close(s2, (a.float() * b.float()).sum(0), tol=1e-3, atol=0.05)
+    dy, xx = torch.randn(5000, 128, device="cuda").to(BF), torch.randn(5000, 3, device="cuda")
+    close(ops.wgrad3(dy, xx), dy.float().t() @ xx, tol=1e-3, atol=0.05)
+    w = torch.randn(128, 3, device="cuda")
+    out, pre = ops.linear3(xx, w, torch.ones(128, device="cuda"), torch.zeros(128, device="cuda"), 2, want_pre=True)
+    close(pre, xx @ w.t())
+    close(out, F.gelu(xx @ w.t()))
+    A = torch.randn(520, 256, device="cuda").to(BF)
+    Bm = (torch.randn(1024, 256, device="cuda") * 0.1).to(BF)
+    res = torch.randn(520, 1024, device="cuda").to(BF)
+    acc = A.float() @ Bm.float().t()
+    close(ops.gemm(A, Bm, epilogue=ops.EPI_GELU_BWD, aux_in=res, act_quick=2), acc * (res.float() > 0))

@@ -17,6 +17,8 @@ def _check(name, grad_cos=0.97):
     gold = C.load_golden(name)
     model, sd, args = build_model(case, device="cuda")
     inp = C.build_inputs(case, args)
+    if "fps_start" in gold:
+        inp["fps_start"] = gold["fps_start"]
     feats, ls, loss = run_model(case, model, inp)
     for k, v in feats.items():
         c = cosine(v.detach().cpu(), gold[k])
@@ -44,12 +46,12 @@ def _check(name, grad_cos=0.97):
     assert not bad, bad[:10]
 
 
-@pytest.mark.parametrize("name", ["tiny_clip", "tiny_tri_audio", "tiny_tri_depth"])
+@pytest.mark.parametrize("name", ["tiny_clip", "tiny_tri_audio", "tiny_tri_depth", "tiny_tri_pc"])
 def test_tiny_models_vs_reference_fixture(name):
     _check(name)
 
 
-@pytest.mark.parametrize("name", ["vitb32_clip_bs8", "vitl14_audio128_bs2", "vitl14_depth_bs2"])
+@pytest.mark.parametrize("name", ["vitb32_clip_bs8", "vitl14_audio128_bs2", "vitl14_depth_bs2", "vitl14_pc_bs2"])
 def test_full_size_models_vs_reference_fixture(name):
     _check(name, grad_cos=0.95)
 

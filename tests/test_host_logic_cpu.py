@@ -5,7 +5,7 @@ import torch
 
 from tests.common import C, build_model, cosine, relerr, run_model
 
-CASES = ["tiny_clip", "tiny_tri_audio", "tiny_tri_depth"]
+CASES = ["tiny_clip", "tiny_tri_audio", "tiny_tri_depth", "tiny_tri_pc"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -14,6 +14,8 @@ def test_forward_backward_vs_reference(name, emu):
     gold = C.load_golden(name)
     model, sd, args = build_model(case)
     inp = C.build_inputs(case, args)
+    if "fps_start" in gold:
+        inp["fps_start"] = gold["fps_start"]
     feats, ls, loss = run_model(case, model, inp)
     for k, v in feats.items():
         assert cosine(v, gold[k]) > 0.999, (k, cosine(v, gold[k]))

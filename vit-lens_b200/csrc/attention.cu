@@ -260,6 +260,7 @@ struct AttnBwdParams {
   int B, H, nq, nk;
   int nq_main, nk_main;  // rows / keys covered by the tensor-core tiles; the short tails [n_main, n) are
   int tq, tk;            // folded in on CUDA cores (epilogue corrections here + attn_bwd_tail_kernel)
+  long long* dbg;        // optional clock64 timeline (first 8 CTAs)
   const __nv_bfloat16 *q, *k, *v;
   long long ldq, ldk, ldv;
   int q_rows_per_batch, kv_rows_per_batch;
@@ -410,6 +411,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int r = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const float sl2 = p.scale * kLog2e;
+    int dbg_n = 0;
+    const bool dbg_on = p.dbg != nullptr && blockIdx.x < 8 && r == 0;
+#define VL_STAMP()                                             \
+  do {                                                         \
+    if (dbg_on && dbg_n < 63) p.dbg[blockIdx.x * 64 + (dbg_n++)] = clock64(); \
+  } while (0)
+    VL_STAMP();  // 0: compute warps start (after TMEM alloc + barrier init + __syncthreads)
     // prologue: lse (pre-multiplied by log2e) and D = rowsum(dO * O) for every query row of this head
     for (int i = 0; i < nqt; ++i) {
       const int qrow = i * kTQ + r;
@@ -457,6 +465,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");  // the four compute warps only
     }
+    VL_STAMP();  // 1: prologue done
     uint32_t pair = 0;
     for (int j = 0; j < nkblk; ++j) {
       const int nkb = min(kTK, ((p.nk_main - j * kTK) + 15) & ~15);
@@ -467,7 +476,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const float lse2 = s_lse[i * kTQ + r], Di = s_D[i * kTQ + r];
         mbar_wait(bar_sfull, pair & 1);
         tc_fence_after();
+        VL_STAMP();  // S ready
         if (pair > 0) mbar_wait(bar_pairdone, (pair - 1) & 1);  // previous pair's MMAs finished reading P / dS smem
+        VL_STAMP();  // previous pair retired
         uint32_t pk[64];  // P of this row, packed bf16 (128 keys)
 #pragma unroll
         for (int c = 0; c < kTK; c += 32) {
@@ -496,9 +507,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(bar_pfull);
+        VL_STAMP();  // P written
         // dS = P * (dP - D) * scale
         mbar_wait(bar_dpfull, pair & 1);
         tc_fence_after();
+        VL_STAMP();  // dP ready
 #pragma unroll
         for (int c = 0; c < kTK; c += 32) {
           uint32_t v[32];
@@ -527,10 +540,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(bar_dsfull);
+        VL_STAMP();  // dS written
       }
       // dK_j / dV_j -> global (thread r owns key row j*128 + r)
       mbar_wait(bar_dkvfull, j & 1);
       tc_fence_after();
+      VL_STAMP();  // dK/dV accumulators complete
       {
         const int krow = j * kTK + r;
         const bool ok = krow < p.nk_main;
@@ -578,10 +593,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_before();
       mbar_arrive(bar_dkvfree);
       mbar_arrive(bar_kvempty);
+      VL_STAMP();  // dK/dV written
     }
     // dQ tiles -> global
     mbar_wait(bar_dqfull, 0);
     tc_fence_after();
+    VL_STAMP();  // dQ complete
     for (int i = 0; i < nqt; ++i) {
       const int qrow = i * kTQ + r;
       const bool ok = qrow < p.nq_main;
@@ -620,6 +637,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   }
 
+  if (p.dbg != nullptr && blockIdx.x < 8 && threadIdx.x == 64) p.dbg[blockIdx.x * 64 + 63] = clock64();  // compute done
+#undef VL_STAMP
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -939,6 +958,7 @@ int vl_attention_bwd(const void* q, const void* k, const void* v, const void* o,
   p.ldo = ldo; p.lddo = lddo; p.lse = lse;
   p.dq = reinterpret_cast<__nv_bfloat16*>(dq); p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.dv = reinterpret_cast<__nv_bfloat16*>(dv);
   p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
+  p.dbg = debug_buffer();
   static bool attr = false;
   if (!attr) {
     VL_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));

@@ -190,7 +190,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
               up[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]), pack_bf16(f[8 * j + 4], f[8 * j + 5]),
                                  pack_bf16(f[8 * j + 6], f[8 * j + 7]));
         }
-        if (p.act_quick) {
+        if (p.act_quick == 2) {
+#pragma unroll
+          for (int j = 0; j < CW; ++j) f[j] = fmaxf(f[j], 0.f);
+        } else if (p.act_quick) {
 #pragma unroll
           for (int j = 0; j < CW; ++j) f[j] = gelu_quick_fwd(f[j]);
         } else {
@@ -204,6 +207,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
           for (int j = 0; j < CW / 2; ++j) {
             f[2 * j] += bf16_lo(aw[j]);
             f[2 * j + 1] += bf16_hi(aw[j]);
+          }
+        } else if (p.act_quick == 2) {
+#pragma unroll
+          for (int j = 0; j < CW / 2; ++j) {
+            f[2 * j] = bf16_lo(aw[j]) > 0.f ? f[2 * j] : 0.f;
+            f[2 * j + 1] = bf16_hi(aw[j]) > 0.f ? f[2 * j + 1] : 0.f;
           }
         } else if (p.act_quick) {
 #pragma unroll

@@ -17,6 +17,8 @@ void set_error(const char* fmt, ...) {
 }
 
 int debug_get(int key) { return (key >= 0 && key < 64) ? g_debug[key] : 0; }
+static long long* g_dbg_buf = nullptr;
+long long* debug_buffer() { return g_dbg_buf; }
 
 int num_sms() {
   static int n = 0;
@@ -88,6 +90,10 @@ extern "C" {
 
 int vl_abi_version(void) { return VL_ABI_VERSION; }
 const char* vl_last_error(void) { return vl::g_err; }
+int vl_debug_buffer(void* dev_ptr) {
+  vl::g_dbg_buf = reinterpret_cast<long long*>(dev_ptr);
+  return 0;
+}
 int vl_debug_set(int key, int value) {
   if (key < 0 || key >= 64) return VL_EINVAL;
   vl::g_debug[key] = value;

@@ -159,19 +159,21 @@ __global__ void __launch_bounds__(256) knn_group_kernel(const float* __restrict_
 // first_conv.0 (+ folded BatchNorm + ReLU, dvae.py:200-203) and pos_embed.0 (+ GELU, point_encoder.py:325-327).
 // act: 0 none, 1 relu, 2 gelu(erf).  scale/shift are per-output-channel fp32 (bias and BN already folded in).
 __global__ void __launch_bounds__(256) linear3_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
-                                                      const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, long long R, int C, int act) {
+                                                      const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
+                                                      __nv_bfloat16* __restrict__ pre_out, long long R, int C, int act) {
   const int cvec = C >> 3;
   const long long total = R * cvec;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int cv = static_cast<int>(idx % cvec);
     const long long r = idx / cvec;
     const float x0 = x[3 * r], x1 = x[3 * r + 1], x2 = x[3 * r + 2];
-    float f[8];
+    float f[8], pre[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int c = cv * 8 + e;
       float v = x0 * __ldg(w + 3 * c) + x1 * __ldg(w + 3 * c + 1) + x2 * __ldg(w + 3 * c + 2);
       v = v * __ldg(scale + c) + __ldg(shift + c);
+      pre[e] = v;
       if (act == 1) v = fmaxf(v, 0.f);
       if (act == 2) v = gelu_erf_fwd(v);
       f[e] = v;
@@ -179,6 +181,11 @@ __global__ void __launch_bounds__(256) linear3_kernel(const float* __restrict__ 
     uint4 u;
     u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]); u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
     *reinterpret_cast<uint4*>(out + r * C + cv * 8) = u;
+    if (pre_out) {
+      uint4 q;
+      q.x = pack_bf16(pre[0], pre[1]); q.y = pack_bf16(pre[2], pre[3]); q.z = pack_bf16(pre[4], pre[5]); q.w = pack_bf16(pre[6], pre[7]);
+      *reinterpret_cast<uint4*>(pre_out + r * C + cv * 8) = q;
+    }
   }
 }
 
@@ -218,6 +225,112 @@ __global__ void __launch_bounds__(256) group_max_kernel(const __nv_bfloat16* __r
   }
 }
 
+
+// ------------------------------------------------------------------------------------ backward helpers
+// dx[g*G + r, c] = (arg[g, c] == r) ? dout[g, c] : 0   (backward of the per-group max)
+__global__ void __launch_bounds__(256) group_max_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const int* __restrict__ arg,
+                                                            __nv_bfloat16* __restrict__ dx, long long groups, int G, int C) {
+  const int cvec = C >> 3;
+  const long long total = groups * cvec;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(idx % cvec);
+    const long long g = idx / cvec;
+    const uint4 u = *reinterpret_cast<const uint4*>(dout + g * C + cv * 8);
+    const uint16_t* h = reinterpret_cast<const uint16_t*>(&u);
+    int a[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = arg[g * C + cv * 8 + e];
+    for (int r = 0; r < G; ++r) {
+      uint16_t o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (a[e] == r) ? h[e] : static_cast<uint16_t>(0);
+      *reinterpret_cast<uint4*>(dx + (g * G + r) * C + cv * 8) = *reinterpret_cast<const uint4*>(o);
+    }
+  }
+}
+
+// out[g, c] = sum_r x[g*G + r, c]
+__global__ void __launch_bounds__(256) group_sum_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, long long groups, int G,
+                                                        int C) {
+  const int cvec = C >> 3;
+  const long long total = groups * cvec;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(idx % cvec);
+    const long long g = idx / cvec;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int r = 0; r < G; ++r) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + (g * G + r) * C + cv * 8);
+      acc[0] += bf16_lo(u.x); acc[1] += bf16_hi(u.x); acc[2] += bf16_lo(u.y); acc[3] += bf16_hi(u.y);
+      acc[4] += bf16_lo(u.z); acc[5] += bf16_hi(u.z); acc[6] += bf16_lo(u.w); acc[7] += bf16_hi(u.w);
+    }
+    uint4 o;
+    o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]); o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(out + g * C + cv * 8) = o;
+  }
+}
+
+// s1[n] += sum_t a[t,n];  s2[n] += sum_t a[t,n] * b[t,n]   (BatchNorm / bias gradients behind a ReLU)
+__global__ void __launch_bounds__(256) colsum2_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, float* __restrict__ s1,
+                                                      float* __restrict__ s2, long long T, int N, long long rows_per_cta) {
+  __shared__ float red[2][8][256];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + tx) * 8;
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_cta;
+  const long long r1 = min(T, r0 + rows_per_cta);
+  float a1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (col < N) {
+    for (long long r = r0 + ty; r < r1; r += 8) {
+      const uint4 ua = *reinterpret_cast<const uint4*>(a + r * N + col);
+      const uint4 ub = *reinterpret_cast<const uint4*>(b + r * N + col);
+      const float fa[8] = {bf16_lo(ua.x), bf16_hi(ua.x), bf16_lo(ua.y), bf16_hi(ua.y), bf16_lo(ua.z), bf16_hi(ua.z), bf16_lo(ua.w), bf16_hi(ua.w)};
+      const float fb[8] = {bf16_lo(ub.x), bf16_hi(ub.x), bf16_lo(ub.y), bf16_hi(ub.y), bf16_lo(ub.z), bf16_hi(ub.z), bf16_lo(ub.w), bf16_hi(ub.w)};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        a1[e] += fa[e];
+        a2[e] += fa[e] * fb[e];
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    red[0][ty][tx * 8 + e] = a1[e];
+    red[1][ty][tx * 8 + e] = a2[e];
+  }
+  __syncthreads();
+  const int c = threadIdx.x;
+  float v1 = 0.f, v2 = 0.f;
+#pragma unroll
+  for (int y = 0; y < 8; ++y) {
+    v1 += red[0][y][c];
+    v2 += red[1][y][c];
+  }
+  const int gc = blockIdx.x * 256 + c;
+  if (gc < N) {
+    atomicAdd(s1 + gc, v1);
+    atomicAdd(s2 + gc, v2);
+  }
+}
+
+// dw[c, j] += sum_r dy[r, c] * x[r, j]   (weight gradient of a 3-input linear layer)
+__global__ void __launch_bounds__(256) wgrad3_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw, long long R,
+                                                     int C, long long rows_per_cta) {
+  // thread = one channel (blockIdx.x * 256 + tid), loops over the CTA's row range
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_cta;
+  const long long r1 = min(R, r0 + rows_per_cta);
+  if (c >= C) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    const float g = __bfloat162float(dy[r * C + c]);
+    a0 = fmaf(g, __ldg(x + 3 * r), a0);
+    a1 = fmaf(g, __ldg(x + 3 * r + 1), a1);
+    a2 = fmaf(g, __ldg(x + 3 * r + 2), a2);
+  }
+  atomicAdd(dw + 3 * c, a0);
+  atomicAdd(dw + 3 * c + 1, a1);
+  atomicAdd(dw + 3 * c + 2, a2);
+}
+
 }  // namespace vl
 
 using namespace vl;
@@ -243,12 +356,14 @@ int vl_knn_group(const float* xyz, const float* centers, int32_t B, int32_t N, i
   return launch_check("knn_group");
 }
 
-int vl_linear3(const float* x, const float* w, const float* scale, const float* shift, void* out, int64_t R, int32_t C, int32_t act, void* stream) {
+int vl_linear3(const float* x, const float* w, const float* scale, const float* shift, void* out, void* pre_out, int64_t R, int32_t C, int32_t act,
+               void* stream) {
   VL_CHECK_ARG(x && w && scale && shift && out && R > 0 && C > 0 && C % 8 == 0 && act >= 0 && act <= 2, "vl_linear3: bad arguments");
   long long g = (R * (C / 8) + 255) / 256;
   const long long cap = static_cast<long long>(num_sms()) * 16;
   if (g > cap) g = cap;
-  linear3_kernel<<<(unsigned)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, w, scale, shift, reinterpret_cast<__nv_bfloat16*>(out), R, C, act);
+  linear3_kernel<<<(unsigned)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, w, scale, shift, reinterpret_cast<__nv_bfloat16*>(out),
+                                                                                   reinterpret_cast<__nv_bfloat16*>(pre_out), R, C, act);
   return launch_check("linear3");
 }
 
@@ -260,5 +375,49 @@ int vl_group_max(const void* x, void* out, int32_t* arg, int64_t groups, int32_t
   group_max_kernel<<<(unsigned)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x),
                                                                                      reinterpret_cast<__nv_bfloat16*>(out), arg, groups, G, C);
   return launch_check("group_max");
+}
+
+static inline unsigned pc_grid(long long items) {
+  long long g = (items + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (g > cap) g = cap;
+  return static_cast<unsigned>(g < 1 ? 1 : g);
+}
+
+int vl_group_max_bwd(const void* dout, const int32_t* arg, void* dx, int64_t groups, int32_t G, int32_t C, void* stream) {
+  VL_CHECK_ARG(dout && arg && dx && groups > 0 && G > 0 && C > 0 && C % 8 == 0, "vl_group_max_bwd: bad arguments");
+  group_max_bwd_kernel<<<pc_grid(groups * (C / 8)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dout), arg, reinterpret_cast<__nv_bfloat16*>(dx), groups, G, C);
+  return launch_check("group_max_bwd");
+}
+
+int vl_group_sum(const void* x, void* out, int64_t groups, int32_t G, int32_t C, void* stream) {
+  VL_CHECK_ARG(x && out && groups > 0 && G > 0 && C > 0 && C % 8 == 0, "vl_group_sum: bad arguments");
+  group_sum_kernel<<<pc_grid(groups * (C / 8)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out), groups, G, C);
+  return launch_check("group_sum");
+}
+
+int vl_colsum2_bf16(const void* a, const void* b, float* s1, float* s2, int64_t T, int32_t N, void* stream) {
+  VL_CHECK_ARG(a && b && s1 && s2 && T > 0 && N > 0 && N % 8 == 0, "vl_colsum2_bf16: bad arguments");
+  const int gx = (N + 255) / 256;
+  long long gy = (static_cast<long long>(num_sms()) * 4 + gx - 1) / gx;
+  if (gy > (T + 63) / 64) gy = (T + 63) / 64;
+  if (gy < 1) gy = 1;
+  const long long rows_per = (T + gy - 1) / gy;
+  colsum2_kernel<<<dim3(gx, (unsigned)gy), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(b), s1, s2, T, N, rows_per);
+  return launch_check("colsum2");
+}
+
+int vl_wgrad3(const void* dy, const float* x, float* dw, int64_t R, int32_t C, void* stream) {
+  VL_CHECK_ARG(dy && x && dw && R > 0 && C > 0, "vl_wgrad3: bad arguments");
+  const int gx = (C + 255) / 256;
+  long long gy = (static_cast<long long>(num_sms()) * 8 + gx - 1) / gx;
+  if (gy > (R + 255) / 256) gy = (R + 255) / 256;
+  if (gy < 1) gy = 1;
+  const long long rows_per = (R + gy - 1) / gy;
+  wgrad3_kernel<<<dim3(gx, (unsigned)gy), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(dy), x, dw, R, C, rows_per);
+  return launch_check("wgrad3");
 }
 }

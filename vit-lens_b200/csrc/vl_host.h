@@ -13,6 +13,7 @@ namespace vl {
 void set_error(const char* fmt, ...);
 int num_sms();
 int debug_get(int key);
+long long* debug_buffer();  // optional device buffer for clock64 timelines (bring-up only)
 
 // 2-D / 3-D bf16 tensor map, row-major global tensor, 128B swizzle (or none), zero OOB fill.
 // dims[0] is the contiguous dimension.  strides_bytes[i] is the stride of dims[i+1].

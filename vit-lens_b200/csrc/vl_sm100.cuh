@@ -259,8 +259,8 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-// erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): one EX2 + one RCP
-__device__ __forceinline__ float erf_fast(float x) {
+// erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): one EX2 + one RCP.  Kept for reference / fp32-grade uses.
+__device__ __forceinline__ float erf_as26(float x) {
   float ax = fabsf(x);
   float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
   float poly = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t,
@@ -269,13 +269,33 @@ __device__ __forceinline__ float erf_fast(float x) {
   float r = fmaf(-poly, e, 1.0f);
   return copysignf(r, x);
 }
+// Phi(x) - 1/2 = erf(x / sqrt 2) / 2 via Abramowitz-Stegun 7.1.28, erf(y) ~ 1 - (1 + a1 y + ... + a6 y^6)^-16 (|err| < 3e-7;
+// measured 8e-7 on the half-erf in fp32): 6 FFMA + 4 FMUL + one RCP, no EX2 -- as accurate as 7.1.26 above at ~3/4 of
+// the instructions and half the SFU work.  The coefficients already include the 1/sqrt(2) argument scaling.
+__device__ __forceinline__ float half_erf_scaled(float x) {
+  const float y = fabsf(x);
+  float p = fmaf(5.382975e-06f, y, 4.889063564e-05f);
+  p = fmaf(p, y, 3.8003575e-05f);
+  p = fmaf(p, y, 0.003277626324f);
+  p = fmaf(p, y, 0.02114100615f);
+  p = fmaf(p, y, 0.04986734697f);
+  p = fmaf(p, y, 1.0f);
+  p = p * p;
+  p = p * p;
+  p = p * p;
+  p = p * p;
+  const float r = fmaf(-0.5f, rcp_approx(p), 0.5f);  // (1 - p^-16) / 2
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float erf_fast(float x) { return erf_as26(x); }
+
 // Branch-free activation bodies (callers pick the variant once per loop, never per element, so the
 // unrolled element streams interleave for ILP).
-__device__ __forceinline__ float gelu_erf_fwd(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_fwd(float x) { return fmaf(x, half_erf_scaled(x), 0.5f * x); }
 __device__ __forceinline__ float gelu_quick_fwd(float x) { return x * rcp_approx(1.0f + __expf(-1.702f * x)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  const float cdf = 0.5f + half_erf_scaled(x);
+  const float pdf = 0.3989422804014327f * exp2f(-0.72134752044448170f * x * x);
   return fmaf(x, pdf, cdf);
 }
 __device__ __forceinline__ float gelu_quick_grad(float x) {

@@ -2,9 +2,9 @@
 misc.py:48-68): FPS -> kNN grouping -> mini-PointNet -> Linear, pos = MLP(centres).
 
 Parameter tree and state_dict keys match the reference.  The forward runs vl_fps / vl_knn_group / vl_linear3 /
-vl_group_max and the tcgen05 GEMM (BatchNorm folded into the neighbouring 1x1 convs).  BatchNorm uses its running
-statistics (eval semantics, what ViTLens.encode needs); batch-statistics BatchNorm and the tokenizer backward are the
-next step of this coverage row."""
+vl_group_max and the tcgen05 GEMM (BatchNorm folded into the neighbouring 1x1 convs), forward and backward
+(engine.PointTokenizerFn).  BatchNorm uses its running statistics (eval semantics; its affine parameters still
+train); batch-statistics BatchNorm / SyncBN is not implemented."""
 import torch
 import torch.nn as nn
 
@@ -45,8 +45,6 @@ class PointTokenizer(nn.Module):
     def forward(self, pts, fps_start=None):
         """pts [B, N, 3] fp32.  `fps_start` [B] int64: first FPS index per sample (the reference draws it with
         torch.randint, misc.py:60); drawn the same way when omitted."""
-        if any(p.requires_grad for p in self.parameters()) and torch.is_grad_enabled():
-            raise NotImplementedError("PointTokenizer backward (training BASELINE config 5) is not built yet; run it frozen / under no_grad")
         if self.group_size > 32:
             raise NotImplementedError("group_size > 32")
         B, N, _ = pts.shape

@@ -495,37 +495,96 @@ class AddFn(torch.autograd.Function):
         return d, d
 
 
-# ----------------------------------------------------------------------------- point-cloud tokenizer (forward)
-def _bn_fold(conv, bn):
-    """Conv1d(k=1) followed by eval-mode BatchNorm1d -> (W [out,in] fp32, per-channel scale, shift) with
-    y = (W x) * scale + shift."""
-    w = conv.weight.detach().squeeze(-1)
-    inv = torch.rsqrt(bn.running_var.detach() + bn.eps) * bn.weight.detach()
-    shift = (conv.bias.detach() - bn.running_mean.detach()) * inv + bn.bias.detach()
-    return w, inv, shift
+# ----------------------------------------------------------------------------- point-cloud tokenizer
+def _bn_scale(bn_w, rv, eps):
+    return torch.rsqrt(rv + eps) * bn_w
+
+
+class PointTokenizerFn(torch.autograd.Function):
+    """PointTokenizer.forward (point_encoder.py:350-362): FPS -> kNN groups -> mini-PointNet (dvae.py:196-212) ->
+    reduce_dim, plus pos = MLP(centres).  Returns (tokens, pos) as bf16 [B*G, trans_dim].
+
+    BatchNorm1d layers use their running statistics and act as per-channel affines folded into the neighbouring 1x1
+    convolutions (their weight / bias still receive gradients).  Training with batch statistics (and running-stat
+    updates / SyncBN, pc_tri_main.py:372-373) is not implemented."""
+
+    @staticmethod
+    def forward(ctx, pts, fps_start, w0, b0, g0, be0, rm0, rv0, w3, b3, w10, b10, g1, be1, rm1, rv1, w13, b13, wr, br, wp0, bp0, wp2, bp2,
+                G, k, eps0, eps1):
+        need = any(ctx.needs_input_grad)
+        _, centers = _ops.fps(pts, fps_start, G)
+        nb = _ops.knn_group(pts, centers, G, k)
+        s0 = _bn_scale(g0, rv0, eps0)
+        t0 = (b0 - rm0) * s0 + be0
+        f1 = _ops.linear3(nb, w0.reshape(w0.shape[0], 3), s0, t0, 1)                    # conv + BN + ReLU  [R,128]
+        w3_16 = w16(w3)
+        f2 = _ops.gemm(f1, w3_16, bias=b3)                                               # [R,256]
+        g1f, arg1 = _ops.group_max(f2, k, want_arg=True)                                 # [BG,256]
+        s1 = _bn_scale(g1, rv1, eps1)
+        t1 = (b10 - rm1) * s1 + be1
+        w10f = w10.reshape(w10.shape[0], -1) * s1[:, None]                               # BN scale folded into the conv rows
+        half = w10f.shape[1] // 2
+        wg = _ops.cast_bf16(w10f[:, :half].contiguous())
+        wl = _ops.cast_bf16(w10f[:, half:].contiguous())
+        gp = _ops.gemm(g1f, wg, bias=t1)                                                 # global half + shift, per group
+        f3 = _ops.gemm_grouped_residual_relu(f2, wl, gp, k)                              # [R,512]
+        w13_16 = w16(w13)
+        f4 = _ops.gemm(f3, w13_16, bias=b13)                                             # [R,enc]
+        tokf, arg2 = _ops.group_max(f4, k, want_arg=True)                                # [BG,enc]
+        tok = _ops.gemm(tokf, w16(wr), bias=br)
+        ones = torch.ones_like(bp0)
+        p1, up = _ops.linear3(centers, wp0, ones, bp0, 2, want_pre=True)                 # Linear(3,128) + GELU
+        pos = _ops.gemm(p1, w16(wp2), bias=bp2)
+        if need:
+            ctx.cfg = (G, k)
+            ctx.save_for_backward(nb, f1, f2, arg1, g1f, f3, arg2, tokf, centers, up, p1, wg, wl, s0, s1, g0, be0, g1, be1, w3, w13, wr, wp2)
+        return tok, pos
+
+    @staticmethod
+    def backward(ctx, dtok, dpos):
+        G, k = ctx.cfg
+        nb, f1, f2, arg1, g1f, f3, arg2, tokf, centers, up, p1, wg, wl, s0, s1, g0, be0, g1, be1, w3, w13, wr, wp2 = ctx.saved_tensors
+        dtok, dpos = dtok.contiguous(), dpos.contiguous()
+        # reduce_dim
+        g_wr, g_br = _wgrad(dtok, tokf), _ops.colsum(dtok)
+        dtokf = _dgrad(dtok, w16(wr))
+        df4 = _ops.group_max_bwd(dtokf, arg2, k)
+        # second_conv.3
+        g_w13, g_b13 = _wgrad(df4, f3).unsqueeze(-1), _ops.colsum(df4)
+        dy3 = _dgrad(df4, w16(w13), epilogue=_ops.EPI_GELU_BWD, aux_in=f3, act_quick=2)  # through the ReLU (f3 > 0)
+        # second_conv.1 (BatchNorm as affine) and second_conv.0 on cat(global, local)
+        sdy, sdya = _ops.colsum2(dy3, f3)
+        g_be1 = sdy
+        g_g1 = (sdya - be1 * sdy) / g1
+        g_b10 = s1 * sdy
+        gs = _ops.group_sum(dy3, k)
+        g_w10 = (torch.cat([_wgrad(gs, g1f), _wgrad(dy3, f2)], dim=1) * s1[:, None]).unsqueeze(-1)
+        dg1 = _dgrad(gs, wg)
+        df2 = _dgrad(dy3, wl, epilogue=_ops.EPI_RESIDUAL, aux_in=_ops.group_max_bwd(dg1, arg1, k))
+        # first_conv.3
+        g_w3, g_b3 = _wgrad(df2, f1).unsqueeze(-1), _ops.colsum(df2)
+        dy1 = _dgrad(df2, w16(w3), epilogue=_ops.EPI_GELU_BWD, aux_in=f1, act_quick=2)
+        # first_conv.1 (BatchNorm as affine) and first_conv.0 (3 -> 128)
+        sdy, sdya = _ops.colsum2(dy1, f1)
+        g_be0 = sdy
+        g_g0 = (sdya - be0 * sdy) / g0
+        g_b0 = s0 * sdy
+        g_w0 = (_ops.wgrad3(dy1, nb) * s0[:, None]).unsqueeze(-1)
+        # pos_embed
+        g_wp2, g_bp2 = _wgrad(dpos, p1), _ops.colsum(dpos)
+        dup = _dgrad(dpos, w16(wp2), epilogue=_ops.EPI_GELU_BWD, aux_in=up)
+        g_wp0, g_bp0 = _ops.wgrad3(dup, centers), _ops.colsum(dup)
+        grads = (None, None, g_w0, g_b0, g_g0, g_be0, None, None, g_w3, g_b3, g_w10, g_b10, g_g1, g_be1, None, None, g_w13, g_b13, g_wr, g_br,
+                 g_wp0, g_bp0, g_wp2, g_bp2, None, None, None, None)
+        return tuple(g if (g is None or ctx.needs_input_grad[i]) else None for i, g in enumerate(grads))
 
 
 def point_tokenizer_forward(tk, pts, fps_start):
-    """PointTokenizer.forward (point_encoder.py:350-362) -> (tokens [B*G, trans_dim] bf16, pos [B*G, trans_dim] bf16)."""
-    G, k = tk.num_group, tk.group_size
-    with torch.no_grad():
-        _, centers = _ops.fps(pts, fps_start, G)
-        nb = _ops.knn_group(pts, centers, G, k)
-        enc = tk.encoder
-        w0, s0, t0 = _bn_fold(enc.first_conv[0], enc.first_conv[1])
-        f1 = _ops.linear3(nb, w0, s0, t0, 1)                                            # [R,128]  conv + BN + ReLU
-        f2 = _ops.gemm(f1, w16(enc.first_conv[3].weight), bias=enc.first_conv[3].bias)  # [R,256]
-        g1 = _ops.group_max(f2, k)                                                      # [BG,256]
-        w1, s1, t1 = _bn_fold(enc.second_conv[0], enc.second_conv[1])
-        w1 = w1 * s1[:, None]                                                           # BN scale folded into the conv rows
-        half = w1.shape[1] // 2
-        wg, wl = _ops.cast_bf16(w1[:, :half].contiguous()), _ops.cast_bf16(w1[:, half:].contiguous())
-        gp = _ops.gemm(g1, wg, bias=t1)                                                 # global-feature half + shift, per group
-        f3 = _ops.gemm_grouped_residual_relu(f2, wl, gp, k)                             # [R,512]
-        f4 = _ops.gemm(f3, w16(enc.second_conv[3].weight), bias=enc.second_conv[3].bias)
-        tokf = _ops.group_max(f4, k)                                                    # [BG,enc]
-        tok = _ops.gemm(tokf, w16(tk.reduce_dim.weight), bias=tk.reduce_dim.bias)
-        ones = torch.ones_like(tk.pos_embed[0].bias)
-        p1 = _ops.linear3(centers, tk.pos_embed[0].weight.detach(), ones, tk.pos_embed[0].bias.detach(), 2)
-        pos = _ops.gemm(p1, w16(tk.pos_embed[2].weight), bias=tk.pos_embed[2].bias)
-    return tok, pos
+    enc = tk.encoder
+    c0, bn0, c3 = enc.first_conv[0], enc.first_conv[1], enc.first_conv[3]
+    c10, bn1, c13 = enc.second_conv[0], enc.second_conv[1], enc.second_conv[3]
+    return PointTokenizerFn.apply(
+        pts, fps_start, c0.weight, c0.bias, bn0.weight, bn0.bias, bn0.running_mean, bn0.running_var, c3.weight, c3.bias,
+        c10.weight, c10.bias, bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var, c13.weight, c13.bias,
+        tk.reduce_dim.weight, tk.reduce_dim.bias, tk.pos_embed[0].weight, tk.pos_embed[0].bias, tk.pos_embed[2].weight, tk.pos_embed[2].bias,
+        tk.num_group, tk.group_size, bn0.eps, bn1.eps)

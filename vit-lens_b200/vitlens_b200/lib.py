@@ -146,7 +146,11 @@ _PROTOS = {
     "vl_lse_combine": [_P, _P, _P, _I, _I, _P, _P, _P],
     "vl_fps": [_P, _P, _I, _I, _I, _P, _P, _P],
     "vl_knn_group": [_P, _P, _I, _I, _I, _I, _P, _P, _P],
-    "vl_linear3": [_P, _P, _P, _P, _P, _L, _I, _I, _P],
+    "vl_linear3": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _P],
+    "vl_group_max_bwd": [_P, _P, _P, _L, _I, _I, _P],
+    "vl_group_sum": [_P, _P, _L, _I, _I, _P],
+    "vl_colsum2_bf16": [_P, _P, _P, _P, _L, _I, _P],
+    "vl_wgrad3": [_P, _P, _P, _L, _I, _P],
     "vl_group_max": [_P, _P, _P, _L, _I, _I, _P],
 }
 
@@ -268,8 +272,24 @@ def knn_group(xyz, centers, nb_out, idx_out, *, B, N, G, k):
     _call("vl_knn_group", _p(xyz), _p(centers), B, N, G, k, _p(nb_out), _p(idx_out))
 
 
-def linear3(x, w, scale, shift, out, *, R, C, act):
-    _call("vl_linear3", _p(x), _p(w), _p(scale), _p(shift), _p(out), R, C, act)
+def linear3(x, w, scale, shift, out, *, R, C, act, pre_out=None):
+    _call("vl_linear3", _p(x), _p(w), _p(scale), _p(shift), _p(out), _p(pre_out), R, C, act)
+
+
+def group_max_bwd(dout, arg, dx, *, groups, G, C):
+    _call("vl_group_max_bwd", _p(dout), _p(arg), _p(dx), groups, G, C)
+
+
+def group_sum(x, out, *, groups, G, C):
+    _call("vl_group_sum", _p(x), _p(out), groups, G, C)
+
+
+def colsum2(a, b, s1, s2, *, T, N):
+    _call("vl_colsum2_bf16", _p(a), _p(b), _p(s1), _p(s2), T, N)
+
+
+def wgrad3(dy, x, dw, *, R, C):
+    _call("vl_wgrad3", _p(dy), _p(x), _p(dw), R, C)
 
 
 def group_max(x, out, arg, *, groups, G, C):

@@ -251,12 +251,48 @@ def knn_group(pts, centers, G, k, want_idx=False):
     return (nb, idx) if want_idx else nb
 
 
-def linear3(x, w, scale, shift, act):
-    """act(x[R,3] @ w[C,3]^T * scale + shift) -> bf16 [R,C]; act: 0 none, 1 relu, 2 gelu"""
+def linear3(x, w, scale, shift, act, want_pre=False):
+    """act(x[R,3] @ w[C,3]^T * scale + shift) -> bf16 [R,C] (and the pre-activation); act: 0 none, 1 relu, 2 gelu"""
     R, C = x.shape[0], w.shape[0]
     out = torch.empty((R, C), device=x.device, dtype=BF16)
-    L.linear3(x.contiguous(), w.contiguous(), scale.contiguous(), shift.contiguous(), out, R=R, C=C, act=act)
+    pre = torch.empty((R, C), device=x.device, dtype=BF16) if want_pre else None
+    L.linear3(x.contiguous(), w.contiguous(), scale.contiguous(), shift.contiguous(), out, R=R, C=C, act=act, pre_out=pre)
+    return (out, pre) if want_pre else out
+
+
+def group_max_bwd(dout, arg, G):
+    _v2(dout, BF16)
+    groups, C = dout.shape
+    dx = torch.empty((groups * G, C), device=dout.device, dtype=BF16)
+    L.group_max_bwd(dout.contiguous(), arg, dx, groups=groups, G=G, C=C)
+    return dx
+
+
+def group_sum(x, G):
+    _v2(x, BF16)
+    rows, C = x.shape
+    out = torch.empty((rows // G, C), device=x.device, dtype=BF16)
+    L.group_sum(x, out, groups=rows // G, G=G, C=C)
     return out
+
+
+def colsum2(a, b):
+    """(sum_t a[t,:], sum_t a[t,:]*b[t,:]) in fp32"""
+    _v2(a, BF16), _v2(b, BF16)
+    T, N = a.shape
+    s1 = torch.zeros((N,), device=a.device, dtype=F32)
+    s2 = torch.zeros((N,), device=a.device, dtype=F32)
+    L.colsum2(a.contiguous(), b.contiguous(), s1, s2, T=T, N=N)
+    return s1, s2
+
+
+def wgrad3(dy, x):
+    """dy[R,C]^T @ x[R,3] -> fp32 [C,3]"""
+    _v2(dy, BF16)
+    R, C = dy.shape
+    dw = torch.zeros((C, 3), device=dy.device, dtype=F32)
+    L.wgrad3(dy.contiguous(), x.contiguous(), dw, R=R, C=C)
+    return dw
 
 
 def group_max(x, G, want_arg=False):
