@@ -161,6 +161,11 @@ int vl_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream
 /* Decoupled-weight-decay Adam step on one fp32 tensor (optim.AdamW, training/point_cloud/pc_tri_main.py:394-419). */
 int vl_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
+/* The same update for every parameter in ONE launch.  ptrs: [n_tensors][5] device pointers (p, g, m, v, bf16 copy of p or
+ * 0); sizes / wds: per tensor element count / weight decay; chunk_tab: [n_chunks][2] int32 (tensor id, chunk index), chunks
+ * of 16384 elements.  The bf16 copy (the tensor-core operand cache) is refreshed in the same pass. */
+int vl_adamw_multi(const int64_t* ptrs, const int64_t* sizes, const float* wds, const int32_t* chunk_tab, int32_t n_chunks,
+                   float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Point-cloud tokenizer (reference modal_3d/models/pointbert): farthest point sampling with explicit start indices

@@ -210,6 +210,33 @@ def test_adamw(ops):
     close(p, pr.detach(), tol=1e-5, atol=1e-6)
 
 
+def test_adamw_multi_tensor(ops):
+    """The one-launch optimizer equals torch.optim.AdamW over decay / no-decay groups (open_clip main.py:328-345
+    grouping) and refreshes the cached bf16 operand copies in the same pass."""
+    from vitlens_b200 import engine, optim
+
+    torch.manual_seed(1)
+    shapes = {"a.weight": (300, 130), "a.bias": (300,), "ln.weight": (130,), "big.weight": (40000, 3), "logit_scale": ()}
+    ours = {k: torch.nn.Parameter(torch.randn(s, device="cuda")) for k, s in shapes.items()}
+    ref = {k: torch.nn.Parameter(v.detach().clone()) for k, v in ours.items()}
+    no_decay = [k for k, v in ref.items() if v.ndim < 2 or "ln" in k or "bias" in k or "logit_scale" in k]
+    ropt = torch.optim.AdamW([dict(params=[ref[k] for k in no_decay], weight_decay=0.0),
+                              dict(params=[ref[k] for k in ref if k not in no_decay], weight_decay=0.2)], lr=1e-3, betas=(0.9, 0.98), eps=1e-6)
+    opt = optim.AdamW(list(ours.items()), lr=1e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.2)
+    cached = engine.w16(ours["a.weight"])
+    for step in range(3):
+        for k in ours:
+            g = torch.randn(shapes[k], device="cuda")
+            ours[k].grad = g.clone()
+            ref[k].grad = g.clone()
+        opt.step()
+        ropt.step()
+        assert engine.w16(ours["a.weight"]) is cached  # refreshed in place, not re-cast
+    for k in ours:
+        close(ours[k].detach(), ref[k].detach(), tol=1e-5, atol=1e-6)
+    close(cached.float(), ours["a.weight"].detach().bfloat16().float(), tol=0, atol=0)
+
+
 @pytest.mark.parametrize("B,N,G,k", [(3, 256, 16, 8), (2, 8192, 512, 32), (2, 1000, 64, 32)])
 def test_point_cloud_sampling_and_grouping(ops, B, N, G, k):
     """FPS indices are bit-exact against the oracle's restatement of misc.fps; kNN neighbourhoods equal the exact

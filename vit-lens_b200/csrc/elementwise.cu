@@ -88,52 +88,56 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16*
   }
 }
 
-// dx = rstd * (w*dy - mean(w*dy) - xhat * mean(w*dy*xhat)) [+ dres];  dw += sum_t dy*xhat; db += sum_t dy.
-// Rows may be scattered back through row_index (dx row r = row_index[i]; other rows untouched).
-template <int CH>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy,
-                                                            const __nv_bfloat16* __restrict__ x, long long ldx,
-                                                            const long long* __restrict__ row_index,
-                                                            const float* __restrict__ w, const float* __restrict__ mean,
-                                                            const float* __restrict__ rstd,
-                                                            const __nv_bfloat16* __restrict__ dres, long long lddres,
-                                                            __nv_bfloat16* __restrict__ dx, long long lddx,
-                                                            float* __restrict__ dw, float* __restrict__ db,
-                                                            float* __restrict__ dres_sum, int T, int D) {
+// dx = rstd * (w*dy - mean(w*dy) - xhat * mean(w*dy*xhat)) [+ dres];  dw += sum_t dy*xhat; db += sum_t dy;
+// dres_sum += sum_t dres (template RS).  Rows may be scattered back through row_index (dx row r = row_index[i]).
+// Two passes over the row: pass 1 reduces the two row statistics, pass 2 re-reads x / dy (L1 hits: a row is 2-4 KB) and
+// writes dx.  Not holding the row in registers keeps the kernel at <= 128 registers -> 16 warps / SM, which is what a
+// streaming kernel needs to cover HBM latency.
+template <int CH, bool RS>
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy,
+                                                               const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                               const long long* __restrict__ row_index,
+                                                               const float* __restrict__ w, const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd,
+                                                               const __nv_bfloat16* __restrict__ dres, long long lddres,
+                                                               __nv_bfloat16* __restrict__ dx, long long lddx,
+                                                               float* __restrict__ dw, float* __restrict__ db,
+                                                               float* __restrict__ dres_sum, int T, int D) {
   extern __shared__ float red[];  // [warps][D] reused for dw, db, dres_sum
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
   const int nvec = D >> 3;
-  float aw[CH][8], ab[CH][8], ar[CH][8];
+  const bool want_w = dw != nullptr;
+  float aw[CH][8], ab[CH][8], ar[RS ? CH : 1][8];
 #pragma unroll
   for (int c = 0; c < CH; ++c)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) aw[c][j] = ab[c][j] = ar[c][j] = 0.f;
+    for (int j = 0; j < 8; ++j) {
+      aw[c][j] = ab[c][j] = 0.f;
+      if (RS) ar[c][j] = 0.f;
+    }
 
   for (long long row = (long long)blockIdx.x * wpb + warp; row < T; row += (long long)gridDim.x * wpb) {
     const long long src = row_index ? row_index[row] : row;
     const uint4* xr = reinterpret_cast<const uint4*>(x + src * ldx);
     const uint4* gr = reinterpret_cast<const uint4*>(dy + row * lddy);
     const float mu = mean[row], rs = rstd[row];
-    float xh[CH][8], g[CH][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int i = lane + c * 32;
       if (i < nvec) {
-        unpack8(xr[i], xh[c]);
-        unpack8(gr[i], g[c]);
+        float xv[8], gv[8];
+        unpack8(xr[i], xv);
+        unpack8(gr[i], gv);
         const float4 w0 = __ldg(reinterpret_cast<const float4*>(w) + 2 * i), w1 = __ldg(reinterpret_cast<const float4*>(w) + 2 * i + 1);
         const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          xh[c][j] = (xh[c][j] - mu) * rs;
-          aw[c][j] += g[c][j] * xh[c][j];
-          ab[c][j] += g[c][j];
-          g[c][j] *= wv[j];  // g now holds w*dy
-          s1 += g[c][j];
-          s2 += g[c][j] * xh[c][j];
+          const float wg = gv[j] * wv[j];
+          s1 += wg;
+          s2 += wg * ((xv[j] - mu) * rs);
         }
       }
     }
@@ -145,25 +149,36 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
     for (int c = 0; c < CH; ++c) {
       const int i = lane + c * 32;
       if (i < nvec) {
-        float o[8];
+        float xv[8], gv[8], o[8];
+        unpack8(xr[i], xv);
+        unpack8(gr[i], gv);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w) + 2 * i), w1 = __ldg(reinterpret_cast<const float4*>(w) + 2 * i + 1);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rs * (g[c][j] - s1 - xh[c][j] * s2);
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - mu) * rs;
+          if (want_w) {
+            aw[c][j] += gv[j] * xh;
+            ab[c][j] += gv[j];
+          }
+          o[j] = rs * (gv[j] * wv[j] - s1 - xh * s2);
+        }
         if (rr) {
           float r[8];
           unpack8(rr[i], r);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             o[j] += r[j];
-            ar[c][j] += r[j];
+            if (RS) ar[c][j] += r[j];
           }
         }
         dr[i] = pack8(o);
       }
     }
   }
-  if (dw == nullptr && dres_sum == nullptr) return;
+  if (dw == nullptr && (!RS || dres_sum == nullptr)) return;
   // block reduction of the per-warp partial column sums, then one atomic per column per CTA
-  for (int pass = 0; pass < 3; ++pass) {
+  for (int pass = 0; pass < (RS ? 3 : 2); ++pass) {
     float* dst = pass == 0 ? dw : (pass == 1 ? db : dres_sum);
     if (dst == nullptr) continue;
     __syncthreads();
@@ -172,7 +187,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
       const int i = lane + c * 32;
       if (i < nvec) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) red[warp * D + i * 8 + j] = pass == 0 ? aw[c][j] : (pass == 1 ? ab[c][j] : ar[c][j]);
+        for (int j = 0; j < 8; ++j) red[warp * D + i * 8 + j] = pass == 0 ? aw[c][j] : (pass == 1 ? ab[c][j] : ar[RS ? c : 0][j]);
       }
     }
     __syncthreads();
@@ -480,6 +495,36 @@ __global__ void __launch_bounds__(256) lse_combine_kernel(const float* __restric
   }
 }
 
+// Multi-tensor AdamW: one launch for every parameter.  chunk_tab[c] = (tensor id, element offset); per tensor a row of
+// five pointers (p, g, m, v, p16 | NULL) and a weight-decay value.  Also refreshes the bf16 operand copy of the weight.
+constexpr int kAdamChunk = 16384;
+__global__ void __launch_bounds__(256) adamw_multi_kernel(const long long* __restrict__ ptrs, const long long* __restrict__ sizes,
+                                                          const float* __restrict__ wds, const int2* __restrict__ chunk_tab, float lr, float b1,
+                                                          float b2, float eps, float bc1, float bc2, float grad_scale) {
+  const int2 ct = chunk_tab[blockIdx.x];
+  const long long* pr = ptrs + 5ll * ct.x;
+  float* p = reinterpret_cast<float*>(pr[0]);
+  const float* g = reinterpret_cast<const float*>(pr[1]);
+  float* m = reinterpret_cast<float*>(pr[2]);
+  float* v = reinterpret_cast<float*>(pr[3]);
+  __nv_bfloat16* p16 = reinterpret_cast<__nv_bfloat16*>(pr[4]);
+  const float wd = wds[ct.x];
+  const long long n = sizes[ct.x];
+  const long long base = static_cast<long long>(ct.y) * kAdamChunk;
+  const long long end = min(n, base + kAdamChunk);
+  for (long long i = base + threadIdx.x; i < end; i += 256) {
+    const float gi = g[i] * grad_scale;
+    float pi = p[i] * (1.0f - lr * wd);
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    pi -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+    p[i] = pi;
+    if (p16) p16[i] = __float2bfloat16(pi);
+  }
+}
+
 static inline int grid_for(long long work_items, int threads) {
   long long g = (work_items + threads - 1) / threads;
   const long long cap = (long long)num_sms() * 16;
@@ -519,19 +564,25 @@ int vl_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, c
   VL_CHECK_ARG(T > 0 && D > 0 && D % 8 == 0 && D <= 256 * kMaxLnChunks, "vl_layernorm_bwd: D=%d unsupported", D);
   VL_CHECK_ARG(ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0 && lddres % 8 == 0, "vl_layernorm_bwd: ld must be a multiple of 8");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  int grid = num_sms() * 2;
+  int grid = num_sms() * 4;
   if ((long long)grid * 8 > T) grid = (T + 7) / 8;
   const size_t smem = (dw || dres_sum) ? (size_t)8 * D * sizeof(float) : 0;
   const int ch = (D / 8 + 31) / 32;
-#define VL_LN_BWD(CH)                                                                                                     \
+#define VL_LN_BWD2(CH, RS)                                                                                               \
   do {                                                                                                                    \
-    if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    layernorm_bwd_kernel<CH><<<grid, 256, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy,                    \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_kernel<CH, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    layernorm_bwd_kernel<CH, RS><<<grid, 256, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy,                \
         reinterpret_cast<const __nv_bfloat16*>(x), ldx, (const long long*)row_index, w, mean, rstd,                       \
         reinterpret_cast<const __nv_bfloat16*>(dres), lddres, reinterpret_cast<__nv_bfloat16*>(dx), lddx, dw, db, dres_sum, T, D); \
   } while (0)
+#define VL_LN_BWD(CH)                  \
+  do {                                 \
+    if (dres_sum) VL_LN_BWD2(CH, true); \
+    else VL_LN_BWD2(CH, false);        \
+  } while (0)
   if (ch <= 1) VL_LN_BWD(1); else if (ch <= 2) VL_LN_BWD(2); else if (ch <= 4) VL_LN_BWD(4); else VL_LN_BWD(8);
 #undef VL_LN_BWD
+#undef VL_LN_BWD2
   return launch_check("layernorm_bwd");
 }
 
@@ -648,5 +699,15 @@ int vl_lse_combine(const float* part_max, const float* part_sum, const float* di
   VL_CHECK_ARG(part_max && part_sum && diag && lse && M > 0 && nparts > 0, "vl_lse_combine: bad arguments");
   lse_combine_kernel<<<(M + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(part_max, part_sum, diag, M, nparts, lse, loss_sum);
   return launch_check("lse_combine");
+}
+
+int vl_adamw_multi(const int64_t* ptrs, const int64_t* sizes, const float* wds, const int32_t* chunk_tab, int32_t n_chunks, float lr,
+                   float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream) {
+  VL_CHECK_ARG(ptrs && sizes && wds && chunk_tab && n_chunks > 0 && step >= 1, "vl_adamw_multi: bad arguments");
+  const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
+  adamw_multi_kernel<<<n_chunks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const long long*)ptrs, (const long long*)sizes, wds,
+                                                                                     reinterpret_cast<const int2*>(chunk_tab), lr, beta1, beta2, eps,
+                                                                                     bc1, bc2, grad_scale);
+  return launch_check("adamw_multi");
 }
 }

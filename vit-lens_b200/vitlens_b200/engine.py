@@ -42,6 +42,17 @@ class _WeightCache:
     def clear(self):
         self._c.clear()
 
+    def plain_copy(self, p):
+        """The cached plain bf16 copy of parameter `p` if it is current (used by the fused optimizer)."""
+        hit = self._c.get((id(p), ""))
+        if hit is not None and hit[0] == (p._version, p.data_ptr(), tuple(p.shape)):
+            return hit[1]
+        return None
+
+    def clear_derived(self):
+        for k in [k for k in self._c if not (isinstance(k, tuple) and len(k) == 2 and k[1] == "" and isinstance(k[0], int))]:
+            del self._c[k]
+
 
 WEIGHTS = _WeightCache()
 
@@ -131,10 +142,10 @@ class VitBlockFn(torch.autograd.Function):
             g[10] = _ops.colsum(du)
         dxn2 = _dgrad(du, w16(fcw))
         want_ln2 = _need(ctx, 7) or _need(ctx, 8)
-        # the column sums of the residual-branch gradient (= c_proj bias gradient) ride along in the LN backward pass
-        dx1, g7, g8, g12 = _ops.layernorm_bwd(dxn2, x1, ln2w, m2, r2, dres=dy, want_wgrad=want_ln2, want_dres_sum=True)
+        dx1, g7, g8 = _ops.layernorm_bwd(dxn2, x1, ln2w, m2, r2, dres=dy, want_wgrad=want_ln2)
         g[7], g[8] = (g7, g8) if want_ln2 else (None, None)
-        g[12] = g12 if _need(ctx, 12) else None
+        if _need(ctx, 12):
+            g[12] = _ops.colsum(dy)
         # ---- attention
         if _need(ctx, 5):
             g[5] = _wgrad(dx1, o)
@@ -149,11 +160,10 @@ class VitBlockFn(torch.autograd.Function):
         if _need(ctx, 0) or _need(ctx, 1) or _need(ctx, 2):
             dxn1 = _dgrad(dqkv, w16(inw))
             want_ln1 = _need(ctx, 1) or _need(ctx, 2)
-            dx, g1, g2, g6 = _ops.layernorm_bwd(dxn1, x, ln1w, m1, r1, dres=dx1, want_wgrad=want_ln1, want_dres_sum=True)
+            dx, g1, g2 = _ops.layernorm_bwd(dxn1, x, ln1w, m1, r1, dres=dx1, want_wgrad=want_ln1)
             g[0] = dx
             g[1], g[2] = (g1, g2) if want_ln1 else (None, None)
-            g[6] = g6 if _need(ctx, 6) else None
-        elif _need(ctx, 6):
+        if _need(ctx, 6):
             g[6] = _ops.colsum(dx1)
         return tuple(g)
 

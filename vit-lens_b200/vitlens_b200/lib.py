@@ -143,6 +143,7 @@ _PROTOS = {
     "vl_cast_f32_bf16": [_P, _P, _L, _P],
     "vl_add_bf16": [_P, _P, _P, _L, _P],
     "vl_adamw_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
+    "vl_adamw_multi": [_P, _P, _P, _P, _I, _F, _F, _F, _F, _I, _F, _P],
     "vl_lse_combine": [_P, _P, _P, _I, _I, _P, _P, _P],
     "vl_fps": [_P, _P, _I, _I, _I, _P, _P, _P],
     "vl_knn_group": [_P, _P, _I, _I, _I, _I, _P, _P, _P],
@@ -294,3 +295,10 @@ def wgrad3(dy, x, dw, *, R, C):
 
 def group_max(x, out, arg, *, groups, G, C):
     _call("vl_group_max", _p(x), _p(out), _p(arg), groups, G, C)
+
+
+ADAM_CHUNK = 16384
+
+
+def adamw_multi(ptrs, sizes, wds, chunk_tab, *, n_chunks, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    _call("vl_adamw_multi", _p(ptrs), _p(sizes), _p(wds), _p(chunk_tab), n_chunks, lr, beta1, beta2, eps, step, grad_scale)

@@ -21,32 +21,73 @@ def split_decay(named_parameters):
 
 
 class AdamW:
+    """All parameters are updated by ONE vl_adamw_multi launch per step; the same pass rewrites the cached bf16 operand
+    copies of the weights (engine.WEIGHTS) so no separate cast kernels run in the next forward."""
+
     def __init__(self, named_parameters: Iterable, lr=5e-4, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.2):
         no_decay, decay = split_decay(list(named_parameters))
         self.groups = [dict(params=no_decay, weight_decay=0.0), dict(params=decay, weight_decay=weight_decay)]
         self.lr, self.betas, self.eps = lr, betas, eps
-        self.state = {}
         self.t = 0
+        self._plan = None
+        self._copied = None
 
     def zero_grad(self):
         for g in self.groups:
             for p in g["params"]:
                 p.grad = None
 
-    @torch.no_grad()
-    def step(self, grad_scale: float = 1.0):
-        self.t += 1
+    def _build_plan(self):
+        params, wds = [], []
         for g in self.groups:
             for p in g["params"]:
-                if p.grad is None:
-                    continue
-                st = self.state.get(id(p))
-                if st is None:
-                    st = self.state[id(p)] = (torch.zeros_like(p), torch.zeros_like(p))
-                grad = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-                L.adamw_step(p, grad, st[0], st[1], lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
-                             weight_decay=g["weight_decay"], step=self.t, grad_scale=grad_scale)
-        engine.WEIGHTS.clear()  # master weights moved: bf16 operand copies are stale
+                params.append(p)
+                wds.append(g["weight_decay"])
+        dev = params[0].device
+        self.params = params
+        self.m = [torch.zeros_like(p) for p in params]
+        self.v = [torch.zeros_like(p) for p in params]
+        tab = []
+        for i, p in enumerate(params):
+            for c in range((p.numel() + L.ADAM_CHUNK - 1) // L.ADAM_CHUNK):
+                tab.append((i, c))
+        self.chunk_tab = torch.tensor(tab, dtype=torch.int32, device=dev).contiguous()
+        self.sizes = torch.tensor([p.numel() for p in params], dtype=torch.int64, device=dev)
+        self.wds = torch.tensor(wds, dtype=torch.float32, device=dev)
+        self.ptr_host = torch.zeros((len(params), 5), dtype=torch.int64).pin_memory()
+        self.ptr_host[:, 0] = torch.tensor([p.data_ptr() for p in params], dtype=torch.int64)
+        self.ptr_host[:, 2] = torch.tensor([t.data_ptr() for t in self.m], dtype=torch.int64)
+        self.ptr_host[:, 3] = torch.tensor([t.data_ptr() for t in self.v], dtype=torch.int64)
+        self.ptr_dev = torch.zeros((len(params), 5), dtype=torch.int64, device=dev)
+        self._plan = True
+
+    @torch.no_grad()
+    def step(self, grad_scale: float = 1.0):
+        if self._plan is None:
+            self._build_plan()
+        self.t += 1
+        keep, gp, wp = [], [], []
+        rows = self.ptr_host
+        for p in self.params:
+            g = p.grad
+            if g is None:
+                raise RuntimeError("AdamW.step: a parameter has no gradient (frozen parameters must not be passed to the optimizer)")
+            if not g.is_contiguous() or g.dtype != torch.float32:
+                g = g.contiguous().float()
+                keep.append(g)
+            w16 = engine.WEIGHTS.plain_copy(p)  # bf16 operand copy to refresh in place (None if this weight has none)
+            gp.append(g.data_ptr())
+            wp.append(0 if w16 is None else w16.data_ptr())
+        if self._copied is not None:
+            self._copied.synchronize()  # the previous step's async table upload must have left the pinned buffer
+        rows[:, 1] = torch.tensor(gp, dtype=torch.int64)
+        rows[:, 4] = torch.tensor(wp, dtype=torch.int64)
+        self.ptr_dev.copy_(rows, non_blocking=True)
+        self._copied = torch.cuda.Event()
+        self._copied.record()
+        L.adamw_multi(self.ptr_dev, self.sizes, self.wds, self.chunk_tab, n_chunks=self.chunk_tab.shape[0], lr=self.lr, beta1=self.betas[0],
+                      beta2=self.betas[1], eps=self.eps, step=self.t, grad_scale=grad_scale)
+        engine.WEIGHTS.clear_derived()  # concatenated / padded / folded copies are rebuilt lazily; plain copies were refreshed above
 
 
 def clamp_logit_scale(model, max_val=math.log(100)):
