@@ -42,17 +42,22 @@ struct GemmParams {
   const float* alpha_dev;
   const float* fparam_dev;
   int aux_row_div, relu;
+  int dbg;  // bring-up knob 9: 1 skip epilogue, 2 no global traffic in the epilogue, 4 sleeping epilogue waits, 8 MMA ignores full barriers
   uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;  // bytes
 };
 
-template <int BN>
+// TE = true: the epilogue stages each warp's 32 x 64 output block in shared memory (128B-swizzled, 4 KB per warp) and
+// moves it with TMA (bulk tensor store; the residual / pre-activation block arrives the same way), so global traffic is
+// whole 128-byte lines issued by the copy engine instead of 16-byte per-thread stores.  One pipeline stage pays for it.
+constexpr int kEpiBufBytes = 32 * 64 * 2;
+template <int BN, bool TE = false>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (BN == 256) ? (TE ? 3 : 4) : 6;
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = 0;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = TE ? (BN / 16) * kEpiBufBytes : 0;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 512 /*barriers*/;
   static constexpr int kTmemCols = 2 * BN;
 };
 
@@ -88,7 +93,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
   const float alpha_eff = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f);
   const float fparam_eff = p.fparam * (p.fparam_dev ? __ldg(p.fparam_dev) : 1.0f);
   const int row = row_base + quarter * 32 + lane;
-  const bool row_ok = row < p.M;
+  const bool row_ok = row < p.M && !(p.dbg & 2);
   const bool lead_split = (ks == 0);  // bias / aux terms are added by split 0 only
   float lse_m = -INFINITY, lse_s = 0.f, clip_ds = 0.f;
   const long long arow = p.aux_row_div > 1 ? row / p.aux_row_div : row;
@@ -264,10 +269,123 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
   }
 }
 
-template <int BN>
+
+// TMA-staged epilogue for bf16 outputs (LINEAR / GELU / RESIDUAL / GELU_BWD).  The warp owns rows [row_w, row_w + 32) x
+// columns [col_s, col_s + 64) of the output; `buf` is its private 4 KB staging block (layout = TMA SWIZZLE_128B: 16-byte
+// chunk j of row r lives at r*128 + ((j ^ (r & 7)) << 4), conflict-free for per-row 16-byte accesses).  When the mode
+// needs an aux block the caller has already issued its TMA load into `buf` (completion on aux_bar / aux_phase).
+// `release` hands the TMEM accumulator back as soon as the last tcgen05.ld has landed, before any store is issued.
+template <int BN, typename Release>
+__device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUtensorMap* tmD, const CUtensorMap* tmX, uint32_t tmem_base,
+                                                  uint32_t acc_col, int row_w, int col_s, int slice, int quarter, int lane, uint32_t buf,
+                                                  uint32_t aux_bar, uint32_t aux_phase, bool aux_loaded, Release release) {
+  const float alpha_eff = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f);
+  const bool need_aux = p.epi == VL_EPI_RESIDUAL || p.epi == VL_EPI_GELU_BWD;
+  const bool need_bias = p.bias != nullptr && p.epi != VL_EPI_GELU_BWD;
+  const bool keep_pre = p.epi == VL_EPI_GELU && p.aux_out != nullptr;
+  const uint32_t row_addr = buf + lane * 128;
+  const uint32_t sw = lane & 7;
+  uint32_t pre[32];  // packed pre-activations of the 64 columns (GELU forward keeps them for the second store)
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int col0 = col_s + c * 16;
+    uint32_t v[16];
+    tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc_col + slice * 64 + c * 16, v);
+    float bv[16];
+    if (need_bias) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b4 = (col0 + j < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j)) : make_float4(0, 0, 0, 0);
+        bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
+      }
+    }
+    tc_wait_ld();
+    if (c == 3) release();
+    float f[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * alpha_eff;
+    if (need_bias) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] += bv[j];
+    }
+    const uint32_t a0 = row_addr + (((2 * c) ^ sw) << 4), a1 = row_addr + (((2 * c + 1) ^ sw) << 4);
+    if (p.epi == VL_EPI_GELU) {
+      if (keep_pre) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pre[8 * c + j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+      }
+      if (p.act_quick == 2) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+      } else if (p.act_quick) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = gelu_quick_fwd(f[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = gelu_erf_fwd(f[j]);
+      }
+    } else if (need_aux) {
+      if (c == 0 && aux_loaded) mbar_wait(aux_bar, aux_phase);
+      const uint4 x0 = ld_shared_v4(a0), x1 = ld_shared_v4(a1);
+      const uint32_t aw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      if (p.epi == VL_EPI_RESIDUAL) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          f[2 * j] += bf16_lo(aw[j]);
+          f[2 * j + 1] += bf16_hi(aw[j]);
+        }
+      } else if (p.act_quick == 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          f[2 * j] = bf16_lo(aw[j]) > 0.f ? f[2 * j] : 0.f;
+          f[2 * j + 1] = bf16_hi(aw[j]) > 0.f ? f[2 * j + 1] : 0.f;
+        }
+      } else if (p.act_quick) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          f[2 * j] *= gelu_quick_grad(bf16_lo(aw[j]));
+          f[2 * j + 1] *= gelu_quick_grad(bf16_hi(aw[j]));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          f[2 * j] *= gelu_erf_grad(bf16_lo(aw[j]));
+          f[2 * j + 1] *= gelu_erf_grad(bf16_hi(aw[j]));
+        }
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    st_shared_v4(a0, pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+    st_shared_v4(a1, pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0 && !(p.dbg & 2)) {
+    tma_store_2d(tmD, buf, col_s, row_w);
+    tma_store_commit();
+  }
+  if (keep_pre) {
+    if (lane == 0) tma_store_wait_read<0>();
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) st_shared_v4(row_addr + ((j ^ sw) << 4), pre[4 * j], pre[4 * j + 1], pre[4 * j + 2], pre[4 * j + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && !(p.dbg & 2)) {
+      tma_store_2d(tmX, buf, col_s, row_w);
+      tma_store_commit();
+    }
+  }
+}
+
+template <int BN, bool TE>
 __global__ void __launch_bounds__(EpiCfg<BN>::kThreads, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
+                 const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
+  using Cfg = GemmCfg<BN, TE>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stg_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
@@ -277,6 +395,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  auto aux_bar = [&](int e) { return bar_base + 8u * (2 * Cfg::kStages + 5 + e); };
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -287,6 +406,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (TE) {
+      tma_prefetch_desc(&tmD);
+      tma_prefetch_desc(&tmX);
+      for (int e = 0; e < EpiCfg<BN>::kWarps; ++e) mbar_init(aux_bar(e), 1);
+    }
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -359,7 +483,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+          if (!(p.dbg & 8)) mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
@@ -388,20 +512,58 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
+    [[maybe_unused]] uint32_t aux_phase = 0;
+    [[maybe_unused]] const uint32_t buf = stg_base + e * kEpiBufBytes;
+    [[maybe_unused]] const bool need_aux = p.epi == VL_EPI_RESIDUAL || p.epi == VL_EPI_GELU_BWD;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int m_blk, n_blk, ks;
       tile_coords(p, t, m_blk, n_blk, ks);
-      mbar_wait(tfull_bar(acc), acc_phase);
+      [[maybe_unused]] const int row_w = m_blk * kBM + quarter * 32;
+      [[maybe_unused]] const int col_s = n_blk * BN + (e >> 2) * 64;
+      [[maybe_unused]] const bool active = row_w < p.M && col_s < p.N;
+      if constexpr (TE) {
+        if (lane == 0 && active) {
+          tma_store_wait_read<0>();  // the previous tile's store has finished reading the staging block
+          if (need_aux && !(p.dbg & 3)) {
+            mbar_expect_tx(aux_bar(e), kEpiBufBytes);
+            tma_load_2d(buf, &tmX, aux_bar(e), col_s, row_w);
+          }
+        }
+        __syncwarp();
+      }
+      if (p.dbg & 4) {
+        while (!mbar_try_wait(tfull_bar(acc), acc_phase)) __nanosleep(64);
+      } else {
+        mbar_wait(tfull_bar(acc), acc_phase);
+      }
       tc_fence_after();
-      epilogue_tile<BN, EpiCfg<BN>::kChunk>(p, tmem_base, acc * BN, m_blk * kBM, n_blk, ks, e, quarter, lane);
-      // accumulator drained -> hand the TMEM buffer back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if constexpr (TE) {
+        auto release = [&]() {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        };
+        if (active && !(p.dbg & 1)) {
+          epilogue_tile_tma<BN>(p, &tmD, &tmX, tmem_base, acc * BN, row_w, col_s, e >> 2, quarter, lane, buf, aux_bar(e),
+                                aux_phase, need_aux && !(p.dbg & 3), release);
+          if (need_aux) aux_phase ^= 1;
+        } else {
+          release();
+        }
+      } else {
+        if (!(p.dbg & 1)) epilogue_tile<BN, EpiCfg<BN>::kChunk>(p, tmem_base, acc * BN, m_blk * kBM, n_blk, ks, e, quarter, lane);
+        // accumulator drained -> hand the TMEM buffer back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
       }
+    }
+    if constexpr (TE) {
+      if (lane == 0) tma_store_wait<0>();  // all bulk stores complete before the CTA exits
     }
   }
 
@@ -416,9 +578,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 template <int BN>
 static int launch_gemm2(const VlGemmArgs& a, GemmParams p, cudaStream_t stream);
 
+// The TMA-staged epilogue applies to bf16 outputs of the four activation-path modes.  debug knob 10: 1 = force the
+// per-thread global-store epilogue.
+template <int BN>
+static bool tma_epilogue_ok(const VlGemmArgs& a, const GemmParams& p) {
+  return BN == 256 && !a.d_f32 && !a.accumulate && p.split_k == 1 && p.aux_row_div == 1 &&
+         (a.epilogue == VL_EPI_LINEAR || a.epilogue == VL_EPI_GELU || a.epilogue == VL_EPI_RESIDUAL || a.epilogue == VL_EPI_GELU_BWD) &&
+         (reinterpret_cast<uintptr_t>(a.d) & 15) == 0 && debug_get(10) != 1;
+}
+
+static int make_epilogue_maps(const VlGemmArgs& a, CUtensorMap* tmD, CUtensorMap* tmX) {
+  int rc = make_tmap_bf16_2d(tmD, a.d, a.N, a.M, a.ldd, 64, 32);
+  if (rc) return rc;
+  const void* xptr = (a.epilogue == VL_EPI_GELU) ? a.aux_out : a.aux_in;
+  if (xptr != nullptr && a.epilogue != VL_EPI_LINEAR) {
+    VL_CHECK_ARG((reinterpret_cast<uintptr_t>(xptr) & 15) == 0, "vl_gemm_bf16: aux pointer must be 16-byte aligned");
+    return make_tmap_bf16_2d(tmX, xptr, a.N, a.M, a.ldaux, 64, 32);
+  }
+  *tmX = *tmD;
+  return 0;
+}
+
 // debug knob 8: 0 = default kernel choice, 1 = force the single-CTA kernel, 2 = force the CTA-pair kernel.
-// Measured on B200 (profiles/r01_probe_gemm_pair_vs_single.log): the pair kernel equals the single-CTA kernel on the
-// K-major shapes and is 8-10 % faster on the MN-major weight-gradient shapes, so it is the default only there.
+// Measured on B200 (profiles/r01_gemm_epilogue_attribution.log): with the TMA-staged epilogue the pair kernel wins on every
+// ViT-L shape (its main loop alone sustains 1.55-1.62 PFLOP/s against 1.44-1.49 for the single-CTA kernel), so it is the
+// default whenever there are at least two 256-row tiles; the contrastive-loss epilogues stay on the single-CTA kernel.
 
 template <int BN>
 static int launch_gemm(const VlGemmArgs& a, cudaStream_t stream) {
@@ -459,6 +643,7 @@ static int launch_gemm(const VlGemmArgs& a, cudaStream_t stream) {
   p.fparam_dev = a.fparam_dev;
   p.aux_row_div = a.aux_row_div > 1 ? a.aux_row_div : 1;
   p.relu = a.relu;
+  p.dbg = debug_get(9);
   // K-major: 8-row groups 1024 B apart, +32 B per UMMA_K inside the swizzle row.
   // MN-major: 64-wide chunks kBK*128 B apart (LBO), 8-K groups 1024 B apart (SBO), +2048 B per UMMA_K.
   p.a_lbo = p.a_mn ? kBK * 128 : 16;
@@ -477,10 +662,10 @@ static int launch_gemm(const VlGemmArgs& a, cudaStream_t stream) {
   {
     const int mode = debug_get(8);
     const bool pair_ok = a.M >= 4 * kBM && BN == 256;
-    const bool pair_default = p.a_mn && p.b_mn;
+    const bool pair_default = a.epilogue != VL_EPI_ROWLSE && a.epilogue != VL_EPI_CLIPGRAD;
     if (mode == 2 || (mode == 0 && pair_default && pair_ok)) return launch_gemm2<BN>(a, p, stream);
   }
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmD, tmX;
   int rc;
   if (!p.a_mn)
     rc = make_tmap_bf16_2d(&tmA, a.a, a.K, a.M, a.lda, kBK, kBM);
@@ -493,15 +678,30 @@ static int launch_gemm(const VlGemmArgs& a, cudaStream_t stream) {
     rc = make_tmap_bf16_2d(&tmB, a.b, a.N, a.K, a.ldb, 64, kBK);
   if (rc) return rc;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    VL_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  const bool te = tma_epilogue_ok<BN>(a, p);
   const int total = p.tiles_m * p.tiles_n * p.split_k;
   int grid = total < num_sms() ? total : num_sms();
   if (debug_get(7) > 0 && debug_get(7) < grid) grid = debug_get(7);
-  gemm_bf16_kernel<BN><<<grid, EpiCfg<BN>::kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  if constexpr (BN == 256) {
+    if (te) {
+      using CfgT = GemmCfg<BN, true>;
+      rc = make_epilogue_maps(a, &tmD, &tmX);
+      if (rc) return rc;
+      static bool attr_set_t = false;
+      if (!attr_set_t) {
+        VL_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgT::kSmemBytes));
+        attr_set_t = true;
+      }
+      gemm_bf16_kernel<BN, true><<<grid, EpiCfg<BN>::kThreads, CfgT::kSmemBytes, stream>>>(tmA, tmB, tmD, tmX, p);
+      return launch_check("gemm_bf16_kernel<tma epilogue>");
+    }
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    VL_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  gemm_bf16_kernel<BN, false><<<grid, EpiCfg<BN>::kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmA, tmA, p);
   return launch_check("gemm_bf16_kernel");
 }
 
@@ -515,14 +715,14 @@ static int launch_gemm(const VlGemmArgs& a, cudaStream_t stream) {
 //   empty[s]  (one per CTA)                                   <- leader's tcgen05.commit, multicast to both CTAs
 //   tfull[a]  (one per CTA)                                   <- leader's tcgen05.commit, multicast
 //   tempty[a] (leader's, 2 x 8 arrivals)                      <- epilogue warps of both CTAs
-template <int BN>
+template <int BN, bool TE = false>
 struct Gemm2Cfg {
-  static constexpr int kStages = (BN == 256) ? 6 : 8;
+  static constexpr int kStages = (BN == 256) ? (TE ? 5 : 6) : 8;
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = (BN / 2) * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = 0;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kStagingBytes = TE ? (BN / 16) * kEpiBufBytes : 0;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 512;
   static constexpr int kTmemCols = 2 * BN;
 };
 
@@ -548,10 +748,11 @@ __device__ __forceinline__ void tile_coords2(const GemmParams& p, int tiles_m2, 
   m_blk = m_first + (r - n_blk * gm);
 }
 
-template <int BN>
+template <int BN, bool TE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<BN>::kThreads, 1)
-gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = Gemm2Cfg<BN>;
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
+                  const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
+  using Cfg = Gemm2Cfg<BN, TE>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0) __trap();  // both CTAs must use identical offsets (the MMA addresses the peer by offset)
@@ -562,6 +763,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  auto aux_bar = [&](int e) { return bar_base + 8u * (2 * Cfg::kStages + 5 + e); };
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5;
@@ -576,6 +778,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (TE) {
+      tma_prefetch_desc(&tmD);
+      tma_prefetch_desc(&tmX);
+      for (int e = 0; e < EpiCfg<BN>::kWarps; ++e) mbar_init(aux_bar(e), 1);
+    }
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(full_bar(s), 1);  // the leader's arrive.expect_tx; the peer only contributes transaction bytes
       mbar_init(empty_bar(s), 1);
@@ -653,7 +860,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait_guarded(full_bar(stage), phase);
+          if (!(p.dbg & 8)) mbar_wait_guarded(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
@@ -682,19 +889,56 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int quarter = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
+    [[maybe_unused]] uint32_t aux_phase = 0;
+    [[maybe_unused]] const uint32_t buf = stg_base + e * kEpiBufBytes;
+    [[maybe_unused]] const bool need_aux = p.epi == VL_EPI_RESIDUAL || p.epi == VL_EPI_GELU_BWD;
     for (int t = cluster_id; t < total_tiles; t += num_clusters) {
       int m_blk, n_blk, ks;
       tile_coords2(p, tiles_m2, t, m_blk, n_blk, ks);
-      mbar_wait_guarded(tfull_bar(acc), acc_phase);
+      const int row_base = m_blk * 2 * kBM + static_cast<int>(rank) * kBM;
+      [[maybe_unused]] const int row_w = row_base + quarter * 32;
+      [[maybe_unused]] const int col_s = n_blk * BN + (e >> 2) * 64;
+      [[maybe_unused]] const bool active = row_w < p.M && col_s < p.N;
+      if constexpr (TE) {
+        if (lane == 0 && active) {
+          tma_store_wait_read<0>();
+          if (need_aux && !(p.dbg & 3)) {
+            mbar_expect_tx(aux_bar(e), kEpiBufBytes);
+            tma_load_2d(buf, &tmX, aux_bar(e), col_s, row_w);
+          }
+        }
+        __syncwarp();
+      }
+      if (p.dbg & 4) {
+        while (!mbar_try_wait(tfull_bar(acc), acc_phase)) __nanosleep(64);
+      } else {
+        mbar_wait_guarded(tfull_bar(acc), acc_phase);
+      }
       tc_fence_after();
-      epilogue_tile<BN, EpiCfg<BN>::kChunk>(p, tmem_base, acc * BN, m_blk * 2 * kBM + static_cast<int>(rank) * kBM, n_blk, ks, e, quarter, lane);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+      auto release = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+      };
+      if constexpr (TE) {
+        if (active && !(p.dbg & 1)) {
+          epilogue_tile_tma<BN>(p, &tmD, &tmX, tmem_base, acc * BN, row_w, col_s, e >> 2, quarter, lane, buf, aux_bar(e), aux_phase,
+                                need_aux && !(p.dbg & 3), release);
+          if (need_aux) aux_phase ^= 1;
+        } else {
+          release();
+        }
+      } else {
+        if (!(p.dbg & 1)) epilogue_tile<BN, EpiCfg<BN>::kChunk>(p, tmem_base, acc * BN, row_base, n_blk, ks, e, quarter, lane);
+        release();
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
       }
+    }
+    if constexpr (TE) {
+      if (lane == 0) tma_store_wait<0>();
     }
   }
 
@@ -710,9 +954,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 template <int BN>
 static int launch_gemm2(const VlGemmArgs& a, GemmParams p, cudaStream_t stream) {
-  using Cfg = Gemm2Cfg<BN>;
+  using Cfg = Gemm2Cfg<BN, false>;
   // MN-major chunk strides are the same; only B's per-CTA row count halves
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmD, tmX;
   int rc;
   if (!p.a_mn)
     rc = make_tmap_bf16_2d(&tmA, a.a, a.K, a.M, a.lda, kBK, kBM);
@@ -724,17 +968,31 @@ static int launch_gemm2(const VlGemmArgs& a, GemmParams p, cudaStream_t stream) 
   else
     rc = make_tmap_bf16_2d(&tmB, a.b, a.N, a.K, a.ldb, 64, kBK);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VL_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
   const int tiles_m2 = (a.M + 2 * kBM - 1) / (2 * kBM);
   const int total = tiles_m2 * p.tiles_n * p.split_k;
   int clusters = num_sms() / 2;
   if (total < clusters) clusters = total;
   if (debug_get(7) > 0 && debug_get(7) < clusters) clusters = debug_get(7);
-  gemm2_bf16_kernel<BN><<<2 * clusters, EpiCfg<BN>::kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  if constexpr (BN == 256) {
+    if (tma_epilogue_ok<BN>(a, p)) {
+      using CfgT = Gemm2Cfg<BN, true>;
+      rc = make_epilogue_maps(a, &tmD, &tmX);
+      if (rc) return rc;
+      static bool attr_set_t = false;
+      if (!attr_set_t) {
+        VL_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgT::kSmemBytes));
+        attr_set_t = true;
+      }
+      gemm2_bf16_kernel<BN, true><<<2 * clusters, EpiCfg<BN>::kThreads, CfgT::kSmemBytes, stream>>>(tmA, tmB, tmD, tmX, p);
+      return launch_check("gemm2_bf16_kernel<tma epilogue>");
+    }
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    VL_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  gemm2_bf16_kernel<BN, false><<<2 * clusters, EpiCfg<BN>::kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmA, tmA, p);
   return launch_check("gemm2_bf16_kernel");
 }
 
