@@ -73,7 +73,9 @@ def _ref_attn(q, k, v, causal):
 
 @pytest.mark.parametrize("B,H,nq,nk,causal,packed", [
     (2, 2, 257, 257, False, True), (3, 2, 77, 77, True, True), (2, 16, 256, 256, False, True), (2, 1, 256, 600, False, False),
-    (2, 2, 17, 17, False, True), (4, 12, 50, 50, False, True), (2, 1, 128, 512, False, False), (1, 1, 1, 1, False, True)])
+    (2, 2, 17, 17, False, True), (4, 12, 50, 50, False, True), (2, 1, 128, 512, False, False), (1, 1, 1, 1, False, True),
+    (2, 2, 513, 513, False, True), (2, 1, 229, 229, False, True), (1, 2, 130, 259, False, False), (2, 1, 300, 300, True, True),
+    (1, 1, 640, 132, False, False)])
 def test_attention_fwd_bwd(ops, B, H, nq, nk, causal, packed):
     D = H * 64
     if packed:

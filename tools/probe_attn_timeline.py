@@ -1,4 +1,4 @@
-"""clock64 timeline of attn_bwd_kernel's compute warps (first 8 CTAs) -- where does a CTA's time go?"""
+"""clock64 timeline of attn_bwd2_kernel's two compute groups (first CTAs) -- where does a CTA's time go?"""
 import ctypes, os, sys, torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "vit-lens_b200"))
 from vitlens_b200 import lib as L
@@ -23,25 +23,22 @@ bwd()
 torch.cuda.synchronize()
 h.vl_debug_buffer(ctypes.c_void_p(0))
 t = buf.cpu().reshape(8, 64)
-names = ["start", "prologue done"]
-for pr in range(4):
-    names += [f"p{pr} S ready", f"p{pr} prev retired", f"p{pr} P written", f"p{pr} dP ready", f"p{pr} dS written"]
-# insertion points of dK/dV stamps: after pairs of each key block (2 pairs per block)
+# per group (32 slots each): start, prologue done, then per key block: [S ready, P written, dP ready, dS written] (when the
+# group has a pair), dKV complete, block done; then dQ complete, tile outputs written, end.
 seq = ["start", "prologue done"]
 for j in range(2):
-    for i in range(2):
-        pr = j * 2 + i
-        seq += [f"p{pr} S ready", f"p{pr} prev retired", f"p{pr} P written", f"p{pr} dP ready", f"p{pr} dS written"]
-    seq += [f"blk{j} dKV complete", f"blk{j} dKV written"]
-seq += ["dQ complete"]
-for c in range(3):
-    row = t[c]
-    base = int(row[0])
-    print(f"--- CTA {c}: total to compute-done {int(row[63]) - base} cycles")
-    prev = base
-    for n, nm in enumerate(seq):
-        val = int(row[n])
-        if val == 0:
-            break
-        print(f"   {nm:22s} +{val - prev:7d}   (t={val - base})")
-        prev = val
+    seq += [f"blk{j} S ready", f"blk{j} P written", f"blk{j} dP ready", f"blk{j} dS written", f"blk{j} dKV complete", f"blk{j} tail dots",
+            f"blk{j} dKV rows stored", f"blk{j} done (mat-vec)"]
+seq += ["dQ complete", "tail-key dots", "dQ rows stored", "tail mat-vecs done", "end"]
+for c in range(2):
+    for g in range(2):
+        row = t[c][g * 32:(g + 1) * 32]
+        base = int(t[c][0])
+        print(f"--- CTA {c} group {g}")
+        prev = int(row[0])
+        for n, nm in enumerate(seq):
+            val = int(row[n])
+            if val == 0:
+                break
+            print(f"   {nm:28s} +{val - prev:7d}   (t={val - base})")
+            prev = val

@@ -40,15 +40,16 @@ def timeit(M, N, K, epi, iters=8):
 
 
 if __name__ == "__main__":
-    for kern, kname in ((1, "single"), (2, "pair")):
+    for kern, kname in ((2, "pair"), (1, "single")):
         L.debug_set(8, kern)
-        for te, tname in ((0, "tma-epi"), (1, "direct ")):
-            L.debug_set(10, te)
+        for ew in (8, 16, 0):
+            L.debug_set(10, 1 if ew == 0 else 0)
+            L.debug_set(11, ew)
+            tname = f"tma-epi/{ew}w" if ew else "direct/16w "
             for dbg, dname in ((0, "normal"), (2, "epilogue without global traffic"), (1, "no epilogue")):
                 L.debug_set(9, dbg)
                 for name, M, N, K, epi in SHAPES:
                     ms, tf = timeit(M, N, K, epi)
-                    print(f"[{kname:6s} {tname}] {dname:32s} {name:9s} {ms:.3f} ms {tf:6.0f} TFLOP/s", flush=True)
-    L.debug_set(8, 0)
-    L.debug_set(9, 0)
-    L.debug_set(10, 0)
+                    print(f"[{kname:6s} {tname}] {dname:32s} {name:11s} {ms:.3f} ms {tf:6.0f} TFLOP/s", flush=True)
+    for k in (8, 9, 10, 11):
+        L.debug_set(k, 0)

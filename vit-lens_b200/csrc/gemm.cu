@@ -84,6 +84,17 @@ struct EpiCfg {
   static constexpr int kChunk = (kWarps > 8) ? 16 : 32;  // accumulator columns per step (register budget: 65536 / kThreads)
 };
 
+// Kernel flavours: EW = 0 -> per-thread global stores, EpiCfg<BN>::kWarps epilogue warps; EW = 8 -> TMA-staged epilogue with
+// 8 warps that own two 64-column slices each.  (Measured: 16 warps at the 96-register cap of an 18-warp CTA serialise the
+// activation math through one register; 8 warps with 168 registers keep 16 independent element streams in flight and
+// are faster on every shape - profiles/r01_gemm_epilogue_attribution.log.)
+template <int BN, int EW>
+struct KernelCfg {
+  static constexpr bool kTE = EW > 0;
+  static constexpr int kEpiWarps = EW > 0 ? EW : EpiCfg<BN>::kWarps;
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
+};
+
 // One output tile's epilogue for the calling warp: rows [row_base + quarter*32, +32), columns of slice (e >> 2) of n-tile
 // n_blk; thread t owns row quarter*32 + t and processes it 32 accumulator columns at a time.
 template <int BN, int CW>
@@ -278,35 +289,56 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
 template <int BN, typename Release>
 __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUtensorMap* tmD, const CUtensorMap* tmX, uint32_t tmem_base,
                                                   uint32_t acc_col, int row_w, int col_s, int slice, int quarter, int lane, uint32_t buf,
-                                                  uint32_t aux_bar, uint32_t aux_phase, bool aux_loaded, Release release) {
+                                                  uint32_t buf2, uint32_t aux_bar, uint32_t aux_phase, bool aux_loaded, bool last_slice,
+                                                  Release release) {
   const float alpha_eff = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f);
   const bool need_aux = p.epi == VL_EPI_RESIDUAL || p.epi == VL_EPI_GELU_BWD;
   const bool need_bias = p.bias != nullptr && p.epi != VL_EPI_GELU_BWD;
   const bool keep_pre = p.epi == VL_EPI_GELU && p.aux_out != nullptr;
-  const uint32_t row_addr = buf + lane * 128;
   const uint32_t sw = lane & 7;
+  // GELU forward issues two stores per slice; when the warp owns a second staging block (buf2 != buf) the stores alternate
+  // between the two so that a block is only rewritten two stores later (no wait on the store that was just issued).
+  const bool ring = keep_pre && buf2 != buf;
+  if (ring) {
+    if (lane == 0) tma_store_wait_read<1>();
+    __syncwarp();
+  }
+  const uint32_t row_addr = buf + lane * 128;
   uint32_t pre[32];  // packed pre-activations of the 64 columns (GELU forward keeps them for the second store)
+  float bnext[16];
+  auto load_bias = [&](int c, float (&bv)[16]) {
+    const int col0 = col_s + c * 16;
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 b4 = (col0 + j < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j)) : make_float4(0, 0, 0, 0);
+      bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
+    }
+  };
+  if (need_bias) load_bias(0, bnext);
+  const uint32_t tsrc = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc_col + slice * 64;
+  uint32_t vnext[16];
+  tmem_ld16(tsrc, vnext);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    const int col0 = col_s + c * 16;
     uint32_t v[16];
-    tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc_col + slice * 64 + c * 16, v);
     float bv[16];
-    if (need_bias) {
-#pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        const float4 b4 = (col0 + j < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j)) : make_float4(0, 0, 0, 0);
-        bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
-      }
-    }
     tc_wait_ld();
-    if (c == 3) release();
-    float f[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * alpha_eff;
+    for (int j = 0; j < 16; ++j) v[j] = vnext[j];
+    if (c < 3) tmem_ld16(tsrc + (c + 1) * 16, vnext);  // next chunk's accumulators stream in during this chunk's math
+    if (c == 3 && last_slice) release();
     if (need_bias) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) f[j] += bv[j];
+      for (int j = 0; j < 16; ++j) bv[j] = bnext[j];
+      if (c < 3) load_bias(c + 1, bnext);  // likewise the next chunk's bias
+    }
+    float f[16];
+    if (need_bias) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = fmaf(__uint_as_float(v[j]), alpha_eff, bv[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * alpha_eff;
     }
     const uint32_t a0 = row_addr + (((2 * c) ^ sw) << 4), a1 = row_addr + (((2 * c + 1) ^ sw) << 4);
     if (p.epi == VL_EPI_GELU) {
@@ -368,23 +400,28 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
     tma_store_commit();
   }
   if (keep_pre) {
-    if (lane == 0) tma_store_wait_read<0>();
+    if (lane == 0) {
+      if (ring) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+    }
     __syncwarp();
+    const uint32_t row2 = (ring ? buf2 : buf) + lane * 128;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) st_shared_v4(row_addr + ((j ^ sw) << 4), pre[4 * j], pre[4 * j + 1], pre[4 * j + 2], pre[4 * j + 3]);
+    for (int j = 0; j < 8; ++j) st_shared_v4(row2 + ((j ^ sw) << 4), pre[4 * j], pre[4 * j + 1], pre[4 * j + 2], pre[4 * j + 3]);
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0 && !(p.dbg & 2)) {
-      tma_store_2d(tmX, buf, col_s, row_w);
+      tma_store_2d(tmX, ring ? buf2 : buf, col_s, row_w);
       tma_store_commit();
     }
   }
 }
 
-template <int BN, bool TE>
-__global__ void __launch_bounds__(EpiCfg<BN>::kThreads, 1)
+template <int BN, int EW>
+__global__ void __launch_bounds__((KernelCfg<BN, EW>::kThreads), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
                  const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
+  constexpr bool TE = EW > 0;
+  constexpr int kEpiWarps = KernelCfg<BN, EW>::kEpiWarps;
   using Cfg = GemmCfg<BN, TE>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -409,7 +446,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (TE) {
       tma_prefetch_desc(&tmD);
       tma_prefetch_desc(&tmX);
-      for (int e = 0; e < EpiCfg<BN>::kWarps; ++e) mbar_init(aux_bar(e), 1);
+      for (int e = 0; e < 16; ++e) mbar_init(aux_bar(e), 1);
     }
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(full_bar(s), 1);
@@ -417,7 +454,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), EpiCfg<BN>::kWarps);
+      mbar_init(tempty_bar(a), kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -513,20 +550,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     [[maybe_unused]] uint32_t aux_phase = 0;
-    [[maybe_unused]] const uint32_t buf = stg_base + e * kEpiBufBytes;
     [[maybe_unused]] const bool need_aux = p.epi == VL_EPI_RESIDUAL || p.epi == VL_EPI_GELU_BWD;
+    constexpr int kGroups = kEpiWarps / 4;             // warps per TMEM lane quarter
+    [[maybe_unused]] constexpr int kSlicesPerWarp = (BN / 64) / kGroups;  // 64-column slices each warp owns (TE path)
+    // GELU forward (two stores per slice): the warp's two staging blocks form a ring, activation -> first, pre-activation ->
+    // second, for both of its slices (see epilogue_tile_tma).
+    [[maybe_unused]] const bool ring2 = kSlicesPerWarp > 1 && p.epi == VL_EPI_GELU && p.aux_out != nullptr;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int m_blk, n_blk, ks;
       tile_coords(p, t, m_blk, n_blk, ks);
-      [[maybe_unused]] const int row_w = m_blk * kBM + quarter * 32;
-      [[maybe_unused]] const int col_s = n_blk * BN + (e >> 2) * 64;
-      [[maybe_unused]] const bool active = row_w < p.M && col_s < p.N;
+      const int row_base = m_blk * kBM;
+      [[maybe_unused]] const int row_w = row_base + quarter * 32;
       if constexpr (TE) {
-        if (lane == 0 && active) {
-          tma_store_wait_read<0>();  // the previous tile's store has finished reading the staging block
+        if (lane == 0 && row_w < p.M) {
+          tma_store_wait_read<0>();  // the previous tile's stores have finished reading the staging blocks
           if (need_aux && !(p.dbg & 3)) {
-            mbar_expect_tx(aux_bar(e), kEpiBufBytes);
-            tma_load_2d(buf, &tmX, aux_bar(e), col_s, row_w);
+#pragma unroll
+            for (int si = 0; si < kSlicesPerWarp; ++si) {
+              const int slice = (e >> 2) + si * kGroups;
+              const int col_s = n_blk * BN + slice * 64;
+              if (col_s < p.N) {
+                mbar_expect_tx(aux_bar(slice * 4 + quarter), kEpiBufBytes);
+                tma_load_2d(stg_base + (slice * 4 + quarter) * kEpiBufBytes, &tmX, aux_bar(slice * 4 + quarter), col_s, row_w);
+              }
+            }
           }
         }
         __syncwarp();
@@ -537,25 +584,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(tfull_bar(acc), acc_phase);
       }
       tc_fence_after();
-      if constexpr (TE) {
-        auto release = [&]() {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
-        };
-        if (active && !(p.dbg & 1)) {
-          epilogue_tile_tma<BN>(p, &tmD, &tmX, tmem_base, acc * BN, row_w, col_s, e >> 2, quarter, lane, buf, aux_bar(e),
-                                aux_phase, need_aux && !(p.dbg & 3), release);
-          if (need_aux) aux_phase ^= 1;
-        } else {
-          release();
-        }
-      } else {
-        if (!(p.dbg & 1)) epilogue_tile<BN, EpiCfg<BN>::kChunk>(p, tmem_base, acc * BN, m_blk * kBM, n_blk, ks, e, quarter, lane);
-        // accumulator drained -> hand the TMEM buffer back to the MMA warp
+      auto release = [&]() {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
+      };
+      if constexpr (TE) {
+        bool released = false;
+        if (row_w < p.M && !(p.dbg & 1)) {
+#pragma unroll
+          for (int si = 0; si < kSlicesPerWarp; ++si) {
+            const int slice = (e >> 2) + si * kGroups;
+            const int col_s = n_blk * BN + slice * 64;
+            if (col_s < p.N) {
+              const bool last = (si == kSlicesPerWarp - 1) || (col_s + kGroups * 64 >= p.N);
+              epilogue_tile_tma<BN>(p, &tmD, &tmX, tmem_base, acc * BN, row_w, col_s, slice, quarter, lane,
+                                    stg_base + ((ring2 ? (e >> 2) : slice) * 4 + quarter) * kEpiBufBytes,
+                                    stg_base + ((ring2 ? (e >> 2) + kGroups : slice) * 4 + quarter) * kEpiBufBytes,
+                                    aux_bar(slice * 4 + quarter), aux_phase,
+                                    need_aux && !(p.dbg & 3), last, release);
+              released |= last;
+            }
+          }
+        }
+        if (!released) release();
+        if (need_aux) aux_phase ^= 1;
+      } else {
+        if (!(p.dbg & 1)) epilogue_tile<BN, EpiCfg<BN>::kChunk>(p, tmem_base, acc * BN, row_base, n_blk, ks, e, quarter, lane);
+        release();  // accumulator drained -> hand the TMEM buffer back to the MMA warp
       }
       if (++acc == 2) {
         acc = 0;
@@ -689,19 +745,19 @@ static int launch_gemm(const VlGemmArgs& a, cudaStream_t stream) {
       if (rc) return rc;
       static bool attr_set_t = false;
       if (!attr_set_t) {
-        VL_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgT::kSmemBytes));
+        VL_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgT::kSmemBytes));
         attr_set_t = true;
       }
-      gemm_bf16_kernel<BN, true><<<grid, EpiCfg<BN>::kThreads, CfgT::kSmemBytes, stream>>>(tmA, tmB, tmD, tmX, p);
+      gemm_bf16_kernel<BN, 8><<<grid, KernelCfg<BN, 8>::kThreads, CfgT::kSmemBytes, stream>>>(tmA, tmB, tmD, tmX, p);
       return launch_check("gemm_bf16_kernel<tma epilogue>");
     }
   }
   static bool attr_set = false;
   if (!attr_set) {
-    VL_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    VL_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  gemm_bf16_kernel<BN, false><<<grid, EpiCfg<BN>::kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmA, tmA, p);
+  gemm_bf16_kernel<BN, 0><<<grid, KernelCfg<BN, 0>::kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmA, tmA, p);
   return launch_check("gemm_bf16_kernel");
 }
 
@@ -748,10 +804,12 @@ __device__ __forceinline__ void tile_coords2(const GemmParams& p, int tiles_m2, 
   m_blk = m_first + (r - n_blk * gm);
 }
 
-template <int BN, bool TE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<BN>::kThreads, 1)
+template <int BN, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((KernelCfg<BN, EW>::kThreads), 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
                   const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
+  constexpr bool TE = EW > 0;
+  constexpr int kEpiWarps = KernelCfg<BN, EW>::kEpiWarps;
   using Cfg = Gemm2Cfg<BN, TE>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
@@ -781,7 +839,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (TE) {
       tma_prefetch_desc(&tmD);
       tma_prefetch_desc(&tmX);
-      for (int e = 0; e < EpiCfg<BN>::kWarps; ++e) mbar_init(aux_bar(e), 1);
+      for (int e = 0; e < 16; ++e) mbar_init(aux_bar(e), 1);
     }
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(full_bar(s), 1);  // the leader's arrive.expect_tx; the peer only contributes transaction bytes
@@ -789,7 +847,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 2 * EpiCfg<BN>::kWarps);
+      mbar_init(tempty_bar(a), 2 * kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -886,25 +944,34 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else {
     // ------------------------------------------------------------------ epilogue warps (both CTAs, own 128 rows)
     const int e = warp - 2;
-    const int quarter = warp & 3;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
     [[maybe_unused]] uint32_t aux_phase = 0;
-    [[maybe_unused]] const uint32_t buf = stg_base + e * kEpiBufBytes;
     [[maybe_unused]] const bool need_aux = p.epi == VL_EPI_RESIDUAL || p.epi == VL_EPI_GELU_BWD;
+    constexpr int kGroups = kEpiWarps / 4;             // warps per TMEM lane quarter
+    [[maybe_unused]] constexpr int kSlicesPerWarp = (BN / 64) / kGroups;  // 64-column slices each warp owns (TE path)
+    // GELU forward (two stores per slice): the warp's two staging blocks form a ring, activation -> first, pre-activation ->
+    // second, for both of its slices (see epilogue_tile_tma).
+    [[maybe_unused]] const bool ring2 = kSlicesPerWarp > 1 && p.epi == VL_EPI_GELU && p.aux_out != nullptr;
     for (int t = cluster_id; t < total_tiles; t += num_clusters) {
       int m_blk, n_blk, ks;
       tile_coords2(p, tiles_m2, t, m_blk, n_blk, ks);
       const int row_base = m_blk * 2 * kBM + static_cast<int>(rank) * kBM;
       [[maybe_unused]] const int row_w = row_base + quarter * 32;
-      [[maybe_unused]] const int col_s = n_blk * BN + (e >> 2) * 64;
-      [[maybe_unused]] const bool active = row_w < p.M && col_s < p.N;
       if constexpr (TE) {
-        if (lane == 0 && active) {
-          tma_store_wait_read<0>();
+        if (lane == 0 && row_w < p.M) {
+          tma_store_wait_read<0>();  // the previous tile's stores have finished reading the staging blocks
           if (need_aux && !(p.dbg & 3)) {
-            mbar_expect_tx(aux_bar(e), kEpiBufBytes);
-            tma_load_2d(buf, &tmX, aux_bar(e), col_s, row_w);
+#pragma unroll
+            for (int si = 0; si < kSlicesPerWarp; ++si) {
+              const int slice = (e >> 2) + si * kGroups;
+              const int col_s = n_blk * BN + slice * 64;
+              if (col_s < p.N) {
+                mbar_expect_tx(aux_bar(slice * 4 + quarter), kEpiBufBytes);
+                tma_load_2d(stg_base + (slice * 4 + quarter) * kEpiBufBytes, &tmX, aux_bar(slice * 4 + quarter), col_s, row_w);
+              }
+            }
           }
         }
         __syncwarp();
@@ -918,19 +985,31 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       auto release = [&]() {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+        if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(tempty_bar(acc), 0));
       };
       if constexpr (TE) {
-        if (active && !(p.dbg & 1)) {
-          epilogue_tile_tma<BN>(p, &tmD, &tmX, tmem_base, acc * BN, row_w, col_s, e >> 2, quarter, lane, buf, aux_bar(e), aux_phase,
-                                need_aux && !(p.dbg & 3), release);
-          if (need_aux) aux_phase ^= 1;
-        } else {
-          release();
+        bool released = false;
+        if (row_w < p.M && !(p.dbg & 1)) {
+#pragma unroll
+          for (int si = 0; si < kSlicesPerWarp; ++si) {
+            const int slice = (e >> 2) + si * kGroups;
+            const int col_s = n_blk * BN + slice * 64;
+            if (col_s < p.N) {
+              const bool last = (si == kSlicesPerWarp - 1) || (col_s + kGroups * 64 >= p.N);
+              epilogue_tile_tma<BN>(p, &tmD, &tmX, tmem_base, acc * BN, row_w, col_s, slice, quarter, lane,
+                                    stg_base + ((ring2 ? (e >> 2) : slice) * 4 + quarter) * kEpiBufBytes,
+                                    stg_base + ((ring2 ? (e >> 2) + kGroups : slice) * 4 + quarter) * kEpiBufBytes,
+                                    aux_bar(slice * 4 + quarter), aux_phase,
+                                    need_aux && !(p.dbg & 3), last, release);
+              released |= last;
+            }
+          }
         }
+        if (!released) release();
+        if (need_aux) aux_phase ^= 1;
       } else {
         if (!(p.dbg & 1)) epilogue_tile<BN, EpiCfg<BN>::kChunk>(p, tmem_base, acc * BN, row_base, n_blk, ks, e, quarter, lane);
-        release();
+        release();  // accumulator drained -> hand the TMEM buffer back to the MMA warp
       }
       if (++acc == 2) {
         acc = 0;
@@ -938,7 +1017,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
     if constexpr (TE) {
-      if (lane == 0) tma_store_wait<0>();
+      if (lane == 0) tma_store_wait<0>();  // all bulk stores complete before the CTA exits
     }
   }
 
@@ -980,19 +1059,19 @@ static int launch_gemm2(const VlGemmArgs& a, GemmParams p, cudaStream_t stream) 
       if (rc) return rc;
       static bool attr_set_t = false;
       if (!attr_set_t) {
-        VL_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgT::kSmemBytes));
+        VL_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<BN, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgT::kSmemBytes));
         attr_set_t = true;
       }
-      gemm2_bf16_kernel<BN, true><<<2 * clusters, EpiCfg<BN>::kThreads, CfgT::kSmemBytes, stream>>>(tmA, tmB, tmD, tmX, p);
+      gemm2_bf16_kernel<BN, 8><<<2 * clusters, KernelCfg<BN, 8>::kThreads, CfgT::kSmemBytes, stream>>>(tmA, tmB, tmD, tmX, p);
       return launch_check("gemm2_bf16_kernel<tma epilogue>");
     }
   }
   static bool attr_set = false;
   if (!attr_set) {
-    VL_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    VL_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<BN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  gemm2_bf16_kernel<BN, false><<<2 * clusters, EpiCfg<BN>::kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmA, tmA, p);
+  gemm2_bf16_kernel<BN, 0><<<2 * clusters, KernelCfg<BN, 0>::kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmA, tmA, p);
   return launch_check("gemm2_bf16_kernel");
 }
 

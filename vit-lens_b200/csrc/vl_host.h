@@ -46,6 +46,11 @@ inline int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner,
     }                                                                           \
   } while (0)
 
+// attention_bwd2.cu
+int launch_attn_bwd2(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, void* dq, void* dk, void* dv,
+                     int B, int H, int nq, int nk, long long ldq, long long ldk, long long ldv, long long ldo, long long lddo, long long lddq,
+                     long long lddk, long long lddv, float scale, int causal, cudaStream_t stream);
+
 inline int launch_check(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

@@ -163,6 +163,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t ra
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Relaxed variant for hand-offs that only order tcgen05 traffic (already fenced by tcgen05.fence::before_thread_sync):
+// the release form costs a MEMBAR.ALL.CTA + ERRBAR per arrival.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA load issued by either CTA of a pair; completion bytes are signalled on the mbarrier at `bar_cluster_addr`
 // (a shared::cluster address, normally the leader CTA's barrier).
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* map, uint32_t bar_cluster_addr, int c0, int c1) {

@@ -31,12 +31,23 @@ def _ld(t: torch.Tensor) -> int:
 
 
 def pick_split_k(M: int, N: int, K: int) -> int:
-    """Split the reduction when an (M, N) grid alone cannot fill the 148 SMs (weight gradients)."""
-    tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 128 else 1)
+    """Split the reduction of a weight-gradient GEMM when its (M, N) grid alone cannot fill the GPU.
+
+    Cost model fitted to the B200 sweep in profiles/r01_splitk_sweep.log: time ~ waves(s) / s for the main loops plus a
+    per-extra-split charge for the fp32 atomics that merge the partial tiles (it grows with the output size).  The kernel
+    choice mirrors vl_gemm_bf16: CTA pairs (256 x 256 tiles, 74 clusters) when M >= 512 and N > 128, else 148 single CTAs."""
     kb = (K + 63) // 64
-    if tiles >= 120 or kb < 8:
-        return 1
-    return max(1, min(kb // 4, (296 + tiles - 1) // tiles))
+    if M >= 512 and N > 128:
+        tiles, slots = ((M + 255) // 256) * ((N + 255) // 256), 74
+    else:
+        tiles, slots = ((M + 127) // 128) * ((N + 255) // 256 if N > 128 else 1), 148
+    charge = 0.0012 * (M * N / 65536.0)
+    best, best_cost = 1, None
+    for s in range(1, max(1, min(16, kb // 8)) + 1):
+        cost = -(-tiles * s // slots) / s + charge * (s - 1)
+        if best_cost is None or cost < best_cost - 1e-9:
+            best, best_cost = s, cost
+    return best
 
 
 def gemm(a, b, *, a_t=False, b_t=False, bias=None, epilogue=EPI_LINEAR, aux_in=None, want_aux_out=False, out=None,
@@ -46,17 +57,20 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, epilogue=EPI_LINEAR, aux_in=N
     M, K = (a.shape[1], a.shape[0]) if a_t else (a.shape[0], a.shape[1])
     N, Kb = (b.shape[1], b.shape[0]) if b_t else (b.shape[0], b.shape[1])
     assert K == Kb, f"K mismatch {K} vs {Kb}"
-    if out is None:
-        out = (torch.zeros if accumulate else torch.empty)((M, N), device=a.device, dtype=out_dtype)
-    _v2(out)
-    assert tuple(out.shape) == (M, N)
+    fresh = out is None
     aux_out = torch.empty((M, N), device=a.device, dtype=BF16) if want_aux_out else None
     if aux_in is not None:
         _v2(aux_in, BF16)
         assert tuple(aux_in.shape) == (M, N)
     ldaux = _ld(aux_in) if aux_in is not None else (N if want_aux_out else 0)
     if split_k is None:
-        split_k = pick_split_k(M, N, K) if (accumulate and out.dtype == F32 and epilogue == EPI_LINEAR) else 1
+        split_k = pick_split_k(M, N, K) if (accumulate and (out_dtype if fresh else out.dtype) == F32 and epilogue == EPI_LINEAR) else 1
+    if fresh:
+        if accumulate and split_k == 1:
+            accumulate = False  # a single split writes every element exactly once: plain stores, no zero fill, no atomics
+        out = (torch.zeros if accumulate else torch.empty)((M, N), device=a.device, dtype=out_dtype)
+    _v2(out)
+    assert tuple(out.shape) == (M, N)
     L.gemm(a, b, out, M=M, N=N, K=K, lda=_ld(a), ldb=_ld(b), ldd=_ld(out), a_mn=a_t, b_mn=b_t, epilogue=epilogue, bias=bias,
            aux_in=aux_in, aux_out=aux_out, ldaux=ldaux, alpha=alpha, accumulate=accumulate, split_k=split_k, act_quick=act_quick,
            alpha_dev=alpha_dev)
