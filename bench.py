@@ -287,6 +287,23 @@ def run_cuda(args):
     e2e = world * B * args.steps / (ms_e2e / 1e3)
     final_loss = float(host_loss)
 
+    # ---- diagnostic pass (outside both timed regions): CUDA events around every entry point of the C ABI for one step
+    L.CALL_TIMING = []
+    sync()
+    e0.record()
+    train_step(dev_imgs[0])
+    e1.record()
+    sync()
+    calls, L.CALL_TIMING = L.CALL_TIMING, None
+    by_kernel = {}
+    for name, a, b in calls:
+        ent = by_kernel.setdefault(name, [0, 0.0])
+        ent[0] += 1
+        ent[1] += a.elapsed_time(b)
+    step_ms_diag = e0.elapsed_time(e1)
+    breakdown = {"step_ms": round(step_ms_diag, 2), "sum_kernels_ms": round(sum(v[1] for v in by_kernel.values()), 2),
+                 "by_entry_point": {k: {"launches": v[0], "ms": round(v[1], 3)} for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1][1])}}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -334,7 +351,7 @@ def run_cuda(args):
                    "tflops_per_gpu": FLOP_PER_SAMPLE * B * args.steps / (ms / 1e3) / 1e12, "final_loss": final_loss},
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": B * 3 * IMG * IMG * 4 * world, "d2h_bytes_per_step": 4 * world,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches,
+        "gpu_launches": launches, "breakdown": breakdown,
         "clocks": clocks,
         "roofline": roof,
         "roofline_mhsa": mhsa,

@@ -134,10 +134,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int qrow = q0 + r;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const float sl2 = p.scale * kLog2e;
-    float m = -INFINITY, l = 0.f;
+    // Online softmax with a lazily updated offset: exponents are taken relative to m_off, which only moves when the running
+    // row maximum has grown by more than kLazy (log2 units) since it was set.  softmax is invariant to the offset, P stays
+    // <= 2^kLazy (exact in bf16 range, fp32 row sums), and the O-accumulator rescale -- a TMEM read-modify-write that has to
+    // wait for the previous P V MMA -- only runs for the rare warps where some row's maximum jumped.
+    constexpr float kLazy = 8.0f;
+    float m = -INFINITY, l = 0.f, m_off = -INFINITY;  // m, m_off in raw score units
     for (int j = 0; j < nblk; ++j) {
       const int nkb = min(kTK, ((nk_eff - j * kTK) + 15) & ~15);
       const int kmax = p.causal ? min(p.nk, qrow + 1) : p.nk;  // valid keys are < kmax
+      const bool need_mask = p.causal || (j * kTK + nkb > p.nk);
       mbar_wait(bar_sfull, j & 1);
       tc_fence_after();
       // pass 1: block row max
@@ -146,31 +152,44 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         uint32_t v[32];
         tmem_ld32(tS + lane_off + c, v);
         tc_wait_ld();
+        if (!need_mask) {
 #pragma unroll
-        for (int t = 0; t < 32; ++t)
-          if (j * kTK + c + t < kmax && c + t < nkb) bm = fmaxf(bm, __uint_as_float(v[t]));
+          for (int t = 0; t < 32; ++t) bm = fmaxf(bm, __uint_as_float(v[t]));
+        } else {
+#pragma unroll
+          for (int t = 0; t < 32; ++t)
+            if (j * kTK + c + t < kmax && c + t < nkb) bm = fmaxf(bm, __uint_as_float(v[t]));
+        }
       }
       const float m_new = fmaxf(m, bm);
-      const float msub = (m_new == -INFINITY) ? 0.f : m_new * sl2;
-      const float alpha = exp2f(m * sl2 - msub);  // m = -inf on the first block -> 0
+      const bool move = (m_new - m_off) * sl2 > kLazy || m_off == -INFINITY;  // first block: m_off = -inf
+      const float off_new = move ? m_new : m_off;
+      const float msub = (off_new == -INFINITY) ? 0.f : off_new * sl2;
+      const float alpha = move ? ex2_approx(m_off * sl2 - msub) : 1.0f;  // m_off = -inf on the first block -> 0
       float bs = 0.f;
-      // pass 2: P = exp2(s*sl2 - m_new*sl2), bf16 into swizzled smem (first nkb columns; masked -> 0)
+      // pass 2: P = exp2(s*sl2 - offset), bf16 into swizzled smem (first nkb columns; masked -> 0)
       for (int c = 0; c < nkb; c += 32) {
         uint32_t v[32];
-        if (c < nkb) {
-          tmem_ld32(tS + lane_off + c, v);
-          tc_wait_ld();
-        }
+        tmem_ld32(tS + lane_off + c, v);
+        tc_wait_ld();
         uint32_t pk[16];
+        if (!need_mask) {
 #pragma unroll
-        for (int t = 0; t < 32; t += 2) {
-          float e0 = 0.f, e1 = 0.f;
-          if (c < nkb) {
-            if (j * kTK + c + t < kmax && c + t < nkb) e0 = exp2f(fmaf(__uint_as_float(v[t]), sl2, -msub));
-            if (j * kTK + c + t + 1 < kmax && c + t + 1 < nkb) e1 = exp2f(fmaf(__uint_as_float(v[t + 1]), sl2, -msub));
+          for (int t = 0; t < 32; t += 2) {
+            const float e0 = ex2_approx(fmaf(__uint_as_float(v[t]), sl2, -msub));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(v[t + 1]), sl2, -msub));
+            bs += e0 + e1;
+            pk[t >> 1] = pack_bf16(e0, e1);
           }
-          bs += e0 + e1;
-          pk[t >> 1] = pack_bf16(e0, e1);
+        } else {
+#pragma unroll
+          for (int t = 0; t < 32; t += 2) {
+            float e0 = 0.f, e1 = 0.f;
+            if (j * kTK + c + t < kmax && c + t < nkb) e0 = ex2_approx(fmaf(__uint_as_float(v[t]), sl2, -msub));
+            if (j * kTK + c + t + 1 < kmax && c + t + 1 < nkb) e1 = ex2_approx(fmaf(__uint_as_float(v[t + 1]), sl2, -msub));
+            bs += e0 + e1;
+            pk[t >> 1] = pack_bf16(e0, e1);
+          }
         }
         uint8_t* chunk = sP_ptr + (c >> 6) * 16384;
 #pragma unroll
@@ -181,8 +200,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       l = l * alpha + bs;
       m = m_new;
-      if (j > 0) {
-        // O *= alpha (previous PV must have retired)
+      m_off = off_new;
+      if (j > 0 && __any_sync(0xffffffffu, move)) {
+        // O *= alpha for the rows whose offset moved (previous PV must have retired)
         mbar_wait(bar_odone, (j - 1) & 1);
         tc_fence_after();
 #pragma unroll
@@ -223,7 +243,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
-    if (ok && p.lse) p.lse[(static_cast<long long>(b) * p.H + h) * p.nq + qrow] = m * p.scale + __logf(l);
+    if (ok && p.lse) p.lse[(static_cast<long long>(b) * p.H + h) * p.nq + qrow] = m_off * p.scale + __logf(l);
   }
 
   tc_fence_before();

@@ -123,9 +123,19 @@ __device__ __forceinline__ void store_row32(__nv_bfloat16* dst, const uint32_t (
   }
 }
 
+// row r, columns [c, c + 32) of a 128B-swizzled [128 x 64] bf16 staging tile <- 32 fp32 accumulators
+__device__ __forceinline__ void stage_row32(uint8_t* tile, int r, int c, const uint32_t (&v)[32]) {
+#pragma unroll
+  for (int t = 0; t < 32; t += 8)
+    *reinterpret_cast<uint4*>(tile + sw128_off(r, c + t)) =
+        make_uint4(pack_bf16(__uint_as_float(v[t]), __uint_as_float(v[t + 1])), pack_bf16(__uint_as_float(v[t + 2]), __uint_as_float(v[t + 3])),
+                   pack_bf16(__uint_as_float(v[t + 4]), __uint_as_float(v[t + 5])), pack_bf16(__uint_as_float(v[t + 6]), __uint_as_float(v[t + 7])));
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                 const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmO, const Params p) {
+                 const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmDQ,
+                 const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* bp = smem_raw + (base - smem_u32(smem_raw));
@@ -141,7 +151,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   auto bar_dpfull = [&](int g) { return bars + 8u * (9 + g); };
   auto bar_dsfull = [&](int g) { return bars + 8u * (11 + g); };
   auto bar_pairdone = [&](int g) { return bars + 8u * (13 + g); };
-  const uint32_t bar_dkvfull = bars + 8u * 15, bar_dkvfree = bars + 8u * 16, bar_dqfull = bars + 8u * 17, tmem_slot = bars + 8u * 18;
+  const uint32_t bar_dkvfull = bars + 8u * 15, bar_dkvfree = bars + 8u * 16, bar_dqfull = bars + 8u * 17, tmem_slot = bars + 8u * 18,
+                 bar_do = bars + 8u * 19;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(bp + kOffBar + 8 * 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -161,6 +172,10 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tma_prefetch_desc(&tmDO);
     tma_prefetch_desc(&tmO);
     mbar_init(bar_qdo, 1);
+    mbar_init(bar_do, 1);
+    tma_prefetch_desc(&tmDQ);
+    tma_prefetch_desc(&tmDK);
+    tma_prefetch_desc(&tmDV);
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_kvfull(s), 1);
       mbar_init(bar_kvempty(s), 1 + 8);  // MMA commit + the eight compute warps (tail corrections read K / V rows)
@@ -194,15 +209,13 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 0) {
     // ================================================================== TMA producer
     if (elect_one()) {
+      // issue order = need order: Q tiles and the first K/V block feed S; dO and O are first needed for dP / D
       if (nqt > 0) {
-        mbar_expect_tx(bar_qdo, nqt * 3 * 16384);
-        for (int g = 0; g < nqt; ++g) {
-          tma_load_2d(sQ + g * 16384, &tmQ, bar_qdo, h * kHD, static_cast<int>(qrow0) + g * kT);
-          tma_load_2d(sDO + g * 16384, &tmDO, bar_qdo, h * kHD, static_cast<int>(qrow0) + g * kT);
-          tma_load_2d(sPD + g * 32768, &tmO, bar_qdo, h * kHD, static_cast<int>(qrow0) + g * kT);
-        }
+        mbar_expect_tx(bar_qdo, nqt * 16384);
+        for (int g = 0; g < nqt; ++g) tma_load_2d(sQ + g * 16384, &tmQ, bar_qdo, h * kHD, static_cast<int>(qrow0) + g * kT);
       }
       int n = 0;
+      bool rest_issued = false;
       for (int j = 0; j < nkblk; ++j) {
         if (!block_active(j)) continue;
         const int s = n & 1;
@@ -211,6 +224,14 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tma_load_2d(sK + s * 16384, &tmK, bar_kvfull(s), h * kHD, static_cast<int>(krow0) + j * kT);
         tma_load_2d(sV + s * 16384, &tmV, bar_kvfull(s), h * kHD, static_cast<int>(krow0) + j * kT);
         ++n;
+        if (!rest_issued && nqt > 0) {
+          rest_issued = true;
+          mbar_expect_tx(bar_do, nqt * 2 * 16384);
+          for (int g = 0; g < nqt; ++g) {
+            tma_load_2d(sDO + g * 16384, &tmDO, bar_do, h * kHD, static_cast<int>(qrow0) + g * kT);
+            tma_load_2d(sPD + g * 32768 + 16384, &tmO, bar_do, h * kHD, static_cast<int>(qrow0) + g * kT);  // O: second half of the block
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -250,6 +271,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         bool first = true;
         for (int g = 0; g < 2; ++g) {
           if (!pair_active(j, g)) continue;
+          if (n == 0 && first) mbar_wait(bar_do, 0);
           mbar_wait(bar_pfull(g), np[g] & 1);
           tc_fence_after();
           const uint32_t sDOg = sDO + g * 16384, sPg = sPD + g * 32768;
@@ -330,26 +352,28 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const float* s_tq = sf + kFTq;                       // [t][q|dO][64]
     const float* s_tk = sf + kFTq + p.tq * 2 * kHD;      // [t'][k|v][64]
     float* s_stat = sf + kFStat;
-    if (g == 0 && x < p.tq) {
-      const long long grow = qrow0 + p.nq_main + x;
-      float dsum = 0.f;
-      for (int d = 0; d < kHD; ++d)
-        dsum += __bfloat162float(p.o[grow * p.ldo + h * kHD + d]) * __bfloat162float(p.dout[grow * p.lddo + h * kHD + d]);
-      s_stat[2 * x] = p.lse[(static_cast<long long>(b) * p.H + h) * p.nq + p.q0 + p.nq_main + x] * kLog2e;
-      s_stat[2 * x + 1] = dsum;
+    if (warp == 2) {  // lse and D = rowsum(dO * O) of the tail queries: one warp, two dims per lane, coalesced 128-byte rows
+      for (int t = 0; t < p.tq; ++t) {
+        const long long grow = qrow0 + p.nq_main + t;
+        const uint32_t ow = *reinterpret_cast<const uint32_t*>(p.o + grow * p.ldo + h * kHD + 2 * lane);
+        const uint32_t gw = *reinterpret_cast<const uint32_t*>(p.dout + grow * p.lddo + h * kHD + 2 * lane);
+        float dsum = bf16_lo(ow) * bf16_lo(gw) + bf16_hi(ow) * bf16_hi(gw);
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o2);
+        if (lane == 0) {
+          s_stat[2 * t] = p.lse[(static_cast<long long>(b) * p.H + h) * p.nq + p.q0 + p.nq_main + t] * kLog2e;
+          s_stat[2 * t + 1] = dsum;
+        }
+      }
     }
     const bool tile_ok = g < nqt;
     const int qrow = g * kT + r;                       // row inside this launch's main range
     const bool row_ok = tile_ok && qrow < p.nq_main;
     float lse2 = INFINITY, Di = 0.f;                   // invalid rows: exp2(s - inf) = 0
-    if (tile_ok) {
-      mbar_wait(bar_qdo, 0);
-      if (row_ok) {
-        lse2 = p.lse[(static_cast<long long>(b) * p.H + h) * p.nq + p.q0 + qrow] * kLog2e;
-        Di = dot_rows_sw128(sDOg, sPDg, r);  // D = rowsum(dO * O); the O tile sits in this group's staging block
-      }
-    }
-    both_groups_sync();  // tail vectors / stats visible to everyone; O rows consumed before P overwrites the block
+    if (row_ok) lse2 = p.lse[(static_cast<long long>(b) * p.H + h) * p.nq + p.q0 + qrow] * kLog2e;
+    both_groups_sync();  // tail vectors / stats visible to everyone
+    bool have_D = false;
+    bool store_pending = false;  // a TMA store issued by this group may still be reading its staging block
     VL_STAMP();
 
     uint32_t np = 0;  // pairs processed by this group
@@ -368,9 +392,21 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_after();
         VL_STAMP();
         if (np > 0) mbar_wait(bar_pairdone(g), (np - 1) & 1);  // previous pair's MMAs finished reading the staging block
+        if (store_pending) {  // ... and so has the bulk store of the previous block's dK / dV rows
+          if (x == 0) tma_store_wait_read<0>();
+          group_sync(g);
+          store_pending = false;
+        }
         uint32_t pk[64];  // P of this row, packed bf16 (128 keys)
 #pragma unroll
         for (int c = 0; c < kT; c += 32) {
+          if (c == 64 && !have_D) {
+            // D = rowsum(dO * O): the O tile sits in the second half of this group's staging block, which P is about to
+            // overwrite (each thread reads and then writes only its own row)
+            mbar_wait(bar_do, 0);
+            Di = row_ok ? dot_rows_sw128(sDOg, sPDg + 16384, r) : 0.f;
+            have_D = true;
+          }
           uint32_t v[32];
           if (c < nkb) {
             tmem_ld32(tS(g) + lane_off + c, v);
@@ -408,6 +444,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_wait(bar_dpfull(g), np & 1);
         tc_fence_after();
         VL_STAMP();
+        const float nDs = -Di * p.scale;
 #pragma unroll
         for (int c = 0; c < kT; c += 32) {
           uint32_t v[32];
@@ -421,8 +458,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             float d0 = 0.f, d1 = 0.f;
             if (c < nkb) {
               const uint32_t pp = pk[(c + t) >> 1];
-              d0 = bf16_lo(pp) * (__uint_as_float(v[t]) - Di) * p.scale;
-              d1 = bf16_hi(pp) * (__uint_as_float(v[t + 1]) - Di) * p.scale;
+              d0 = bf16_lo(pp) * fmaf(__uint_as_float(v[t]), p.scale, nDs);
+              d1 = bf16_hi(pp) * fmaf(__uint_as_float(v[t + 1]), p.scale, nDs);
             }
             dk[t >> 1] = pack_bf16(d0, d1);
           }
@@ -474,11 +511,24 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
             for (int e2 = 0; e2 < 32; ++e2) v[e2] = __float_as_uint(fmaf(cf[t], vec[e2], __uint_as_float(v[e2])));
           }
-          if (ok) store_row32(dst + c, v, p.accum_kv != 0);
+          if (p.accum_kv) {
+            if (ok) store_row32(dst + c, v, true);
+          } else {
+            stage_row32(sPDg, r, c, v);  // the staging block is idle here: every MMA of this key block has retired
+          }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_dkvfree);
+        if (!p.accum_kv) {  // one bulk tensor store per group: whole 128-byte lines, rows past nk_main clipped by the map
+          fence_proxy_async_smem();
+          group_sync(g);
+          if (x == 0) {
+            tma_store_3d(g == 0 ? &tmDV : &tmDK, sPD + g * 32768, h * kHD, j * kT, b);
+            tma_store_commit();
+          }
+          store_pending = true;
+        }
         VL_STAMP();  // dK / dV rows stored
         if (g == 1 && p.tq > 0) {  // dQ_t += sum_r ds_tr k_r
           for (int t = 0; t < p.tq; ++t) {
@@ -498,9 +548,14 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // ---- dQ tile of this group -> global (+ tail keys' contributions), tail keys' dK / dV from this tile's rows
     if (tile_ok) {
       mbar_wait(bar_dqfull, 0);
+      mbar_wait(bar_qdo, 0);
       tc_fence_after();
       VL_STAMP();
-      __nv_bfloat16* dst = p.dq + (qrow0 + qrow) * p.lddq + h * kHD;
+      if (store_pending) {
+        if (x == 0) tma_store_wait_read<0>();
+        group_sync(g);
+        store_pending = false;
+      }
       float dsk[kMaxTail], ptk[kMaxTail];
       for (int t = 0; t < p.tk; ++t) {
         const float* kv = s_tk + (2 * t) * kHD;
@@ -521,7 +576,13 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
           for (int e2 = 0; e2 < 32; ++e2) v[e2] = __float_as_uint(fmaf(dsk[t], vec[e2], __uint_as_float(v[e2])));
         }
-        if (row_ok) store_row32(dst + c, v, false);
+        stage_row32(sPDg, r, c, v);
+      }
+      fence_proxy_async_smem();
+      group_sync(g);
+      if (x == 0) {  // rows past the last main query are clipped by the tensor map
+        tma_store_3d(&tmDQ, sPD + g * 32768, h * kHD, p.q0 + g * kT, b);
+        tma_store_commit();
       }
       VL_STAMP();  // dQ rows stored
       for (int t = 0; t < p.tk; ++t) {  // dV_t' += sum_r p_rt' dO_r ; dK_t' += sum_r ds_rt' q_r
@@ -581,6 +642,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
     }
+    if (x == 0) tma_store_wait<0>();  // bulk stores complete before the CTA retires
     VL_STAMP();
 #undef VL_STAMP
   }
@@ -608,17 +670,30 @@ int launch_attn_bwd2(const void* q, const void* k, const void* v, const void* o,
   if ((rc = make_tmap_bf16_2d(&tmV, v, (uint64_t)H * kHD, (uint64_t)B * nk, ldv, kHD, kT))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmDO, dout, (uint64_t)H * kHD, (uint64_t)B * nq, lddo, kHD, kT))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmO, o, (uint64_t)H * kHD, (uint64_t)B * nq, ldo, kHD, kT))) return rc;
-  static bool attr = false;
-  if (!attr) {
-    VL_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    attr = true;
-  }
   auto tail = [&](int n) {
     const int t = n % kT;
     return (!causal && n > kT && t > 0 && t <= kMaxTail) ? t : 0;
   };
   const int tq_all = tail(nq), tk = tail(nk);
   const int nq_main_all = nq - tq_all;
+  // outputs as [cols, main rows of one batch element, batch]: the row box is clipped per batch element, so partial tiles
+  // never spill into the tail rows (written separately) or the next batch element
+  CUtensorMap tmDQ, tmDK, tmDV;
+  auto out_map = [&](CUtensorMap* m, const void* ptr, long long ld, int rows_main, int rows_all) {
+    VL_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "vl_attention_bwd: output pointers must be 16-byte aligned");
+    const uint64_t dims[3] = {(uint64_t)H * kHD, (uint64_t)rows_main, (uint64_t)B};
+    const uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)rows_all * (uint64_t)ld * 2};
+    const uint32_t box[3] = {kHD, kT, 1};
+    return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ptr, dims, strides, box, true);
+  };
+  if ((rc = out_map(&tmDQ, dq, lddq, nq_main_all, nq))) return rc;
+  if ((rc = out_map(&tmDK, dk, lddk, nk - tk, nk))) return rc;
+  if ((rc = out_map(&tmDV, dv, lddv, nk - tk, nk))) return rc;
+  static bool attr = false;
+  if (!attr) {
+    VL_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    attr = true;
+  }
   Params p;
   p.B = B; p.H = H; p.nq = nq; p.nk = nk;
   p.nk_main = nk - tk; p.tk = tk;
@@ -635,7 +710,7 @@ int launch_attn_bwd2(const void* q, const void* k, const void* v, const void* o,
     p.nq_main = nq_main_all - q0 < 2 * kT ? nq_main_all - q0 : 2 * kT;
     p.tq = (q0 + 2 * kT >= nq_main_all) ? tq_all : 0;  // the tail rides with the last range
     p.accum_kv = q0 > 0;
-    attn_bwd2_kernel<<<(unsigned)(B * H), kThreads, kSmem, stream>>>(tmQ, tmK, tmV, tmDO, tmO, p);
+    attn_bwd2_kernel<<<(unsigned)(B * H), kThreads, kSmem, stream>>>(tmQ, tmK, tmV, tmDO, tmO, tmDQ, tmDK, tmDV, p);
     if (int rc2 = launch_check("attn_bwd2_kernel")) return rc2;
   }
   return 0;

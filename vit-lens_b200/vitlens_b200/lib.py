@@ -20,6 +20,7 @@ launch_count = 0  # number of vl_* kernel-launching calls issued (bench.py repor
 # the launching stream and (start, end, algorithmic flops | kind, bytes) is appended.
 GEMM_TIMING = None
 ATTN_TIMING = None
+CALL_TIMING = None  # bench.py's per-kernel breakdown pass: list of (entry point, start event, end event)
 
 
 def _timed(store, payload, fn):
@@ -118,6 +119,14 @@ def gemm(a, b, d, *, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, epilogue=EP
         _ptr(row_vec), _ptr(col_vec), _ptr(out_vec0), _ptr(out_vec1), _ptr(out_vec2), _ptr(scalar_out), int(iparam), float(fparam),
         _ptr(alpha_dev), _ptr(fparam_dev), int(aux_row_div), int(relu))
     _count()
+    if CALL_TIMING is not None:
+        kind = "wgrad" if (a_mn and b_mn) else ("dgrad" if b_mn else "fwd")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _check(_fn("vl_gemm_bf16")(C.cast(C.pointer(args), C.c_void_p), _stream()), "vl_gemm_bf16")
+        e1.record()
+        CALL_TIMING.append((f"vl_gemm_bf16/{kind}/epi{int(epilogue)}", e0, e1))
+        return
     _timed(GEMM_TIMING, (2.0 * M * N * K, (M, N, K, int(epilogue), int(a_mn), int(b_mn))),
            lambda: _check(_fn("vl_gemm_bf16")(C.cast(C.pointer(args), C.c_void_p), _stream()), "vl_gemm_bf16"))
 
@@ -168,7 +177,14 @@ def _fn(name):
 
 def _call(name, *args):
     _count()
-    rc = _fn(name)(*args, _stream())
+    if CALL_TIMING is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = _fn(name)(*args, _stream())
+        e1.record()
+        CALL_TIMING.append((name, e0, e1))
+    else:
+        rc = _fn(name)(*args, _stream())
     if rc != 0:
         _check(rc, name)
 
