@@ -273,14 +273,44 @@ def run_cuda(args):
     L.GEMM_TIMING = L.ATTN_TIMING = None
     value = world * B * args.steps / (ms / 1e3)
 
-    # ---- timed: end to end through the public API with HOST buffers (pinned H2D of the batch + loss D2H every step)
+    # ---- timed: end to end through the public API with HOST buffers.  Every step copies its batch from pinned host memory
+    # (on a copy stream, one step ahead: the input pipeline of a real training loop) and reads its loss back to the host
+    # (asynchronously; the host waits for step i-1's value while step i is queued, and for the last one before the clock stops).
+    copy_stream = torch.cuda.Stream()
+    dev_in = [torch.empty_like(dev_imgs[0]) for _ in range(2)]
+    host_losses = torch.zeros(args.steps, dtype=torch.float32).pin_memory()
+
+    def prefetch(i, after):
+        buf = dev_in[i % 2]
+        with torch.cuda.stream(copy_stream):
+            if after is not None:
+                copy_stream.wait_event(after)  # the step that last read this buffer has finished
+            buf.copy_(host_imgs[i % n_host], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        return buf, ev
+
     sync()
     e0.record()
+    nxt = prefetch(0, None)
+    read_ev, done = [], []
     for i in range(args.steps):
-        imgs = host_imgs[i % n_host].to(dev, non_blocking=True)
+        imgs, ev = nxt
+        torch.cuda.current_stream().wait_event(ev)
+        if i + 1 < args.steps:  # queued before step i's kernels so the copy runs underneath them
+            nxt = prefetch(i + 1, done[i - 1] if i >= 1 else None)
         loss = train_step(imgs)
-        host_loss.copy_(loss, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        d = torch.cuda.Event()
+        d.record()
+        done.append(d)
+        host_losses[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
+        rev = torch.cuda.Event()
+        rev.record()
+        read_ev.append(rev)
+        if i > 0:
+            read_ev[i - 1].synchronize()  # the host consumes step i-1's loss here
+    read_ev[-1].synchronize()
+    host_loss.copy_(host_losses[-1])
     e1.record()
     sync()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
@@ -325,6 +355,11 @@ def run_cuda(args):
                             for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][0])[:14]]
         roof["achieved"] = tot_fl / tot_ms / 1e9
         roof["frac"] = roof["achieved"] / pk["tf"]
+        # DRAM bytes of one launch of the fc+GELU GEMM (M=65792 N=4096 K=1024, the largest single share of the step), from the
+        # committed ncu --set full capture profiles/r01_ncu_gemm_fc_gelu_pair8.txt: 164.4 MB read + 1023.4 MB written, against
+        # 143.1 MB + 1077.9 MB algorithmic (activations + weights in, activation + pre-activation out).
+        roof["traffic"] = int((164438784 + 1023405000) * B / 256)  # captured at batch 256; the GEMM is linear in tokens
+        roof["traffic_kernel"] = "gemm2_bf16_kernel<256,8> fc+GELU, per launch; algorithmic 1221036032 B"
         roof["launches_timed"] = len(gemm_t)
         roof["share_of_step"] = tot_ms / ms
     mhsa = None

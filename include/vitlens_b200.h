@@ -92,6 +92,11 @@ typedef struct {
    * the per-group "global feature" term is broadcast over the group's points); relu != 0 clamps the result at 0. */
   int32_t aux_row_div;
   int32_t relu;
+  /* Optional fp32 [M]: rowsum_out[m] += sum_k A[m, k] (atomic), computed on the tensor cores from the A tiles already in
+   * shared memory (an extra N = 16 MMA against a tile of ones).  With A = dY^T this is the bias gradient of the Linear whose
+   * weight gradient the GEMM produces (replaces a separate vl_colsum_bf16 pass over dY).  Requires the CTA-pair kernel:
+   * M >= 512, N > 128, LINEAR epilogue, fp32 output; rejected (VL_ENOTSUP) otherwise. */
+  float* rowsum_out;
 } VlGemmArgs;
 
 int vl_gemm_bf16(const VlGemmArgs* args, void* stream);

@@ -37,8 +37,12 @@ def _act_grad(x, quick):
     return 0.5 * (1 + torch.erf(x / math.sqrt(2))) + x * torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi)
 
 
+def rowsum_fusable(M, N):
+    return M >= 512 and N > 128
+
+
 def gemm(a, b, *, a_t=False, b_t=False, bias=None, epilogue=EPI_LINEAR, aux_in=None, want_aux_out=False, out=None,
-         out_dtype=BF16, alpha=1.0, accumulate=False, split_k=None, act_quick=False, alpha_dev=None):
+         out_dtype=BF16, alpha=1.0, accumulate=False, split_k=None, act_quick=False, alpha_dev=None, want_rowsum=False):
     _n()
     if alpha_dev is not None:
         alpha = alpha * float(alpha_dev)
@@ -67,6 +71,8 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, epilogue=EPI_LINEAR, aux_in=N
         out += res.to(out.dtype)
     else:
         out.copy_(res.to(out.dtype))
+    if want_rowsum:
+        return out, A.sum(1)
     return (out, aux_out) if want_aux_out else out
 
 

@@ -55,12 +55,41 @@ def test_gemm_epilogues(ops, quick):
     close(ops.gemm(A, B, epilogue=ops.EPI_GELU_BWD, aux_in=res, act_quick=quick), acc * g)
 
 
+@pytest.mark.parametrize("M,N,K", [(34, 192, 192), (300, 576, 200), (130, 768, 3072), (500, 264, 64)])
+def test_gemm_epilogues_small_m(ops, M, N, K):
+    """M < 512 takes the single-CTA kernel with the TMA-staged epilogue (row and column tails clipped by the tensor maps)."""
+    A = torch.randn(M, K, device="cuda").to(BF)
+    B = torch.randn(N, K, device="cuda").to(BF) * 0.1
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda").to(BF)
+    acc = A.float() @ B.float().t()
+    close(ops.gemm(A, B, bias=bias), acc + bias)
+    h, u = ops.gemm(A, B, bias=bias, epilogue=ops.EPI_GELU, want_aux_out=True)
+    close(u, acc + bias)
+    close(h, F.gelu(acc + bias))
+    close(ops.gemm(A, B, bias=bias, epilogue=ops.EPI_RESIDUAL, aux_in=res), acc + bias + res.float())
+    xr = res.float().requires_grad_(True)
+    g = torch.autograd.grad(F.gelu(xr).sum(), xr)[0]
+    close(ops.gemm(A, B, epilogue=ops.EPI_GELU_BWD, aux_in=res), acc * g)
+
+
 def test_gemm_splitk_accumulate(ops):
     M, N, K = 384, 512, 8192
     A = torch.randn(K, M, device="cuda").to(BF)
     B = torch.randn(K, N, device="cuda").to(BF)
     out = ops.gemm(A, B, a_t=True, b_t=True, out_dtype=torch.float32, accumulate=True)
     close(out, A.float().t() @ B.float(), tol=1e-3)
+
+
+@pytest.mark.parametrize("M,N,K", [(1024, 512, 8192), (4096, 1024, 4112), (520, 136, 1000)])
+def test_gemm_wgrad_with_fused_bias_grad(ops, M, N, K):
+    """dW = dy^T x with the bias gradient (column sums of dy = row sums of the A operand) produced by the same GEMM."""
+    dy = torch.randn(K, M, device="cuda").to(BF)
+    x = torch.randn(K, N, device="cuda").to(BF)
+    assert ops.rowsum_fusable(M, N)
+    dw, db = ops.gemm(dy, x, a_t=True, b_t=True, out_dtype=torch.float32, accumulate=True, want_rowsum=True)
+    close(dw, dy.float().t() @ x.float(), tol=1e-3)
+    close(db, dy.float().sum(0), tol=1e-3, atol=0.05)
 
 
 def _ref_attn(q, k, v, causal):
@@ -75,7 +104,8 @@ def _ref_attn(q, k, v, causal):
     (2, 2, 257, 257, False, True), (3, 2, 77, 77, True, True), (2, 16, 256, 256, False, True), (2, 1, 256, 600, False, False),
     (2, 2, 17, 17, False, True), (4, 12, 50, 50, False, True), (2, 1, 128, 512, False, False), (1, 1, 1, 1, False, True),
     (2, 2, 513, 513, False, True), (2, 1, 229, 229, False, True), (1, 2, 130, 259, False, False), (2, 1, 300, 300, True, True),
-    (1, 1, 640, 132, False, False)])
+    (1, 1, 640, 132, False, False), (2, 2, 16, 48, False, False), (2, 1, 8, 16, False, False), (1, 2, 40, 208, False, False),
+    (2, 1, 80, 80, True, True)])
 def test_attention_fwd_bwd(ops, B, H, nq, nk, causal, packed):
     D = H * 64
     if packed:

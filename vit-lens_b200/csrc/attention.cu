@@ -143,7 +143,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int j = 0; j < nblk; ++j) {
       const int nkb = min(kTK, ((nk_eff - j * kTK) + 15) & ~15);
       const int kmax = p.causal ? min(p.nk, qrow + 1) : p.nk;  // valid keys are < kmax
-      const bool need_mask = p.causal || (j * kTK + nkb > p.nk);
+      const bool need_mask = p.causal || (j * kTK + kTK > p.nk);  // any partial block: tcgen05.ld reads whole 32-column groups
       mbar_wait(bar_sfull, j & 1);
       tc_fence_after();
       // pass 1: block row max

@@ -42,6 +42,7 @@ struct GemmParams {
   const float* alpha_dev;
   const float* fparam_dev;
   int aux_row_div, relu;
+  float* rowsum_out;  // fp32 [M] or null: += row sums of A over this tile's K range (bias gradient of a weight-gradient GEMM)
   int dbg;  // bring-up knob 9: 1 skip epilogue, 2 no global traffic in the epilogue, 4 sleeping epilogue waits, 8 MMA ignores full barriers
   uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;  // bytes
 };
@@ -549,7 +550,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    [[maybe_unused]] uint32_t aux_phase = 0;
+    [[maybe_unused]] uint32_t aux_phase[4] = {0, 0, 0, 0};  // per owned slice: flips only when that slice's block was loaded
     [[maybe_unused]] const bool need_aux = p.epi == VL_EPI_RESIDUAL || p.epi == VL_EPI_GELU_BWD;
     constexpr int kGroups = kEpiWarps / 4;             // warps per TMEM lane quarter
     [[maybe_unused]] constexpr int kSlicesPerWarp = (BN / 64) / kGroups;  // 64-column slices each warp owns (TE path)
@@ -601,14 +602,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               epilogue_tile_tma<BN>(p, &tmD, &tmX, tmem_base, acc * BN, row_w, col_s, slice, quarter, lane,
                                     stg_base + ((ring2 ? (e >> 2) : slice) * 4 + quarter) * kEpiBufBytes,
                                     stg_base + ((ring2 ? (e >> 2) + kGroups : slice) * 4 + quarter) * kEpiBufBytes,
-                                    aux_bar(slice * 4 + quarter), aux_phase,
+                                    aux_bar(slice * 4 + quarter), aux_phase[si],
                                     need_aux && !(p.dbg & 3), last, release);
               released |= last;
+              if (need_aux && !(p.dbg & 3)) aux_phase[si] ^= 1;
             }
           }
         }
         if (!released) release();
-        if (need_aux) aux_phase ^= 1;
       } else {
         if (!(p.dbg & 1)) epilogue_tile<BN, EpiCfg<BN>::kChunk>(p, tmem_base, acc * BN, row_base, n_blk, ks, e, quarter, lane);
         release();  // accumulator drained -> hand the TMEM buffer back to the MMA warp
@@ -699,6 +700,7 @@ static int launch_gemm(const VlGemmArgs& a, cudaStream_t stream) {
   p.fparam_dev = a.fparam_dev;
   p.aux_row_div = a.aux_row_div > 1 ? a.aux_row_div : 1;
   p.relu = a.relu;
+  p.rowsum_out = a.rowsum_out;
   p.dbg = debug_get(9);
   // K-major: 8-row groups 1024 B apart, +32 B per UMMA_K inside the swizzle row.
   // MN-major: 64-wide chunks kBK*128 B apart (LBO), 8-K groups 1024 B apart (SBO), +2048 B per UMMA_K.
@@ -777,7 +779,7 @@ struct Gemm2Cfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = (BN / 2) * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = TE ? (BN / 16) * kEpiBufBytes : 0;
+  static constexpr int kStagingBytes = TE ? (BN / 16) * kEpiBufBytes : 1024;  // direct-store flavour: 8 x 64 tile of ones (row sums)
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 512;
   static constexpr int kTmemCols = 2 * BN;
 };
@@ -832,6 +834,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int num_clusters = gridDim.x >> 1;
   const int tiles_m2 = (p.M + 2 * kBM - 1) / (2 * kBM);
   const int total_tiles = tiles_m2 * p.tiles_n * p.split_k;
+  // Row sums of A (bias gradient riding on a weight-gradient GEMM): tiles of the first n-column also run an N = 16 MMA of the
+  // A tiles against a tile of ones into TMEM columns [BN, BN + 16); the accumulators are then single-buffered.
+  const bool rs = !TE && p.rowsum_out != nullptr;
+  const int nacc = rs ? 1 : 2;
+  if (rs && threadIdx.x >= 64 && threadIdx.x < 128) {
+    st_shared_v4(stg_base + (threadIdx.x - 64) * 16, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);  // bf16 1.0 x 8
+    fence_proxy_async_smem();
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -905,6 +915,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (leader && elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(2 * kBM, BN, p.a_mn, p.b_mn);
+      const uint32_t idesc_ones = umma_idesc_bf16(2 * kBM, 16, p.a_mn, 0);
+      const uint64_t ones_desc = umma_desc_sw128(stg_base, 16, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -927,6 +939,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint64_t ad = umma_desc_sw128(sa + k * p.a_kstep, p.a_lbo, p.a_sbo);
             const uint64_t bd = umma_desc_sw128(sb + k * p.b_kstep, p.b_lbo, p.b_sbo);
             umma_ss_pair(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (rs && n_blk == 0) umma_ss_pair(tmem_base + BN, ad, ones_desc, idesc_ones, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit_pair_mc(empty_bar(stage), 3);
           if (++stage == Cfg::kStages) {
@@ -935,7 +948,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         umma_commit_pair_mc(tfull_bar(acc), 3);
-        if (++acc == 2) {
+        if (++acc == nacc) {
           acc = 0;
           acc_phase ^= 1;
         }
@@ -947,7 +960,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    [[maybe_unused]] uint32_t aux_phase = 0;
+    [[maybe_unused]] uint32_t aux_phase[4] = {0, 0, 0, 0};  // per owned slice: flips only when that slice's block was loaded
     [[maybe_unused]] const bool need_aux = p.epi == VL_EPI_RESIDUAL || p.epi == VL_EPI_GELU_BWD;
     constexpr int kGroups = kEpiWarps / 4;             // warps per TMEM lane quarter
     [[maybe_unused]] constexpr int kSlicesPerWarp = (BN / 64) / kGroups;  // 64-column slices each warp owns (TE path)
@@ -999,19 +1012,26 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               epilogue_tile_tma<BN>(p, &tmD, &tmX, tmem_base, acc * BN, row_w, col_s, slice, quarter, lane,
                                     stg_base + ((ring2 ? (e >> 2) : slice) * 4 + quarter) * kEpiBufBytes,
                                     stg_base + ((ring2 ? (e >> 2) + kGroups : slice) * 4 + quarter) * kEpiBufBytes,
-                                    aux_bar(slice * 4 + quarter), aux_phase,
+                                    aux_bar(slice * 4 + quarter), aux_phase[si],
                                     need_aux && !(p.dbg & 3), last, release);
               released |= last;
+              if (need_aux && !(p.dbg & 3)) aux_phase[si] ^= 1;
             }
           }
         }
         if (!released) release();
-        if (need_aux) aux_phase ^= 1;
       } else {
         if (!(p.dbg & 1)) epilogue_tile<BN, EpiCfg<BN>::kChunk>(p, tmem_base, acc * BN, row_base, n_blk, ks, e, quarter, lane);
+        if (rs && n_blk == 0 && (e >> 2) == 0) {  // one warp per lane quarter adds this tile's row sums of A
+          uint32_t v[16];
+          tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + BN, v);
+          tc_wait_ld();
+          const int row = row_base + quarter * 32 + lane;
+          if (row < p.M) atomicAdd(p.rowsum_out + row, __uint_as_float(v[0]));
+        }
         release();  // accumulator drained -> hand the TMEM buffer back to the MMA warp
       }
-      if (++acc == 2) {
+      if (++acc == nacc) {
         acc = 0;
         acc_phase ^= 1;
       }
@@ -1105,6 +1125,10 @@ extern "C" int vl_gemm_bf16(const VlGemmArgs* a, void* stream) {
     VL_CHECK_ARG(a->out_vec0 && a->out_vec1 && a->out_vec2 && a->split_k <= 1, "vl_gemm_bf16: ROWLSE needs out_vec0/1/2 and split_k == 1");
   if (a->epilogue == VL_EPI_CLIPGRAD)
     VL_CHECK_ARG(a->row_vec && !a->d_f32 && a->split_k <= 1, "vl_gemm_bf16: CLIPGRAD needs row_vec, bf16 output, split_k == 1");
+  if (a->rowsum_out != nullptr && !(a->M >= 4 * kBM && a->N > 128 && a->epilogue == VL_EPI_LINEAR && a->d_f32 && debug_get(8) != 1)) {
+    set_error("vl_gemm_bf16: rowsum_out needs the CTA-pair kernel (M >= 512, N > 128), the LINEAR epilogue and fp32 output");
+    return VL_ENOTSUP;
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (a->epilogue == VL_EPI_ROWLSE || a->epilogue == VL_EPI_CLIPGRAD) return launch_gemm<256>(*a, s);  // fixed part geometry
   if (a->N <= 128) return launch_gemm<128>(*a, s);

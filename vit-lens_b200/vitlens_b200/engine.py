@@ -92,6 +92,14 @@ def _wgrad(dy, x):
     return _ops.gemm(dy, x, a_t=True, b_t=True, out_dtype=F32, accumulate=True)
 
 
+def _wgrad_bias(dy, x, want_w=True, want_b=True):
+    """(dW, db) of a Linear: dW = dy^T x and db = column sums of dy.  When the weight-gradient GEMM runs on the CTA-pair
+    kernel the bias gradient rides on it (row sums of its A operand, VlGemmArgs.rowsum_out) instead of a second pass over dy."""
+    if want_w and want_b and _ops.rowsum_fusable(dy.shape[1], x.shape[1]):
+        return _ops.gemm(dy, x, a_t=True, b_t=True, out_dtype=F32, accumulate=True, want_rowsum=True)
+    return (_wgrad(dy, x) if want_w else None), (_ops.colsum(dy) if want_b else None)
+
+
 def _dgrad(dy, w, **kw):
     """dx[T, in] = dy[T, out] @ W[out, in]  (W consumed in place as an MN-major B operand)."""
     return _ops.gemm(dy, w, b_t=True, **kw)
@@ -133,38 +141,26 @@ class VitBlockFn(torch.autograd.Function):
         dy = dy.contiguous()
         g = [None] * 18
         # ---- MLP
-        if _need(ctx, 11):
-            g[11] = _wgrad(dy, h)
+        g[11], g[12] = _wgrad_bias(dy, h, _need(ctx, 11), _need(ctx, 12))
         du = _dgrad(dy, w16(pjw), epilogue=_ops.EPI_GELU_BWD, aux_in=u, act_quick=quick)
-        if _need(ctx, 9):
-            g[9] = _wgrad(du, xn2)
-        if _need(ctx, 10):
-            g[10] = _ops.colsum(du)
+        g[9], g[10] = _wgrad_bias(du, xn2, _need(ctx, 9), _need(ctx, 10))
         dxn2 = _dgrad(du, w16(fcw))
         want_ln2 = _need(ctx, 7) or _need(ctx, 8)
         dx1, g7, g8 = _ops.layernorm_bwd(dxn2, x1, ln2w, m2, r2, dres=dy, want_wgrad=want_ln2)
         g[7], g[8] = (g7, g8) if want_ln2 else (None, None)
-        if _need(ctx, 12):
-            g[12] = _ops.colsum(dy)
         # ---- attention
-        if _need(ctx, 5):
-            g[5] = _wgrad(dx1, o)
+        g[5], g[6] = _wgrad_bias(dx1, o, _need(ctx, 5), _need(ctx, 6))
         do = _dgrad(dx1, w16(outw))
         dqkv = torch.empty_like(qkv)
         _ops.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], o, do, lse, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
                            B=B, H=H, nq=N, nk=N, causal=causal)
-        if _need(ctx, 3):
-            g[3] = _wgrad(dqkv, xn1)
-        if _need(ctx, 4):
-            g[4] = _ops.colsum(dqkv)
+        g[3], g[4] = _wgrad_bias(dqkv, xn1, _need(ctx, 3), _need(ctx, 4))
         if _need(ctx, 0) or _need(ctx, 1) or _need(ctx, 2):
             dxn1 = _dgrad(dqkv, w16(inw))
             want_ln1 = _need(ctx, 1) or _need(ctx, 2)
             dx, g1, g2 = _ops.layernorm_bwd(dxn1, x, ln1w, m1, r1, dres=dx1, want_wgrad=want_ln1)
             g[0] = dx
             g[1], g[2] = (g1, g2) if want_ln1 else (None, None)
-        if _need(ctx, 6):
-            g[6] = _ops.colsum(dx1)
         return tuple(g)
 
 

@@ -48,7 +48,7 @@ class GemmArgs(C.Structure):
         ("bias", C.c_void_p), ("aux_in", C.c_void_p), ("aux_out", C.c_void_p), ("ldaux", C.c_int64),
         ("row_vec", C.c_void_p), ("col_vec", C.c_void_p), ("out_vec0", C.c_void_p), ("out_vec1", C.c_void_p),
         ("out_vec2", C.c_void_p), ("scalar_out", C.c_void_p), ("iparam", C.c_int32), ("fparam", C.c_float),
-        ("alpha_dev", C.c_void_p), ("fparam_dev", C.c_void_p), ("aux_row_div", C.c_int32), ("relu", C.c_int32),
+        ("alpha_dev", C.c_void_p), ("fparam_dev", C.c_void_p), ("aux_row_div", C.c_int32), ("relu", C.c_int32), ("rowsum_out", C.c_void_p),
     ]
 
 
@@ -107,7 +107,7 @@ def _count():
 def gemm(a, b, d, *, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, epilogue=EPI_LINEAR, bias=None,
          aux_in=None, aux_out=None, ldaux=0, alpha=1.0, accumulate=False, split_k=1, act_quick=False,
          row_vec=None, col_vec=None, out_vec0=None, out_vec1=None, out_vec2=None, scalar_out=None, iparam=0, fparam=0.0,
-         alpha_dev=None, fparam_dev=None, aux_row_div=0, relu=False):
+         alpha_dev=None, fparam_dev=None, aux_row_div=0, relu=False, rowsum_out=None):
     """Raw GEMM call; see include/vitlens_b200.h.  a, b bf16; d bf16 or fp32; bias fp32."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     assert d is None or d.dtype in (torch.bfloat16, torch.float32)
@@ -117,7 +117,7 @@ def gemm(a, b, d, *, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, epilogue=EP
         int(d is not None and d.dtype == torch.float32), int(accumulate), int(split_k), int(epilogue), int(act_quick), float(alpha),
         _ptr(bias), _ptr(aux_in), _ptr(aux_out), ldaux,
         _ptr(row_vec), _ptr(col_vec), _ptr(out_vec0), _ptr(out_vec1), _ptr(out_vec2), _ptr(scalar_out), int(iparam), float(fparam),
-        _ptr(alpha_dev), _ptr(fparam_dev), int(aux_row_div), int(relu))
+        _ptr(alpha_dev), _ptr(fparam_dev), int(aux_row_div), int(relu), _ptr(rowsum_out))
     _count()
     if CALL_TIMING is not None:
         kind = "wgrad" if (a_mn and b_mn) else ("dgrad" if b_mn else "fwd")

@@ -50,9 +50,16 @@ def pick_split_k(M: int, N: int, K: int) -> int:
     return best
 
 
+def rowsum_fusable(M: int, N: int) -> bool:
+    """True when a weight-gradient GEMM of this shape runs on the CTA-pair kernel, which can also emit the row sums of A
+    (= the bias gradient) from the tiles it already holds (VlGemmArgs.rowsum_out)."""
+    return M >= 512 and N > 128
+
+
 def gemm(a, b, *, a_t=False, b_t=False, bias=None, epilogue=EPI_LINEAR, aux_in=None, want_aux_out=False, out=None,
-         out_dtype=BF16, alpha=1.0, accumulate=False, split_k=None, act_quick=False, alpha_dev=None):
-    """out[M,N] = epilogue(alpha * A @ B^T); A = a ([M,K]) or a^T when a_t (a is [K,M]); B = b ([N,K]) or b^T when b_t."""
+         out_dtype=BF16, alpha=1.0, accumulate=False, split_k=None, act_quick=False, alpha_dev=None, want_rowsum=False):
+    """out[M,N] = epilogue(alpha * A @ B^T); A = a ([M,K]) or a^T when a_t (a is [K,M]); B = b ([N,K]) or b^T when b_t.
+    want_rowsum (fp32 LINEAR outputs, rowsum_fusable shapes): also returns sum_k A[m, k] as fp32 [M]."""
     _v2(a, BF16), _v2(b, BF16)
     M, K = (a.shape[1], a.shape[0]) if a_t else (a.shape[0], a.shape[1])
     N, Kb = (b.shape[1], b.shape[0]) if b_t else (b.shape[0], b.shape[1])
@@ -71,9 +78,15 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, epilogue=EPI_LINEAR, aux_in=N
         out = (torch.zeros if accumulate else torch.empty)((M, N), device=a.device, dtype=out_dtype)
     _v2(out)
     assert tuple(out.shape) == (M, N)
+    rowsum = None
+    if want_rowsum:
+        assert rowsum_fusable(M, N) and out.dtype == F32 and epilogue == EPI_LINEAR and not want_aux_out
+        rowsum = torch.zeros((M,), device=a.device, dtype=F32)
     L.gemm(a, b, out, M=M, N=N, K=K, lda=_ld(a), ldb=_ld(b), ldd=_ld(out), a_mn=a_t, b_mn=b_t, epilogue=epilogue, bias=bias,
            aux_in=aux_in, aux_out=aux_out, ldaux=ldaux, alpha=alpha, accumulate=accumulate, split_k=split_k, act_quick=act_quick,
-           alpha_dev=alpha_dev)
+           alpha_dev=alpha_dev, rowsum_out=rowsum)
+    if want_rowsum:
+        return out, rowsum
     return (out, aux_out) if want_aux_out else out
 
 
