@@ -929,6 +929,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait_guarded(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
+        bool rs_started = false;
+        int rs_wait = rs ? ((n_blk - kb0) % p.tiles_n + p.tiles_n) % p.tiles_n : -1;  // k-blocks until this tile's next row-sum turn
         for (int kb = kb0; kb < kb1; ++kb) {
           if (!(p.dbg & 8)) mbar_wait_guarded(full_bar(stage), phase);
           tc_fence_after();
@@ -939,7 +941,17 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint64_t ad = umma_desc_sw128(sa + k * p.a_kstep, p.a_lbo, p.a_sbo);
             const uint64_t bd = umma_desc_sw128(sb + k * p.b_kstep, p.b_lbo, p.b_sbo);
             umma_ss_pair(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            if (rs && n_blk == 0) umma_ss_pair(tmem_base + BN, ad, ones_desc, idesc_ones, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          // Row sums of A: the n-tiles of one m-row share the work (k-block kb belongs to n-tile kb % tiles_n), four MMAs back
+          // to back so the pipe switches instruction shape twice per k-block; partial sums meet in rowsum_out (atomics).
+          if (rs_wait-- == 0) {
+            rs_wait = p.tiles_n - 1;
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t ad = umma_desc_sw128(sa + k * p.a_kstep, p.a_lbo, p.a_sbo);
+              umma_ss_pair(tmem_base + BN, ad, ones_desc, idesc_ones, (rs_started || k > 0) ? 1u : 0u);
+            }
+            rs_started = true;
           }
           umma_commit_pair_mc(empty_bar(stage), 3);
           if (++stage == Cfg::kStages) {
@@ -1022,7 +1034,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (!released) release();
       } else {
         if (!(p.dbg & 1)) epilogue_tile<BN, EpiCfg<BN>::kChunk>(p, tmem_base, acc * BN, row_base, n_blk, ks, e, quarter, lane);
-        if (rs && n_blk == 0 && (e >> 2) == 0) {  // one warp per lane quarter adds this tile's row sums of A
+        const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int kb_first = kb0 + ((n_blk - kb0) % p.tiles_n + p.tiles_n) % p.tiles_n;  // first k-block this tile summed
+        if (rs && kb_first < kb1 && (e >> 2) == 0) {  // one warp per lane quarter adds this tile's partial row sums of A
           uint32_t v[16];
           tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + BN, v);
           tc_wait_ld();
