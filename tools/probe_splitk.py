@@ -14,7 +14,7 @@ for name, M, N in (("fc", 4096, 1024), ("proj", 1024, 4096), ("qkv", 3072, 1024)
     B = torch.randn(T, N, device=dev).bfloat16()
     D = torch.zeros(M, N, device=dev)
     res = []
-    for s in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 16, 18, 24, 37):
+    for s in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 16):
         def call():
             L.gemm(A, B, D, M=M, N=N, K=T, lda=M, ldb=N, ldd=N, a_mn=True, b_mn=True, accumulate=True, split_k=s)
         for _ in range(2):

@@ -257,8 +257,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
         float* dp = reinterpret_cast<float*>(p.d) + doff;
         if (p.accumulate) {
 #pragma unroll
-          for (int j = 0; j < CW; ++j)
-            if (col0 + j < p.N) atomicAdd(dp + j, f[j]);
+          for (int j = 0; j < CW; j += 4)
+            if (col0 + j < p.N) red_add_v4_f32(dp + j, f[j], f[j + 1], f[j + 2], f[j + 3]);  // N % 4 == 0 and 16-byte aligned rows (checked at launch)
         } else {
 #pragma unroll
           for (int j = 0; j < CW; j += 4)
@@ -287,15 +287,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
 // chunk j of row r lives at r*128 + ((j ^ (r & 7)) << 4), conflict-free for per-row 16-byte accesses).  When the mode
 // needs an aux block the caller has already issued its TMA load into `buf` (completion on aux_bar / aux_phase).
 // `release` hands the TMEM accumulator back as soon as the last tcgen05.ld has landed, before any store is issued.
-template <int BN, typename Release>
+template <int BN, int EPI, typename Release>
 __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUtensorMap* tmD, const CUtensorMap* tmX, uint32_t tmem_base,
                                                   uint32_t acc_col, int row_w, int col_s, int slice, int quarter, int lane, uint32_t buf,
                                                   uint32_t buf2, uint32_t aux_bar, uint32_t aux_phase, bool aux_loaded, bool last_slice,
                                                   Release release) {
+  const int epi = EPI >= 0 ? EPI : epi;  // compile-time constant in the specialised kernels
   const float alpha_eff = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f);
-  const bool need_aux = p.epi == VL_EPI_RESIDUAL || p.epi == VL_EPI_GELU_BWD;
-  const bool need_bias = p.bias != nullptr && p.epi != VL_EPI_GELU_BWD;
-  const bool keep_pre = p.epi == VL_EPI_GELU && p.aux_out != nullptr;
+  const bool need_aux = epi == VL_EPI_RESIDUAL || epi == VL_EPI_GELU_BWD;
+  const bool need_bias = p.bias != nullptr && epi != VL_EPI_GELU_BWD;
+  const bool keep_pre = epi == VL_EPI_GELU && p.aux_out != nullptr;
   const uint32_t sw = lane & 7;
   // GELU forward issues two stores per slice; when the warp owns a second staging block (buf2 != buf) the stores alternate
   // between the two so that a block is only rewritten two stores later (no wait on the store that was just issued).
@@ -307,12 +308,21 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
   const uint32_t row_addr = buf + lane * 128;
   uint32_t pre[32];  // packed pre-activations of the 64 columns (GELU forward keeps them for the second store)
   float bnext[16];
+  const bool full64 = col_s + 64 <= p.N;
   auto load_bias = [&](int c, float (&bv)[16]) {
     const int col0 = col_s + c * 16;
+    if (full64) {
 #pragma unroll
-    for (int j = 0; j < 16; j += 4) {
-      const float4 b4 = (col0 + j < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j)) : make_float4(0, 0, 0, 0);
-      bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b4 = (col0 + j < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j)) : make_float4(0, 0, 0, 0);
+        bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
+      }
     }
   };
   if (need_bias) load_bias(0, bnext);
@@ -342,7 +352,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
       for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * alpha_eff;
     }
     const uint32_t a0 = row_addr + (((2 * c) ^ sw) << 4), a1 = row_addr + (((2 * c + 1) ^ sw) << 4);
-    if (p.epi == VL_EPI_GELU) {
+    if (epi == VL_EPI_GELU) {
       if (keep_pre) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) pre[8 * c + j] = pack_bf16(f[2 * j], f[2 * j + 1]);
@@ -361,7 +371,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
       if (c == 0 && aux_loaded) mbar_wait(aux_bar, aux_phase);
       const uint4 x0 = ld_shared_v4(a0), x1 = ld_shared_v4(a1);
       const uint32_t aw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-      if (p.epi == VL_EPI_RESIDUAL) {
+      if (epi == VL_EPI_RESIDUAL) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           f[2 * j] += bf16_lo(aw[j]);
@@ -417,7 +427,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
   }
 }
 
-template <int BN, int EW>
+template <int BN, int EW, int EPI = -1>
 __global__ void __launch_bounds__((KernelCfg<BN, EW>::kThreads), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
                  const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
@@ -551,12 +561,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     [[maybe_unused]] uint32_t aux_phase[4] = {0, 0, 0, 0};  // per owned slice: flips only when that slice's block was loaded
-    [[maybe_unused]] const bool need_aux = p.epi == VL_EPI_RESIDUAL || p.epi == VL_EPI_GELU_BWD;
+    [[maybe_unused]] const int epi = EPI >= 0 ? EPI : p.epi;
+    [[maybe_unused]] const bool need_aux = epi == VL_EPI_RESIDUAL || epi == VL_EPI_GELU_BWD;
     constexpr int kGroups = kEpiWarps / 4;             // warps per TMEM lane quarter
     [[maybe_unused]] constexpr int kSlicesPerWarp = (BN / 64) / kGroups;  // 64-column slices each warp owns (TE path)
     // GELU forward (two stores per slice): the warp's two staging blocks form a ring, activation -> first, pre-activation ->
     // second, for both of its slices (see epilogue_tile_tma).
-    [[maybe_unused]] const bool ring2 = kSlicesPerWarp > 1 && p.epi == VL_EPI_GELU && p.aux_out != nullptr;
+    [[maybe_unused]] const bool ring2 = kSlicesPerWarp > 1 && epi == VL_EPI_GELU && p.aux_out != nullptr;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int m_blk, n_blk, ks;
       tile_coords(p, t, m_blk, n_blk, ks);
@@ -599,7 +610,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int col_s = n_blk * BN + slice * 64;
             if (col_s < p.N) {
               const bool last = (si == kSlicesPerWarp - 1) || (col_s + kGroups * 64 >= p.N);
-              epilogue_tile_tma<BN>(p, &tmD, &tmX, tmem_base, acc * BN, row_w, col_s, slice, quarter, lane,
+              epilogue_tile_tma<BN, EPI>(p, &tmD, &tmX, tmem_base, acc * BN, row_w, col_s, slice, quarter, lane,
                                     stg_base + ((ring2 ? (e >> 2) : slice) * 4 + quarter) * kEpiBufBytes,
                                     stg_base + ((ring2 ? (e >> 2) + kGroups : slice) * 4 + quarter) * kEpiBufBytes,
                                     aux_bar(slice * 4 + quarter), aux_phase[si],
@@ -745,12 +756,23 @@ static int launch_gemm(const VlGemmArgs& a, cudaStream_t stream) {
       using CfgT = GemmCfg<BN, true>;
       rc = make_epilogue_maps(a, &tmD, &tmX);
       if (rc) return rc;
-      static bool attr_set_t = false;
-      if (!attr_set_t) {
-        VL_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgT::kSmemBytes));
-        attr_set_t = true;
+      // one kernel per epilogue mode: the mode tests and the dead activation variants drop out of the epilogue's inner loop
+#define VL_LAUNCH_TE1(EPI_)                                                                                                          \
+  do {                                                                                                                              \
+    static bool attr_ = false;                                                                                                      \
+    if (!attr_) {                                                                                                                   \
+      VL_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, 8, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgT::kSmemBytes));   \
+      attr_ = true;                                                                                                                 \
+    }                                                                                                                               \
+    gemm_bf16_kernel<BN, 8, EPI_><<<grid, KernelCfg<BN, 8>::kThreads, CfgT::kSmemBytes, stream>>>(tmA, tmB, tmD, tmX, p);           \
+  } while (0)
+      switch (a.epilogue) {
+        case VL_EPI_LINEAR: VL_LAUNCH_TE1(VL_EPI_LINEAR); break;
+        case VL_EPI_GELU: VL_LAUNCH_TE1(VL_EPI_GELU); break;
+        case VL_EPI_RESIDUAL: VL_LAUNCH_TE1(VL_EPI_RESIDUAL); break;
+        default: VL_LAUNCH_TE1(VL_EPI_GELU_BWD); break;
       }
-      gemm_bf16_kernel<BN, 8><<<grid, KernelCfg<BN, 8>::kThreads, CfgT::kSmemBytes, stream>>>(tmA, tmB, tmD, tmX, p);
+#undef VL_LAUNCH_TE1
       return launch_check("gemm_bf16_kernel<tma epilogue>");
     }
   }
@@ -806,7 +828,7 @@ __device__ __forceinline__ void tile_coords2(const GemmParams& p, int tiles_m2, 
   m_blk = m_first + (r - n_blk * gm);
 }
 
-template <int BN, int EW>
+template <int BN, int EW, int EPI = -1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((KernelCfg<BN, EW>::kThreads), 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
                   const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
@@ -973,12 +995,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     [[maybe_unused]] uint32_t aux_phase[4] = {0, 0, 0, 0};  // per owned slice: flips only when that slice's block was loaded
-    [[maybe_unused]] const bool need_aux = p.epi == VL_EPI_RESIDUAL || p.epi == VL_EPI_GELU_BWD;
+    [[maybe_unused]] const int epi = EPI >= 0 ? EPI : p.epi;
+    [[maybe_unused]] const bool need_aux = epi == VL_EPI_RESIDUAL || epi == VL_EPI_GELU_BWD;
     constexpr int kGroups = kEpiWarps / 4;             // warps per TMEM lane quarter
     [[maybe_unused]] constexpr int kSlicesPerWarp = (BN / 64) / kGroups;  // 64-column slices each warp owns (TE path)
     // GELU forward (two stores per slice): the warp's two staging blocks form a ring, activation -> first, pre-activation ->
     // second, for both of its slices (see epilogue_tile_tma).
-    [[maybe_unused]] const bool ring2 = kSlicesPerWarp > 1 && p.epi == VL_EPI_GELU && p.aux_out != nullptr;
+    [[maybe_unused]] const bool ring2 = kSlicesPerWarp > 1 && epi == VL_EPI_GELU && p.aux_out != nullptr;
     for (int t = cluster_id; t < total_tiles; t += num_clusters) {
       int m_blk, n_blk, ks;
       tile_coords2(p, tiles_m2, t, m_blk, n_blk, ks);
@@ -1021,7 +1044,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int col_s = n_blk * BN + slice * 64;
             if (col_s < p.N) {
               const bool last = (si == kSlicesPerWarp - 1) || (col_s + kGroups * 64 >= p.N);
-              epilogue_tile_tma<BN>(p, &tmD, &tmX, tmem_base, acc * BN, row_w, col_s, slice, quarter, lane,
+              epilogue_tile_tma<BN, EPI>(p, &tmD, &tmX, tmem_base, acc * BN, row_w, col_s, slice, quarter, lane,
                                     stg_base + ((ring2 ? (e >> 2) : slice) * 4 + quarter) * kEpiBufBytes,
                                     stg_base + ((ring2 ? (e >> 2) + kGroups : slice) * 4 + quarter) * kEpiBufBytes,
                                     aux_bar(slice * 4 + quarter), aux_phase[si],
@@ -1091,12 +1114,22 @@ static int launch_gemm2(const VlGemmArgs& a, GemmParams p, cudaStream_t stream) 
       using CfgT = Gemm2Cfg<BN, true>;
       rc = make_epilogue_maps(a, &tmD, &tmX);
       if (rc) return rc;
-      static bool attr_set_t = false;
-      if (!attr_set_t) {
-        VL_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<BN, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgT::kSmemBytes));
-        attr_set_t = true;
+#define VL_LAUNCH_TE2(EPI_)                                                                                                          \
+  do {                                                                                                                              \
+    static bool attr_ = false;                                                                                                      \
+    if (!attr_) {                                                                                                                   \
+      VL_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<BN, 8, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgT::kSmemBytes));  \
+      attr_ = true;                                                                                                                 \
+    }                                                                                                                               \
+    gemm2_bf16_kernel<BN, 8, EPI_><<<2 * clusters, KernelCfg<BN, 8>::kThreads, CfgT::kSmemBytes, stream>>>(tmA, tmB, tmD, tmX, p);  \
+  } while (0)
+      switch (a.epilogue) {
+        case VL_EPI_LINEAR: VL_LAUNCH_TE2(VL_EPI_LINEAR); break;
+        case VL_EPI_GELU: VL_LAUNCH_TE2(VL_EPI_GELU); break;
+        case VL_EPI_RESIDUAL: VL_LAUNCH_TE2(VL_EPI_RESIDUAL); break;
+        default: VL_LAUNCH_TE2(VL_EPI_GELU_BWD); break;
       }
-      gemm2_bf16_kernel<BN, 8><<<2 * clusters, KernelCfg<BN, 8>::kThreads, CfgT::kSmemBytes, stream>>>(tmA, tmB, tmD, tmX, p);
+#undef VL_LAUNCH_TE2
       return launch_check("gemm2_bf16_kernel<tma epilogue>");
     }
   }

@@ -85,6 +85,10 @@ __device__ __forceinline__ void tma_store_3d(const void* map, uint32_t src, int 
                "r"(c2)
                : "memory");
 }
+// fp32 x4 reduction into global memory in one instruction (sm_90+): split-K partial tiles
+__device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
