@@ -177,7 +177,7 @@ def run_cuda(args):
 
     import open_clip
     from vitlens_b200 import lib as L
-    from vitlens_b200 import optim, synth
+    from vitlens_b200 import grad_sync, optim, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -209,24 +209,15 @@ def run_cuda(args):
     dev_imgs = [h.to(dev) for h in host_imgs]
     anchors = torch.nn.functional.normalize(synth.synth_normal("anchors", (B, EMBED), seed=gen_seed), dim=-1).to(dev)
     host_loss = torch.zeros((), dtype=torch.float32).pin_memory()
-    flat = torch.empty(n_params, device=dev, dtype=torch.float32) if world > 1 else None
+    # N > 1: DDP-style bucketed gradient all-reduce, overlapped with backward (vitlens_b200/grad_sync.py)
+    reducer = grad_sync.GradReducer(params) if world > 1 else None
 
     def train_step(images):
         feats = open_clip.model._normalize(tower(images))
         loss = loss_fn(feats, anchors, logit_scale.exp())
         loss.backward()
-        if world > 1:  # one flat gradient all-reduce (mean), as DDP would (pc_tri_main.py:378-380)
-            off = 0
-            for p in params:
-                n = p.numel()
-                flat[off:off + n].copy_(p.grad.reshape(-1))
-                off += n
-            dist.all_reduce(flat)
-            off = 0
-            for p in params:
-                n = p.numel()
-                p.grad = flat[off:off + n].view_as(p)
-                off += n
+        if reducer is not None:
+            reducer.finish()
             opt.step(grad_scale=1.0 / world)
         else:
             opt.step()
@@ -331,8 +322,32 @@ def run_cuda(args):
         ent[0] += 1
         ent[1] += a.elapsed_time(b)
     step_ms_diag = e0.elapsed_time(e1)
+    # algorithmic work per step of the entry points that matter: T tokens, D = 1024, 24 blocks
+    T_tok, D_w, n_blk = B * 257, 1024, 24
+    gemm_fl = 2.0 * T_tok * D_w * D_w
+    work = {  # entry point -> (bound, algorithmic FLOPs or bytes per step)
+        "vl_gemm_bf16/fwd/epi0": ("tensor", n_blk * 3 * gemm_fl), "vl_gemm_bf16/fwd/epi1": ("tensor", n_blk * 4 * gemm_fl),
+        "vl_gemm_bf16/fwd/epi2": ("tensor", n_blk * 5 * gemm_fl), "vl_gemm_bf16/dgrad/epi0": ("tensor", n_blk * 8 * gemm_fl),
+        "vl_gemm_bf16/dgrad/epi3": ("tensor", n_blk * 4 * gemm_fl), "vl_gemm_bf16/wgrad/epi0": ("tensor", n_blk * 12 * gemm_fl),
+        "vl_attention_fwd": ("hbm", n_blk * 4.0 * T_tok * D_w * 2), "vl_attention_bwd": ("hbm", n_blk * 8.0 * T_tok * D_w * 2),
+        "vl_layernorm_fwd": ("hbm", (2 * n_blk + 1) * 2.0 * T_tok * D_w * 2), "vl_layernorm_bwd": ("hbm", (2 * n_blk + 1) * 4.0 * T_tok * D_w * 2),
+        "vl_adamw_multi": ("hbm", n_params * 30.0),
+    }
+    pk_ = peaks()
+    rows = {}
+    for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1][1]):
+        row = {"launches": v[0], "ms": round(v[1], 3)}
+        if k in work and v[1] > 0:
+            bound, amount = work[k]
+            if bound == "tensor":
+                row.update(bound="tensor", achieved=round(amount / v[1] / 1e9, 1), unit="TFLOP/s", frac=round(amount / v[1] / 1e9 / pk_["tf"], 3))
+            else:
+                row.update(bound="hbm", achieved=round(amount / v[1] / 1e6, 1), unit="GB/s", frac=round(amount / v[1] / 1e6 / pk_["hbm"], 3))
+        rows[k] = row
     breakdown = {"step_ms": round(step_ms_diag, 2), "sum_kernels_ms": round(sum(v[1] for v in by_kernel.values()), 2),
-                 "by_entry_point": {k: {"launches": v[0], "ms": round(v[1], 3)} for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1][1])}}
+                 "note": "untimed diagnostic step, CUDA events around each C-ABI call; algorithmic FLOPs/bytes of the ViT-L blocks only "
+                         "(patch embed / head / loss GEMMs, < 0.5 % of the work, are left out of the numerators)",
+                 "by_entry_point": rows}
 
     if rank != 0:
         if world > 1:

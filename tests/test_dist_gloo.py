@@ -101,3 +101,44 @@ def test_sharded_contrastive_loss_matches_reference_semantics(tri, tmp_path):
             for a, b in pairs:
                 err = float((a - b).abs().max())
                 assert err < 3e-2 * float(b.abs().max()) + 1e-5, (key, r, err, float(b.abs().max()))
+
+
+def _reducer_worker(rank, port, out):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=W)
+    from vitlens_b200.grad_sync import GradReducer
+
+    torch.manual_seed(0)  # identical weights on both ranks
+    net = torch.nn.Sequential(torch.nn.Linear(16, 64), torch.nn.GELU(), torch.nn.Linear(64, 64), torch.nn.GELU(), torch.nn.Linear(64, 8))
+    frozen = net[2].bias
+    frozen.requires_grad_(False)
+    params = [p for p in net.parameters()]
+    red = GradReducer(params, bucket_bytes=4096)  # several buckets
+    res = []
+    for step in range(2):
+        g = torch.Generator().manual_seed(10 * step + rank)
+        x = torch.randn(5, 16, generator=g)
+        net(x).square().sum().backward()
+        local = [p.grad.clone() for p in params if p.requires_grad]
+        red.finish()
+        res.append(dict(local=local, reduced=[p.grad.clone() for p in params if p.requires_grad]))
+        for p in params:
+            p.grad = None
+    torch.save(dict(res=res, n_buckets=len(red.buckets)), out.format(rank))
+    dist.destroy_process_group()
+
+
+def test_bucketed_gradient_all_reduce(tmp_path):
+    """GradReducer (the overlapped DDP-style exchange, pc_tri_main.py:378-380): every p.grad ends up as the cross-rank sum,
+    buckets are re-armed for the next step, frozen parameters are skipped."""
+    out = str(tmp_path / "r{}.pt")
+    mp.spawn(_reducer_worker, args=(_free_port(), out), nprocs=W, join=True)
+    r = [torch.load(out.format(i)) for i in range(W)]
+    assert r[0]["n_buckets"] > 1
+    for step in range(2):
+        for k in range(len(r[0]["res"][step]["local"])):
+            want = r[0]["res"][step]["local"][k] + r[1]["res"][step]["local"][k]
+            for rank in range(W):
+                assert torch.allclose(r[rank]["res"][step]["reduced"][k], want, rtol=1e-6, atol=1e-6)
