@@ -48,10 +48,12 @@ def check(name, got, ref, tol=3e-2):
     return ok
 
 
-def run(B, H, nq, nk, causal=False, packed=True, bwd=False):
+def run(B, H, nq, nk, causal=False, packed=True, bwd=False, qmul=1.0):
     D = H * 64
     scale = 64 ** -0.5
     hold, q, k, v, ldq, ldk, ldv = make(B, H, nq, nk, packed)
+    if qmul != 1.0:  # large score spread: exercises the lazily moved softmax offset (O rescale in TMEM)
+        q.mul_(qmul)
     o = torch.zeros(B * nq, D, device=dev, dtype=torch.bfloat16)
     lse = torch.zeros(B, H, nq, device=dev)
     L.attention_fwd(q, k, v, o, lse, B=B, H=H, nq=nq, nk=nk, ldq=ldq, ldk=ldk, ldv=ldv, ldo=D, scale=scale, causal=causal)
@@ -103,7 +105,13 @@ def timing():
         L.attention_bwd(q, k, v, o, do, lse, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], B=B, H=H, nq=N, nk=N, ldq=3 * D, ldk=3 * D,
                         ldv=3 * D, ldo=D, lddo=D, lddq=3 * D, lddk=3 * D, lddv=3 * D, scale=scale)
 
-    for name, fn, byts, flops in (("fwd", f, 4 * B * N * D * 2, 4.0 * B * H * N * N * 64), ("bwd", g, 8 * B * N * D * 2, 10.0 * B * H * N * N * 64)):
+    def f_old():
+        L.debug_set(13, 1)
+        f()
+        L.debug_set(13, 0)
+
+    for name, fn, byts, flops in (("fwd", f, 4 * B * N * D * 2, 4.0 * B * H * N * N * 64), ("fwd(one-tile kernel)", f_old, 4 * B * N * D * 2, 4.0 * B * H * N * N * 64),
+                                  ("bwd", g, 8 * B * N * D * 2, 10.0 * B * H * N * N * 64)):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
@@ -152,4 +160,11 @@ if __name__ == "__main__":
         run(2, 2, 17, 17, bwd=b)
         run(2, 2, 300, 300, causal=True, bwd=b)
         run(4, 12, 50, 50, bwd=b)
+        run(40, 16, 257, 257, bwd=b)
+        run(2, 2, 513, 513, bwd=b)
+        run(1, 1, 640, 132, packed=False, bwd=b)
+        run(2, 1, 229, 229, bwd=b)
+        run(2, 2, 260, 260, bwd=b)
+        run(3, 4, 257, 257, bwd=b, qmul=8.0)
+        run(2, 2, 384, 700, packed=False, bwd=b, qmul=6.0)
     print("done", flush=True)

@@ -915,6 +915,14 @@ int vl_attention_fwd(const void* q, const void* k, const void* v, void* o, float
   if (int rc = check_common("vl_attention_fwd", B, H, nq, nk, ldq, ldk, ldv)) return rc;
   VL_CHECK_ARG(ldo % 8 == 0 && ldo >= (int64_t)H * kHD, "vl_attention_fwd: bad ldo");
   VL_CHECK_ARG(!causal || nq == nk, "vl_attention_fwd: causal requires nq == nk");
+  {
+    // two or more full query tiles, non-causal: the persistent two-group kernel (attention_fwd2.cu).
+    // debug knob 13: 1 = keep the one-tile-per-CTA kernel below for every shape
+    const int t2 = nq % kTQ;
+    const int tq2 = (nq > kTQ && t2 == 1) ? 1 : 0;  // the kernel folds one tail row (N = 128 k + 1) in on CUDA cores
+    if (!causal && nq - tq2 > kTQ && debug_get(13) != 1)
+      return launch_attn_fwd2(q, k, v, o, lse, B, H, nq, nk, ldq, ldk, ldv, ldo, scale, reinterpret_cast<cudaStream_t>(stream));
+  }
   CUtensorMap tmQ, tmK, tmV;
   int rc;
   if ((rc = make_tmap_bf16_2d(&tmQ, q, (uint64_t)H * kHD, (uint64_t)B * nq, ldq, kHD, kTQ))) return rc;
