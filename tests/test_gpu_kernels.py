@@ -135,6 +135,29 @@ def test_attention_fwd_bwd(ops, B, H, nq, nk, causal, packed):
     close(dv.reshape(B, nk, H, 64), gv, tol=3e-2)
 
 
+@pytest.mark.parametrize("B,H,nq,nk,qmul,packed", [
+    (3, 4, 257, 257, 8.0, True),     # large score spread: the lazily moved softmax offset rescales O in TMEM
+    (2, 2, 384, 700, 6.0, False),    # odd number of query tiles (one group idles in the last range), 11 key blocks, masked last block
+    (40, 16, 257, 257, 1.0, True),   # 640 work items over 148 persistent CTAs: K/V ring wrap, Q stage recycling, deferred epilogues
+    (2, 3, 257, 64, 1.0, False),     # a single key block per item (nothing to defer the epilogue behind)
+    (1, 2, 260, 33, 2.0, False)])    # remainder 4 -> padded third tile (second range with one tile), 33 keys
+def test_attention_fwd_persistent_kernel(ops, B, H, nq, nk, qmul, packed):
+    """Shapes that route to attn_fwd2_kernel (non-causal, more than one 128-row query tile): O and LSE against fp32 torch."""
+    D = H * 64
+    if packed:
+        qkv = torch.randn(B * nq, 3 * D, device="cuda").to(BF)
+        q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    else:
+        q = torch.randn(B * nq, D, device="cuda").to(BF)
+        kv = torch.randn(B * nk, 2 * D, device="cuda").to(BF)
+        k, v = kv[:, :D], kv[:, D:]
+    q.mul_(qmul)
+    o, lse = ops.attention_fwd(q, k, v, B=B, H=H, nq=nq, nk=nk, causal=False)
+    oref, lref = _ref_attn(q.float().reshape(B, nq, H, 64), k.float().reshape(B, nk, H, 64), v.float().reshape(B, nk, H, 64), False)
+    close(o.reshape(B, nq, H, 64), oref, tol=3e-2)
+    close(lse, lref, tol=1e-3, atol=2e-3)
+
+
 @pytest.mark.parametrize("T,D,gather", [(1000, 1024, False), (77, 128, False), (513, 768, True), (300, 512, False)])
 def test_layernorm(ops, T, D, gather):
     x = (torch.randn(T, D, device="cuda") * 2 + 0.5).to(BF)

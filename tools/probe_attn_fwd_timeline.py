@@ -19,8 +19,8 @@ fwd()
 torch.cuda.synchronize()
 h.vl_debug_buffer(ctypes.c_void_p(0))
 t = buf.cpu().reshape(4, 4, 64)
-names = {0: ["stage free"], 1: ["KV landed", "S buf free", "S issued", "waiting P", "P ready/issue PV"],
-         2: ["block start", "S ready", "scores in regs", "exps done", "staging free", "P handed over"], 3: ["KV landed", "dot", "stats", "tail done"]}
+names = {0: ["stage free"], 1: ["KV landed", "S issued", "waiting P", "P ready/issue PV"],
+         2: ["block start", "S ready", "scores in regs", "exps done", "P handed over", "(rows stored)"], 3: ["KV landed", "tail done"]}
 roles = ["producer", "mma0", "softmax w4", "tail w12"]
 for c in range(2):
     base = min(int(x) for x in t[c].flatten() if int(x) > 0)

@@ -59,7 +59,8 @@ def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False) -> 
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
         if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src), hdr_m):
             return obj, ""
-        cmd = [nvcc, *NVCC_FLAGS, *(["-Xptxas", "-v"] if ptxas_v else []), "-c", src, "-o", obj]
+        extra = os.environ.get("VL_NVCC_EXTRA", "").split()  # bring-up switches, e.g. -DVL_FWD2_TIMELINE
+        cmd = [nvcc, *NVCC_FLAGS, *extra, *(["-Xptxas", "-v"] if ptxas_v else []), "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

@@ -13,6 +13,8 @@ from __future__ import annotations
 
 from typing import Optional
 
+import weakref
+
 import torch
 
 from . import ops as _ops
@@ -23,20 +25,43 @@ BF16, F32 = torch.bfloat16, torch.float32
 # ----------------------------------------------------------------------------- bf16 weight cache
 class _WeightCache:
     """bf16 copies of fp32 master weights, refreshed when the parameter changes (its autograd
-    version counter moves on every in-place optimizer update)."""
+    version counter moves on every in-place optimizer update).
+
+    An entry belongs to one live parameter OBJECT: it holds a weak reference to it and dies with it.  (Keying on id() alone
+    is not enough: a freed parameter's id, storage address, version and shape can all be reused by the next model built in
+    the same process, which would hand that model the previous model's weights.)"""
 
     def __init__(self):
         self._c = {}
+
+    def _alive(self, hit, ps) -> bool:
+        return hit is not None and len(hit[2]) == len(ps) and all(r() is q for r, q in zip(hit[2], ps))
+
+    def _put(self, key, ver, t, ps):
+        drop = lambda _ref, key=key, c=self._c: c.pop(key, None)  # noqa: E731  (entry dies with its parameter)
+        self._c[key] = (ver, t, tuple(weakref.ref(q, drop) for q in ps))
 
     def get(self, p: torch.Tensor, tag: str = "", make=None) -> torch.Tensor:
         key = (id(p), tag)
         ver = (p._version, p.data_ptr(), tuple(p.shape))
         hit = self._c.get(key)
-        if hit is not None and hit[0] == ver:
+        if self._alive(hit, (p,)) and hit[0] == ver:
             return hit[1]
         with torch.no_grad():
             t = make(p) if make is not None else _ops.cast_bf16(p.detach().reshape(p.shape[0], -1) if p.dim() > 1 else p.detach())
-        self._c[key] = (ver, t)
+        self._put(key, ver, t, (p,))
+        return t
+
+    def get_cat(self, tag: str, ps) -> torch.Tensor:
+        """bf16 concat of several weights along dim 0 (one cached tensor per tuple of parameters)."""
+        key = (tuple(id(q) for q in ps), tag)
+        ver = tuple((q._version, q.data_ptr(), tuple(q.shape)) for q in ps)
+        hit = self._c.get(key)
+        if self._alive(hit, ps) and hit[0] == ver:
+            return hit[1]
+        with torch.no_grad():
+            t = torch.cat([self.get(q) for q in ps], dim=0).contiguous()
+        self._put(key, ver, t, tuple(ps))
         return t
 
     def clear(self):
@@ -45,7 +70,7 @@ class _WeightCache:
     def plain_copy(self, p):
         """The cached plain bf16 copy of parameter `p` if it is current (used by the fused optimizer)."""
         hit = self._c.get((id(p), ""))
-        if hit is not None and hit[0] == (p._version, p.data_ptr(), tuple(p.shape)):
+        if self._alive(hit, (p,)) and hit[0] == (p._version, p.data_ptr(), tuple(p.shape)):
             return hit[1]
         return None
 
@@ -63,15 +88,7 @@ def w16(p):
 
 def _cat16(tag, *ps):
     """bf16 concat of several weights along dim 0 (Lens to_q | to_kv -> one QKV GEMM)."""
-    key = (tuple(id(p) for p in ps), tag)
-    ver = tuple((p._version, p.data_ptr()) for p in ps)
-    hit = WEIGHTS._c.get(key)
-    if hit is not None and hit[0] == ver:
-        return hit[1]
-    with torch.no_grad():
-        t = torch.cat([w16(p) for p in ps], dim=0).contiguous()
-    WEIGHTS._c[key] = (ver, t)
-    return t
+    return WEIGHTS.get_cat(tag, ps)
 
 
 def _conv_w16(p, kpad):

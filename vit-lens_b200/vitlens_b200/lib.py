@@ -78,6 +78,11 @@ def load(build_if_missing: bool = True):
         lib.vl_last_error.restype = C.c_char_p
         lib.vl_abi_version.restype = C.c_int
         _lib = lib
+        # bring-up knobs for A/B runs (kernel variants; see vl_debug_set call sites in csrc/): VL_DEBUG="13=1,12=1"
+        for kv in os.environ.get("VL_DEBUG", "").split(","):
+            if "=" in kv:
+                k, v = kv.split("=")
+                lib.vl_debug_set(int(k), int(v))
         return lib
 
 
