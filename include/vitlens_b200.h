@@ -189,6 +189,13 @@ int vl_group_max_bwd(const void* dout, const int32_t* arg, void* dx, int64_t gro
 int vl_group_sum(const void* x, void* out, int64_t groups, int32_t G, int32_t C, void* stream);
 int vl_colsum2_bf16(const void* a, const void* b, float* s1, float* s2, int64_t T, int32_t N, void* stream);
 int vl_wgrad3(const void* dy, const float* x, float* dw, int64_t R, int32_t C, void* stream);
+/* BatchNorm1d with batch statistics inside the point tokenizer (training mode; reference dvae.py:185-193 under model.train(),
+ * SyncBN per pc_tri_main.py:372-373).  vl_moments3: out12 += [sum x (3) | sum x x^T (3x3)] over the R rows of x[R,3] -- the
+ * statistics of first_conv.0's outputs follow in closed form.  vl_col_affine_bf16: out = act(p0[c]*a + p1[c]*b + p2[c]) per
+ * column (b, p1 optional; act 0 none / 1 relu): the normalise+ReLU pass and the BatchNorm backward correction. */
+int vl_moments3(const float* x, float* out12, int64_t R, void* stream);
+int vl_col_affine_bf16(const void* a, const void* b, const float* p0, const float* p1, const float* p2, void* out, int64_t R, int32_t C,
+                       int32_t act, void* stream);
 
 #ifdef __cplusplus
 }

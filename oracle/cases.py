@@ -41,6 +41,7 @@ class Case:
     overrides: Dict = field(default_factory=dict)  # fields of the reference's `args`
     lock: Dict = field(default_factory=dict)  # kwargs of lock_visual_tower for tri models
     full_grads: bool = True  # store every gradient (tiny) or only norms + a few small ones
+    bn_train: bool = False  # point tokenizer: BatchNorm layers in training mode (batch statistics), as under model.train()
     seed: int = 0
 
 
@@ -56,6 +57,10 @@ CASES = {c.name: c for c in [
     Case("tiny_tri_pc", "ViT-tiny-16", "tri", 3, "pc",
          dict(_TINY_LENS, perceiver_input_chan=96, perceiver_self_per_cross_attn=1, pc_npoints=256,
               pc_num_group=16, pc_group_size=8, pc_trans_dim=96, pc_encoder_dims=64), dict(unlock_cls=True)),
+    # the same with the tokenizer's BatchNorm layers in training mode (batch statistics + running-statistics update)
+    Case("tiny_tri_pc_bntrain", "ViT-tiny-16", "tri", 3, "pc",
+         dict(_TINY_LENS, perceiver_input_chan=96, perceiver_self_per_cross_attn=1, pc_npoints=256,
+              pc_num_group=16, pc_group_size=8, pc_trans_dim=96, pc_encoder_dims=64), dict(unlock_cls=True), bn_train=True),
     # BASELINE.json configs[0]: ViT-B/32 image-text ClipLoss, batch 8
     Case("vitb32_clip_bs8", "ViT-B-32", "clip", 8, full_grads=False),
     # reduced-batch versions of configs[2..4] (full-size weights, reference runs them in seconds)
@@ -64,7 +69,24 @@ CASES = {c.name: c for c in [
     Case("vitl14_depth_bs2", "ViT-L-14", "tri", 2, "depth", {}, dict(unlock_cls=True, unlock_trans_first_n_layers=4),
          full_grads=False),
     Case("vitl14_pc_bs2", "ViT-L-14", "tri", 2, "pc", {}, dict(unlock_cls=True), full_grads=False),
+    Case("vitl14_pc_bs2_bntrain", "ViT-L-14", "tri", 2, "pc", {}, dict(unlock_cls=True), full_grads=False, bn_train=True),
 ]}
+
+
+BN_KEYS = ("first_conv.1.running_mean", "first_conv.1.running_var", "second_conv.1.running_mean", "second_conv.1.running_var")
+
+
+def set_bn_train(model) -> None:
+    """Training-mode BatchNorm in the point tokenizer only (everything else stays in eval mode: no dropout noise)."""
+    for m in model.visual.visual_adapter.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.train()
+
+
+def bn_running(state_dict) -> torch.Tensor:
+    """The tokenizer's four running-statistics buffers, concatenated (checked after a training-mode forward)."""
+    pre = "visual.visual_adapter.encoder."
+    return torch.cat([state_dict[pre + k].detach().float().cpu().flatten() for k in BN_KEYS])
 
 
 def model_cfg(case: Case) -> dict:

@@ -169,10 +169,23 @@ def batchnorm1d_eval(x, sd: SD, pre: str, eps: float = 1e-5):
     return (x - m) * torch.rsqrt(v + eps) * sd[pre + "weight"].view(1, -1, 1) + sd[pre + "bias"].view(1, -1, 1)
 
 
-def point_adapter(sd: SD, pre: str, pts, fps_start, num_group: int = 512, group_size: int = 32):
+def batchnorm1d_train(x, sd: SD, pre: str, eps: float = 1e-5, momentum: float = 0.1, new_stats=None):
+    """nn.BatchNorm1d in training mode on [B, C, L] (what model.train() gives dvae.py:185-193): biased batch statistics over
+    (B, L); `new_stats[pre]` receives the updated (running_mean, running_var) -- unbiased variance, torch's momentum rule."""
+    m = x.mean(dim=(0, 2))
+    v = x.var(dim=(0, 2), unbiased=False)
+    if new_stats is not None:
+        n = x.shape[0] * x.shape[2]
+        new_stats[pre] = ((1 - momentum) * sd[pre + "running_mean"] + momentum * m.detach(),
+                          (1 - momentum) * sd[pre + "running_var"] + momentum * v.detach() * n / max(n - 1, 1))
+    return (x - m.view(1, -1, 1)) * torch.rsqrt(v.view(1, -1, 1) + eps) * sd[pre + "weight"].view(1, -1, 1) + sd[pre + "bias"].view(1, -1, 1)
+
+
+def point_adapter(sd: SD, pre: str, pts, fps_start, num_group: int = 512, group_size: int = 32, bn_train: bool = False, new_stats=None):
     """PointTokenizer.forward point_encoder.py:350-362 -> Group.forward dvae.py:150-176
     (fps, knn_point dvae.py:107-118, centre subtraction) -> Encoder.forward dvae.py:196-212
-    (BatchNorm in eval mode) -> reduce_dim; pos = MLP(centres)."""
+    (BatchNorm in eval mode, or with batch statistics when bn_train) -> reduce_dim; pos = MLP(centres)."""
+    bn = (lambda x, q: batchnorm1d_train(x, sd, q, new_stats=new_stats)) if bn_train else (lambda x, q: batchnorm1d_eval(x, sd, q))
     B, N, _ = pts.shape
     cidx = fps_indices(pts, num_group, fps_start)
     center = torch.gather(pts, 1, cidx.unsqueeze(-1).expand(-1, -1, 3))
@@ -184,12 +197,12 @@ def point_adapter(sd: SD, pre: str, pts, fps_start, num_group: int = 512, group_
     g = nb.reshape(B * num_group, group_size, 3).transpose(1, 2)  # [BG, 3, n]
     e = pre + "encoder."
     f = torch.einsum("oc,bcn->bon", sd[e + "first_conv.0.weight"].squeeze(-1), g) + sd[e + "first_conv.0.bias"].view(1, -1, 1)
-    f = torch.relu(batchnorm1d_eval(f, sd, e + "first_conv.1."))
+    f = torch.relu(bn(f, e + "first_conv.1."))
     f = torch.einsum("oc,bcn->bon", sd[e + "first_conv.3.weight"].squeeze(-1), f) + sd[e + "first_conv.3.bias"].view(1, -1, 1)
     fg = f.max(dim=2, keepdim=True)[0]
     f = torch.cat([fg.expand(-1, -1, group_size), f], dim=1)
     f = torch.einsum("oc,bcn->bon", sd[e + "second_conv.0.weight"].squeeze(-1), f) + sd[e + "second_conv.0.bias"].view(1, -1, 1)
-    f = torch.relu(batchnorm1d_eval(f, sd, e + "second_conv.1."))
+    f = torch.relu(bn(f, e + "second_conv.1."))
     f = torch.einsum("oc,bcn->bon", sd[e + "second_conv.3.weight"].squeeze(-1), f) + sd[e + "second_conv.3.bias"].view(1, -1, 1)
     tok = f.max(dim=2)[0].reshape(B, num_group, -1)
     tok = linear(tok, sd[pre + "reduce_dim.weight"], sd[pre + "reduce_dim.bias"])

@@ -36,6 +36,8 @@ def build_model(case, device="cpu"):
         model.lock_image_tower()
         model.lock_text_tower()
         model.lock_visual_tower(**case.lock)
+    if case.bn_train:
+        C.set_bn_train(model)
     model.to(device)
     return model, sd, args
 
@@ -62,7 +64,7 @@ def run_model(case, model, inp, loss_mod=None):
     return feats, ls, loss
 
 
-def run_oracle(case, sd, args, inp, grad_keys=()):
+def run_oracle(case, sd, args, inp, grad_keys=(), new_stats=None):
     cfg = C.model_cfg(case)
     vh = cfg["vision_cfg"]["width"] // 64
     th = cfg["text_cfg"]["heads"]
@@ -77,6 +79,8 @@ def run_oracle(case, sd, args, inp, grad_keys=()):
             kw = dict(fstride=args.audio_fstride, tstride=args.audio_tstride)
         if case.modality == "pc":
             kw = dict(fps_start=inp["fps_start"], num_group=args.pc_num_group, group_size=args.pc_group_size)
+            if case.bn_train:
+                kw.update(bn_train=True, new_stats=new_stats if new_stats is not None else {})
         fi, ft, fv, ls = O.triclip_forward(sd, inp["image"], inp["text"], inp["visual"], case.modality, vh, th,
                                            perceiver_as_identity=bool(args.perceiver_as_identity),
                                            latent_heads=args.perceiver_latent_heads, cross_heads=args.perceiver_cross_heads, **kw)

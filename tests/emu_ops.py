@@ -317,6 +317,18 @@ def colsum2(a, b):
     return a.float().sum(0), (a.float() * b.float()).sum(0)
 
 
+def moments3(x):
+    x = x.float()
+    return torch.cat([x.sum(0), (x.t() @ x).reshape(9)])
+
+
+def col_affine(a, p0, p2, *, b=None, p1=None, relu=False):
+    y = a.float() * p0.float() + p2.float()
+    if b is not None:
+        y = y + b.float() * p1.float()
+    return (torch.relu(y) if relu else y).to(torch.bfloat16)
+
+
 def wgrad3(dy, x):
     _n()
     return dy.float().t() @ x
@@ -329,10 +341,10 @@ def group_max(x, G, want_arg=False):
     return (v.to(BF16), a.to(torch.int32)) if want_arg else v.to(BF16)
 
 
-def gemm_grouped_residual_relu(a, b, gp, group, *, bias=None):
+def gemm_grouped_residual_relu(a, b, gp, group, *, bias=None, relu=True):
     _n()
     acc = a.float() @ b.float().t()
     if bias is not None:
         acc = acc + bias
     acc = acc + gp.float().repeat_interleave(group, dim=0)
-    return torch.relu(acc).to(BF16)
+    return (torch.relu(acc) if relu else acc).to(BF16)

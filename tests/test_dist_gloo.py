@@ -142,3 +142,104 @@ def test_bucketed_gradient_all_reduce(tmp_path):
             want = r[0]["res"][step]["local"][k] + r[1]["res"][step]["local"][k]
             for rank in range(W):
                 assert torch.allclose(r[rank]["res"][step]["reduced"][k], want, rtol=1e-6, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------- SyncBatchNorm in the point tokenizer
+def _pc_tokenizer(sync):
+    """The tiny point tokenizer of oracle case tiny_tri_pc (16 groups of 8, 64 encoder channels), deterministic weights."""
+    from types import SimpleNamespace
+
+    from open_clip.modal_3d.models.pointbert.point_encoder import PointTokenizer
+
+    torch.manual_seed(0)
+    tk = PointTokenizer(SimpleNamespace(trans_dim=96, group_size=8, num_group=16, encoder_dims=64))
+    with torch.no_grad():  # non-trivial BatchNorm affines / running statistics
+        for bn in (tk.encoder.first_conv[1], tk.encoder.second_conv[1]):
+            bn.weight.uniform_(0.5, 1.5)
+            bn.bias.uniform_(-0.2, 0.2)
+    if sync:
+        tk = torch.nn.SyncBatchNorm.convert_sync_batchnorm(tk)
+    return tk.train()
+
+
+def _pc_inputs():
+    g = torch.Generator().manual_seed(7)
+    pts = torch.randn(4, 128, 3, generator=g)
+    start = torch.randint(0, 128, (4,), generator=g)
+    return pts, start
+
+
+def _pc_run(tk, pts, start):
+    out = tk(pts, fps_start=start)
+    x, pos = out["x"].t.float(), out["pos"].t.float()
+    w = torch.linspace(-1, 1, x.numel()).reshape(x.shape)
+    (x * w).sum().add((pos * w.flip(0)).sum()).backward()
+    grads = {k: p.grad.clone() for k, p in tk.named_parameters()}
+    stats = {k: v.clone() for k, v in tk.state_dict().items() if "running" in k}
+    return x.detach(), grads, stats
+
+
+def _syncbn_worker(rank, port, out):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=W)
+    from tests import emu_ops
+    from vitlens_b200 import engine
+
+    engine._ops = emu_ops
+    tk = _pc_tokenizer(sync=True)
+    pts, start = _pc_inputs()
+    sl = slice(2 * rank, 2 * rank + 2)
+    x, grads, stats = _pc_run(tk, pts[sl], start[sl])
+    torch.save(dict(x=x, grads=grads, stats=stats), out.format(rank))
+    dist.destroy_process_group()
+
+
+def test_point_tokenizer_sync_batchnorm(tmp_path):
+    """--use-bn-sync (pc_tri_main.py:372-373): with SyncBatchNorm layers two ranks holding half the clouds each produce the
+    tokens of one process holding all of them, the same running statistics, and parameter gradients that SUM to its
+    gradients (the weights of the loss below are per global row; DDP's averaging is a separate step)."""
+    from tests import emu_ops
+    from vitlens_b200 import engine
+
+    out = str(tmp_path / "s{}.pt")
+    mp.spawn(_syncbn_worker, args=(_free_port(), out), nprocs=W, join=True)
+    r = [torch.load(out.format(i)) for i in range(W)]
+    old = engine._ops
+    engine._ops = emu_ops
+    try:
+        tk = _pc_tokenizer(sync=False)
+        pts, start = _pc_inputs()
+        # single process, all four clouds; per-rank losses used the same weight pattern on their own rows, so rebuild that
+        outs, gsum = [], None
+        full = tk(pts, fps_start=start)
+        x = full["x"].t.float()
+        pos = full["pos"].t.float()
+        half = x.shape[0] // 2
+        loss = 0
+        for rk in range(W):
+            xs, ps = x[rk * half:(rk + 1) * half], pos[rk * half:(rk + 1) * half]
+            w = torch.linspace(-1, 1, xs.numel()).reshape(xs.shape)
+            loss = loss + (xs * w).sum() + (ps * w.flip(0)).sum()
+        loss.backward()
+        ref_g = {k: p.grad for k, p in tk.named_parameters()}
+        ref_s = {k: v for k, v in tk.state_dict().items() if "running" in k}
+    finally:
+        engine._ops = old
+        engine.WEIGHTS.clear()
+    got_x = torch.cat([r[0]["x"], r[1]["x"]])
+    assert float((got_x - x.detach()).abs().max()) < 3e-2 * float(x.detach().abs().max())
+    for k, v in ref_s.items():
+        for rk in range(W):
+            assert torch.allclose(r[rk]["stats"][k], v, rtol=2e-2, atol=1e-3), k
+    for k, g in ref_g.items():
+        tot = r[0]["grads"][k] + r[1]["grads"][k]
+        if float(g.abs().max()) < 1e-4:
+            continue
+        if k.endswith("_conv.0.bias") or k.endswith("first_conv.3.bias"):
+            continue  # shifts a batch-statistics BatchNorm removes again: zero gradient, rounding noise on both sides
+        err = float((tot - g).abs().max())
+        cos = float(torch.nn.functional.cosine_similarity(tot.flatten(), g.flatten(), dim=0))
+        assert err < 8e-2 * float(g.abs().max()) + 1e-4 and cos > 0.998, (k, err, float(g.abs().max()), cos)  # bf16 activations
+

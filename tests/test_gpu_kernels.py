@@ -355,3 +355,24 @@ def test_point_cloud_backward_kernels(ops):
     res = torch.randn(520, 1024, device="cuda").to(BF)
     acc = A.float() @ Bm.float().t()
     close(ops.gemm(A, Bm, epilogue=ops.EPI_GELU_BWD, aux_in=res, act_quick=2), acc * (res.float() > 0))
+
+
+def test_point_cloud_batchnorm_kernels(ops):
+    """vl_moments3 / vl_col_affine_bf16 (training-mode BatchNorm of the point tokenizer) and the ReLU-free grouped GEMM."""
+    x = torch.randn(70001, 3, device="cuda") * torch.tensor([1.0, 0.3, 2.0], device="cuda") + torch.tensor([0.1, -0.2, 0.05], device="cuda")
+    m = ops.moments3(x)
+    xd = x.double()
+    ref = torch.cat([xd.sum(0), (xd.t() @ xd).reshape(9)]).float()
+    close(m, ref, tol=1e-4, atol=1e-2)
+    R, C = 4099, 512
+    a, b = torch.randn(R, C, device="cuda").to(BF), torch.randn(R, C, device="cuda").to(BF)
+    p0, p1, p2 = (torch.randn(C, device="cuda") for _ in range(3))
+    close(ops.col_affine(a, p0, p2, relu=True), torch.relu(a.float() * p0 + p2))
+    close(ops.col_affine(a, p0, p2, b=b, p1=p1), a.float() * p0 + b.float() * p1 + p2)
+    k = 8
+    A = torch.randn(64 * k, 256, device="cuda").to(BF)
+    Bm = (torch.randn(512, 256, device="cuda") * 0.1).to(BF)
+    gp = torch.randn(64, 512, device="cuda").to(BF)
+    want = A.float() @ Bm.float().t() + gp.float().repeat_interleave(k, dim=0)
+    close(ops.gemm_grouped_residual_relu(A, Bm, gp, k, relu=False), want)
+    close(ops.gemm_grouped_residual_relu(A, Bm, gp, k), torch.relu(want))

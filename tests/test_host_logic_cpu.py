@@ -5,7 +5,7 @@ import torch
 
 from tests.common import C, build_model, cosine, relerr, run_model
 
-CASES = ["tiny_clip", "tiny_tri_audio", "tiny_tri_depth", "tiny_tri_pc"]
+CASES = ["tiny_clip", "tiny_tri_audio", "tiny_tri_depth", "tiny_tri_pc", "tiny_tri_pc_bntrain"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -20,6 +20,8 @@ def test_forward_backward_vs_reference(name, emu):
     for k, v in feats.items():
         assert cosine(v, gold[k]) > 0.999, (k, cosine(v, gold[k]))
     assert abs(float(loss.detach()) - float(gold["loss"])) < 2e-2 * abs(float(gold["loss"]))
+    if case.bn_train:  # running statistics after one training-mode forward (bf16 activations: 1 % of the largest entry)
+        assert relerr(C.bn_running(model.state_dict()), gold["bn_running"]) < 1e-2
     loss.backward()
     got = {k: p.grad for k, p in model.named_parameters() if p.requires_grad}
     assert all(g is not None for g in got.values()), [k for k, g in got.items() if g is None]
@@ -29,7 +31,7 @@ def test_forward_backward_vs_reference(name, emu):
     bad = []
     for i, k in enumerate(keys):
         gk = "grad:" + k
-        if gk in gold and float(gold[gk].abs().max()) > 0:
+        if gk in gold and float(gold["grad_norms"][i]) > 1e-4:  # (mathematically zero gradients hold rounding noise)
             c = cosine(got[k], gold[gk])
             if c < 0.98:
                 bad.append((k, c))

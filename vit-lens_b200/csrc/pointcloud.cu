@@ -331,6 +331,79 @@ __global__ void __launch_bounds__(256) wgrad3_kernel(const __nv_bfloat16* __rest
   atomicAdd(dw + 3 * c + 2, a2);
 }
 
+
+// out[0..2] += sum_r x[r, :],  out[3 + 3 i + j] += sum_r x[r, i] * x[r, j]   (x: [R, 3] fp32)
+// First and second moments of the centre-normalised neighbourhood points: first_conv.0 is linear in them, so the batch
+// statistics of its 128 outputs (BatchNorm in training mode, dvae.py:185-188) follow in closed form from these 12 numbers.
+__global__ void __launch_bounds__(256) moments3_kernel(const float* __restrict__ x, float* __restrict__ out, long long R) {
+  float s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // x y z xx xy xz yy yz zz
+  for (long long r = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; r < R; r += static_cast<long long>(gridDim.x) * 256) {
+    const float a = x[3 * r], b = x[3 * r + 1], c = x[3 * r + 2];
+    s[0] += a; s[1] += b; s[2] += c;
+    s[3] = fmaf(a, a, s[3]); s[4] = fmaf(a, b, s[4]); s[5] = fmaf(a, c, s[5]);
+    s[6] = fmaf(b, b, s[6]); s[7] = fmaf(b, c, s[7]); s[8] = fmaf(c, c, s[8]);
+  }
+  __shared__ float red[8][9];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[e] += __shfl_xor_sync(0xffffffffu, s[e], o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) {
+#pragma unroll
+    for (int e = 0; e < 9; ++e) red[w][e] = s[e];
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    float v = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) v += red[y][threadIdx.x];
+    // x y z | xx xy xz | xy yy yz | xz yz zz
+    const int e = threadIdx.x;
+    if (e < 3) {
+      atomicAdd(out + e, v);
+    } else {
+      const int ij[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
+      const int i = ij[e - 3][0], j = ij[e - 3][1];
+      atomicAdd(out + 3 + 3 * i + j, v);
+      if (i != j) atomicAdd(out + 3 + 3 * j + i, v);
+    }
+  }
+}
+
+// out[r, c] = act(p0[c] * a[r, c] + p1[c] * b[r, c] + p2[c])   (b / p1 optional; act: 0 none, 1 relu)
+// BatchNorm with batch statistics around the grouped GEMMs: forward normalise + ReLU (a = pre-BN activations), backward
+// dz = s (dy - mean dy - xhat mean(dy xhat)) (a = dy, b = pre-BN activations) -- one read of each operand, one write.
+__global__ void __launch_bounds__(256) col_affine_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                                         const float* __restrict__ p0, const float* __restrict__ p1, const float* __restrict__ p2,
+                                                         __nv_bfloat16* __restrict__ out, long long nvec, int cvec, int act) {
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < nvec; i += static_cast<long long>(gridDim.x) * 256) {
+    const int c = static_cast<int>(i % cvec) * 8;
+    const uint4 ua = reinterpret_cast<const uint4*>(a)[i];
+    float v[8] = {bf16_lo(ua.x), bf16_hi(ua.x), bf16_lo(ua.y), bf16_hi(ua.y), bf16_lo(ua.z), bf16_hi(ua.z), bf16_lo(ua.w), bf16_hi(ua.w)};
+    const float4 q0 = *reinterpret_cast<const float4*>(p0 + c), q1 = *reinterpret_cast<const float4*>(p0 + c + 4);
+    const float4 r0 = *reinterpret_cast<const float4*>(p2 + c), r1 = *reinterpret_cast<const float4*>(p2 + c + 4);
+    const float m0[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    const float m2[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = fmaf(m0[e], v[e], m2[e]);
+    if (b != nullptr) {
+      const uint4 ub = reinterpret_cast<const uint4*>(b)[i];
+      const float w[8] = {bf16_lo(ub.x), bf16_hi(ub.x), bf16_lo(ub.y), bf16_hi(ub.y), bf16_lo(ub.z), bf16_hi(ub.z), bf16_lo(ub.w), bf16_hi(ub.w)};
+      const float4 t0 = *reinterpret_cast<const float4*>(p1 + c), t1 = *reinterpret_cast<const float4*>(p1 + c + 4);
+      const float m1[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaf(m1[e], w[e], v[e]);
+    }
+    if (act == 1) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+    }
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+}
+
 }  // namespace vl
 
 using namespace vl;
@@ -419,5 +492,29 @@ int vl_wgrad3(const void* dy, const float* x, float* dw, int64_t R, int32_t C, v
   const long long rows_per = (R + gy - 1) / gy;
   wgrad3_kernel<<<dim3(gx, (unsigned)gy), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(dy), x, dw, R, C, rows_per);
   return launch_check("wgrad3");
+}
+
+int vl_moments3(const float* x, float* out12, int64_t R, void* stream) {
+  VL_CHECK_ARG(x && out12 && R > 0, "vl_moments3: bad arguments");
+  long long g = (R + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 4;
+  if (g > cap) g = cap;
+  moments3_kernel<<<(unsigned)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, out12, R);
+  return launch_check("moments3");
+}
+
+int vl_col_affine_bf16(const void* a, const void* b, const float* p0, const float* p1, const float* p2, void* out, int64_t R, int32_t C,
+                       int32_t act, void* stream) {
+  VL_CHECK_ARG(a && p0 && p2 && out && R > 0 && C > 0 && C % 8 == 0, "vl_col_affine_bf16: bad arguments (C must be a multiple of 8)");
+  VL_CHECK_ARG((b == nullptr) == (p1 == nullptr), "vl_col_affine_bf16: b and p1 go together");
+  VL_CHECK_ARG(act == 0 || act == 1, "vl_col_affine_bf16: act must be 0 (none) or 1 (relu)");
+  const long long nvec = static_cast<long long>(R) * (C / 8);
+  long long g = (nvec + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  if (g > cap) g = cap;
+  col_affine_kernel<<<(unsigned)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(b), p0, p1, p2, reinterpret_cast<__nv_bfloat16*>(out), nvec,
+      C / 8, act);
+  return launch_check("col_affine");
 }
 }

@@ -3,8 +3,9 @@ misc.py:48-68): FPS -> kNN grouping -> mini-PointNet -> Linear, pos = MLP(centre
 
 Parameter tree and state_dict keys match the reference.  The forward runs vl_fps / vl_knn_group / vl_linear3 /
 vl_group_max and the tcgen05 GEMM (BatchNorm folded into the neighbouring 1x1 convs), forward and backward
-(engine.PointTokenizerFn).  BatchNorm uses its running statistics (eval semantics; its affine parameters still
-train); batch-statistics BatchNorm / SyncBN is not implemented."""
+(engine.PointTokenizerFn).  BatchNorm follows nn.BatchNorm1d: running statistics in eval mode (an affine folded into the
+convs), batch statistics + running-statistics update in training mode, and cross-rank statistics when the layers were
+converted with torch.nn.SyncBatchNorm.convert_sync_batchnorm (--use-bn-sync, pc_tri_main.py:372-373)."""
 import torch
 import torch.nn as nn
 

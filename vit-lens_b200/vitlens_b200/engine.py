@@ -523,34 +523,86 @@ def _bn_scale(bn_w, rv, eps):
     return torch.rsqrt(rv + eps) * bn_w
 
 
+def _allreduce_sum(t, group):
+    import torch.distributed as dist
+
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
 class PointTokenizerFn(torch.autograd.Function):
     """PointTokenizer.forward (point_encoder.py:350-362): FPS -> kNN groups -> mini-PointNet (dvae.py:196-212) ->
-    reduce_dim, plus pos = MLP(centres).  Returns (tokens, pos) as bf16 [B*G, trans_dim].
+    reduce_dim, plus pos = MLP(centres).  Returns (tokens, pos, bn_stats): tokens / pos bf16 [B*G, trans_dim].
 
-    BatchNorm1d layers use their running statistics and act as per-channel affines folded into the neighbouring 1x1
-    convolutions (their weight / bias still receive gradients).  Training with batch statistics (and running-stat
-    updates / SyncBN, pc_tri_main.py:372-373) is not implemented."""
+    BatchNorm1d, eval mode (`train` False): running statistics, i.e. a per-channel affine folded into the neighbouring 1x1
+    convolutions (its weight / bias still receive gradients).
+
+    BatchNorm1d, training mode (`train` True; what model.train() gives the reference, dvae.py:185-193): batch statistics
+    over all B*G*k positions.  first_conv.0 is linear in the 3-d neighbourhood points, so the mean / variance of its 128
+    outputs come in closed form from the points' 3-vector mean and 3x3 second-moment matrix (vl_moments3) and the layer
+    still runs as one fused conv+BN+ReLU kernel; its backward needs no per-element pass either (everything reduces to
+    `wgrad3`, a column sum and the same moments).  second_conv.0's pre-BN output is materialised once (bf16), reduced with
+    vl_colsum2 (sum, sum of squares), and normalised + ReLU'd by vl_col_affine; backward applies the batch-norm correction
+    dz = s (dy - mean dy - xhat mean(dy xhat)) with the same kernel.  `bn_stats` = [mean0 | var0 | mean1 | var1 | n]
+    (biased variances) feeds the running-statistics update.  `sync_group`: SyncBatchNorm (pc_tri_main.py:372-373) -- the
+    sums are all-reduced over that process group in forward and backward."""
 
     @staticmethod
     def forward(ctx, pts, fps_start, w0, b0, g0, be0, rm0, rv0, w3, b3, w10, b10, g1, be1, rm1, rv1, w13, b13, wr, br, wp0, bp0, wp2, bp2,
-                G, k, eps0, eps1):
+                G, k, eps0, eps1, train=False, sync_group=None):
         need = any(ctx.needs_input_grad)
         _, centers = _ops.fps(pts, fps_start, G)
         nb = _ops.knn_group(pts, centers, G, k)
-        s0 = _bn_scale(g0, rv0, eps0)
-        t0 = (b0 - rm0) * s0 + be0
-        f1 = _ops.linear3(nb, w0.reshape(w0.shape[0], 3), s0, t0, 1)                    # conv + BN + ReLU  [R,128]
+        W0 = w0.reshape(w0.shape[0], 3)
+        w10m = w10.reshape(w10.shape[0], -1)
+        half = w10m.shape[1] // 2
+        stats = torch.empty(0, device=pts.device)
+        if not train:
+            s0 = _bn_scale(g0, rv0, eps0)
+            t0 = (b0 - rm0) * s0 + be0
+        else:
+            mom = _ops.moments3(nb).double()
+            cnt = torch.tensor([float(nb.shape[0])], device=pts.device, dtype=torch.float64)
+            if sync_group is not None:
+                packed = _allreduce_sum(torch.cat([mom, cnt]), sync_group)
+                mom, cnt = packed[:12], packed[12:]
+            m1 = mom[:3] / cnt
+            M2 = mom[3:].view(3, 3) / cnt
+            W0d, b0d = W0.double(), b0.double()
+            mu0 = W0d @ m1 + b0d
+            var0 = ((W0d @ (M2 - torch.outer(m1, m1))) * W0d).sum(1).clamp_min(0)
+            rstd0 = torch.rsqrt(var0 + eps0)
+            s0 = (g0.double() * rstd0).float()
+            t0 = ((b0d - mu0) * g0.double() * rstd0 + be0.double()).float()
+        f1 = _ops.linear3(nb, W0, s0, t0, 1)                                             # conv + BN + ReLU  [R,128]
         w3_16 = w16(w3)
         f2 = _ops.gemm(f1, w3_16, bias=b3)                                               # [R,256]
         g1f, arg1 = _ops.group_max(f2, k, want_arg=True)                                 # [BG,256]
-        s1 = _bn_scale(g1, rv1, eps1)
-        t1 = (b10 - rm1) * s1 + be1
-        w10f = w10.reshape(w10.shape[0], -1) * s1[:, None]                               # BN scale folded into the conv rows
-        half = w10f.shape[1] // 2
-        wg = _ops.cast_bf16(w10f[:, :half].contiguous())
-        wl = _ops.cast_bf16(w10f[:, half:].contiguous())
-        gp = _ops.gemm(g1f, wg, bias=t1)                                                 # global half + shift, per group
-        f3 = _ops.gemm_grouped_residual_relu(f2, wl, gp, k)                              # [R,512]
+        y1 = None
+        if not train:
+            s1 = _bn_scale(g1, rv1, eps1)
+            t1 = (b10 - rm1) * s1 + be1
+            w10f = w10m * s1[:, None]                                                    # BN scale folded into the conv rows
+            wg = _ops.cast_bf16(w10f[:, :half].contiguous())
+            wl = _ops.cast_bf16(w10f[:, half:].contiguous())
+            gp = _ops.gemm(g1f, wg, bias=t1)                                             # global half + shift, per group
+            f3 = _ops.gemm_grouped_residual_relu(f2, wl, gp, k)                          # [R,512]
+        else:
+            wg = _ops.cast_bf16(w10m[:, :half].contiguous())
+            wl = _ops.cast_bf16(w10m[:, half:].contiguous())
+            gp = _ops.gemm(g1f, wg, bias=b10)
+            y1 = _ops.gemm_grouped_residual_relu(f2, wl, gp, k, relu=False)              # pre-BN conv output [R,512]
+            sy, syy = _ops.colsum2(y1, y1)
+            if sync_group is not None:
+                packed = _allreduce_sum(torch.cat([sy, syy]), sync_group)
+                sy, syy = packed[: sy.numel()], packed[sy.numel():]
+            n = cnt.float()
+            mu1 = sy / n
+            var1 = (syy / n - mu1 * mu1).clamp_min(0)
+            rstd1 = torch.rsqrt(var1 + eps1)
+            s1 = g1 * rstd1
+            f3 = _ops.col_affine(y1, s1, be1 - mu1 * s1, relu=True)                      # normalise + affine + ReLU
+            stats = torch.cat([mu0.float(), var0.float(), mu1, var1, n])
         w13_16 = w16(w13)
         f4 = _ops.gemm(f3, w13_16, bias=b13)                                             # [R,enc]
         tokf, arg2 = _ops.group_max(f4, k, want_arg=True)                                # [BG,enc]
@@ -559,14 +611,18 @@ class PointTokenizerFn(torch.autograd.Function):
         p1, up = _ops.linear3(centers, wp0, ones, bp0, 2, want_pre=True)                 # Linear(3,128) + GELU
         pos = _ops.gemm(p1, w16(wp2), bias=bp2)
         if need:
-            ctx.cfg = (G, k)
-            ctx.save_for_backward(nb, f1, f2, arg1, g1f, f3, arg2, tokf, centers, up, p1, wg, wl, s0, s1, g0, be0, g1, be1, w3, w13, wr, wp2)
-        return tok, pos
+            ctx.cfg = (G, k, train, sync_group)
+            dummy = torch.empty(0, device=pts.device)
+            extra = (y1, mom.float(), cnt.float(), mu0.float(), rstd0.float(), mu1, rstd1, W0, b0) if train else (dummy,) * 9
+            ctx.save_for_backward(nb, f1, f2, arg1, g1f, f3, arg2, tokf, centers, up, p1, wg, wl, s0, s1, g0, be0, g1, be1, w3, w13, wr, wp2, *extra)
+        ctx.mark_non_differentiable(stats)
+        return tok, pos, stats
 
     @staticmethod
-    def backward(ctx, dtok, dpos):
-        G, k = ctx.cfg
-        nb, f1, f2, arg1, g1f, f3, arg2, tokf, centers, up, p1, wg, wl, s0, s1, g0, be0, g1, be1, w3, w13, wr, wp2 = ctx.saved_tensors
+    def backward(ctx, dtok, dpos, _dstats):
+        G, k, train, sync_group = ctx.cfg
+        (nb, f1, f2, arg1, g1f, f3, arg2, tokf, centers, up, p1, wg, wl, s0, s1, g0, be0, g1, be1, w3, w13, wr, wp2,
+         y1, mom, cnt, mu0, rstd0, mu1, rstd1, W0, b0) = ctx.saved_tensors
         dtok, dpos = dtok.contiguous(), dpos.contiguous()
         # reduce_dim
         g_wr, g_br = _wgrad(dtok, tokf), _ops.colsum(dtok)
@@ -575,39 +631,108 @@ class PointTokenizerFn(torch.autograd.Function):
         # second_conv.3
         g_w13, g_b13 = _wgrad(df4, f3).unsqueeze(-1), _ops.colsum(df4)
         dy3 = _dgrad(df4, w16(w13), epilogue=_ops.EPI_GELU_BWD, aux_in=f3, act_quick=2)  # through the ReLU (f3 > 0)
-        # second_conv.1 (BatchNorm as affine) and second_conv.0 on cat(global, local)
-        sdy, sdya = _ops.colsum2(dy3, f3)
-        g_be1 = sdy
-        g_g1 = (sdya - be1 * sdy) / g1
-        g_b10 = s1 * sdy
-        gs = _ops.group_sum(dy3, k)
-        g_w10 = (torch.cat([_wgrad(gs, g1f), _wgrad(dy3, f2)], dim=1) * s1[:, None]).unsqueeze(-1)
+        # second_conv.1 (BatchNorm) and second_conv.0 on cat(global, local)
+        if not train:   # BatchNorm as a fixed affine: its scale rides in wg / wl
+            sdy, sdya = _ops.colsum2(dy3, f3)
+            g_be1 = sdy
+            g_g1 = (sdya - be1 * sdy) / g1
+            g_b10 = s1 * sdy
+            dz, wscale = dy3, s1[:, None]
+        else:           # batch statistics: dz = s (dy - mean dy - xhat mean(dy xhat)),  xhat = (y1 - mu) rstd
+            sdy, sdyy = _ops.colsum2(dy3, y1)
+            g_be1 = sdy                                                                  # gamma / beta: this rank's rows only (as torch's
+            g_g1 = rstd1 * (sdyy - mu1 * sdy)                                            # SyncBatchNorm; DDP averages them afterwards)
+            if sync_group is not None:
+                packed = _allreduce_sum(torch.cat([sdy, sdyy]), sync_group)
+                sdy, sdyy = packed[: sdy.numel()], packed[sdy.numel():]
+            g_b10 = torch.zeros_like(sdy)                                                # a bias in front of a batch-norm has no gradient
+            c1 = s1 * rstd1 * rstd1 * (sdyy - mu1 * sdy) / cnt
+            dz = _ops.col_affine(dy3, s1, -(s1 * sdy / cnt - mu1 * c1), b=y1, p1=-c1)
+            wscale = 1.0
+        gs = _ops.group_sum(dz, k)
+        g_w10 = (torch.cat([_wgrad(gs, g1f), _wgrad(dz, f2)], dim=1) * wscale).unsqueeze(-1)
         dg1 = _dgrad(gs, wg)
-        df2 = _dgrad(dy3, wl, epilogue=_ops.EPI_RESIDUAL, aux_in=_ops.group_max_bwd(dg1, arg1, k))
+        df2 = _dgrad(dz, wl, epilogue=_ops.EPI_RESIDUAL, aux_in=_ops.group_max_bwd(dg1, arg1, k))
         # first_conv.3
         g_w3, g_b3 = _wgrad(df2, f1).unsqueeze(-1), _ops.colsum(df2)
         dy1 = _dgrad(df2, w16(w3), epilogue=_ops.EPI_GELU_BWD, aux_in=f1, act_quick=2)
-        # first_conv.1 (BatchNorm as affine) and first_conv.0 (3 -> 128)
-        sdy, sdya = _ops.colsum2(dy1, f1)
-        g_be0 = sdy
-        g_g0 = (sdya - be0 * sdy) / g0
-        g_b0 = s0 * sdy
-        g_w0 = (_ops.wgrad3(dy1, nb) * s0[:, None]).unsqueeze(-1)
+        # first_conv.1 (BatchNorm) and first_conv.0 (3 -> 128)
+        if not train:
+            sdy, sdya = _ops.colsum2(dy1, f1)
+            g_be0 = sdy
+            g_g0 = (sdya - be0 * sdy) / g0
+            g_b0 = s0 * sdy
+            g_w0 = (_ops.wgrad3(dy1, nb) * s0[:, None]).unsqueeze(-1)
+        else:
+            # y0 = W0 x + b0 is never materialised: with A = sum_r dy_r x_r^T (wgrad3), sum dy and the points' moments,
+            #   sum dy xhat = rstd ((W0 * A).sum(1) + (b0 - mu) sum dy)
+            #   dW0 = s (A - mean(dy) sum x^T - mean(dy xhat) rstd (W0 sum x x^T + (b0 - mu) sum x^T))
+            A = _ops.wgrad3(dy1, nb)
+            sdy = _ops.colsum(dy1)
+            sdyx = rstd0 * ((W0 * A).sum(1) + (b0 - mu0) * sdy)
+            sx, sxx = mom[:3], mom[3:].view(3, 3)            # global sums under SyncBN ...
+            n = cnt
+            if sync_group is not None:                        # ... but dW0 sums over the local rows only
+                loc = _ops.moments3(nb)
+                sx_l, sxx_l = loc[:3], loc[3:].view(3, 3)
+                packed = _allreduce_sum(torch.cat([sdy, sdyx]), sync_group)
+                sdy_g, sdyx_g = packed[: sdy.numel()], packed[sdy.numel():]
+            else:
+                sx_l, sxx_l, sdy_g, sdyx_g = sx, sxx, sdy, sdyx
+            g_be0 = sdy
+            g_g0 = sdyx
+            g_b0 = torch.zeros_like(sdy)
+            corr = (sdy_g / n)[:, None] * sx_l[None, :] + (sdyx_g / n * rstd0)[:, None] * (W0 @ sxx_l + (b0 - mu0)[:, None] * sx_l[None, :])
+            g_w0 = (s0[:, None] * (A - corr)).unsqueeze(-1)
         # pos_embed
         g_wp2, g_bp2 = _wgrad(dpos, p1), _ops.colsum(dpos)
         dup = _dgrad(dpos, w16(wp2), epilogue=_ops.EPI_GELU_BWD, aux_in=up)
         g_wp0, g_bp0 = _ops.wgrad3(dup, centers), _ops.colsum(dup)
         grads = (None, None, g_w0, g_b0, g_g0, g_be0, None, None, g_w3, g_b3, g_w10, g_b10, g_g1, g_be1, None, None, g_w13, g_b13, g_wr, g_br,
-                 g_wp0, g_bp0, g_wp2, g_bp2, None, None, None, None)
+                 g_wp0, g_bp0, g_wp2, g_bp2, None, None, None, None, None, None)
         return tuple(g if (g is None or ctx.needs_input_grad[i]) else None for i, g in enumerate(grads))
+
+
+def _bn_sync_group(bn):
+    """The process group a converted SyncBatchNorm layer reduces over (None: plain BatchNorm or a single process)."""
+    import torch.distributed as dist
+
+    if not isinstance(bn, torch.nn.SyncBatchNorm) or not (dist.is_available() and dist.is_initialized()):
+        return None
+    group = bn.process_group if bn.process_group is not None else dist.group.WORLD
+    return group if dist.get_world_size(group) > 1 else None
+
+
+def _bn_update_running(bn, mean, var_biased, n):
+    """nn.BatchNorm1d's running-statistics update (momentum None = cumulative average), unbiased variance."""
+    with torch.no_grad():
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+        if bn.running_mean is None:
+            return
+        m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+        bn.running_mean.mul_(1 - m).add_(mean.to(bn.running_mean.dtype), alpha=m)
+        bn.running_var.mul_(1 - m).add_((var_biased * (n / (n - 1).clamp_min(1))).to(bn.running_var.dtype), alpha=m)
 
 
 def point_tokenizer_forward(tk, pts, fps_start):
     enc = tk.encoder
     c0, bn0, c3 = enc.first_conv[0], enc.first_conv[1], enc.first_conv[3]
     c10, bn1, c13 = enc.second_conv[0], enc.second_conv[1], enc.second_conv[3]
-    return PointTokenizerFn.apply(
-        pts, fps_start, c0.weight, c0.bias, bn0.weight, bn0.bias, bn0.running_mean, bn0.running_var, c3.weight, c3.bias,
-        c10.weight, c10.bias, bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var, c13.weight, c13.bias,
-        tk.reduce_dim.weight, tk.reduce_dim.bias, tk.pos_embed[0].weight, tk.pos_embed[0].bias, tk.pos_embed[2].weight, tk.pos_embed[2].bias,
-        tk.num_group, tk.group_size, bn0.eps, bn1.eps)
+    # nn.BatchNorm1d semantics: batch statistics in training mode (or when the layer tracks no running statistics)
+    train = bn0.training or bn0.running_mean is None
+    assert train == (bn1.training or bn1.running_mean is None), "the two BatchNorm layers of the point tokenizer must be in the same mode"
+    zeros = lambda bn: torch.zeros_like(bn.weight)  # noqa: E731
+    tok, pos, stats = PointTokenizerFn.apply(
+        pts, fps_start, c0.weight, c0.bias, bn0.weight, bn0.bias,
+        bn0.running_mean if bn0.running_mean is not None else zeros(bn0), bn0.running_var if bn0.running_var is not None else zeros(bn0),
+        c3.weight, c3.bias, c10.weight, c10.bias, bn1.weight, bn1.bias,
+        bn1.running_mean if bn1.running_mean is not None else zeros(bn1), bn1.running_var if bn1.running_var is not None else zeros(bn1),
+        c13.weight, c13.bias, tk.reduce_dim.weight, tk.reduce_dim.bias, tk.pos_embed[0].weight, tk.pos_embed[0].bias,
+        tk.pos_embed[2].weight, tk.pos_embed[2].bias, tk.num_group, tk.group_size, bn0.eps, bn1.eps, train, _bn_sync_group(bn0) if train else None)
+    if train and bn0.training:
+        c0n, c1n = bn0.num_features, bn1.num_features
+        n = stats[-1]
+        _bn_update_running(bn0, stats[:c0n], stats[c0n:2 * c0n], n)
+        _bn_update_running(bn1, stats[2 * c0n:2 * c0n + c1n], stats[2 * c0n + c1n:2 * c0n + 2 * c1n], n)
+    return tok, pos

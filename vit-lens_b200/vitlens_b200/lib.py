@@ -166,6 +166,8 @@ _PROTOS = {
     "vl_group_sum": [_P, _P, _L, _I, _I, _P],
     "vl_colsum2_bf16": [_P, _P, _P, _P, _L, _I, _P],
     "vl_wgrad3": [_P, _P, _P, _L, _I, _P],
+    "vl_moments3": [_P, _P, _L, _P],
+    "vl_col_affine_bf16": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _P],
     "vl_group_max": [_P, _P, _P, _L, _I, _I, _P],
 }
 
@@ -312,6 +314,14 @@ def colsum2(a, b, s1, s2, *, T, N):
 
 def wgrad3(dy, x, dw, *, R, C):
     _call("vl_wgrad3", _p(dy), _p(x), _p(dw), R, C)
+
+
+def moments3(x, out12, *, R):
+    _call("vl_moments3", _p(x), _p(out12), R)
+
+
+def col_affine(a, b, p0, p1, p2, out, *, R, C, act):
+    _call("vl_col_affine_bf16", _p(a), _p(b), _p(p0), _p(p1), _p(p2), _p(out), R, C, act)
 
 
 def group_max(x, out, arg, *, groups, G, C):

@@ -313,6 +313,27 @@ def colsum2(a, b):
     return s1, s2
 
 
+def moments3(x):
+    """[sum x (3) | sum x x^T (9)] over the rows of x[R,3] fp32 -> fp32 [12]"""
+    assert x.is_cuda and x.dtype == F32 and x.dim() == 2 and x.shape[1] == 3
+    out = torch.zeros((12,), device=x.device, dtype=F32)
+    L.moments3(x.contiguous(), out, R=x.shape[0])
+    return out
+
+
+def col_affine(a, p0, p2, *, b=None, p1=None, relu=False):
+    """act(p0[c] * a + p1[c] * b + p2[c]) per column, bf16 [R,C] (b / p1 optional)"""
+    _v2(a, BF16)
+    if b is not None:
+        _v2(b, BF16)
+        assert b.shape == a.shape and p1 is not None
+    R, C = a.shape
+    out = torch.empty((R, C), device=a.device, dtype=BF16)
+    f = lambda t: None if t is None else t.to(F32).contiguous()  # noqa: E731
+    L.col_affine(a.contiguous(), None if b is None else b.contiguous(), f(p0), f(p1), f(p2), out, R=R, C=C, act=1 if relu else 0)
+    return out
+
+
 def wgrad3(dy, x):
     """dy[R,C]^T @ x[R,3] -> fp32 [C,3]"""
     _v2(dy, BF16)
@@ -331,12 +352,13 @@ def group_max(x, G, want_arg=False):
     return (out, arg) if want_arg else out
 
 
-def gemm_grouped_residual_relu(a, b, gp, group, *, bias=None):
-    """relu(a @ b^T + gp[row // group]) -- second_conv.0 on cat(global, local) with folded BatchNorm (dvae.py:206-208)."""
+def gemm_grouped_residual_relu(a, b, gp, group, *, bias=None, relu=True):
+    """relu(a @ b^T + gp[row // group]) -- second_conv.0 on cat(global, local) with folded BatchNorm (dvae.py:206-208);
+    relu=False: the pre-BatchNorm conv output (training mode normalises it with batch statistics afterwards)."""
     _v2(a, BF16), _v2(b, BF16), _v2(gp, BF16)
     M, K = a.shape
     N = b.shape[0]
     out = torch.empty((M, N), device=a.device, dtype=BF16)
     L.gemm(a, b, out, M=M, N=N, K=K, lda=_ld(a), ldb=_ld(b), ldd=N, epilogue=L.EPI_RESIDUAL, bias=bias, aux_in=gp, ldaux=_ld(gp),
-           aux_row_div=group, relu=True)
+           aux_row_div=group, relu=relu)
     return out
