@@ -28,18 +28,38 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 
 // ------------------------------------------------------------------------------------ LayerNorm
 // y[i,:] = (x[r,:] - mean) * rstd * w + b with r = row_index ? row_index[i] : i.
+// Warp per row; lane l owns the 16-byte vectors l, l + 32, ... of every row, so its slice of w / b is loop-invariant and lives
+// in registers (re-reading it per row made the kernel L1-bound: 8 KB of weight traffic per 2 KB row, l1tex 80 % busy in ncu).
+// The row itself stays packed (bf16) in registers and is unpacked in each of the three passes; the next row is in flight
+// while the current one is normalised.
 template <int CH>
-__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
-                                                            const long long* __restrict__ row_index,
-                                                            const float* __restrict__ w, const float* __restrict__ b,
-                                                            __nv_bfloat16* __restrict__ y, long long ldy,
-                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                                            int T, int D, float eps) {
+__global__ void __launch_bounds__(256, 2) layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                               const long long* __restrict__ row_index,
+                                                               const float* __restrict__ w, const float* __restrict__ b,
+                                                               __nv_bfloat16* __restrict__ y, long long ldy,
+                                                               float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                               int T, int D, float eps) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int nvec = D >> 3;
   const long long stride = (long long)gridDim.x * wpb;
   long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5);
+  constexpr bool kRegW = CH <= 4;  // D <= 1024: 64 registers of weights; wider rows re-read them per row (L1 hits)
+  constexpr int WCH = kRegW ? CH : 1;
+  float wr[WCH][8], br[WCH][8];
+#pragma unroll
+  for (int c = 0; c < WCH; ++c) {
+    const int i = lane + c * 32;
+    if (kRegW && i < nvec) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w) + 2 * i), w1 = __ldg(reinterpret_cast<const float4*>(w) + 2 * i + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(b) + 2 * i), b1 = __ldg(reinterpret_cast<const float4*>(b) + 2 * i + 1);
+      wr[c][0] = w0.x; wr[c][1] = w0.y; wr[c][2] = w0.z; wr[c][3] = w0.w; wr[c][4] = w1.x; wr[c][5] = w1.y; wr[c][6] = w1.z; wr[c][7] = w1.w;
+      br[c][0] = b0.x; br[c][1] = b0.y; br[c][2] = b0.z; br[c][3] = b0.w; br[c][4] = b1.x; br[c][5] = b1.y; br[c][6] = b1.z; br[c][7] = b1.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wr[c][j] = br[c][j] = 0.f;
+    }
+  }
   uint4 nxt[CH];  // the next row of this warp is already in flight while the current one is normalised
   auto fetch = [&](long long r) {
     const long long src = row_index ? row_index[r] : r;
@@ -51,45 +71,53 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16*
     }
   };
   if (row < T) fetch(row);
+  const float invD = 1.0f / D;
   for (; row < T; row += stride) {
-    float v[CH][8];
+    uint4 cur[CH];
     float s = 0.f;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
-      unpack8(nxt[c], v[c]);
-      const int i = lane + c * 32;
-      if (i < nvec) {
+      cur[c] = nxt[c];
+      float v[8];
+      unpack8(cur[c], v);  // vectors past the row are zero
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s += v[c][j];
-      }
+      for (int j = 0; j < 8; ++j) s += v[j];
     }
     if (row + stride < T) fetch(row + stride);
-    const float mu = warp_sum(s) / D;
+    const float mu = warp_sum(s) * invD;
     float q = 0.f;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int i = lane + c * 32;
       if (i < nvec) {
+        float v[8];
+        unpack8(cur[c], v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float d = v[c][j] - mu;
-          q += d * d;
+          const float d = v[j] - mu;
+          q = fmaf(d, d, q);
         }
       }
     }
-    const float rs = rsqrtf(warp_sum(q) / D + eps);
+    const float rs = rsqrtf(warp_sum(q) * invD + eps);
+    const float nmr = -mu * rs;
     uint4* yr = reinterpret_cast<uint4*>(y + row * ldy);
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int i = lane + c * 32;
       if (i < nvec) {
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w) + 2 * i), w1 = __ldg(reinterpret_cast<const float4*>(w) + 2 * i + 1);
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(b) + 2 * i), b1 = __ldg(reinterpret_cast<const float4*>(b) + 2 * i + 1);
-        float o[8];
-        o[0] = (v[c][0] - mu) * rs * w0.x + b0.x; o[1] = (v[c][1] - mu) * rs * w0.y + b0.y;
-        o[2] = (v[c][2] - mu) * rs * w0.z + b0.z; o[3] = (v[c][3] - mu) * rs * w0.w + b0.w;
-        o[4] = (v[c][4] - mu) * rs * w1.x + b1.x; o[5] = (v[c][5] - mu) * rs * w1.y + b1.y;
-        o[6] = (v[c][6] - mu) * rs * w1.z + b1.z; o[7] = (v[c][7] - mu) * rs * w1.w + b1.w;
+        float v[8], o[8];
+        unpack8(cur[c], v);
+        if constexpr (kRegW) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(fmaf(v[j], rs, nmr), wr[c][j], br[c][j]);
+        } else {
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(w) + 2 * i), w1 = __ldg(reinterpret_cast<const float4*>(w) + 2 * i + 1);
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(b) + 2 * i), b1 = __ldg(reinterpret_cast<const float4*>(b) + 2 * i + 1);
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w}, bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(fmaf(v[j], rs, nmr), wv[j], bv[j]);
+        }
         yr[i] = pack8(o);
       }
     }

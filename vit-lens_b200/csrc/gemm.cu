@@ -292,7 +292,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
                                                   uint32_t acc_col, int row_w, int col_s, int slice, int quarter, int lane, uint32_t buf,
                                                   uint32_t buf2, uint32_t aux_bar, uint32_t aux_phase, bool aux_loaded, bool last_slice,
                                                   Release release) {
-  const int epi = EPI >= 0 ? EPI : epi;  // compile-time constant in the specialised kernels
+  const int epi = EPI >= 0 ? EPI : p.epi;  // compile-time constant in the specialised kernels
   const float alpha_eff = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f);
   const bool need_aux = epi == VL_EPI_RESIDUAL || epi == VL_EPI_GELU_BWD;
   const bool need_bias = p.bias != nullptr && epi != VL_EPI_GELU_BWD;
@@ -346,10 +346,18 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
     float f[16];
     if (need_bias) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) f[j] = fmaf(__uint_as_float(v[j]), alpha_eff, bv[j]);
+      for (int j = 0; j < 16; j += 2) {
+        const float2 r = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), make_float2(alpha_eff, alpha_eff), make_float2(bv[j], bv[j + 1]));
+        f[j] = r.x;
+        f[j + 1] = r.y;
+      }
     } else {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * alpha_eff;
+      for (int j = 0; j < 16; j += 2) {
+        const float2 r = __fmul2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), make_float2(alpha_eff, alpha_eff));
+        f[j] = r.x;
+        f[j + 1] = r.y;
+      }
     }
     const uint32_t a0 = row_addr + (((2 * c) ^ sw) << 4), a1 = row_addr + (((2 * c + 1) ^ sw) << 4);
     if (epi == VL_EPI_GELU) {
@@ -365,7 +373,11 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
         for (int j = 0; j < 16; ++j) f[j] = gelu_quick_fwd(f[j]);
       } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = gelu_erf_fwd(f[j]);
+        for (int j = 0; j < 16; j += 2) {  // two elements per FMA-pipe instruction
+          const float2 r = gelu_erf_fwd2(make_float2(f[j], f[j + 1]));
+          f[j] = r.x;
+          f[j + 1] = r.y;
+        }
       }
     } else if (need_aux) {
       if (c == 0 && aux_loaded) mbar_wait(aux_bar, aux_phase);
@@ -392,8 +404,9 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          f[2 * j] *= gelu_erf_grad(bf16_lo(aw[j]));
-          f[2 * j + 1] *= gelu_erf_grad(bf16_hi(aw[j]));
+          const float2 r = __fmul2_rn(make_float2(f[2 * j], f[2 * j + 1]), gelu_erf_grad2(make_float2(bf16_lo(aw[j]), bf16_hi(aw[j]))));
+          f[2 * j] = r.x;
+          f[2 * j + 1] = r.y;
         }
       }
     }

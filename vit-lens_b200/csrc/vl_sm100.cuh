@@ -363,6 +363,27 @@ __device__ __forceinline__ float gelu_quick_grad(float x) {
   const float s = rcp_approx(1.0f + __expf(-1.702f * x));
   return s * fmaf(1.702f * x, 1.0f - s, 1.0f);
 }
+// Two elements per instruction: sm_100 executes fp32 FMA / ADD / MUL on register pairs (FFMA2 / FADD2 / FMUL2), which halves
+// the FMA-pipe instruction count of the activation epilogues (they are issue- and latency-bound next to the MMA main loop);
+// the two MUFU ops per element stay scalar.  Same polynomial and the same results as the scalar bodies above up to the
+// rounding of individual operations.
+__device__ __forceinline__ float2 norm_cdf_fast2(float2 x, float2 x2) {
+  float2 g = __ffma2_rn(x2, make_float2(-3.133493464702042e-06f, -3.133493464702042e-06f), make_float2(8.992205403046682e-05f, 8.992205403046682e-05f));
+  g = __ffma2_rn(g, x2, make_float2(3.281688259448856e-04f, 3.281688259448856e-04f));
+  g = __ffma2_rn(g, x2, make_float2(-0.10511893779039383f, -0.10511893779039383f));
+  g = __ffma2_rn(g, x2, make_float2(-2.3021240234375f, -2.3021240234375f));
+  const float2 t = __fmul2_rn(x, g);
+  const float2 d = __fadd2_rn(make_float2(ex2_approx(t.x), ex2_approx(t.y)), make_float2(1.0f, 1.0f));
+  return make_float2(rcp_approx(d.x), rcp_approx(d.y));
+}
+__device__ __forceinline__ float2 gelu_erf_fwd2(float2 x) { return __fmul2_rn(x, norm_cdf_fast2(x, __fmul2_rn(x, x))); }
+__device__ __forceinline__ float2 gelu_erf_grad2(float2 x) {
+  const float2 x2 = __fmul2_rn(x, x);
+  const float2 cdf = norm_cdf_fast2(x, x2);
+  const float2 a = __fmul2_rn(x2, make_float2(-0.72134752044448170f, -0.72134752044448170f));
+  const float2 xs = __fmul2_rn(x, make_float2(0.3989422804014327f, 0.3989422804014327f));
+  return __ffma2_rn(xs, make_float2(ex2_approx(a.x), ex2_approx(a.y)), cdf);
+}
 // act: 0 = erf-GELU (nn.GELU), 1 = QuickGELU x*sigmoid(1.702x)
 __device__ __forceinline__ float gelu_fwd(float x, int quick) { return quick ? gelu_quick_fwd(x) : gelu_erf_fwd(x); }
 __device__ __forceinline__ float gelu_grad(float x, int quick) { return quick ? gelu_quick_grad(x) : gelu_erf_grad(x); }

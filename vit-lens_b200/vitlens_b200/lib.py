@@ -56,7 +56,8 @@ EPI_LINEAR, EPI_GELU, EPI_RESIDUAL, EPI_GELU_BWD, EPI_GEGLU, EPI_ROWLSE, EPI_CLI
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    # VL_LIB_PATH: load another build of the same ABI (A/B timing of two kernel versions on one box)
+    return os.environ.get("VL_LIB_PATH") or _build.LIB_PATH
 
 
 def load(build_if_missing: bool = True):
@@ -66,7 +67,7 @@ def load(build_if_missing: bool = True):
         if _lib is not None:
             return _lib
         path = lib_path()
-        if build_if_missing and _build.needs_build():
+        if build_if_missing and not os.environ.get("VL_LIB_PATH") and _build.needs_build():
             try:
                 _build.build()
             except Exception as e:  # stale .so is still better than nothing only if it exists
