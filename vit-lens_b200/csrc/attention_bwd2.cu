@@ -236,8 +236,19 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer
+    // One thread issues 32 MMAs per (key block, query tile); its instruction stream is on the critical path of every
+    // hand-off (S -> P -> dP -> dS -> dK/dQ), so descriptors are not re-encoded per MMA: the high word is shared and the low
+    // word (14-bit start address + leading-dimension field) is a base plus a multiple of 16 bytes.
     if (elect_one() && nqt > 0) {
       mbar_wait(bar_qdo, 0);
+      constexpr uint32_t kHi = 0x40004040u;      // SBO = 1024 B, descriptor version 1, SWIZZLE_128B
+      constexpr uint32_t kLoK = 1u << 16;        // K-major operands: LBO field unused (16 B)
+      constexpr uint32_t kLoMN = 1024u << 16;    // MN-major operands: LBO = 16 KB between 64-wide chunks
+      const uint32_t q_k = (sQ >> 4) | kLoK, q_mn = (sQ >> 4) | kLoMN;        // + g * 1024 (16 KB tiles)
+      const uint32_t do_k = (sDO >> 4) | kLoK, do_mn = (sDO >> 4) | kLoMN;    // + g * 1024
+      const uint32_t pd_k = (sPD >> 4) | kLoK, pd_mn = (sPD >> 4) | kLoMN;    // + g * 2048 (32 KB blocks)
+      const uint32_t k_k = (sK >> 4) | kLoK, k_mn = (sK >> 4) | kLoMN;        // + s * 1024
+      const uint32_t v_k = (sV >> 4) | kLoK;                                  // + s * 1024
       const uint32_t idesc_kv = umma_idesc_bf16(kT, kHD, 1, 1);  // dV / dK: A = P^T / dS^T (MN-major), B MN-major
       const uint32_t idesc_q = umma_idesc_bf16(kT, kHD, 0, 1);   // dQ: A = dS (K-major), B = K (MN-major)
       uint32_t np[2] = {0, 0};  // pairs issued per group (barrier phases)
@@ -247,20 +258,21 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (!block_active(j)) continue;
         const int s = n & 1;
         const int nkb = min(kT, ((p.nk_main - j * kT) + 15) & ~15);
-        const uint32_t sKs = sK + s * 16384, sVs = sV + s * 16384;
+        const uint32_t ks_k = k_k + s * 1024u, ks_mn = k_mn + s * 1024u, vs_k = v_k + s * 1024u;
         const uint32_t idesc_s = umma_idesc_bf16(kT, nkb, 0, 0);
         mbar_wait(bar_kvfull(s), (n >> 1) & 1);
         tc_fence_after();
         // S_g = Q_g K_j^T  (the S/dP region of group g is free: the group signalled ds_full of its previous pair)
+#pragma unroll
         for (int g = 0; g < 2; ++g) {
           if (!pair_active(j, g)) continue;
           if (np[g] > 0) {
             mbar_wait(bar_dsfull(g), (np[g] - 1) & 1);
             tc_fence_after();
           }
+          const uint32_t a = q_k + g * 1024u;
 #pragma unroll
-          for (int k = 0; k < kHD / 16; ++k)
-            umma_ss(tS(g), umma_desc_sw128(sQ + g * 16384 + k * 32, 16, 1024), umma_desc_sw128(sKs + k * 32, 16, 1024), idesc_s, k > 0);
+          for (int k = 0; k < kHD / 16; ++k) umma_ss_lohi(tS(g), a + 2 * k, ks_k + 2 * k, kHi, idesc_s, k > 0);
           umma_commit(bar_sfull(g));
         }
         // dK_j / dV_j accumulators: drained by the compute groups after the previous block
@@ -269,36 +281,36 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tc_fence_after();
         }
         bool first = true;
+#pragma unroll
         for (int g = 0; g < 2; ++g) {
           if (!pair_active(j, g)) continue;
           if (n == 0 && first) mbar_wait(bar_do, 0);
           mbar_wait(bar_pfull(g), np[g] & 1);
           tc_fence_after();
-          const uint32_t sDOg = sDO + g * 16384, sPg = sPD + g * 32768;
+          const uint32_t a = do_k + g * 1024u;
 #pragma unroll
-          for (int k = 0; k < kHD / 16; ++k)
-            umma_ss(tS(g), umma_desc_sw128(sDOg + k * 32, 16, 1024), umma_desc_sw128(sVs + k * 32, 16, 1024), idesc_s, k > 0);
+          for (int k = 0; k < kHD / 16; ++k) umma_ss_lohi(tS(g), a + 2 * k, vs_k + 2 * k, kHi, idesc_s, k > 0);
+          const uint32_t pa = pd_mn + g * 2048u, db = do_mn + g * 1024u;
 #pragma unroll
-          for (int kq = 0; kq < kT / 16; ++kq)
-            umma_ss(tDV, umma_desc_sw128(sPg + kq * 2048, 16384, 1024), umma_desc_sw128(sDOg + kq * 2048, 16384, 1024), idesc_kv,
-                    (!first || kq > 0) ? 1u : 0u);
+          for (int kq = 0; kq < kT / 16; ++kq) umma_ss_lohi(tDV, pa + 128 * kq, db + 128 * kq, kHi, idesc_kv, (!first || kq > 0) ? 1u : 0u);
           umma_commit(bar_dpfull(g));  // dP ready and P consumed: the group may overwrite P with dS
           first = false;
         }
         first = true;
+#pragma unroll
         for (int g = 0; g < 2; ++g) {
           if (!pair_active(j, g)) continue;
           mbar_wait(bar_dsfull(g), np[g] & 1);
           tc_fence_after();
-          const uint32_t sQg = sQ + g * 16384, sDSg = sPD + g * 32768;
+          const uint32_t da = pd_mn + g * 2048u, qb = q_mn + g * 1024u;
 #pragma unroll
-          for (int kq = 0; kq < kT / 16; ++kq)
-            umma_ss(tDK, umma_desc_sw128(sDSg + kq * 2048, 16384, 1024), umma_desc_sw128(sQg + kq * 2048, 16384, 1024), idesc_kv,
-                    (!first || kq > 0) ? 1u : 0u);
+          for (int kq = 0; kq < kT / 16; ++kq) umma_ss_lohi(tDK, da + 128 * kq, qb + 128 * kq, kHi, idesc_kv, (!first || kq > 0) ? 1u : 0u);
           const bool dq_acc = (dq_started >> g) & 1u;
-          for (int kk = 0; kk < nkb / 16; ++kk)
-            umma_ss(tDQ(g), umma_desc_sw128(sDSg + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024), umma_desc_sw128(sKs + kk * 2048, 16384, 1024),
-                    idesc_q, (dq_acc || kk > 0) ? 1u : 0u);
+          const uint32_t dsa = pd_k + g * 2048u;
+#pragma unroll
+          for (int kk = 0; kk < kT / 16; ++kk)
+            if (kk < nkb / 16)
+              umma_ss_lohi(tDQ(g), dsa + (kk >> 2) * 1024u + (kk & 3) * 2u, ks_mn + 128 * kk, kHi, idesc_q, (dq_acc || kk > 0) ? 1u : 0u);
           dq_started |= 1u << g;
           umma_commit(bar_pairdone(g));  // dS staging block reusable
           ++np[g];
@@ -376,6 +388,33 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     bool store_pending = false;  // a TMA store issued by this group may still be reading its staging block
     VL_STAMP();
 
+    // Tail keys (the cls key of N = 257): per query row r of this tile  p_rt = exp(s_rt - lse_r), ds_rt = p_rt (dp_rt - D_r) scale.
+    // dsk[] corrects this row's dQ in the epilogue; dV_t += sum_r p_rt dO_r and dK_t += sum_r ds_rt q_r are small mat-vecs
+    // over the tile (shared-memory atomics into the tail accumulators).  None of it depends on the MMAs.
+    float dsk[kMaxTail] = {0.f, 0.f, 0.f, 0.f};
+    bool tailk_done = false;
+    auto tail_keys = [&]() {
+      tailk_done = true;
+      if (!tile_ok || p.tk == 0) return;
+      float ptk[kMaxTail];
+      for (int t = 0; t < p.tk; ++t) {
+        const float* kv = s_tk + (2 * t) * kHD;
+        const float sdot = dot_row_sw128(sQg, r, kv);
+        const float dpv = dot_row_sw128(sDOg, r, kv + kHD);
+        const float pv = row_ok ? ex2_approx(fmaf(sdot, sl2, -lse2)) : 0.f;
+        ptk[t] = pv;
+        dsk[t] = pv * (dpv - Di) * p.scale;
+      }
+      for (int t = 0; t < p.tk; ++t) {
+        coef0[r] = ptk[t];
+        coef1[r] = dsk[t];
+        group_sync(g);
+        matvec_rows(coef0, sDOg, sf + kFDv + t * kHD, x);
+        matvec_rows(coef1, sQg, sf + kFDk + t * kHD, x);
+        group_sync(g);
+      }
+    };
+
     uint32_t np = 0;  // pairs processed by this group
     int n = 0;        // key blocks processed
     for (int j = 0; j < nkblk; ++j) {
@@ -384,7 +423,23 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int nkb = min(kT, ((p.nk_main - j * kT) + 15) & ~15);
       uint8_t* sKs = bp + kOffK + s * 16384;
       uint8_t* sVs = bp + kOffV + s * 16384;
-      mbar_wait(bar_kvfull(s), (n >> 1) & 1);  // the epilogue below reads K / V rows with ordinary loads
+      mbar_wait(bar_kvfull(s), (n >> 1) & 1);  // K / V rows are also read with ordinary loads (tail corrections)
+      // tail queries' coefficients for this thread's key row (dV_r += p_tr dO_t ; dK_r += ds_tr q_t ; dQ_t += ds_tr k_r): they
+      // depend on K / V and the tail vectors only, so they are computed here, under the S MMA, not after the dK / dV MMAs
+      const int krow = j * kT + r;
+      const bool krow_ok = krow < p.nk_main;
+      float cf[kMaxTail];
+      for (int t = 0; t < p.tq; ++t) {
+        const float* qv = s_tq + (2 * t) * kHD;
+        const float sdot = dot_row_sw128(sKs, r, qv);
+        const float pv = krow_ok ? ex2_approx(fmaf(sdot, sl2, -s_stat[2 * t])) : 0.f;
+        if (g == 0) {
+          cf[t] = pv;
+        } else {
+          const float dpv = dot_row_sw128(sVs, r, qv + kHD);
+          cf[t] = pv * (dpv - s_stat[2 * t + 1]) * p.scale;
+        }
+      }
       if (pair_active(j, g)) {
         const int kmax = p.causal ? min(p.nk_main, p.q0 + qrow + 1) : p.nk_main;
         const bool need_mask = p.causal || (j * kT + kT > p.nk_main);
@@ -476,29 +531,16 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (lane == 0) mbar_arrive(bar_dsfull(g));
         VL_STAMP();
         ++np;
+        if (!tailk_done) tail_keys();  // needs D (known since this pair); runs under this pair's dK / dQ MMAs
       }
       // ---- dK_j / dV_j -> global: group 0 writes dV, group 1 writes dK (thread r owns key row j*128 + r)
       mbar_wait(bar_dkvfull, n & 1);
       tc_fence_after();
       VL_STAMP();
       {
-        const int krow = j * kT + r;
-        const bool ok = krow < p.nk_main;
+        const bool ok = krow_ok;
         const long long grow = krow0 + krow;
-        // tail queries' contributions to this key row: dV_r += p_tr dO_t ; dK_r += ds_tr q_t ; dQ_t += ds_tr k_r
-        float cf[kMaxTail];
-        for (int t = 0; t < p.tq; ++t) {
-          const float* qv = s_tq + (2 * t) * kHD;
-          const float sdot = dot_row_sw128(sKs, r, qv);
-          const float pv = ok ? ex2_approx(fmaf(sdot, sl2, -s_stat[2 * t])) : 0.f;
-          if (g == 0) {
-            cf[t] = pv;
-          } else {
-            const float dpv = dot_row_sw128(sVs, r, qv + kHD);
-            cf[t] = pv * (dpv - s_stat[2 * t + 1]) * p.scale;
-          }
-        }
-        VL_STAMP();  // tail-query dots done
+        VL_STAMP();  // (tail-query dots: moved to the top of the block)
         __nv_bfloat16* dst = g == 0 ? p.dv + grow * p.lddv + h * kHD : p.dk + grow * p.lddk + h * kHD;
         const uint32_t t0 = g == 0 ? tDV : tDK;
 #pragma unroll
@@ -556,16 +598,12 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         group_sync(g);
         store_pending = false;
       }
-      float dsk[kMaxTail], ptk[kMaxTail];
-      for (int t = 0; t < p.tk; ++t) {
-        const float* kv = s_tk + (2 * t) * kHD;
-        const float sdot = dot_row_sw128(sQg, r, kv);
-        const float dpv = dot_row_sw128(sDOg, r, kv + kHD);
-        const float pv = row_ok ? ex2_approx(fmaf(sdot, sl2, -lse2)) : 0.f;
-        ptk[t] = pv;
-        dsk[t] = pv * (dpv - Di) * p.scale;
+      if (!tailk_done) {  // (a group without any active pair, causal launches: D was never needed before)
+        mbar_wait(bar_do, 0);
+        Di = row_ok ? dot_rows_sw128(sDOg, sPDg + 16384, r) : 0.f;
+        tail_keys();
       }
-      VL_STAMP();  // tail-key dots done
+      VL_STAMP();  // (tail-key dots: done after the group's first pair)
 #pragma unroll
       for (int c = 0; c < kHD; c += 32) {
         uint32_t v[32];
@@ -585,14 +623,6 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tma_store_commit();
       }
       VL_STAMP();  // dQ rows stored
-      for (int t = 0; t < p.tk; ++t) {  // dV_t' += sum_r p_rt' dO_r ; dK_t' += sum_r ds_rt' q_r
-        coef0[r] = ptk[t];
-        coef1[r] = dsk[t];
-        group_sync(g);
-        matvec_rows(coef0, sDOg, sf + kFDv + t * kHD, x);
-        matvec_rows(coef1, sQg, sf + kFDk + t * kHD, x);
-        group_sync(g);
-      }
     }
     VL_STAMP();
     // ---- tail x tail and the tail rows' outputs (one warp; 2 dims per lane)
