@@ -183,6 +183,31 @@ def test_layernorm(ops, T, D, gather):
         assert float(dx[mask].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("T", [2048, 4099, 6 * 257 + 2048])
+def test_layernorm_d1024_fast_paths(ops, T):
+    """The D = 1024 kernels of every ViT-L LayerNorm (T >= 2048, no row gather): forward with its weight slice in registers,
+    backward with eight columns per thread (with / without the residual-gradient add, with / without weight gradients)."""
+    D = 1024
+    x = (torch.randn(T, D, device="cuda") * 2 + 0.5).to(BF)
+    w = torch.randn(D, device="cuda") * 0.1 + 1
+    b = torch.randn(D, device="cuda") * 0.1
+    y, mean, rstd = ops.layernorm_fwd(x, w, b)
+    xr, wr, br = x.float().clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.layer_norm(xr, (D,), wr, br, 1e-5)
+    close(y, yr.detach())
+    close(mean, x.float().mean(1), tol=1e-4, atol=1e-4)
+    dy = torch.randn_like(yr).to(BF)
+    yr.backward(dy.float())
+    dres = torch.randn(T, D, device="cuda").to(BF)
+    dx, dw, db = ops.layernorm_bwd(dy, x, w, mean, rstd, dres=dres)
+    close(dx, xr.grad + dres.float())
+    close(dw, wr.grad, tol=1e-3, atol=0.05)
+    close(db, br.grad, tol=1e-3, atol=0.05)
+    dx2, dw2, db2 = ops.layernorm_bwd(dy, x, w, mean, rstd, want_wgrad=False)
+    assert dw2 is None and db2 is None
+    close(dx2, xr.grad)
+
+
 def test_row_kernels(ops):
     dy = torch.randn(5000, 3072, device="cuda").to(BF)
     close(ops.colsum(dy), dy.float().sum(0), tol=1e-3, atol=0.05)

@@ -344,6 +344,133 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_d1024_kernel(const __nv_
   }
 }
 
+// D = 1024, second generation.  ncu on the kernel above: 1332 warp-instructions per row, issue slots 60 % busy at 16 warps / SM,
+// i.e. instruction-bound before it is HBM-bound.  Here a thread owns EIGHT columns (16-byte loads; 128 threads per row, two row
+// slots per CTA, R rows per slot and step), the fp32 math runs two elements per instruction (FFMA2 / FMUL2 / FADD2), the
+// normalised x and the gradient stay unpacked in registers between the statistics pass and the output pass, and the 2 R row
+// statistics are reduced across the warp with a transposing butterfly (4 + 2 + 1 + 2 shuffles instead of 8 x 5).
+template <bool HAS_RES>
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_d1024_v2_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy,
+                                                                        const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                                        const float* __restrict__ w, const float* __restrict__ mean,
+                                                                        const float* __restrict__ rstd,
+                                                                        const __nv_bfloat16* __restrict__ dres, long long lddres,
+                                                                        __nv_bfloat16* __restrict__ dx, long long lddx,
+                                                                        float* __restrict__ dw, float* __restrict__ db, int T) {
+  constexpr int R = 4;  // rows per slot and step (8 rows per CTA step)
+  __shared__ float red[2][4][2 * R];
+  __shared__ float tot[2][2 * R];
+  __shared__ float comb[128][16];
+  const int t = threadIdx.x, lane = t & 31;
+  const int slot = t >> 7, tt = t & 127, wslot = (t >> 5) & 3;
+  const int c0 = 8 * tt;
+  float2 wv[4];
+  {
+    const float4 a = *reinterpret_cast<const float4*>(w + c0), b = *reinterpret_cast<const float4*>(w + c0 + 4);
+    wv[0] = make_float2(a.x, a.y); wv[1] = make_float2(a.z, a.w); wv[2] = make_float2(b.x, b.y); wv[3] = make_float2(b.z, b.w);
+  }
+  float2 aw[4], ab[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) aw[j] = ab[j] = make_float2(0.f, 0.f);
+  const long long step = (long long)gridDim.x * (2 * R);
+  for (long long r0 = (long long)blockIdx.x * (2 * R) + slot * R; r0 - slot * R < T; r0 += step) {
+    uint4 xr[R], gr[R], rr[R];
+    float mu[R], rs[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const long long row = r0 + i;
+      const bool ok = row < T;
+      xr[i] = ok ? *reinterpret_cast<const uint4*>(x + row * ldx + c0) : make_uint4(0u, 0u, 0u, 0u);
+      gr[i] = ok ? *reinterpret_cast<const uint4*>(dy + row * lddy + c0) : make_uint4(0u, 0u, 0u, 0u);
+      if (HAS_RES) rr[i] = ok ? *reinterpret_cast<const uint4*>(dres + row * lddres + c0) : make_uint4(0u, 0u, 0u, 0u);
+      mu[i] = ok ? mean[row] : 0.f;
+      rs[i] = ok ? rstd[row] : 0.f;
+    }
+    float2 xh[R][4], g[R][4];
+    float s[2 * R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const uint32_t xw[4] = {xr[i].x, xr[i].y, xr[i].z, xr[i].w}, gw[4] = {gr[i].x, gr[i].y, gr[i].z, gr[i].w};
+      const float2 a2 = make_float2(rs[i], rs[i]), b2 = make_float2(-mu[i] * rs[i], -mu[i] * rs[i]);
+      float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        xh[i][j] = __ffma2_rn(make_float2(bf16_lo(xw[j]), bf16_hi(xw[j])), a2, b2);  // (x - mean) * rstd
+        g[i][j] = make_float2(bf16_lo(gw[j]), bf16_hi(gw[j]));
+        const float2 wg = __fmul2_rn(g[i][j], wv[j]);
+        s1 = __fadd2_rn(s1, wg);
+        s2 = __ffma2_rn(wg, xh[i][j], s2);
+      }
+      s[2 * i] = s1.x + s1.y;
+      s[2 * i + 1] = s2.x + s2.y;
+    }
+    // transposing butterfly: 8 values x 32 lanes -> lane l ends with the warp sum of value ((l >> 4) & 1) * 4 + ((l >> 3) & 1) * 2 + ((l >> 2) & 1)
+    {
+      const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+      float a[4], b2[2], c;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float keep = h16 ? s[4 + k] : s[k], send = h16 ? s[k] : s[4 + k];
+        a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float keep = h8 ? a[2 + k] : a[k], send = h8 ? a[k] : a[2 + k];
+        b2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      {
+        const float keep = h4 ? b2[1] : b2[0], send = h4 ? b2[0] : b2[1];
+        c = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      c += __shfl_xor_sync(0xffffffffu, c, 2);
+      c += __shfl_xor_sync(0xffffffffu, c, 1);
+      if ((lane & 3) == 0) red[slot][wslot][lane >> 2] = c;
+    }
+    __syncthreads();
+    if (tt < 2 * R) tot[slot][tt] = (red[slot][0][tt] + red[slot][1][tt] + red[slot][2][tt] + red[slot][3][tt]) * (1.0f / 1024.0f);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const long long row = r0 + i;
+      if (row < T) {
+        const float s1 = tot[slot][2 * i], s2 = tot[slot][2 * i + 1];
+        const float2 ns1 = make_float2(-s1, -s1), ns2 = make_float2(-s2, -s2), r2 = make_float2(rs[i], rs[i]);
+        const uint32_t rw[4] = {HAS_RES ? rr[i].x : 0u, HAS_RES ? rr[i].y : 0u, HAS_RES ? rr[i].z : 0u, HAS_RES ? rr[i].w : 0u};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          aw[j] = __ffma2_rn(g[i][j], xh[i][j], aw[j]);
+          ab[j] = __fadd2_rn(ab[j], g[i][j]);
+          float2 v = __ffma2_rn(g[i][j], wv[j], ns1);  // w dy - mean(w dy)
+          v = __ffma2_rn(xh[i][j], ns2, v);            // - xhat mean(w dy xhat)
+          if (HAS_RES) v = __ffma2_rn(v, r2, make_float2(bf16_lo(rw[j]), bf16_hi(rw[j])));
+          else v = __fmul2_rn(v, r2);
+          o[j] = pack_bf16(v.x, v.y);
+        }
+        *reinterpret_cast<uint4*>(dx + row * lddx + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+  if (dw != nullptr) {  // the two row slots own the same columns: combine through shared memory, one atomic per column and CTA
+    if (slot == 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        comb[tt][4 * j] = aw[j].x; comb[tt][4 * j + 1] = aw[j].y; comb[tt][4 * j + 2] = ab[j].x; comb[tt][4 * j + 3] = ab[j].y;
+      }
+    }
+    __syncthreads();
+    if (slot == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        atomicAdd(dw + c0 + 2 * j, aw[j].x + comb[tt][4 * j]);
+        atomicAdd(dw + c0 + 2 * j + 1, aw[j].y + comb[tt][4 * j + 1]);
+        atomicAdd(db + c0 + 2 * j, ab[j].x + comb[tt][4 * j + 2]);
+        atomicAdd(db + c0 + 2 * j + 1, ab[j].y + comb[tt][4 * j + 3]);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ column sums (bias grads)
 // db[n] += sum_t dy[t, n]
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ dy, long long ld, float* __restrict__ db,
@@ -712,6 +839,17 @@ int vl_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, c
   if (D == 1024 && row_index == nullptr && dres_sum == nullptr && T >= 2048 && ldx % 4 == 0 && debug_get(13) != 1) {  // knob 13: 1 = generic kernel
     int g2 = num_sms() * 2;
     if ((long long)g2 * 8 > T) g2 = (T + 7) / 8;
+    const bool al16 = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dres)) & 15) == 0;
+    if (al16 && debug_get(14) != 1) {  // knob 14: 1 = first-generation D = 1024 kernel (four columns per thread)
+      if (dres)
+        layernorm_bwd_d1024_v2_kernel<true><<<g2, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(x), ldx, w,
+                                                               mean, rstd, reinterpret_cast<const __nv_bfloat16*>(dres), lddres,
+                                                               reinterpret_cast<__nv_bfloat16*>(dx), lddx, dw, db, T);
+      else
+        layernorm_bwd_d1024_v2_kernel<false><<<g2, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(x), ldx,
+                                                                w, mean, rstd, nullptr, 0, reinterpret_cast<__nv_bfloat16*>(dx), lddx, dw, db, T);
+      return launch_check("layernorm_bwd_d1024_v2");
+    }
     if (dres)
       layernorm_bwd_d1024_kernel<true><<<g2, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(x), ldx, w,
                                                           mean, rstd, reinterpret_cast<const __nv_bfloat16*>(dres), lddres,
