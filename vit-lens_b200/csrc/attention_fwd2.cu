@@ -411,17 +411,20 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         float bs0 = 0.f, bs1 = 0.f;
         uint32_t pk[32];
         if (full) {
+          const float2 sl22 = make_float2(sl2, sl2), nms = make_float2(-msub, -msub);
+          float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int t = 0; t < 32; t += 2) {
-            const float e0 = ex2_approx(fmaf(__uint_as_float(va[t]), sl2, -msub));
-            const float e1 = ex2_approx(fmaf(__uint_as_float(va[t + 1]), sl2, -msub));
-            const float f0 = ex2_approx(fmaf(__uint_as_float(vb[t]), sl2, -msub));
-            const float f1 = ex2_approx(fmaf(__uint_as_float(vb[t + 1]), sl2, -msub));
-            bs0 += e0 + e1;
-            bs1 += f0 + f1;
-            pk[t >> 1] = pack_bf16(e0, e1);
-            pk[16 + (t >> 1)] = pack_bf16(f0, f1);
+          for (int t = 0; t < 32; t += 2) {  // FFMA2 / FADD2: two scores per FMA-pipe instruction
+            const float2 a = __ffma2_rn(make_float2(__uint_as_float(va[t]), __uint_as_float(va[t + 1])), sl22, nms);
+            const float2 b2 = __ffma2_rn(make_float2(__uint_as_float(vb[t]), __uint_as_float(vb[t + 1])), sl22, nms);
+            const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y)), f = make_float2(ex2_approx(b2.x), ex2_approx(b2.y));
+            acc0 = __fadd2_rn(acc0, e);
+            acc1 = __fadd2_rn(acc1, f);
+            pk[t >> 1] = pack_bf16(e.x, e.y);
+            pk[16 + (t >> 1)] = pack_bf16(f.x, f.y);
           }
+          bs0 = acc0.x + acc0.y;
+          bs1 = acc1.x + acc1.y;
         }
         m = m_new;
         m_off = off_new;
