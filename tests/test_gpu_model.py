@@ -41,7 +41,9 @@ def _check(name, grad_cos=0.97, norm_tol=0.1):
         if gn > 1e-4 and abs(float(got[k].norm()) - gn) > norm_tol * gn + slack:
             bad.append((k, float(got[k].norm()), gn))
         gk = "grad:" + k
-        if gk in gold and gn > 1e-4:  # (mathematically zero gradients, e.g. a bias in front of a batch-norm, hold rounding noise)
+        # (mathematically zero gradients, e.g. a bias in front of a batch-norm, hold rounding noise; a one-element gradient has
+        # no direction: d(logit_scale) is covered by the norm check with its absolute slack above)
+        if gk in gold and gn > 1e-4 and gold[gk].numel() > 1:
             c = cosine(got[k].cpu(), gold[gk])
             if c < grad_cos:
                 bad.append((k, "cos", c))
