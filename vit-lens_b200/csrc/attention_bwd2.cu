@@ -1,12 +1,12 @@
 // FlashAttention backward for sm_100a, head_dim = 64 -- two-group pipelined version.
 //
 // One CTA per (batch, head) and per launch a range of at most 256 query rows (+ up to 4 "tail" query rows) against every
-// key.  320 threads:
+// key.  384 threads (three warpgroups; setmaxnreg moves registers from the producer / issuer warpgroup to the compute groups):
 //   warp 0      TMA producer   Q / dO / O tiles once, K / V 128-key blocks through a 2-stage ring
 //   warp 1      tcgen05 issuer five GEMMs per (key block, query tile): S = Q K^T, dP = dO V^T, dV += P^T dO,
 //                              dK += dS^T Q, dQ += dS K -- accumulators in TMEM
-//   warps 2-5   compute group 0 (query tile 0): thread r owns query row r of its tile
-//   warps 6-9   compute group 1 (query tile 1)
+//   warps 4-7   compute group 0 (query tile 0): thread r owns query row r of its tile
+//   warps 8-11  compute group 1 (query tile 1)
 // The two groups work on the two query tiles of a key block at the same time (own S/dP TMEM region, own P/dS staging
 // block), so the exp / dS arithmetic of one tile overlaps the MMAs and TMEM traffic of the other, and every SM
 // sub-partition has two resident compute warps.  The dK / dV / dQ epilogues are split between the groups.
@@ -26,7 +26,7 @@ namespace bwd2 {
 constexpr int kHD = 64;
 constexpr int kT = 128;  // query tile / key block
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr int kThreads = 320;
+constexpr int kThreads = 384;  // warpgroup 0: TMA producer, MMA issuer (+ two idle warps); warpgroups 1, 2: the two compute groups
 constexpr int kMaxTail = 4;
 
 // shared memory map (bytes)
@@ -206,7 +206,11 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tDV = tmem + 256, tDK = tmem + 320;
   auto tDQ = [&](int g) { return tmem + 384u + 64u * g; };
 
-  if (warp == 0) {
+  // Register budget per warpgroup (384 threads x 168 at launch): the compute groups hold a row's 128 packed probabilities plus
+  // two in-flight TMEM chunks; the producer / issuer need little.  56 + 2 x 224 = 504 <= 3 x 168.
+  if (warp < 4) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+   if (warp == 0) {
     // ================================================================== TMA producer
     if (elect_one()) {
       // issue order = need order: Q tiles and the first K/V block feed S; dO and O are first needed for dP / D
@@ -234,7 +238,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1) {
+   } else if (warp == 1) {
     // ================================================================== MMA issuer
     // One thread issues 32 MMAs per (key block, query tile); its instruction stream is on the critical path of every
     // hand-off (S -> P -> dP -> dS -> dK/dQ), so descriptors are not re-encoded per MMA: the high word is shared and the low
@@ -322,12 +326,14 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       umma_commit(bar_dqfull);
     }
+   }
   } else {
     // ================================================================== compute groups
-    const int g = (warp - 2) >> 2;      // 0 or 1
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int g = (warp - 4) >> 2;      // 0 or 1
     const int quarter = warp & 3;       // TMEM lane quarter of this warp
     const int r = quarter * 32 + lane;  // row inside the tile
-    const int x = ((warp - 2) & 3) * 32 + lane;  // thread index inside the group
+    const int x = ((warp - 4) & 3) * 32 + lane;  // thread index inside the group
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const float sl2 = p.scale * kLog2e;
     uint8_t* sQg = bp + kOffQ + g * 16384;
@@ -347,7 +353,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // ---- prologue: tail vectors (fp32) and per-row statistics
     {
       const int nvec = (p.tq + p.tk) * 2 * kHD;
-      for (int idx = threadIdx.x - 64; idx < nvec; idx += 256) {
+      for (int idx = threadIdx.x - 128; idx < nvec; idx += 256) {
         const int d = idx % kHD, which = (idx / kHD) & 1, t = idx / (2 * kHD);
         float val;
         if (t < p.tq) {
@@ -364,7 +370,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const float* s_tq = sf + kFTq;                       // [t][q|dO][64]
     const float* s_tk = sf + kFTq + p.tq * 2 * kHD;      // [t'][k|v][64]
     float* s_stat = sf + kFStat;
-    if (warp == 2) {  // lse and D = rowsum(dO * O) of the tail queries: one warp, two dims per lane, coalesced 128-byte rows
+    if (warp == 4) {  // lse and D = rowsum(dO * O) of the tail queries: one warp, two dims per lane, coalesced 128-byte rows
       for (int t = 0; t < p.tq; ++t) {
         const long long grow = qrow0 + p.nq_main + t;
         const uint32_t ow = *reinterpret_cast<const uint32_t*>(p.o + grow * p.ldo + h * kHD + 2 * lane);
@@ -628,7 +634,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // ---- tail x tail and the tail rows' outputs (one warp; 2 dims per lane)
     if (p.tq + p.tk > 0) {
       both_groups_sync();
-      if (warp == 2) {
+      if (warp == 4) {
         const int d0 = 2 * lane;
         for (int t = 0; t < p.tq; ++t) {
           float dq0 = sf[kFDq + t * kHD + d0], dq1 = sf[kFDq + t * kHD + d0 + 1];
