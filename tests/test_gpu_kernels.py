@@ -183,6 +183,19 @@ def test_layernorm(ops, T, D, gather):
         assert float(dx[mask].abs().max()) == 0.0
 
 
+def test_attention_fwd_persistent_kernel_is_deterministic(ops):
+    """attn_fwd2_kernel has no atomics: repeated launches on the same inputs must agree bit for bit.  A race in its
+    mbarrier / TMEM hand-offs (S and P share TMEM columns, O tiles are staged in retired Q tiles) would show up here."""
+    B, H, N = 64, 16, 257
+    D = H * 64
+    qkv = torch.randn(B * N, 3 * D, device="cuda").to(BF)
+    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    o0, l0 = ops.attention_fwd(q, k, v, B=B, H=H, nq=N, nk=N)
+    for _ in range(25):
+        o, lse = ops.attention_fwd(q, k, v, B=B, H=H, nq=N, nk=N)
+        assert torch.equal(o, o0) and torch.equal(lse, l0)
+
+
 @pytest.mark.parametrize("T", [2048, 4099, 6 * 257 + 2048])
 def test_layernorm_d1024_fast_paths(ops, T):
     """The D = 1024 kernels of every ViT-L LayerNorm (T >= 2048, no row gather): forward with its weight slice in registers,
