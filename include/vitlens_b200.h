@@ -171,6 +171,13 @@ int vl_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float
  * of 16384 elements.  The bf16 copy (the tensor-core operand cache) is refreshed in the same pass. */
 int vl_adamw_multi(const int64_t* ptrs, const int64_t* sizes, const float* wds, const int32_t* chunk_tab, int32_t n_chunks,
                    float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream);
+/* Gradient-norm clipping (torch.nn.utils.clip_grad_norm_, reference training/train.py:212-240) without an extra pass over the
+ * gradients: vl_multi_sqnorm adds sum(g^2) over every tensor of the same tables to *sumsq (zero it first); vl_adamw_multi_clip is
+ * vl_adamw_multi with every gradient scaled by min(1, max_norm / (grad_scale * sqrt(*sumsq) + 1e-6)). */
+int vl_multi_sqnorm(const int64_t* ptrs, const int64_t* sizes, const int32_t* chunk_tab, int32_t n_chunks, float* sumsq, void* stream);
+int vl_adamw_multi_clip(const int64_t* ptrs, const int64_t* sizes, const float* wds, const int32_t* chunk_tab, int32_t n_chunks,
+                        float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale, const float* sumsq,
+                        float max_norm, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Point-cloud tokenizer (reference modal_3d/models/pointbert): farthest point sampling with explicit start indices

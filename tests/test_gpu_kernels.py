@@ -330,6 +330,33 @@ def test_adamw_multi_tensor(ops):
     close(cached.float(), ours["a.weight"].detach().bfloat16().float(), tol=0, atol=0)
 
 
+@pytest.mark.parametrize("max_norm,gscale", [(0.5, 1.0), (1e4, 1.0), (2.0, 0.25)])
+def test_adamw_gradient_norm_clipping(ops, max_norm, gscale):
+    """--grad-clip-norm (train.py:212-240): clip_grad_norm_ over ALL parameters + AdamW == vl_multi_sqnorm + vl_adamw_multi_clip
+    (the clip coefficient is applied inside the fused update; the gradients themselves are left alone)."""
+    from vitlens_b200 import optim
+
+    torch.manual_seed(2)
+    shapes = {"a.weight": (257, 130), "a.bias": (257,), "big.weight": (50000, 3), "logit_scale": ()}
+    ours = {k: torch.nn.Parameter(torch.randn(s, device="cuda")) for k, s in shapes.items()}
+    ref = {k: torch.nn.Parameter(v.detach().clone()) for k, v in ours.items()}
+    no_decay = [k for k, v in ref.items() if v.ndim < 2 or "bias" in k or "logit_scale" in k]
+    ropt = torch.optim.AdamW([dict(params=[ref[k] for k in no_decay], weight_decay=0.0),
+                              dict(params=[ref[k] for k in ref if k not in no_decay], weight_decay=0.2)], lr=1e-3, betas=(0.9, 0.98), eps=1e-6)
+    opt = optim.AdamW(list(ours.items()), lr=1e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.2)
+    for step in range(3):
+        for k in ours:
+            g = torch.randn(shapes[k], device="cuda") * (0.01 if step == 1 else 1.0)
+            ours[k].grad = g.clone()
+            ref[k].grad = g.clone() * gscale
+        want_norm = torch.nn.utils.clip_grad_norm_(list(ref.values()), max_norm, norm_type=2.0)
+        ropt.step()
+        opt.step(grad_scale=gscale, clip_norm=max_norm)
+        assert abs(float(opt.grad_norm) - float(want_norm)) < 1e-4 * float(want_norm)
+    for k in ours:
+        close(ours[k].detach(), ref[k].detach(), tol=1e-5, atol=2e-6)
+
+
 @pytest.mark.parametrize("B,N,G,k", [(3, 256, 16, 8), (2, 8192, 512, 32), (2, 1000, 64, 32)])
 def test_point_cloud_sampling_and_grouping(ops, B, N, G, k):
     """FPS indices are bit-exact against the oracle's restatement of misc.fps; kNN neighbourhoods equal the exact

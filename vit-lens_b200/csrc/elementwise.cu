@@ -770,9 +770,14 @@ __global__ void __launch_bounds__(256) lse_combine_kernel(const float* __restric
 // Multi-tensor AdamW: one launch for every parameter.  chunk_tab[c] = (tensor id, element offset); per tensor a row of
 // five pointers (p, g, m, v, p16 | NULL) and a weight-decay value.  Also refreshes the bf16 operand copy of the weight.
 constexpr int kAdamChunk = 16384;
+// sumsq and max_norm: gradient-norm clipping (torch.nn.utils.clip_grad_norm_, training/train.py:212-240) folded into the
+// update: with *sumsq = sum over ALL gradients of g^2 (vl_multi_sqnorm), every gradient is scaled by
+// min(1, max_norm / (grad_scale * sqrt(*sumsq) + 1e-6)) on its way into the moments -- no extra pass over the gradients.
 __global__ void __launch_bounds__(256) adamw_multi_kernel(const long long* __restrict__ ptrs, const long long* __restrict__ sizes,
                                                           const float* __restrict__ wds, const int2* __restrict__ chunk_tab, float lr, float b1,
-                                                          float b2, float eps, float bc1, float bc2, float grad_scale) {
+                                                          float b2, float eps, float bc1, float bc2, float grad_scale,
+                                                          const float* __restrict__ sumsq, float max_norm) {
+  if (sumsq != nullptr) grad_scale *= fminf(1.0f, max_norm / (grad_scale * sqrtf(__ldg(sumsq)) + 1e-6f));
   const int2 ct = chunk_tab[blockIdx.x];
   const long long* pr = ptrs + 5ll * ct.x;
   float* p = reinterpret_cast<float*>(pr[0]);
@@ -794,6 +799,28 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const long long* __res
     pi -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
     p[i] = pi;
     if (p16) p16[i] = __float2bfloat16(pi);
+  }
+}
+
+// out[0] += sum of g^2 over one 16384-element chunk of one gradient tensor (same tables as adamw_multi_kernel)
+__global__ void __launch_bounds__(256) multi_sqnorm_kernel(const long long* __restrict__ ptrs, const long long* __restrict__ sizes,
+                                                           const int2* __restrict__ chunk_tab, float* __restrict__ out) {
+  const int2 ct = chunk_tab[blockIdx.x];
+  const float* g = reinterpret_cast<const float*>(ptrs[5ll * ct.x + 1]);
+  const long long n = sizes[ct.x];
+  const long long base = static_cast<long long>(ct.y) * kAdamChunk;
+  const long long end = min(n, base + kAdamChunk);
+  float acc = 0.f;
+  for (long long i = base + threadIdx.x; i < end; i += 256) acc = fmaf(g[i], g[i], acc);
+  __shared__ float red[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < 8; ++w2) t += red[w2];
+    atomicAdd(out, t);
   }
 }
 
@@ -1002,7 +1029,25 @@ int vl_adamw_multi(const int64_t* ptrs, const int64_t* sizes, const float* wds, 
   const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
   adamw_multi_kernel<<<n_chunks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const long long*)ptrs, (const long long*)sizes, wds,
                                                                                      reinterpret_cast<const int2*>(chunk_tab), lr, beta1, beta2, eps,
-                                                                                     bc1, bc2, grad_scale);
+                                                                                     bc1, bc2, grad_scale, nullptr, 0.f);
   return launch_check("adamw_multi");
+}
+
+int vl_multi_sqnorm(const int64_t* ptrs, const int64_t* sizes, const int32_t* chunk_tab, int32_t n_chunks, float* sumsq, void* stream) {
+  VL_CHECK_ARG(ptrs && sizes && chunk_tab && sumsq && n_chunks > 0, "vl_multi_sqnorm: bad arguments");
+  multi_sqnorm_kernel<<<n_chunks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const long long*)ptrs, (const long long*)sizes,
+                                                                                      reinterpret_cast<const int2*>(chunk_tab), sumsq);
+  return launch_check("multi_sqnorm");
+}
+
+int vl_adamw_multi_clip(const int64_t* ptrs, const int64_t* sizes, const float* wds, const int32_t* chunk_tab, int32_t n_chunks, float lr,
+                        float beta1, float beta2, float eps, int32_t step, float grad_scale, const float* sumsq, float max_norm,
+                        void* stream) {
+  VL_CHECK_ARG(ptrs && sizes && wds && chunk_tab && sumsq && n_chunks > 0 && step >= 1 && max_norm > 0.f, "vl_adamw_multi_clip: bad arguments");
+  const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
+  adamw_multi_kernel<<<n_chunks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const long long*)ptrs, (const long long*)sizes, wds,
+                                                                                     reinterpret_cast<const int2*>(chunk_tab), lr, beta1, beta2, eps,
+                                                                                     bc1, bc2, grad_scale, sumsq, max_norm);
+  return launch_check("adamw_multi_clip");
 }
 }

@@ -29,6 +29,7 @@ class AdamW:
         self.groups = [dict(params=no_decay, weight_decay=0.0), dict(params=decay, weight_decay=weight_decay)]
         self.lr, self.betas, self.eps = lr, betas, eps
         self.t = 0
+        self.grad_norm = None
         self._plan = None
         self._copied = None
 
@@ -62,7 +63,10 @@ class AdamW:
         self._plan = True
 
     @torch.no_grad()
-    def step(self, grad_scale: float = 1.0):
+    def step(self, grad_scale: float = 1.0, clip_norm: float = None):
+        """One update.  grad_scale multiplies every gradient (1 / world_size after a summing all-reduce).  clip_norm: the
+        reference's --grad-clip-norm (torch.nn.utils.clip_grad_norm_ over all parameters, train.py:212-240), applied to the
+        scaled gradients inside the fused kernel; the total norm lands in self.grad_norm (a device scalar, no host sync)."""
         if self._plan is None:
             self._build_plan()
         self.t += 1
@@ -85,8 +89,13 @@ class AdamW:
         self.ptr_dev.copy_(rows, non_blocking=True)
         self._copied = torch.cuda.Event()
         self._copied.record()
+        sumsq = None
+        if clip_norm is not None:
+            sumsq = torch.zeros((1,), dtype=torch.float32, device=self.ptr_dev.device)
+            L.multi_sqnorm(self.ptr_dev, self.sizes, self.chunk_tab, sumsq, n_chunks=self.chunk_tab.shape[0])
+            self.grad_norm = sumsq.sqrt() * grad_scale
         L.adamw_multi(self.ptr_dev, self.sizes, self.wds, self.chunk_tab, n_chunks=self.chunk_tab.shape[0], lr=self.lr, beta1=self.betas[0],
-                      beta2=self.betas[1], eps=self.eps, step=self.t, grad_scale=grad_scale)
+                      beta2=self.betas[1], eps=self.eps, step=self.t, grad_scale=grad_scale, sumsq=sumsq, max_norm=clip_norm)
         engine.WEIGHTS.clear_derived()  # concatenated / padded / folded copies are rebuilt lazily; plain copies were refreshed above
 
 
