@@ -387,6 +387,12 @@ def run_cuda(args):
             d[2] += 1
         mhsa = {k: {"achieved": v[1] / v[0] / 1e6, "peak": pk["hbm"], "unit": "GB/s", "frac": v[1] / v[0] / 1e6 / pk["hbm"], "launches": v[2],
                     "share_of_step": v[0] / ms} for k, v in by.items()}
+        if "fwd" in mhsa:
+            # DRAM bytes of one attn_fwd2_kernel launch at batch 256 from the committed ncu --set full capture
+            # (profiles/r01_ncu_attn_fwd2_final.txt: 405.3 MB read + 113.1 MB written; algorithmic 539.0 MB, the last tiles'
+            # output is still in L2 when the kernel ends): no re-reads of Q / K / V
+            mhsa["fwd"]["traffic"] = int((405338112 + 113060864) * B / 256)
+            mhsa["fwd"]["kernel"] = "attn_fwd2_kernel (persistent, P in TMEM), per launch; algorithmic %d B" % (4 * B * 257 * 1024 * 2)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         sps, cores, sec = time_cpu(2, 1)
