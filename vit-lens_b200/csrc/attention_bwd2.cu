@@ -477,9 +477,12 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
             for (int t = 0; t < 16; ++t) pk[(c >> 1) + t] = 0u;
           } else if (!need_mask) {
+            const float2 sl22 = make_float2(sl2, sl2), nl2 = make_float2(-lse2, -lse2);
 #pragma unroll
-            for (int t = 0; t < 32; t += 2)
-              pk[(c + t) >> 1] = pack_bf16(ex2_approx(fmaf(__uint_as_float(v[t]), sl2, -lse2)), ex2_approx(fmaf(__uint_as_float(v[t + 1]), sl2, -lse2)));
+            for (int t = 0; t < 32; t += 2) {  // two scores per FMA-pipe instruction (FFMA2)
+              const float2 a = __ffma2_rn(make_float2(__uint_as_float(v[t]), __uint_as_float(v[t + 1])), sl22, nl2);
+              pk[(c + t) >> 1] = pack_bf16(ex2_approx(a.x), ex2_approx(a.y));
+            }
           } else {
 #pragma unroll
             for (int t = 0; t < 32; t += 2) {
@@ -514,15 +517,16 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tc_wait_ld();
           }
           uint32_t dk[16];
+          const float2 sc2 = make_float2(p.scale, p.scale), nDs2 = make_float2(nDs, nDs);
 #pragma unroll
           for (int t = 0; t < 32; t += 2) {
-            float d0 = 0.f, d1 = 0.f;
-            if (c < nkb) {
+            float2 d = make_float2(0.f, 0.f);
+            if (c < nkb) {  // FFMA2 / FMUL2: two elements per FMA-pipe instruction
               const uint32_t pp = pk[(c + t) >> 1];
-              d0 = bf16_lo(pp) * fmaf(__uint_as_float(v[t]), p.scale, nDs);
-              d1 = bf16_hi(pp) * fmaf(__uint_as_float(v[t + 1]), p.scale, nDs);
+              const float2 u = __ffma2_rn(make_float2(__uint_as_float(v[t]), __uint_as_float(v[t + 1])), sc2, nDs2);
+              d = __fmul2_rn(make_float2(bf16_lo(pp), bf16_hi(pp)), u);
             }
-            dk[t >> 1] = pack_bf16(d0, d1);
+            dk[t >> 1] = pack_bf16(d.x, d.y);
           }
           uint8_t* chunk = sPDg + (c >> 6) * 16384;
 #pragma unroll
