@@ -161,7 +161,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   auto sK = [&](int st) { return base + kOffKV + static_cast<uint32_t>(st) * 16384u; };
 
   // Register budget per warpgroup (512 threads x 128 at launch): the softmax groups hold a block's 64 scores, its packed P
-  // and the deferred epilogue state per thread; producer / issuers / tail warps need little.  56 + 72 + 2 x 192 = 512.
+  // and the deferred epilogue state per thread; producer / issuers / tail warps need little.  48 + 80 + 2 x 192 = 512.
 
   if (warp < 4) {
    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
