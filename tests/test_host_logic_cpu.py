@@ -59,3 +59,29 @@ def test_point_cloud_tower_forward_vs_reference(emu):
     with torch.no_grad():
         fv = model.encode_visual(inp["visual"], normalize=True, fps_start=gold["fps_start"])
     assert cosine(fv, gold["visual_features"]) > 0.999
+
+
+def test_weight_cache_entries_die_with_their_parameter(emu):
+    """engine.WEIGHTS hands out bf16 operand copies keyed by the parameter OBJECT: an entry must not outlive its parameter
+    (a later model can reuse the freed parameter's id, storage address, version and shape) and must follow in-place updates."""
+    import gc
+
+    from vitlens_b200 import engine
+
+    engine.WEIGHTS.clear()
+    p = torch.nn.Parameter(torch.randn(8, 16))
+    q = torch.nn.Parameter(torch.randn(4, 16))
+    a = engine.w16(p)
+    assert engine.w16(p) is a and torch.equal(a.float(), p.detach().bfloat16().float())
+    cat = engine._cat16("qkv", p, q)
+    assert engine._cat16("qkv", p, q) is cat and cat.shape == (12, 16)
+    with torch.no_grad():
+        p.mul_(2.0)  # version bump -> refreshed copy
+    b = engine.w16(p)
+    assert b is not a and torch.equal(b.float(), p.detach().bfloat16().float())
+    n_before = len(engine.WEIGHTS._c)
+    assert n_before >= 2
+    del p, a, b, cat
+    gc.collect()
+    assert all(all(r() is not None for r in hit[2]) for hit in engine.WEIGHTS._c.values())  # no entry points at a dead parameter
+    assert len(engine.WEIGHTS._c) < n_before
