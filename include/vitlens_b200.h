@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define VL_ABI_VERSION 1
+#define VL_ABI_VERSION 2
 #define VL_EINVAL (-1)   /* bad argument (shape / alignment / null pointer) */
 #define VL_ENOTSUP (-2)  /* shape outside what the kernel supports */
 #define VL_EDRIVER (-3)  /* CUDA driver entry point (tensor-map encode) unavailable */
@@ -55,7 +55,10 @@ enum {
                           nparts = ceil(N/BN)*2 is returned through vl_gemm_rowlse_parts(). d unused.     */
   VL_EPI_CLIPGRAD = 6, /* z = alpha*acc; g = exp(z - row_vec[i]) + (col_vec ? exp(z - col_vec[j]) : 0)
                           - (col_vec ? 2 : 1) * [j == i + iparam];  d(bf16) = fparam * g;
-                          *scalar_out += sum fparam * g * acc   (d loss / d alpha)                     */
+                          *scalar_out = sum fparam * g * acc   (d loss / d alpha; written, deterministic);
+                          with loss_flags bit 0 the sum runs over the row-softmax term only:
+                          fparam * (exp(z - row_vec[i]) - [j == i + iparam]) * acc  (the d/d alpha of THIS rank's rows
+                          when the column term carries other ranks' losses: local_loss + gather_with_grad)  */
 };
 
 typedef struct {
@@ -92,17 +95,18 @@ typedef struct {
    * the per-group "global feature" term is broadcast over the group's points); relu != 0 clamps the result at 0. */
   int32_t aux_row_div;
   int32_t relu;
-  /* Optional fp32 [M]: rowsum_out[m] += sum_k A[m, k] (atomic), computed on the tensor cores from the A tiles already in
-   * shared memory (an extra N = 16 MMA against a tile of ones).  With A = dY^T this is the bias gradient of the Linear whose
+  /* Optional fp32 [M]: rowsum_out[m] = sum_k A[m, k] (written; per-tile partials added in a fixed order), computed on the tensor
+   * cores from the A tiles already in shared memory (an extra N = 16 MMA against a tile of ones).  With A = dY^T this is the bias gradient of the Linear whose
    * weight gradient the GEMM produces (replaces a separate vl_colsum_bf16 pass over dY).  Requires the CTA-pair kernel:
    * M >= 512, N > 128, LINEAR epilogue, fp32 output; rejected (VL_ENOTSUP) otherwise. */
   float* rowsum_out;
+  int32_t loss_flags; /* VL_EPI_CLIPGRAD only, see above */
 } VlGemmArgs;
 
 int vl_gemm_bf16(const VlGemmArgs* args, void* stream);
 /* number of column parts VL_EPI_ROWLSE writes per row for an N-column problem */
 int vl_gemm_rowlse_parts(int32_t N);
-/* lse[i] = log sum_p out_vec1[i,p]*exp(out_vec0[i,p] - max_p) + max_p;  *loss_sum += sum_i (lse[i] - diag[i]) */
+/* lse[i] = log sum_p out_vec1[i,p]*exp(out_vec0[i,p] - max_p) + max_p;  *loss_sum = sum_i (lse[i] - diag[i]) (written) */
 int vl_lse_combine(const float* part_max, const float* part_sum, const float* diag, int32_t M, int32_t nparts,
                    float* lse, float* loss_sum, void* stream);
 
@@ -125,18 +129,21 @@ int vl_attention_bwd(const void* q, const void* k, const void* v, const void* o,
 
 /* ---------------------------------------------------------------------------------------------
  * Row kernels (HBM-bound, one pass).  x/y/dy/dx are bf16 unless noted; parameters and their
- * gradients are fp32; gradient outputs named d<param> are ACCUMULATED (+=) with atomics.
+ * gradients are fp32.  Reductions over rows (parameter gradients, column sums, moments, loss sums, gradient norms) are
+ * DETERMINISTIC: every CTA stores one row of partial sums into stream-ordered scratch memory and a second launch adds the
+ * rows in CTA order, so results are bit-identical from run to run and the outputs are WRITTEN (=), never accumulated; they need
+ * no zero fill.  The one exception is vl_embed_tokens_bwd (a scatter by token id: fp32 atomics, outputs accumulated).
  */
 /* LayerNorm eps affine over the last dim (transformer.py:17-34, perceiver.py:71-72); optional row
  * gather: y[i] = LN(x[row_index[i]]) (cls pooling transformer.py:653-657,783; EOT pooling model.py:537-540). */
 int vl_layernorm_fwd(const void* x, int64_t ldx, const int64_t* row_index, const float* w, const float* b, void* y,
                      int64_t ldy, float* mean, float* rstd, int32_t T, int32_t D, float eps, void* stream);
-/* dx[row_index[i] or i] = LN'(dy[i]) (+ dres at the same row); dw += sum dy*xhat; db += sum dy (both or neither);
- * dres_sum[d] += sum_i dres[i, d] (optional: the bias gradient of the Linear that produced the residual branch). */
+/* dx[row_index[i] or i] = LN'(dy[i]) (+ dres at the same row); dw = sum dy*xhat; db = sum dy (both or neither);
+ * dres_sum[d] = sum_i dres[i, d] (optional: the bias gradient of the Linear that produced the residual branch). */
 int vl_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const int64_t* row_index, const float* w,
                      const float* mean, const float* rstd, const void* dres, int64_t lddres, void* dx, int64_t lddx,
                      float* dw, float* db, float* dres_sum, int32_t T, int32_t D, void* stream);
-/* db[n] += sum_t dy[t,n]: bias gradients of every nn.Linear on the path. */
+/* db[n] = sum_t dy[t,n]: bias gradients of every nn.Linear on the path. */
 int vl_colsum_bf16(const void* dy, int64_t ld, float* db, int32_t T, int32_t N, void* stream);
 /* Patch gather feeding conv1-as-GEMM (nn.Conv2d bias=False: transformer.py:464-470, AST_tokenizer.py:22-28,
  * DepthTokenizer.py:22-28): out[(b*OH+oh)*OW+ow, (c*kh+i)*kw+j] = in[b*sb + c*sc + (oh*stride_h+i)*sh + (ow*stride_w+j)*sw],
@@ -150,7 +157,7 @@ int vl_assemble_tokens(const void* tok, const float* cls, const float* pos, void
                        int32_t has_cls, void* stream);
 int vl_assemble_tokens_bwd(const void* dx, void* dtok, float* dpos, float* dcls, int32_t B, int32_t L, int32_t D,
                            int32_t has_cls, void* stream);
-/* out[r] = table[ids[r]] + pos[r % ctx] (model.py:530-532) and its backward. */
+/* out[r] = table[ids[r]] + pos[r % ctx] (model.py:530-532) and its backward (dtable / dpos ACCUMULATED with atomics: zero them). */
 int vl_embed_tokens(const int64_t* ids, const float* table, const float* pos, void* out, int64_t rows, int32_t ctx,
                     int32_t D, void* stream);
 int vl_embed_tokens_bwd(const int64_t* ids, const void* dx, float* dtable, float* dpos, int64_t rows, int32_t ctx,
@@ -172,7 +179,7 @@ int vl_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float
 int vl_adamw_multi(const int64_t* ptrs, const int64_t* sizes, const float* wds, const int32_t* chunk_tab, int32_t n_chunks,
                    float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream);
 /* Gradient-norm clipping (torch.nn.utils.clip_grad_norm_, reference training/train.py:212-240) without an extra pass over the
- * gradients: vl_multi_sqnorm adds sum(g^2) over every tensor of the same tables to *sumsq (zero it first); vl_adamw_multi_clip is
+ * gradients: vl_multi_sqnorm writes sum(g^2) over every tensor of the same tables to *sumsq (deterministic); vl_adamw_multi_clip is
  * vl_adamw_multi with every gradient scaled by min(1, max_norm / (grad_scale * sqrt(*sumsq) + 1e-6)). */
 int vl_multi_sqnorm(const int64_t* ptrs, const int64_t* sizes, const int32_t* chunk_tab, int32_t n_chunks, float* sumsq, void* stream);
 int vl_adamw_multi_clip(const int64_t* ptrs, const int64_t* sizes, const float* wds, const int32_t* chunk_tab, int32_t n_chunks,
@@ -197,7 +204,7 @@ int vl_group_sum(const void* x, void* out, int64_t groups, int32_t G, int32_t C,
 int vl_colsum2_bf16(const void* a, const void* b, float* s1, float* s2, int64_t T, int32_t N, void* stream);
 int vl_wgrad3(const void* dy, const float* x, float* dw, int64_t R, int32_t C, void* stream);
 /* BatchNorm1d with batch statistics inside the point tokenizer (training mode; reference dvae.py:185-193 under model.train(),
- * SyncBN per pc_tri_main.py:372-373).  vl_moments3: out12 += [sum x (3) | sum x x^T (3x3)] over the R rows of x[R,3] -- the
+ * SyncBN per pc_tri_main.py:372-373).  vl_moments3: out12 = [sum x (3) | sum x x^T (3x3)] over the R rows of x[R,3] -- the
  * statistics of first_conv.0's outputs follow in closed form.  vl_col_affine_bf16: out = act(p0[c]*a + p1[c]*b + p2[c]) per
  * column (b, p1 optional; act 0 none / 1 relu): the normalise+ReLU pass and the BatchNorm backward correction. */
 int vl_moments3(const float* x, float* out12, int64_t R, void* stream);

@@ -240,7 +240,7 @@ def rowlse(p16, q16, *, alpha, label_off=0):
     return lse, (lse - diag).sum().reshape(1)
 
 
-def clipgrad(p16, q16, *, alpha, row_lse, col_lse, label_off, gscale, gscale_dev=None):
+def clipgrad(p16, q16, *, alpha, row_lse, col_lse, label_off, gscale, gscale_dev=None, ds_row_only=False):
     _n()
     alpha = float(alpha)
     if gscale_dev is not None:
@@ -249,6 +249,7 @@ def clipgrad(p16, q16, *, alpha, row_lse, col_lse, label_off, gscale, gscale_dev
     z = alpha * acc
     M, N = z.shape
     g = torch.exp(z - row_lse[:, None])
+    grow = g
     k = 1.0
     if col_lse is not None:
         g = g + torch.exp(z - col_lse[None, :])
@@ -256,7 +257,8 @@ def clipgrad(p16, q16, *, alpha, row_lse, col_lse, label_off, gscale, gscale_dev
     onehot = torch.zeros(M, N)
     onehot[torch.arange(M), torch.arange(M) + label_off] = 1.0
     g = gscale * (g - k * onehot)
-    return g.to(BF16), (g * acc).sum().reshape(1)
+    ds = (gscale * (grow - onehot) * acc).sum() if ds_row_only else (g * acc).sum()
+    return g.to(BF16), ds.reshape(1)
 
 
 # ----------------------------------------------------------------------------- point-cloud tokenizer

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(h, n), f"{n} declared in include/vitlens_b200.h but not exported"
-    assert h.vl_abi_version() == 1
+    assert h.vl_abi_version() == 2
 
 
 def test_argument_errors_are_reported_without_a_gpu():

@@ -441,3 +441,44 @@ def test_point_cloud_batchnorm_kernels(ops):
     want = A.float() @ Bm.float().t() + gp.float().repeat_interleave(k, dim=0)
     close(ops.gemm_grouped_residual_relu(A, Bm, gp, k, relu=False), want)
     close(ops.gemm_grouped_residual_relu(A, Bm, gp, k), torch.relu(want))
+
+
+def test_row_reductions_are_bit_deterministic(ops):
+    """Every cross-CTA reduction on the path (LayerNorm dgamma / dbeta, bias-gradient column sums incl. the ones riding on a
+    weight-gradient GEMM, assemble's dpos / dcls, the loss sum and d(logit_scale), BatchNorm sums and moments) is a two-stage
+    fixed-order sum: repeated launches on the same inputs must agree bit for bit, and outputs start from uninitialised memory."""
+    torch.manual_seed(3)
+    T, D = 6 * 257 + 2048, 1024
+    x = torch.randn(T, D, device="cuda").to(BF)
+    dy = torch.randn(T, D, device="cuda").to(BF)
+    w = torch.randn(D, device="cuda")
+    y, mean, rstd = ops.layernorm_fwd(x, w, torch.zeros_like(w))
+    runs = []
+    for _ in range(3):
+        torch.empty(1 << 22, device="cuda").fill_(float("nan"))  # poison the allocator's free blocks
+        r = {}
+        _, r["ln_dw"], r["ln_db"] = ops.layernorm_bwd(dy, x, w, mean, rstd, dres=dy)
+        _, r["lng_dw"], r["lng_db"], r["lng_rs"] = ops.layernorm_bwd(dy[:300, :512].contiguous(), x[:300, :512].contiguous(), w[:512],
+                                                                    mean[:300], rstd[:300], dres=dy[:300, :512].contiguous(), want_dres_sum=True)
+        r["colsum"] = ops.colsum(dy)
+        _, r["rowsum"] = ops.gemm(dy, x, a_t=True, b_t=True, out_dtype=torch.float32, accumulate=True, want_rowsum=True)
+        _, r["dpos"], r["dcls"] = ops.assemble_tokens_bwd(dy[: 6 * 257].contiguous(), B=6, L_=256, D=D, has_cls=True)
+        p16 = torch.nn.functional.normalize(x[:512, :768].float(), dim=-1).to(BF).contiguous()
+        q16 = torch.nn.functional.normalize(dy[:512, :768].float(), dim=-1).to(BF).contiguous()
+        alpha = torch.tensor([14.3], device="cuda")
+        lse, r["loss_sum"] = ops.rowlse(p16, q16, alpha=alpha)
+        _, r["dscale"] = ops.clipgrad(p16, q16, alpha=alpha, row_lse=lse, col_lse=lse, label_off=0, gscale=1.0 / 1024)
+        r["cs2a"], r["cs2b"] = ops.colsum2(dy, x)
+        pts = torch.randn(5000, 3, device="cuda")
+        r["mom"] = ops.moments3(pts)
+        r["wg3"] = ops.wgrad3(dy[:5000, :128].contiguous(), pts)
+        torch.cuda.synchronize()
+        assert all(torch.isfinite(v).all() for v in r.values()), [k for k, v in r.items() if not torch.isfinite(v).all()]
+        runs.append(r)
+    for k in runs[0]:
+        for other in runs[1:]:
+            assert torch.equal(runs[0][k], other[k]), k
+    close(runs[0]["colsum"], dy.float().sum(0), tol=1e-3, atol=0.05)
+    close(runs[0]["ln_db"], dy.float().sum(0), tol=1e-3, atol=0.05)
+    close(runs[0]["dcls"], dy[: 6 * 257].float().reshape(6, 257, D)[:, 0].sum(0), tol=1e-3, atol=0.02)
+    close(runs[0]["mom"][:3], pts.sum(0), tol=1e-3, atol=0.05)

@@ -3,13 +3,32 @@
 size-independent properties at the full BASELINE batch.
 
 Stated bf16 tolerances (activations / residual stream bf16, fp32 accumulate): feature cosine >= 0.999 vs the fp32
-reference, |loss - ref| <= 2e-2 * |ref|, gradient cosine >= 0.97 (tiny models) / norm within 10 %."""
+reference, |loss - ref| <= 2e-2 * |ref|, gradient cosine >= 0.97 (tiny models) / 0.95 (full size), gradient norms within
+10 %.  Every comparison's ACHIEVED numbers are appended to gpurun_out/parity_report.jsonl (one JSON line per case; the
+committed copy of a B200 run lives under profiles/).
+
+Order: cheap and wide first (tiny models, the BASELINE-size batch, the public encode API), the long full-size fixtures last,
+so `-x` never hides the broad checks behind one slow case."""
+import json
+import os
+
 import pytest
 import torch
 
-from tests.common import C, build_model, cosine, relerr, run_model, run_oracle
+from tests.common import C, ROOT, build_model, cosine, relerr, run_model, run_oracle
 
 pytestmark = pytest.mark.gpu
+
+
+def _report(**row):
+    """Append the achieved numbers of one comparison (see module docstring)."""
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "parity_report.jsonl"), "a") as f:
+            f.write(json.dumps(row) + "\n")
+    except OSError:
+        pass
+    print("parity", json.dumps(row))
 
 
 def _check(name, grad_cos=0.97, norm_tol=0.1):
@@ -20,10 +39,14 @@ def _check(name, grad_cos=0.97, norm_tol=0.1):
     if "fps_start" in gold:
         inp["fps_start"] = gold["fps_start"]
     feats, ls, loss = run_model(case, model, inp)
+    row = {"case": name, "vs": "reference fixture"}
     for k, v in feats.items():
         c = cosine(v.detach().cpu(), gold[k])
+        row["cos_" + k] = round(c, 6)
+        row["relerr_" + k] = round(relerr(v.detach().cpu(), gold[k]), 5)
         assert c > 0.999, (name, k, c)
         assert abs(float(v.detach().norm(dim=-1).mean()) - 1.0) < 1e-3
+    row["loss"], row["loss_ref"] = float(loss.detach()), float(gold["loss"])
     assert abs(float(loss.detach()) - float(gold["loss"])) < 2e-2 * abs(float(gold["loss"])), (float(loss.detach()), float(gold["loss"]))
     if case.bn_train:  # running statistics after one training-mode forward (bf16 activations: 1 % of the largest entry)
         assert relerr(C.bn_running(model.state_dict()), gold["bn_running"]) < 1e-2
@@ -34,8 +57,11 @@ def _check(name, grad_cos=0.97, norm_tol=0.1):
     keys = sorted(got)
     assert len(keys) == gold["grad_norms"].numel()
     bad = []
+    worst_cos, worst_norm = (1.0, ""), (0.0, "")
     for i, k in enumerate(keys):
         gn = float(gold["grad_norms"][i])
+        if gn > 1e-4 and k != "logit_scale":
+            worst_norm = max(worst_norm, (abs(float(got[k].norm()) - gn) / gn, k))
         # d(logit_scale) is one scalar built from strongly cancelling terms: absolute slack at tiny batch sizes
         slack = 5e-3 if k == "logit_scale" else 0.0
         if gn > 1e-4 and abs(float(got[k].norm()) - gn) > norm_tol * gn + slack:
@@ -45,25 +71,18 @@ def _check(name, grad_cos=0.97, norm_tol=0.1):
         # no direction: d(logit_scale) is covered by the norm check with its absolute slack above)
         if gk in gold and gn > 1e-4 and gold[gk].numel() > 1:
             c = cosine(got[k].cpu(), gold[gk])
+            worst_cos = min(worst_cos, (c, k))
             if c < grad_cos:
                 bad.append((k, "cos", c))
+    row.update(min_grad_cos=round(worst_cos[0], 5), min_grad_cos_key=worst_cos[1], max_grad_norm_relerr=round(worst_norm[0], 5),
+               max_grad_norm_key=worst_norm[1], n_grads=len(keys), tol_grad_cos=grad_cos, tol_norm=norm_tol)
+    _report(**row)
     assert not bad, bad[:10]
 
 
 @pytest.mark.parametrize("name", ["tiny_clip", "tiny_tri_audio", "tiny_tri_depth", "tiny_tri_pc", "tiny_tri_pc_bntrain"])
 def test_tiny_models_vs_reference_fixture(name):
     _check(name)
-
-
-@pytest.mark.parametrize("name", ["vitb32_clip_bs8", "vitl14_audio128_bs2", "vitl14_depth_bs2", "vitl14_pc_bs2", "vitl14_pc_bs2_bntrain"])
-def test_full_size_models_vs_reference_fixture(name):
-    if name == "vitl14_pc_bs2_bntrain":
-        # batch statistics over only 2 clouds leave the two visual features almost identical (loss = ln 4 to 3 digits): the
-        # gradients are small differences of nearly equal terms and bf16 activations move them by ~10-15 %.  Features, loss
-        # and the BatchNorm running statistics keep the standard tolerances above; gradients get cosine 0.9 / norms 25 %.
-        _check(name, grad_cos=0.9, norm_tol=0.25)
-    else:
-        _check(name, grad_cos=0.95)
 
 
 def test_tiny_grads_vs_oracle_all_parameters():
@@ -136,3 +155,48 @@ def test_point_cloud_tower_forward_vs_reference_fixture(name):
     with torch.no_grad():
         fv = model.encode_visual(inp["visual"].cuda(), normalize=True, fps_start=gold["fps_start"].cuda())
     assert cosine(fv.cpu(), gold["visual_features"]) > 0.999
+
+
+def _grads_once(case_name):
+    case = C.CASES[case_name]
+    gold = C.load_golden(case_name)
+    model, sd, args = build_model(case, device="cuda")
+    inp = C.build_inputs(case, args)
+    if "fps_start" in gold:
+        inp["fps_start"] = gold["fps_start"]
+    feats, ls, loss = run_model(case, model, inp)
+    loss.backward()
+    torch.cuda.synchronize()
+    return float(loss.detach()), {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.requires_grad}
+
+
+@pytest.mark.parametrize("name", ["tiny_tri_pc_bntrain", "vitl14_depth_bs2"])
+def test_gradients_run_to_run_spread(name):
+    """The same step twice from scratch.  Every row reduction on the path is a fixed-order two-stage sum (LayerNorm / bias /
+    BatchNorm parameter gradients, column sums, moments, loss sums), so those gradients must be BIT-identical; what remains
+    non-deterministic is the order of the fp32 red.adds that merge split-K partial tiles of the weight-gradient GEMMs
+    (vitl14_depth_bs2 trains four ViT blocks: qkv / out_proj weight gradients use 3-4 splits).  Bound: relative spread
+    <= 1e-4 per tensor, i.e. >= 250x below the 10 % norm / 0.05 cosine tolerances of the fixture comparisons."""
+    l1, g1 = _grads_once(name)
+    l2, g2 = _grads_once(name)
+    assert l1 == l2, (l1, l2)
+    worst, exact = (0.0, ""), 0
+    for k in g1:
+        d = float((g1[k] - g2[k]).norm())
+        n = float(g1[k].norm())
+        exact += int(d == 0.0)
+        if n > 1e-6:
+            worst = max(worst, (d / n, k))
+    _report(case=name, vs="itself, second run", max_rel_spread=worst[0], max_rel_spread_key=worst[1], bit_identical=exact, n_grads=len(g1))
+    assert worst[0] <= 1e-4, worst
+    for k in g1:  # LayerNorm / bias / BatchNorm / cls / positional gradients: no atomics anywhere on their path
+        if g1[k].dim() == 1 and not k.endswith("in_proj_bias") and "attn.out_proj.bias" not in k:
+            assert torch.equal(g1[k], g2[k]), k
+
+
+@pytest.mark.parametrize("name", ["vitb32_clip_bs8", "vitl14_audio128_bs2", "vitl14_depth_bs2", "vitl14_pc_bs2", "vitl14_pc_bs8_bntrain"])
+def test_full_size_models_vs_reference_fixture(name):
+    """Full-size weights (ViT-B/32 = BASELINE configs[0]; ViT-L/14 + audio / depth / point Lens = reduced-batch configs[2..4]).
+    vitl14_pc_bs8_bntrain: training-mode BatchNorm over eight clouds of distinct shapes (a well-conditioned contrastive batch,
+    oracle/cases.py) -- same tolerances as every other case."""
+    _check(name, grad_cos=0.95)

@@ -8,7 +8,7 @@ import torch
 from tests.common import C, build_model, relerr, run_oracle
 
 FAST = ["tiny_clip", "tiny_tri_audio", "tiny_tri_depth", "tiny_tri_pc", "tiny_tri_pc_bntrain", "vitb32_clip_bs8"]
-SLOW = ["vitl14_audio128_bs2", "vitl14_depth_bs2", "vitl14_pc_bs2", "vitl14_pc_bs2_bntrain"]
+SLOW = ["vitl14_audio128_bs2", "vitl14_depth_bs2", "vitl14_pc_bs2", "vitl14_pc_bs8_bntrain"]
 
 
 def _check(name, with_grads):
@@ -51,3 +51,23 @@ def test_oracle_matches_reference_fixture(name):
 @pytest.mark.parametrize("name", SLOW)
 def test_oracle_matches_reference_fixture_vitl(name):
     _check(name, with_grads=False)
+
+
+def test_oracle_sharded_loss_matches_reference_run_under_gloo():
+    """oracle.clip_loss_sharded (the restatement of gather_features + ClipLoss / TriClipLoss at world_size > 1) against the
+    per-rank results of the REAL reference run as two gloo processes (oracle/make_golden_dist.py), all four
+    (local_loss, gather_with_grad) combinations, both loss classes: loss, d/d(local features), d/d(logit_scale)."""
+    from tests import dist_common as DC
+
+    gold = DC.load_dist_golden()
+    W, bl, e = int(gold["world"]), int(gold["bl"]), int(gold["e"])
+    for tri, ll, gwg in DC.COMBOS:
+        name = DC.combo_name(tri, ll, gwg)
+        ours = DC.oracle_per_rank(tri, ll, gwg, W, bl, e, float(gold["scale_log"]), tuple(gold["seeds"]))
+        for r in range(W):
+            for k, v in ours[r].items():
+                if v is None:
+                    continue
+                ref = gold[f"{name}/rank{r}/{k}"]
+                err = float((v.detach() - ref).abs().max())
+                assert err <= 2e-5 * float(ref.abs().max()) + 1e-7, (name, r, k, err)

@@ -141,14 +141,13 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
                                                                const float* __restrict__ rstd,
                                                                const __nv_bfloat16* __restrict__ dres, long long lddres,
                                                                __nv_bfloat16* __restrict__ dx, long long lddx,
-                                                               float* __restrict__ dw, float* __restrict__ db,
-                                                               float* __restrict__ dres_sum, int T, int D) {
+                                                               float* __restrict__ part, int want_w, int want_r, int T, int D) {
+  // part: [gridDim.x][(2 * want_w + want_r) * D] per-CTA partial sums of dw | db | dres_sum (second stage: launch_colreduce)
   extern __shared__ float red[];  // [warps][D] reused for dw, db, dres_sum
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
   const int nvec = D >> 3;
-  const bool want_w = dw != nullptr;
   float aw[CH][8], ab[CH][8], ar[RS ? CH : 1][8];
 #pragma unroll
   for (int c = 0; c < CH; ++c)
@@ -216,11 +215,12 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
       }
     }
   }
-  if (dw == nullptr && (!RS || dres_sum == nullptr)) return;
-  // block reduction of the per-warp partial column sums, then one atomic per column per CTA
+  if (part == nullptr) return;
+  // block reduction of the per-warp partial column sums, then one partial row per CTA (plain stores)
+  const int nout = 2 * want_w + want_r;
   for (int pass = 0; pass < (RS ? 3 : 2); ++pass) {
-    float* dst = pass == 0 ? dw : (pass == 1 ? db : dres_sum);
-    if (dst == nullptr) continue;
+    if (pass < 2 ? !want_w : !want_r) continue;
+    float* dst = part + (long long)blockIdx.x * nout * D + (pass < 2 ? pass : 2 * want_w) * D;
     __syncthreads();
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
     for (int col = threadIdx.x; col < D; col += blockDim.x) {
       float s = 0.f;
       for (int ww = 0; ww < wpb; ++ww) s += red[ww * D + col];
-      atomicAdd(dst + col, s);
+      dst[col] = s;
     }
   }
 }
@@ -249,7 +249,8 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_d1024_kernel(const __nv_
                                                                      const float* __restrict__ rstd,
                                                                      const __nv_bfloat16* __restrict__ dres, long long lddres,
                                                                      __nv_bfloat16* __restrict__ dx, long long lddx,
-                                                                     float* __restrict__ dw, float* __restrict__ db, int T) {
+                                                                     float* __restrict__ part, int T) {
+  // part: [gridDim.x][2048] per-CTA partial dw | db, or null
   // rows per step.  Measured on B200 (65792 x 1024): R = 8 without register prefetch 136.6 us, R = 4 with the next step
   // prefetched 147.6 us (twice the barriers), the warp-per-row kernel 144.8 us.
   constexpr int R = 8;
@@ -335,12 +336,10 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_d1024_kernel(const __nv_
       *reinterpret_cast<uint2*>(dx + row * lddx + c0) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
     }
   }
-  if (dw != nullptr) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      atomicAdd(dw + c0 + j, aw[j]);
-      atomicAdd(db + c0 + j, ab[j]);
-    }
+  if (part != nullptr) {
+    float* pw = part + (long long)blockIdx.x * 2048;
+    *reinterpret_cast<float4*>(pw + c0) = make_float4(aw[0], aw[1], aw[2], aw[3]);
+    *reinterpret_cast<float4*>(pw + 1024 + c0) = make_float4(ab[0], ab[1], ab[2], ab[3]);
   }
 }
 
@@ -356,7 +355,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_d1024_v2_kernel(const __
                                                                         const float* __restrict__ rstd,
                                                                         const __nv_bfloat16* __restrict__ dres, long long lddres,
                                                                         __nv_bfloat16* __restrict__ dx, long long lddx,
-                                                                        float* __restrict__ dw, float* __restrict__ db, int T) {
+                                                                        float* __restrict__ part, int T) {
   constexpr int R = 4;  // rows per slot and step (8 rows per CTA step)
   __shared__ float red[2][4][2 * R];
   __shared__ float tot[2][2 * R];
@@ -451,7 +450,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_d1024_v2_kernel(const __
       }
     }
   }
-  if (dw != nullptr) {  // the two row slots own the same columns: combine through shared memory, one atomic per column and CTA
+  if (part != nullptr) {  // the two row slots own the same columns: combine through shared memory, one partial row per CTA
     if (slot == 1) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -460,20 +459,26 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_d1024_v2_kernel(const __
     }
     __syncthreads();
     if (slot == 0) {
+      float* pw = part + (long long)blockIdx.x * 2048 + c0;
+      float o[16];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        atomicAdd(dw + c0 + 2 * j, aw[j].x + comb[tt][4 * j]);
-        atomicAdd(dw + c0 + 2 * j + 1, aw[j].y + comb[tt][4 * j + 1]);
-        atomicAdd(db + c0 + 2 * j, ab[j].x + comb[tt][4 * j + 2]);
-        atomicAdd(db + c0 + 2 * j + 1, ab[j].y + comb[tt][4 * j + 3]);
+        o[2 * j] = aw[j].x + comb[tt][4 * j];
+        o[2 * j + 1] = aw[j].y + comb[tt][4 * j + 1];
+        o[8 + 2 * j] = ab[j].x + comb[tt][4 * j + 2];
+        o[8 + 2 * j + 1] = ab[j].y + comb[tt][4 * j + 3];
       }
+      *reinterpret_cast<float4*>(pw) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(pw + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      *reinterpret_cast<float4*>(pw + 1024) = make_float4(o[8], o[9], o[10], o[11]);
+      *reinterpret_cast<float4*>(pw + 1028) = make_float4(o[12], o[13], o[14], o[15]);
     }
   }
 }
 
 // ------------------------------------------------------------------------------------ column sums (bias grads)
-// db[n] += sum_t dy[t, n]
-__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ dy, long long ld, float* __restrict__ db,
+// part[blockIdx.y][n] = sum over this CTA's rows of dy[t, n]   (second stage: launch_colreduce)
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ dy, long long ld, float* __restrict__ part,
                                                      int T, int N, int rows_per_cta) {
   __shared__ float red[8][256];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -497,7 +502,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
 #pragma unroll
   for (int y = 0; y < 8; ++y) s += red[y][c];
   const int gc = blockIdx.x * 256 + c;
-  if (gc < N) atomicAdd(db + gc, s);
+  if (gc < N) part[(long long)blockIdx.y * N + gc] = s;
 }
 
 // ------------------------------------------------------------------------------------ patch gather (im2col)
@@ -562,10 +567,11 @@ __global__ void __launch_bounds__(256) assemble_kernel(const __nv_bfloat16* __re
   }
 }
 
-// Backward of assemble: dtok[b,l,:] = dx[b, off+l, :] (optional);  dpos[lo,:] += sum_b dx[b,lo,:] (optional);
-// dcls[:] += sum_b dx[b,0,:] (optional).  One thread owns (lo, 8 columns) and loops over the batch.
+// Backward of assemble: dtok[b,l,:] = dx[b, off+l, :] (optional);  part[blockIdx.y][lo,:] = sum over this CTA's batch chunk of
+// dx[b,lo,:] for lo < part_rows (optional; dpos = all rows, dcls = row 0; second stage: launch_colreduce).  One thread owns
+// (lo, 8 columns) and loops over the batch chunk.
 __global__ void __launch_bounds__(256) assemble_bwd_kernel(const __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dtok,
-                                                           float* __restrict__ dpos, float* __restrict__ dcls, int B, int L, int D,
+                                                           float* __restrict__ part, int part_rows, int B, int L, int D,
                                                            int has_cls, int bchunk) {
   const int dvec = D >> 3;
   const int Lo = L + has_cls;
@@ -583,10 +589,10 @@ __global__ void __launch_bounds__(256) assemble_bwd_kernel(const __nv_bfloat16* 
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += f[j];
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (dpos) atomicAdd(dpos + (long long)lo * D + dv * 8 + j, acc[j]);
-      if (dcls && has_cls && lo == 0) atomicAdd(dcls + dv * 8 + j, acc[j]);
+    if (part != nullptr && lo < part_rows) {
+      float* pp = part + ((long long)blockIdx.y * part_rows + lo) * D + dv * 8;
+      *reinterpret_cast<float4*>(pp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(pp + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
     }
   }
 }
@@ -741,7 +747,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
 // ------------------------------------------------------------------------------------ contrastive loss: combine per-part LSEs
 __global__ void __launch_bounds__(256) lse_combine_kernel(const float* __restrict__ pm, const float* __restrict__ ps,
                                                           const float* __restrict__ diag, int M, int nparts, float* __restrict__ lse,
-                                                          float* __restrict__ loss_sum) {
+                                                          float* __restrict__ loss_part) {
   __shared__ float red[8];
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   float contrib = 0.f;
@@ -760,10 +766,10 @@ __global__ void __launch_bounds__(256) lse_combine_kernel(const float* __restric
   contrib = warp_sum(contrib);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = contrib;
   __syncthreads();
-  if (threadIdx.x == 0 && loss_sum) {
+  if (threadIdx.x == 0 && loss_part) {  // one partial per CTA; summed in CTA order by launch_colreduce
     float t = 0.f;
     for (int w = 0; w < 8; ++w) t += red[w];
-    atomicAdd(loss_sum, t);
+    loss_part[blockIdx.x] = t;
   }
 }
 
@@ -802,7 +808,7 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const long long* __res
   }
 }
 
-// out[0] += sum of g^2 over one 16384-element chunk of one gradient tensor (same tables as adamw_multi_kernel)
+// out[blockIdx.x] = sum of g^2 over one 16384-element chunk of one gradient tensor (same tables as adamw_multi_kernel)
 __global__ void __launch_bounds__(256) multi_sqnorm_kernel(const long long* __restrict__ ptrs, const long long* __restrict__ sizes,
                                                            const int2* __restrict__ chunk_tab, float* __restrict__ out) {
   const int2 ct = chunk_tab[blockIdx.x];
@@ -820,7 +826,7 @@ __global__ void __launch_bounds__(256) multi_sqnorm_kernel(const long long* __re
     float t = 0.f;
 #pragma unroll
     for (int w2 = 0; w2 < 8; ++w2) t += red[w2];
-    atomicAdd(out, t);
+    out[blockIdx.x] = t;
   }
 }
 
@@ -863,39 +869,57 @@ int vl_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, c
   VL_CHECK_ARG(T > 0 && D > 0 && D % 8 == 0 && D <= 256 * kMaxLnChunks, "vl_layernorm_bwd: D=%d unsupported", D);
   VL_CHECK_ARG(ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0 && lddres % 8 == 0, "vl_layernorm_bwd: ld must be a multiple of 8");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // Parameter gradients: every CTA writes one row of partial column sums into stream-ordered scratch memory and a second
+  // launch adds the rows in CTA order -- deterministic, no floating-point atomics, outputs need no zero fill.
+  float* part = nullptr;
+  auto finish = [&](int nparts) -> int {
+    if (part == nullptr) return 0;
+    int rc = dw ? launch_colreduce(part, nparts, D, dw, db, dres_sum, s) : launch_colreduce(part, nparts, D, dres_sum, nullptr, nullptr, s);
+    if (rc) return rc;
+    return scratch_free(part, s);
+  };
   if (D == 1024 && row_index == nullptr && dres_sum == nullptr && T >= 2048 && ldx % 4 == 0 && debug_get(13) != 1) {  // knob 13: 1 = generic kernel
     int g2 = num_sms() * 2;
     if ((long long)g2 * 8 > T) g2 = (T + 7) / 8;
+    if (dw) {
+      if (int rc = scratch_alloc(reinterpret_cast<void**>(&part), (size_t)g2 * 2048 * sizeof(float), s)) return rc;
+    }
     const bool al16 = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dres)) & 15) == 0;
     if (al16 && debug_get(14) != 1) {  // knob 14: 1 = first-generation D = 1024 kernel (four columns per thread)
       if (dres)
         layernorm_bwd_d1024_v2_kernel<true><<<g2, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(x), ldx, w,
                                                                mean, rstd, reinterpret_cast<const __nv_bfloat16*>(dres), lddres,
-                                                               reinterpret_cast<__nv_bfloat16*>(dx), lddx, dw, db, T);
+                                                               reinterpret_cast<__nv_bfloat16*>(dx), lddx, part, T);
       else
         layernorm_bwd_d1024_v2_kernel<false><<<g2, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(x), ldx,
-                                                                w, mean, rstd, nullptr, 0, reinterpret_cast<__nv_bfloat16*>(dx), lddx, dw, db, T);
-      return launch_check("layernorm_bwd_d1024_v2");
+                                                                w, mean, rstd, nullptr, 0, reinterpret_cast<__nv_bfloat16*>(dx), lddx, part, T);
+      if (int rc = launch_check("layernorm_bwd_d1024_v2")) return rc;
+      return finish(g2);
     }
     if (dres)
       layernorm_bwd_d1024_kernel<true><<<g2, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(x), ldx, w,
                                                           mean, rstd, reinterpret_cast<const __nv_bfloat16*>(dres), lddres,
-                                                          reinterpret_cast<__nv_bfloat16*>(dx), lddx, dw, db, T);
+                                                          reinterpret_cast<__nv_bfloat16*>(dx), lddx, part, T);
     else
       layernorm_bwd_d1024_kernel<false><<<g2, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(x), ldx, w,
-                                                           mean, rstd, nullptr, 0, reinterpret_cast<__nv_bfloat16*>(dx), lddx, dw, db, T);
-    return launch_check("layernorm_bwd_d1024");
+                                                           mean, rstd, nullptr, 0, reinterpret_cast<__nv_bfloat16*>(dx), lddx, part, T);
+    if (int rc = launch_check("layernorm_bwd_d1024")) return rc;
+    return finish(g2);
   }
   int grid = num_sms() * 4;
   if ((long long)grid * 8 > T) grid = (T + 7) / 8;
   const size_t smem = (dw || dres_sum) ? (size_t)8 * D * sizeof(float) : 0;
   const int ch = (D / 8 + 31) / 32;
+  const int want_w = dw ? 1 : 0, want_r = dres_sum ? 1 : 0;
+  if (want_w || want_r) {
+    if (int rc = scratch_alloc(reinterpret_cast<void**>(&part), (size_t)grid * (2 * want_w + want_r) * D * sizeof(float), s)) return rc;
+  }
 #define VL_LN_BWD2(CH, RS)                                                                                               \
   do {                                                                                                                    \
     if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_kernel<CH, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     layernorm_bwd_kernel<CH, RS><<<grid, 256, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy,                \
         reinterpret_cast<const __nv_bfloat16*>(x), ldx, (const long long*)row_index, w, mean, rstd,                       \
-        reinterpret_cast<const __nv_bfloat16*>(dres), lddres, reinterpret_cast<__nv_bfloat16*>(dx), lddx, dw, db, dres_sum, T, D); \
+        reinterpret_cast<const __nv_bfloat16*>(dres), lddres, reinterpret_cast<__nv_bfloat16*>(dx), lddx, part, want_w, want_r, T, D); \
   } while (0)
 #define VL_LN_BWD(CH)                  \
   do {                                 \
@@ -905,7 +929,8 @@ int vl_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, c
   if (ch <= 1) VL_LN_BWD(1); else if (ch <= 2) VL_LN_BWD(2); else if (ch <= 4) VL_LN_BWD(4); else VL_LN_BWD(8);
 #undef VL_LN_BWD
 #undef VL_LN_BWD2
-  return launch_check("layernorm_bwd");
+  if (int rc = launch_check("layernorm_bwd")) return rc;
+  return finish(grid);
 }
 
 int vl_colsum_bf16(const void* dy, int64_t ld, float* db, int32_t T, int32_t N, void* stream) {
@@ -915,8 +940,14 @@ int vl_colsum_bf16(const void* dy, int64_t ld, float* db, int32_t T, int32_t N, 
   if (gy > (T + 63) / 64) gy = (T + 63) / 64;
   if (gy < 1) gy = 1;
   const int rows_per = (T + gy - 1) / gy;
-  colsum_kernel<<<dim3(gx, gy), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(dy), ld, db, T, N, rows_per);
-  return launch_check("colsum");
+  gy = (T + rows_per - 1) / rows_per;  // no empty row ranges: every partial row is written
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  float* part = nullptr;
+  if (int rc = scratch_alloc(reinterpret_cast<void**>(&part), (size_t)gy * N * sizeof(float), s)) return rc;
+  colsum_kernel<<<dim3(gx, gy), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), ld, part, T, N, rows_per);
+  if (int rc = launch_check("colsum")) return rc;
+  if (int rc = launch_colreduce(part, gy, N, db, nullptr, nullptr, s)) return rc;
+  return scratch_free(part, s);
 }
 
 int vl_patchify(const void* in, int32_t in_is_bf16, void* out, int32_t B, int32_t C, int32_t OH, int32_t OW, int32_t kh, int32_t kw,
@@ -950,9 +981,31 @@ int vl_assemble_tokens_bwd(const void* dx, void* dtok, float* dpos, float* dcls,
   if (gy > B) gy = B;
   if (gy < 1) gy = 1;
   const int bchunk = (B + gy - 1) / gy;
-  assemble_bwd_kernel<<<dim3(gx, gy), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(dtok), dpos, dcls, B, L, D, has_cls ? 1 : 0, bchunk);
-  return launch_check("assemble_tokens_bwd");
+  gy = (B + bchunk - 1) / bchunk;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const bool want_cls = dcls != nullptr && has_cls;
+  const int part_rows = dpos ? L + (has_cls ? 1 : 0) : (want_cls ? 1 : 0);  // dcls is row 0 of the same sums
+  float* part = nullptr;
+  if (part_rows > 0) {
+    if (int rc = scratch_alloc(reinterpret_cast<void**>(&part), (size_t)gy * part_rows * D * sizeof(float), s)) return rc;
+  }
+  assemble_bwd_kernel<<<dim3(gx, gy), 256, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(dtok), part, part_rows, B, L, D, has_cls ? 1 : 0, bchunk);
+  if (int rc = launch_check("assemble_tokens_bwd")) return rc;
+  if (part != nullptr) {
+    if (dpos) {
+      if (int rc = launch_colreduce(part, gy, (long long)part_rows * D, dpos, nullptr, nullptr, s)) return rc;
+    }
+    if (want_cls) {
+      if (dpos) {
+        VL_CUDA(cudaMemcpyAsync(dcls, dpos, (size_t)D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      } else {
+        if (int rc = launch_colreduce(part, gy, D, dcls, nullptr, nullptr, s)) return rc;
+      }
+    }
+    return scratch_free(part, s);
+  }
+  return 0;
 }
 
 int vl_embed_tokens(const int64_t* ids, const float* table, const float* pos, void* out, int64_t rows, int32_t ctx, int32_t D, void* stream) {
@@ -1019,8 +1072,17 @@ int vl_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float
 int vl_lse_combine(const float* part_max, const float* part_sum, const float* diag, int32_t M, int32_t nparts, float* lse,
                    float* loss_sum, void* stream) {
   VL_CHECK_ARG(part_max && part_sum && diag && lse && M > 0 && nparts > 0, "vl_lse_combine: bad arguments");
-  lse_combine_kernel<<<(M + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(part_max, part_sum, diag, M, nparts, lse, loss_sum);
-  return launch_check("lse_combine");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int g = (M + 255) / 256;
+  float* part = nullptr;
+  if (loss_sum) {
+    if (int rc = scratch_alloc(reinterpret_cast<void**>(&part), (size_t)g * sizeof(float), s)) return rc;
+  }
+  lse_combine_kernel<<<g, 256, 0, s>>>(part_max, part_sum, diag, M, nparts, lse, part);
+  if (int rc = launch_check("lse_combine")) return rc;
+  if (part == nullptr) return 0;
+  if (int rc = launch_colreduce(part, g, 1, loss_sum, nullptr, nullptr, s)) return rc;
+  return scratch_free(part, s);
 }
 
 int vl_adamw_multi(const int64_t* ptrs, const int64_t* sizes, const float* wds, const int32_t* chunk_tab, int32_t n_chunks, float lr,
@@ -1035,9 +1097,13 @@ int vl_adamw_multi(const int64_t* ptrs, const int64_t* sizes, const float* wds, 
 
 int vl_multi_sqnorm(const int64_t* ptrs, const int64_t* sizes, const int32_t* chunk_tab, int32_t n_chunks, float* sumsq, void* stream) {
   VL_CHECK_ARG(ptrs && sizes && chunk_tab && sumsq && n_chunks > 0, "vl_multi_sqnorm: bad arguments");
-  multi_sqnorm_kernel<<<n_chunks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const long long*)ptrs, (const long long*)sizes,
-                                                                                      reinterpret_cast<const int2*>(chunk_tab), sumsq);
-  return launch_check("multi_sqnorm");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  float* part = nullptr;
+  if (int rc = scratch_alloc(reinterpret_cast<void**>(&part), (size_t)n_chunks * sizeof(float), s)) return rc;
+  multi_sqnorm_kernel<<<n_chunks, 256, 0, s>>>((const long long*)ptrs, (const long long*)sizes, reinterpret_cast<const int2*>(chunk_tab), part);
+  if (int rc = launch_check("multi_sqnorm")) return rc;
+  if (int rc = launch_colreduce(part, n_chunks, 1, sumsq, nullptr, nullptr, s)) return rc;
+  return scratch_free(part, s);
 }
 
 int vl_adamw_multi_clip(const int64_t* ptrs, const int64_t* sizes, const float* wds, const int32_t* chunk_tab, int32_t n_chunks, float lr,

@@ -42,7 +42,9 @@ struct GemmParams {
   const float* alpha_dev;
   const float* fparam_dev;
   int aux_row_div, relu;
-  float* rowsum_out;  // fp32 [M] or null: += row sums of A over this tile's K range (bias gradient of a weight-gradient GEMM)
+  int loss_flags;
+  float* rowsum_out;  // fp32 [tiles_n * split_k][M] partial row sums of A (one row per (n-tile, split); launch_colreduce adds them in
+                      // order -> the bias gradient of a weight-gradient GEMM), or null
   int dbg;  // bring-up knob 9: 1 skip epilogue, 2 no global traffic in the epilogue, 4 sleeping epilogue waits, 8 MMA ignores full barriers
   uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;  // bytes
 };
@@ -100,7 +102,7 @@ struct KernelCfg {
 // n_blk; thread t owns row quarter*32 + t and processes it 32 accumulator columns at a time.
 template <int BN, int CW>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_base, uint32_t acc_col, int row_base, int n_blk, int ks,
-                                              int e, int quarter, int lane) {
+                                              int e, int quarter, int lane, int part_idx) {
   const int slice = e >> 2;
   const float alpha_eff = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f);
   const float fparam_eff = p.fparam * (p.fparam_dev ? __ldg(p.fparam_dev) : 1.0f);
@@ -183,10 +185,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
         float gval = 0.f;
         if (row_ok && col0 + j < p.N) {
           gval = __expf(z - rl);
+          const bool on_diag = col0 + j == row + p.iparam;
+          const float grow = gval - (on_diag ? 1.f : 0.f);  // this row's own cross-entropy term
           if (p.col_vec) gval += __expf(z - __ldg(p.col_vec + col0 + j));
-          if (col0 + j == row + p.iparam) gval -= p.col_vec ? 2.f : 1.f;
+          if (on_diag) gval -= p.col_vec ? 2.f : 1.f;
           gval *= fparam_eff;
-          dsum += gval * accv;
+          dsum += ((p.loss_flags & 1) ? grow * fparam_eff : gval) * accv;
         }
         f[j] = gval;
       }
@@ -277,7 +281,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
   if (p.epi == VL_EPI_CLIPGRAD && p.scalar_out != nullptr) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) clip_ds += __shfl_xor_sync(0xffffffffu, clip_ds, o);
-    if (lane == 0) atomicAdd(p.scalar_out, clip_ds);
+    if (lane == 0) p.scalar_out[part_idx] = clip_ds;  // one partial per (tile, epilogue warp); summed in order by launch_colreduce
   }
 }
 
@@ -635,7 +639,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (!released) release();
       } else {
-        if (!(p.dbg & 1)) epilogue_tile<BN, EpiCfg<BN>::kChunk>(p, tmem_base, acc * BN, row_base, n_blk, ks, e, quarter, lane);
+        if (!(p.dbg & 1)) epilogue_tile<BN, EpiCfg<BN>::kChunk>(p, tmem_base, acc * BN, row_base, n_blk, ks, e, quarter, lane, t * kEpiWarps + e);
         release();  // accumulator drained -> hand the TMEM buffer back to the MMA warp
       }
       if (++acc == 2) {
@@ -725,6 +729,7 @@ static int launch_gemm(const VlGemmArgs& a, cudaStream_t stream) {
   p.aux_row_div = a.aux_row_div > 1 ? a.aux_row_div : 1;
   p.relu = a.relu;
   p.rowsum_out = a.rowsum_out;
+  p.loss_flags = a.loss_flags;
   p.dbg = debug_get(9);
   // K-major: 8-row groups 1024 B apart, +32 B per UMMA_K inside the swizzle row.
   // MN-major: 64-wide chunks kBK*128 B apart (LBO), 8-K groups 1024 B apart (SBO), +2048 B per UMMA_K.
@@ -794,8 +799,20 @@ static int launch_gemm(const VlGemmArgs& a, cudaStream_t stream) {
     VL_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
+  // d(loss)/d(alpha) of the CLIPGRAD epilogue: one partial per (tile, epilogue warp), added in order afterwards (deterministic)
+  float* ds_part = nullptr;
+  const int ds_n = total * KernelCfg<BN, 0>::kEpiWarps;
+  if (a.epilogue == VL_EPI_CLIPGRAD && a.scalar_out != nullptr) {
+    if ((rc = scratch_alloc(reinterpret_cast<void**>(&ds_part), (size_t)ds_n * sizeof(float), stream))) return rc;
+    p.scalar_out = ds_part;
+  }
   gemm_bf16_kernel<BN, 0><<<grid, KernelCfg<BN, 0>::kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmA, tmA, p);
-  return launch_check("gemm_bf16_kernel");
+  if ((rc = launch_check("gemm_bf16_kernel"))) return rc;
+  if (ds_part != nullptr) {
+    if ((rc = launch_colreduce(ds_part, ds_n, 1, a.scalar_out, nullptr, nullptr, stream))) return rc;
+    return scratch_free(ds_part, stream);
+  }
+  return 0;
 }
 
 
@@ -1069,15 +1086,18 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         if (!released) release();
       } else {
-        if (!(p.dbg & 1)) epilogue_tile<BN, EpiCfg<BN>::kChunk>(p, tmem_base, acc * BN, row_base, n_blk, ks, e, quarter, lane);
+        if (!(p.dbg & 1)) epilogue_tile<BN, EpiCfg<BN>::kChunk>(p, tmem_base, acc * BN, row_base, n_blk, ks, e, quarter, lane, t * kEpiWarps + e);
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         const int kb_first = kb0 + ((n_blk - kb0) % p.tiles_n + p.tiles_n) % p.tiles_n;  // first k-block this tile summed
-        if (rs && kb_first < kb1 && (e >> 2) == 0) {  // one warp per lane quarter adds this tile's partial row sums of A
+        if (rs && (e >> 2) == 0) {  // one warp per lane quarter stores this tile's partial row sums of A (0 if it summed no k-block)
           uint32_t v[16];
-          tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + BN, v);
-          tc_wait_ld();
+          v[0] = 0u;
+          if (kb_first < kb1) {
+            tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + BN, v);
+            tc_wait_ld();
+          }
           const int row = row_base + quarter * 32 + lane;
-          if (row < p.M) atomicAdd(p.rowsum_out + row, __uint_as_float(v[0]));
+          if (row < p.M) p.rowsum_out[static_cast<long long>(n_blk * p.split_k + ks) * p.M + row] = __uint_as_float(v[0]);
         }
         release();  // accumulator drained -> hand the TMEM buffer back to the MMA warp
       }
@@ -1151,8 +1171,20 @@ static int launch_gemm2(const VlGemmArgs& a, GemmParams p, cudaStream_t stream) 
     VL_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<BN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
+  // row sums of A (bias gradient): one partial row per (n-tile, split), added in order afterwards (deterministic)
+  float* rs_part = nullptr;
+  const int rs_n = p.tiles_n * p.split_k;
+  if (a.rowsum_out != nullptr) {
+    if ((rc = scratch_alloc(reinterpret_cast<void**>(&rs_part), (size_t)rs_n * a.M * sizeof(float), stream))) return rc;
+    p.rowsum_out = rs_part;
+  }
   gemm2_bf16_kernel<BN, 0><<<2 * clusters, KernelCfg<BN, 0>::kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmA, tmA, p);
-  return launch_check("gemm2_bf16_kernel");
+  if ((rc = launch_check("gemm2_bf16_kernel"))) return rc;
+  if (rs_part != nullptr) {
+    if ((rc = launch_colreduce(rs_part, rs_n, a.M, a.rowsum_out, nullptr, nullptr, stream))) return rc;
+    return scratch_free(rs_part, stream);
+  }
+  return 0;
 }
 
 }  // namespace vl

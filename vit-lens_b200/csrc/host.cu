@@ -84,6 +84,70 @@ int make_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const void*
   return 0;
 }
 
+int scratch_alloc(void** p, size_t bytes, cudaStream_t s) {
+  static bool pool_set[64] = {false};
+  int dev = 0;
+  VL_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !pool_set[dev]) {
+    cudaMemPool_t pool;
+    VL_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    unsigned long long keep = ~0ull;
+    VL_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    pool_set[dev] = true;
+  }
+  VL_CUDA(cudaMallocAsync(p, bytes, s));
+  return 0;
+}
+
+int scratch_free(void* p, cudaStream_t s) {
+  VL_CUDA(cudaFreeAsync(p, s));
+  return 0;
+}
+
+// CB = 32: 32 columns x 8 part slices per CTA (slice y sums parts y, y + 8, ...; the eight slice sums are then added in slice
+// order).  CB = 1: a handful of columns with many parts (scalars): 256 part slices per column, fixed-shape tree over the slices.
+template <int CB>
+__global__ void __launch_bounds__(256) colreduce_kernel(const float* __restrict__ part, int nparts, long long ncols, long long n_each,
+                                                        float* __restrict__ out0, float* __restrict__ out1, float* __restrict__ out2) {
+  __shared__ float red[256];
+  constexpr int kSlices = 256 / CB;
+  const int tx = threadIdx.x % CB, ty = threadIdx.x / CB;
+  const long long col = (long long)blockIdx.x * CB + tx;
+  float acc = 0.f;
+  if (col < ncols)
+    for (int p = ty; p < nparts; p += kSlices) acc += part[(long long)p * ncols + col];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if constexpr (CB == 1) {
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    acc = red[0];
+  } else {
+    if (ty == 0) {
+      acc = 0.f;
+#pragma unroll
+      for (int y = 0; y < kSlices; ++y) acc += red[y * CB + tx];
+    }
+  }
+  if (ty == 0 && col < ncols) {
+    const long long k = col / n_each, c = col - k * n_each;
+    float* out = k == 0 ? out0 : (k == 1 ? out1 : out2);
+    out[c] = acc;
+  }
+}
+
+int launch_colreduce(const float* part, int nparts, long long n_each, float* out0, float* out1, float* out2, cudaStream_t s) {
+  const int nout = 1 + (out1 != nullptr) + (out2 != nullptr);
+  const long long ncols = n_each * nout;
+  if (ncols < 32)
+    colreduce_kernel<1><<<(unsigned)ncols, 256, 0, s>>>(part, nparts, ncols, n_each, out0, out1, out2);
+  else
+    colreduce_kernel<32><<<(unsigned)((ncols + 31) / 32), 256, 0, s>>>(part, nparts, ncols, n_each, out0, out1, out2);
+  return launch_check("colreduce");
+}
+
 }  // namespace vl
 
 extern "C" {

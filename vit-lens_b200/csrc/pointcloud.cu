@@ -269,9 +269,10 @@ __global__ void __launch_bounds__(256) group_sum_kernel(const __nv_bfloat16* __r
   }
 }
 
-// s1[n] += sum_t a[t,n];  s2[n] += sum_t a[t,n] * b[t,n]   (BatchNorm / bias gradients behind a ReLU)
-__global__ void __launch_bounds__(256) colsum2_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, float* __restrict__ s1,
-                                                      float* __restrict__ s2, long long T, int N, long long rows_per_cta) {
+// part[blockIdx.y][0][n] = sum_t a[t,n], part[blockIdx.y][1][n] = sum_t a[t,n] * b[t,n] over this CTA's rows (BatchNorm / bias
+// gradients behind a ReLU; second stage: launch_colreduce)
+__global__ void __launch_bounds__(256) colsum2_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, float* __restrict__ part,
+                                                      long long T, int N, long long rows_per_cta) {
   __shared__ float red[2][8][256];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = (blockIdx.x * 32 + tx) * 8;
@@ -306,13 +307,14 @@ __global__ void __launch_bounds__(256) colsum2_kernel(const __nv_bfloat16* __res
   }
   const int gc = blockIdx.x * 256 + c;
   if (gc < N) {
-    atomicAdd(s1 + gc, v1);
-    atomicAdd(s2 + gc, v2);
+    float* pp = part + static_cast<long long>(blockIdx.y) * 2 * N;
+    pp[gc] = v1;
+    pp[N + gc] = v2;
   }
 }
 
-// dw[c, j] += sum_r dy[r, c] * x[r, j]   (weight gradient of a 3-input linear layer)
-__global__ void __launch_bounds__(256) wgrad3_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw, long long R,
+// part[blockIdx.y][c, j] = sum over this CTA's rows of dy[r, c] * x[r, j]   (weight gradient of a 3-input linear layer)
+__global__ void __launch_bounds__(256) wgrad3_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, float* __restrict__ part, long long R,
                                                      int C, long long rows_per_cta) {
   // thread = one channel (blockIdx.x * 256 + tid), loops over the CTA's row range
   const int c = blockIdx.x * 256 + threadIdx.x;
@@ -326,16 +328,18 @@ __global__ void __launch_bounds__(256) wgrad3_kernel(const __nv_bfloat16* __rest
     a1 = fmaf(g, __ldg(x + 3 * r + 1), a1);
     a2 = fmaf(g, __ldg(x + 3 * r + 2), a2);
   }
-  atomicAdd(dw + 3 * c, a0);
-  atomicAdd(dw + 3 * c + 1, a1);
-  atomicAdd(dw + 3 * c + 2, a2);
+  float* dw = part + static_cast<long long>(blockIdx.y) * 3 * C;
+  dw[3 * c] = a0;
+  dw[3 * c + 1] = a1;
+  dw[3 * c + 2] = a2;
 }
 
 
-// out[0..2] += sum_r x[r, :],  out[3 + 3 i + j] += sum_r x[r, i] * x[r, j]   (x: [R, 3] fp32)
+// part[blockIdx.x][0..2] = sum_r x[r, :],  part[blockIdx.x][3 + 3 i + j] = sum_r x[r, i] * x[r, j]   (x: [R, 3] fp32, this CTA's rows)
 // First and second moments of the centre-normalised neighbourhood points: first_conv.0 is linear in them, so the batch
 // statistics of its 128 outputs (BatchNorm in training mode, dvae.py:185-188) follow in closed form from these 12 numbers.
-__global__ void __launch_bounds__(256) moments3_kernel(const float* __restrict__ x, float* __restrict__ out, long long R) {
+__global__ void __launch_bounds__(256) moments3_kernel(const float* __restrict__ x, float* __restrict__ part, long long R) {
+  float* out = part + static_cast<long long>(blockIdx.x) * 12;
   float s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // x y z xx xy xz yy yz zz
   for (long long r = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; r < R; r += static_cast<long long>(gridDim.x) * 256) {
     const float a = x[3 * r], b = x[3 * r + 1], c = x[3 * r + 2];
@@ -362,12 +366,12 @@ __global__ void __launch_bounds__(256) moments3_kernel(const float* __restrict__
     // x y z | xx xy xz | xy yy yz | xz yz zz
     const int e = threadIdx.x;
     if (e < 3) {
-      atomicAdd(out + e, v);
+      out[e] = v;
     } else {
       const int ij[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
       const int i = ij[e - 3][0], j = ij[e - 3][1];
-      atomicAdd(out + 3 + 3 * i + j, v);
-      if (i != j) atomicAdd(out + 3 + 3 * j + i, v);
+      out[3 + 3 * i + j] = v;
+      if (i != j) out[3 + 3 * j + i] = v;
     }
   }
 }
@@ -478,9 +482,14 @@ int vl_colsum2_bf16(const void* a, const void* b, float* s1, float* s2, int64_t 
   if (gy > (T + 63) / 64) gy = (T + 63) / 64;
   if (gy < 1) gy = 1;
   const long long rows_per = (T + gy - 1) / gy;
-  colsum2_kernel<<<dim3(gx, (unsigned)gy), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(b), s1, s2, T, N, rows_per);
-  return launch_check("colsum2");
+  gy = (T + rows_per - 1) / rows_per;  // no empty row ranges: every partial row is written
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  float* part = nullptr;
+  if (int rc = scratch_alloc(reinterpret_cast<void**>(&part), (size_t)gy * 2 * N * sizeof(float), s)) return rc;
+  colsum2_kernel<<<dim3(gx, (unsigned)gy), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(b), part, T, N, rows_per);
+  if (int rc = launch_check("colsum2")) return rc;
+  if (int rc = launch_colreduce(part, (int)gy, N, s1, s2, nullptr, s)) return rc;
+  return scratch_free(part, s);
 }
 
 int vl_wgrad3(const void* dy, const float* x, float* dw, int64_t R, int32_t C, void* stream) {
@@ -490,8 +499,14 @@ int vl_wgrad3(const void* dy, const float* x, float* dw, int64_t R, int32_t C, v
   if (gy > (R + 255) / 256) gy = (R + 255) / 256;
   if (gy < 1) gy = 1;
   const long long rows_per = (R + gy - 1) / gy;
-  wgrad3_kernel<<<dim3(gx, (unsigned)gy), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(dy), x, dw, R, C, rows_per);
-  return launch_check("wgrad3");
+  gy = (R + rows_per - 1) / rows_per;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  float* part = nullptr;
+  if (int rc = scratch_alloc(reinterpret_cast<void**>(&part), (size_t)gy * 3 * C * sizeof(float), s)) return rc;
+  wgrad3_kernel<<<dim3(gx, (unsigned)gy), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), x, part, R, C, rows_per);
+  if (int rc = launch_check("wgrad3")) return rc;
+  if (int rc = launch_colreduce(part, (int)gy, 3ll * C, dw, nullptr, nullptr, s)) return rc;
+  return scratch_free(part, s);
 }
 
 int vl_moments3(const float* x, float* out12, int64_t R, void* stream) {
@@ -499,8 +514,13 @@ int vl_moments3(const float* x, float* out12, int64_t R, void* stream) {
   long long g = (R + 255) / 256;
   const long long cap = static_cast<long long>(num_sms()) * 4;
   if (g > cap) g = cap;
-  moments3_kernel<<<(unsigned)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, out12, R);
-  return launch_check("moments3");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  float* part = nullptr;
+  if (int rc = scratch_alloc(reinterpret_cast<void**>(&part), (size_t)g * 12 * sizeof(float), s)) return rc;
+  moments3_kernel<<<(unsigned)g, 256, 0, s>>>(x, part, R);
+  if (int rc = launch_check("moments3")) return rc;
+  if (int rc = launch_colreduce(part, (int)g, 12, out12, nullptr, nullptr, s)) return rc;
+  return scratch_free(part, s);
 }
 
 int vl_col_affine_bf16(const void* a, const void* b, const float* p0, const float* p1, const float* p2, void* out, int64_t R, int32_t C,

@@ -46,6 +46,18 @@ inline int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner,
     }                                                                           \
   } while (0)
 
+// Stream-ordered scratch memory for the per-CTA partial results of the deterministic reductions below: cudaMallocAsync /
+// cudaFreeAsync on the device's default memory pool (release threshold raised once so blocks are recycled instead of handed
+// back to the driver).  Ordered on `s` like the kernels that use it, so concurrent callers on different streams never share a
+// buffer.
+int scratch_alloc(void** p, size_t bytes, cudaStream_t s);
+int scratch_free(void* p, cudaStream_t s);
+// Second stage of every cross-CTA reduction on the path (LayerNorm / bias / BatchNorm parameter gradients, loss sums, gradient
+// norms): out_k[c] = sum over p = 0 .. nparts-1, IN THAT ORDER, of part[p * (nout * n_each) + k * n_each + c].  First stages
+// write one partial row per CTA with plain stores; results are bit-identical from run to run (no floating-point atomics) and
+// the outputs need no zero fill.
+int launch_colreduce(const float* part, int nparts, long long n_each, float* out0, float* out1, float* out2, cudaStream_t s);
+
 // attention_bwd2.cu
 int launch_attn_bwd2(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, void* dq, void* dk, void* dv,
                      int B, int H, int nq, int nk, long long ldq, long long ldk, long long ldv, long long ldo, long long lddo, long long lddq,

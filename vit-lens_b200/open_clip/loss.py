@@ -92,7 +92,7 @@ class _ContrastiveBase(nn.Module):
         off = self.rank * Bl
         if self.local_loss:
             col = bool(self.gather_with_grad)
-            return E.ContrastiveFn.apply(x, y, all_x, all_y, logit_scale, off, Bl, Bl, col, self._gather_vec if col else None, None)
+            return E.ContrastiveFn.apply(x, y, all_x, all_y, logit_scale, off, Bl, Bl, col, self._gather_vec if col else None, None, col)
         # full-matrix loss on every rank in the reference: value / d(scale) need cross-rank sums
         grad_rows = Bl if self.gather_with_grad else Bg
 

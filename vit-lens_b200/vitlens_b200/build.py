@@ -47,10 +47,25 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False) -> str:
+    """Compile (if stale) under an exclusive file lock: every rank of a torchrun launch may call this at the same moment; one
+    builds, the others wait and then find the library up to date."""
+    import fcntl
+
     if not force and not needs_build():
         return LIB_PATH
-    nvcc = _nvcc()
     os.makedirs(OBJ_DIR, exist_ok=True)
+    with open(os.path.join(OBJ_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():  # another process built it while this one waited
+                return LIB_PATH
+            return _build_locked(force, verbose, ptxas_v)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool, ptxas_v: bool) -> str:
+    nvcc = _nvcc()
     hdr_m = max(os.path.getmtime(os.path.join(r, f))
                 for r in (CSRC, os.path.join(os.path.dirname(os.path.dirname(HERE)), "include"))
                 for f in os.listdir(r) if f.endswith((".cuh", ".h")))
@@ -74,10 +89,12 @@ def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False) -> 
             if log:
                 print(log, file=sys.stderr)
     # static cudart: the .so must load (and export its symbols) on a box without a GPU / libcuda
-    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-cudart", "static", "-Xcompiler", "-fPIC"]
+    tmp = LIB_PATH + f".tmp{os.getpid()}"  # link beside the target and rename: a concurrent loader never maps a half-written file
+    cmd = [nvcc, "-shared", "-o", tmp, *objs, "-cudart", "static", "-Xcompiler", "-fPIC"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
 

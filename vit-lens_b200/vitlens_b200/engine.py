@@ -466,10 +466,11 @@ class ContrastiveFn(torch.autograd.Function):
     of the opposite direction from all ranks: `gather_lse` all-gathers a [B_loc] vector when
     world_size > 1.  col_term=False is the `local_loss=True, gather_with_grad=False` gradient.
     `ds_post` post-processes d(loss)/d(scale) (cross-rank sum where the reference computes the
-    full matrix on every rank)."""
+    full matrix on every rank).  `ds_rows_only` (local_loss + gather_with_grad): the column term of g carries the OTHER
+    ranks' losses (it is what all_gather's backward sends home), so d(this rank's loss)/d(scale) sums the row term alone."""
 
     @staticmethod
-    def forward(ctx, x, y, all_x, all_y, scale, label_off, val_rows, grad_rows, col_term, gather_lse, ds_post):
+    def forward(ctx, x, y, all_x, all_y, scale, label_off, val_rows, grad_rows, col_term, gather_lse, ds_post, ds_rows_only=False):
         x16, y16 = _ops.cast_bf16(x.detach()), _ops.cast_bf16(y.detach())
         ax16 = x16 if all_x is None else _ops.cast_bf16(all_x.detach())
         ay16 = y16 if all_y is None else _ops.cast_bf16(all_y.detach())
@@ -483,27 +484,29 @@ class ContrastiveFn(torch.autograd.Function):
             col_x = gather_lse(lse_y) if gather_lse is not None else lse_y  # columns of the x-direction = rows of the y-direction
             col_y = gather_lse(lse_x) if gather_lse is not None else lse_x
         ctx.save_for_backward(x16, y16, ax16, ay16, lse_x, lse_y, col_x, col_y, s)
-        ctx.cfg = (label_off, grad_rows, col_term, ds_post)
+        ctx.cfg = (label_off, grad_rows, col_term, ds_post, ds_rows_only)
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, dloss):
         x16, y16, ax16, ay16, lse_x, lse_y, col_x, col_y, s = ctx.saved_tensors
-        label_off, grad_rows, col_term, ds_post = ctx.cfg
+        label_off, grad_rows, col_term, ds_post, ds_rows_only = ctx.cfg
         gs = 1.0 / (2.0 * grad_rows)
         dl = dloss.detach().float().reshape(1).contiguous()  # upstream gradient stays on the device too
-        gx, ds_x = _ops.clipgrad(x16, ay16, alpha=s, row_lse=lse_x, col_lse=col_x if col_term else None, label_off=label_off, gscale=gs, gscale_dev=dl)
-        gy, ds_y = _ops.clipgrad(y16, ax16, alpha=s, row_lse=lse_y, col_lse=col_y if col_term else None, label_off=label_off, gscale=gs, gscale_dev=dl)
+        gx, ds_x = _ops.clipgrad(x16, ay16, alpha=s, row_lse=lse_x, col_lse=col_x if col_term else None, label_off=label_off, gscale=gs, gscale_dev=dl,
+                                 ds_row_only=ds_rows_only)
+        gy, ds_y = _ops.clipgrad(y16, ax16, alpha=s, row_lse=lse_y, col_lse=col_y if col_term else None, label_off=label_off, gscale=gs, gscale_dev=dl,
+                                 ds_row_only=ds_rows_only)
         dx = _ops.gemm(gx, ay16, b_t=True, out_dtype=F32, alpha_dev=s) if _need(ctx, 0) else None
         dy = _ops.gemm(gy, ax16, b_t=True, out_dtype=F32, alpha_dev=s) if _need(ctx, 1) else None
         dscale = None
         if _need(ctx, 4):
             # with the column term every logit's gradient appears in both directions
-            dscale = (ds_x + ds_y) * (0.5 if col_term else 1.0)
+            dscale = (ds_x + ds_y) * (0.5 if (col_term and not ds_rows_only) else 1.0)
             if ds_post is not None:
                 dscale = ds_post(dscale)
             dscale = dscale.reshape(())
-        return dx, dy, None, None, dscale, None, None, None, None, None, None
+        return dx, dy, None, None, dscale, None, None, None, None, None, None, None
 
 
 class AddFn(torch.autograd.Function):

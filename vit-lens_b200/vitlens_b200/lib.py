@@ -49,10 +49,12 @@ class GemmArgs(C.Structure):
         ("row_vec", C.c_void_p), ("col_vec", C.c_void_p), ("out_vec0", C.c_void_p), ("out_vec1", C.c_void_p),
         ("out_vec2", C.c_void_p), ("scalar_out", C.c_void_p), ("iparam", C.c_int32), ("fparam", C.c_float),
         ("alpha_dev", C.c_void_p), ("fparam_dev", C.c_void_p), ("aux_row_div", C.c_int32), ("relu", C.c_int32), ("rowsum_out", C.c_void_p),
+        ("loss_flags", C.c_int32),
     ]
 
 
 EPI_LINEAR, EPI_GELU, EPI_RESIDUAL, EPI_GELU_BWD, EPI_GEGLU, EPI_ROWLSE, EPI_CLIPGRAD = 0, 1, 2, 3, 4, 5, 6
+ABI_VERSION = 2  # include/vitlens_b200.h: VL_ABI_VERSION
 
 
 def lib_path() -> str:
@@ -70,14 +72,19 @@ def load(build_if_missing: bool = True):
         if build_if_missing and not os.environ.get("VL_LIB_PATH") and _build.needs_build():
             try:
                 _build.build()
-            except Exception as e:  # stale .so is still better than nothing only if it exists
-                if not os.path.exists(path):
-                    raise VlError(f"libvitlens_b200.so is missing and could not be built: {e}") from e
+            except Exception as e:
+                # A box without nvcc (the GPU box ships the prebuilt .so whose mtime the snapshot may have reordered) can still
+                # run an existing library -- the ABI check below rejects one that does not match this binding.  A compile
+                # ERROR with nvcc present is never swallowed: the sources and the library would disagree.
+                if not os.path.exists(path) or "nvcc not found" not in str(e):
+                    raise VlError(f"libvitlens_b200.so is stale or missing and could not be built: {e}") from e
         if not os.path.exists(path):
             raise VlError(f"{path} not found: run `python __graft_entry__.py` (build()) first; there is no fallback path")
         lib = C.CDLL(path)
         lib.vl_last_error.restype = C.c_char_p
         lib.vl_abi_version.restype = C.c_int
+        if lib.vl_abi_version() != ABI_VERSION:
+            raise VlError(f"{path} implements ABI {lib.vl_abi_version()}, this binding needs {ABI_VERSION}: rebuild (python __graft_entry__.py)")
         _lib = lib
         # bring-up knobs for A/B runs (kernel variants; see vl_debug_set call sites in csrc/): VL_DEBUG="13=1,12=1"
         for kv in os.environ.get("VL_DEBUG", "").split(","):
@@ -113,7 +120,7 @@ def _count():
 def gemm(a, b, d, *, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, epilogue=EPI_LINEAR, bias=None,
          aux_in=None, aux_out=None, ldaux=0, alpha=1.0, accumulate=False, split_k=1, act_quick=False,
          row_vec=None, col_vec=None, out_vec0=None, out_vec1=None, out_vec2=None, scalar_out=None, iparam=0, fparam=0.0,
-         alpha_dev=None, fparam_dev=None, aux_row_div=0, relu=False, rowsum_out=None):
+         alpha_dev=None, fparam_dev=None, aux_row_div=0, relu=False, rowsum_out=None, loss_flags=0):
     """Raw GEMM call; see include/vitlens_b200.h.  a, b bf16; d bf16 or fp32; bias fp32."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     assert d is None or d.dtype in (torch.bfloat16, torch.float32)
@@ -123,7 +130,7 @@ def gemm(a, b, d, *, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, epilogue=EP
         int(d is not None and d.dtype == torch.float32), int(accumulate), int(split_k), int(epilogue), int(act_quick), float(alpha),
         _ptr(bias), _ptr(aux_in), _ptr(aux_out), ldaux,
         _ptr(row_vec), _ptr(col_vec), _ptr(out_vec0), _ptr(out_vec1), _ptr(out_vec2), _ptr(scalar_out), int(iparam), float(fparam),
-        _ptr(alpha_dev), _ptr(fparam_dev), int(aux_row_div), int(relu), _ptr(rowsum_out))
+        _ptr(alpha_dev), _ptr(fparam_dev), int(aux_row_div), int(relu), _ptr(rowsum_out), int(loss_flags))
     _count()
     if CALL_TIMING is not None:
         kind = "wgrad" if (a_mn and b_mn) else ("dgrad" if b_mn else "fwd")

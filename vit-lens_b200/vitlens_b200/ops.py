@@ -81,7 +81,7 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, epilogue=EPI_LINEAR, aux_in=N
     rowsum = None
     if want_rowsum:
         assert rowsum_fusable(M, N) and out.dtype == F32 and epilogue == EPI_LINEAR and not want_aux_out
-        rowsum = torch.zeros((M,), device=a.device, dtype=F32)
+        rowsum = torch.empty((M,), device=a.device, dtype=F32)
     L.gemm(a, b, out, M=M, N=N, K=K, lda=_ld(a), ldb=_ld(b), ldd=_ld(out), a_mn=a_t, b_mn=b_t, epilogue=epilogue, bias=bias,
            aux_in=aux_in, aux_out=aux_out, ldaux=ldaux, alpha=alpha, accumulate=accumulate, split_k=split_k, act_quick=act_quick,
            alpha_dev=alpha_dev, rowsum_out=rowsum)
@@ -128,11 +128,12 @@ def layernorm_bwd(dy, x, w, mean, rstd, *, dres=None, row_index=None, want_wgrad
         dx = torch.empty((x.shape[0], D), device=x.device, dtype=BF16)
     else:
         dx = torch.zeros((x.shape[0], D), device=x.device, dtype=BF16)
-    dw = torch.zeros((D,), device=x.device, dtype=F32) if want_wgrad else None
-    db = torch.zeros((D,), device=x.device, dtype=F32) if want_wgrad else None
+    # parameter-gradient outputs are written (not accumulated) by a deterministic two-stage reduction: no zero fill
+    dw = torch.empty((D,), device=x.device, dtype=F32) if want_wgrad else None
+    db = torch.empty((D,), device=x.device, dtype=F32) if want_wgrad else None
     if dres is not None:
         _v2(dres, BF16)
-    rsum = torch.zeros((D,), device=x.device, dtype=F32) if want_dres_sum else None
+    rsum = torch.empty((D,), device=x.device, dtype=F32) if want_dres_sum else None
     L.layernorm_bwd(dy, x, w, mean, rstd, dx, dw, db, T=T, D=D, lddy=_ld(dy), ldx=_ld(x), lddx=D, dres=dres,
                     lddres=_ld(dres) if dres is not None else 0, row_index=row_index, dres_sum=rsum)
     return (dx, dw, db, rsum) if want_dres_sum else (dx, dw, db)
@@ -141,7 +142,7 @@ def layernorm_bwd(dy, x, w, mean, rstd, *, dres=None, row_index=None, want_wgrad
 def colsum(dy):
     _v2(dy, BF16)
     T, N = dy.shape
-    db = torch.zeros((N,), device=dy.device, dtype=F32)
+    db = torch.empty((N,), device=dy.device, dtype=F32)
     L.colsum(dy, db, T=T, N=N, ld=_ld(dy))
     return db
 
@@ -163,8 +164,8 @@ def assemble_tokens(tok, cls, pos, *, B, L_, D):
 def assemble_tokens_bwd(dx, *, B, L_, D, has_cls, want_tok=True, want_pos=True, want_cls=True):
     dev = dx.device
     dtok = torch.empty((B * L_, D), device=dev, dtype=BF16) if want_tok else None
-    dpos = torch.zeros((L_ + int(has_cls), D), device=dev, dtype=F32) if want_pos else None
-    dcls = torch.zeros((D,), device=dev, dtype=F32) if (want_cls and has_cls) else None
+    dpos = torch.empty((L_ + int(has_cls), D), device=dev, dtype=F32) if want_pos else None
+    dcls = torch.empty((D,), device=dev, dtype=F32) if (want_cls and has_cls) else None
     L.assemble_tokens_bwd(dx, dtok, dpos, dcls, B=B, L=L_, D=D, has_cls=has_cls)
     return dtok, dpos, dcls
 
@@ -239,22 +240,24 @@ def rowlse(p16, q16, *, alpha, label_off=0):
     L.gemm(p16, q16, None, M=M, N=N, K=E, lda=_ld(p16), ldb=_ld(q16), ldd=0, epilogue=L.EPI_ROWLSE, alpha=1.0, alpha_dev=alpha,
            out_vec0=pm, out_vec1=ps, out_vec2=diag, iparam=label_off)
     lse = torch.empty((M,), device=dev, dtype=F32)
-    loss_sum = torch.zeros((1,), device=dev, dtype=F32)
+    loss_sum = torch.empty((1,), device=dev, dtype=F32)
     L.lse_combine(pm, ps, diag, lse, loss_sum, M=M, nparts=nparts)
     return lse, loss_sum
 
 
-def clipgrad(p16, q16, *, alpha, row_lse, col_lse, label_off, gscale, gscale_dev=None):
+def clipgrad(p16, q16, *, alpha, row_lse, col_lse, label_off, gscale, gscale_dev=None, ds_row_only=False):
     """g[M,N] (bf16) = gscale * (exp(z - row_lse_i) + [col_lse] exp(z - col_lse_j) - k * onehot(j == i + label_off)),
-    z = alpha * P @ Q^T;  also returns sum(g * P@Q^T) (d loss / d alpha) as a 1-element fp32 tensor."""
+    z = alpha * P @ Q^T;  also returns sum(g * P@Q^T) (d loss / d alpha) as a 1-element fp32 tensor -- with ds_row_only the sum
+    runs over the row term gscale * (exp(z - row_lse_i) - onehot) alone."""
     _v2(p16, BF16), _v2(q16, BF16)
     M, E = p16.shape
     N = q16.shape[0]
     N8 = (N + 7) // 8 * 8
     g = torch.zeros((M, N8), device=p16.device, dtype=BF16)
-    ds = torch.zeros((1,), device=p16.device, dtype=F32)
+    ds = torch.empty((1,), device=p16.device, dtype=F32)
     L.gemm(p16, q16, g, M=M, N=N, K=E, lda=_ld(p16), ldb=_ld(q16), ldd=N8, epilogue=L.EPI_CLIPGRAD, alpha=1.0, alpha_dev=alpha,
-           row_vec=row_lse, col_vec=col_lse, iparam=label_off, fparam=gscale, fparam_dev=gscale_dev, scalar_out=ds)
+           row_vec=row_lse, col_vec=col_lse, iparam=label_off, fparam=gscale, fparam_dev=gscale_dev, scalar_out=ds,
+           loss_flags=1 if ds_row_only else 0)
     return g[:, :N], ds
 
 
@@ -307,8 +310,8 @@ def colsum2(a, b):
     """(sum_t a[t,:], sum_t a[t,:]*b[t,:]) in fp32"""
     _v2(a, BF16), _v2(b, BF16)
     T, N = a.shape
-    s1 = torch.zeros((N,), device=a.device, dtype=F32)
-    s2 = torch.zeros((N,), device=a.device, dtype=F32)
+    s1 = torch.empty((N,), device=a.device, dtype=F32)
+    s2 = torch.empty((N,), device=a.device, dtype=F32)
     L.colsum2(a.contiguous(), b.contiguous(), s1, s2, T=T, N=N)
     return s1, s2
 
@@ -316,7 +319,7 @@ def colsum2(a, b):
 def moments3(x):
     """[sum x (3) | sum x x^T (9)] over the rows of x[R,3] fp32 -> fp32 [12]"""
     assert x.is_cuda and x.dtype == F32 and x.dim() == 2 and x.shape[1] == 3
-    out = torch.zeros((12,), device=x.device, dtype=F32)
+    out = torch.empty((12,), device=x.device, dtype=F32)
     L.moments3(x.contiguous(), out, R=x.shape[0])
     return out
 
@@ -338,7 +341,7 @@ def wgrad3(dy, x):
     """dy[R,C]^T @ x[R,3] -> fp32 [C,3]"""
     _v2(dy, BF16)
     R, C = dy.shape
-    dw = torch.zeros((C, 3), device=dy.device, dtype=F32)
+    dw = torch.empty((C, 3), device=dy.device, dtype=F32)
     L.wgrad3(dy.contiguous(), x.contiguous(), dw, R=R, C=C)
     return dw
 

@@ -91,7 +91,7 @@ class AdamW:
         self._copied.record()
         sumsq = None
         if clip_norm is not None:
-            sumsq = torch.zeros((1,), dtype=torch.float32, device=self.ptr_dev.device)
+            sumsq = torch.empty((1,), dtype=torch.float32, device=self.ptr_dev.device)
             L.multi_sqnorm(self.ptr_dev, self.sizes, self.chunk_tab, sumsq, n_chunks=self.chunk_tab.shape[0])
             self.grad_norm = sumsq.sqrt() * grad_scale
         L.adamw_multi(self.ptr_dev, self.sizes, self.wds, self.chunk_tab, n_chunks=self.chunk_tab.shape[0], lr=self.lr, beta1=self.betas[0],

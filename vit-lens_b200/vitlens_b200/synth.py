@@ -84,3 +84,48 @@ def synth_points(batch: int, npoints: int, seed: int = 1):
     rad = torch.rand(batch, npoints, 1, generator=g) ** (1.0 / 3.0)
     start = torch.randint(0, npoints, (batch,), generator=g)
     return d * rad, start
+
+
+def synth_shapes(batch: int, npoints: int, seed: int = 1):
+    """Point clouds of DISTINCT shapes (solid ball, sphere shell, cube surface, cylinder, torus, two blobs, disc, ellipsoid
+    rod; cycled over the batch), each randomly stretched and rotated, then centred and scaled into the unit sphere the way the
+    reference's loader does (modal_3d/processors/pc_processor.py:32-38, pc_norm).  Uniform balls (synth_points) all look alike
+    to the tokenizer, which leaves a contrastive batch with near-identical visual features and ill-conditioned gradients;
+    these do not.  Returns (points [B, N, 3], FPS start indices [B])."""
+    g = _gen(seed, "pc_shapes")
+    out = []
+    for i in range(batch):
+        u = torch.rand(npoints, 3, generator=g)
+        n = torch.randn(npoints, 3, generator=g)
+        unit = n / n.norm(dim=-1, keepdim=True).clamp_min(1e-6)
+        kind = i % 8
+        if kind == 0:      # solid ball
+            p = unit * u[:, :1] ** (1.0 / 3.0)
+        elif kind == 1:    # thin sphere shell
+            p = unit * (1.0 + 0.02 * n[:, :1])
+        elif kind == 2:    # cube surface: one coordinate pushed to a face
+            p = 2 * u - 1
+            face = torch.randint(0, 3, (npoints,), generator=g)
+            sign = torch.where(torch.rand(npoints, generator=g) < 0.5, -1.0, 1.0)
+            p[torch.arange(npoints), face] = sign
+        elif kind == 3:    # cylinder surface
+            a = 2 * math.pi * u[:, 0]
+            p = torch.stack([torch.cos(a), torch.sin(a), 3 * (u[:, 1] - 0.5)], -1)
+        elif kind == 4:    # torus
+            a, b = 2 * math.pi * u[:, 0], 2 * math.pi * u[:, 1]
+            p = torch.stack([(1 + 0.3 * torch.cos(b)) * torch.cos(a), (1 + 0.3 * torch.cos(b)) * torch.sin(a), 0.3 * torch.sin(b)], -1)
+        elif kind == 5:    # two gaussian blobs
+            p = 0.25 * n + torch.where(u[:, :1] < 0.5, -1.0, 1.0) * torch.tensor([0.8, 0.3, 0.0])
+        elif kind == 6:    # flat disc
+            a = 2 * math.pi * u[:, 0]
+            p = torch.stack([torch.sqrt(u[:, 1]) * torch.cos(a), torch.sqrt(u[:, 1]) * torch.sin(a), 0.03 * n[:, 2]], -1)
+        else:              # long ellipsoid
+            p = unit * u[:, :1] ** (1.0 / 3.0) * torch.tensor([1.0, 0.25, 0.15])
+        stretch = 0.6 + 0.8 * torch.rand(3, generator=g)
+        q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+        p = (p * stretch) @ q.t()
+        p = p - p.mean(0, keepdim=True)
+        p = p / p.norm(dim=-1).max().clamp_min(1e-6)
+        out.append(p)
+    start = torch.randint(0, npoints, (batch,), generator=g)
+    return torch.stack(out).contiguous(), start
