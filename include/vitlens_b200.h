@@ -173,17 +173,19 @@ int vl_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream
 /* Decoupled-weight-decay Adam step on one fp32 tensor (optim.AdamW, training/point_cloud/pc_tri_main.py:394-419). */
 int vl_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
-/* The same update for every parameter in ONE launch.  ptrs: [n_tensors][5] device pointers (p, g, m, v, bf16 copy of p or
- * 0); sizes / wds: per tensor element count / weight decay; chunk_tab: [n_chunks][2] int32 (tensor id, chunk index), chunks
- * of 16384 elements.  The bf16 copy (the tensor-core operand cache) is refreshed in the same pass. */
-int vl_adamw_multi(const int64_t* ptrs, const int64_t* sizes, const float* wds, const int32_t* chunk_tab, int32_t n_chunks,
+/* The same update for every parameter in ONE launch.  ptrs: [n_tensors][5] device pointers (p, g or 0, m, v, bf16 copy of p
+ * or 0); sizes / wds: per tensor element count / weight decay; lrs: per tensor learning rate (optimizer param_groups; the
+ * scheduler's assign_learning_rate, training/scheduler.py) or NULL = `lr` for all; chunk_tab: [n_chunks][2] int32 (tensor id,
+ * chunk index), chunks of 16384 elements.  A tensor whose gradient pointer is 0 is skipped (torch.optim semantics for
+ * grad None).  The bf16 copy (the tensor-core operand cache) is refreshed in the same pass. */
+int vl_adamw_multi(const int64_t* ptrs, const int64_t* sizes, const float* wds, const float* lrs, const int32_t* chunk_tab, int32_t n_chunks,
                    float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream);
 /* Gradient-norm clipping (torch.nn.utils.clip_grad_norm_, reference training/train.py:212-240) without an extra pass over the
  * gradients: vl_multi_sqnorm writes sum(g^2) over every tensor of the same tables to *sumsq (deterministic); vl_adamw_multi_clip is
  * vl_adamw_multi with every gradient scaled by min(1, max_norm / (grad_scale * sqrt(*sumsq) + 1e-6)). */
 int vl_multi_sqnorm(const int64_t* ptrs, const int64_t* sizes, const int32_t* chunk_tab, int32_t n_chunks, float* sumsq, void* stream);
-int vl_adamw_multi_clip(const int64_t* ptrs, const int64_t* sizes, const float* wds, const int32_t* chunk_tab, int32_t n_chunks,
-                        float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale, const float* sumsq,
+int vl_adamw_multi_clip(const int64_t* ptrs, const int64_t* sizes, const float* wds, const float* lrs, const int32_t* chunk_tab,
+                        int32_t n_chunks, float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale, const float* sumsq,
                         float max_norm, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -42,6 +42,7 @@ class Case:
     lock: Dict = field(default_factory=dict)  # kwargs of lock_visual_tower for tri models
     full_grads: bool = True  # store every gradient (tiny) or only norms + a few small ones
     bn_train: bool = False  # point tokenizer: BatchNorm layers in training mode (batch statistics), as under model.train()
+    image_frames: int = 0  # > 0: the image input is [B, t, 3, H, W] (per-frame encode + mean aggregation, model.py:591-604)
     shapes: bool = False  # point clouds of distinct shapes (synth_shapes) instead of uniform balls: a well-conditioned contrastive batch
     seed: int = 0
 
@@ -62,6 +63,15 @@ CASES = {c.name: c for c in [
     Case("tiny_tri_pc_bntrain", "ViT-tiny-16", "tri", 3, "pc",
          dict(_TINY_LENS, perceiver_input_chan=96, perceiver_self_per_cross_attn=1, pc_npoints=256,
               pc_num_group=16, pc_group_size=8, pc_trans_dim=96, pc_encoder_dims=64), dict(unlock_cls=True), bn_train=True),
+    # SURVEY 8(f).2 variants on the same kernels: EEG Conv1d patch embed; tactile = image path with the last `unlocked_groups`
+    # ViT groups trainable; the Lens replaced by a plain Transformer (perceiver_as_transformer); 5-D image input
+    Case("tiny_tri_eeg", "ViT-tiny-16", "tri", 4, "eeg",
+         dict(_TINY_LENS, perceiver_depth=1, perceiver_self_per_cross_attn=1, eeg_chans=16, eeg_time_len=34, eeg_window_size=4, eeg_stride=2),
+         dict(unlock_cls=True)),
+    Case("tiny_tri_tactile", "ViT-tiny-16", "tri", 4, "tactile", {}, dict(unlocked_groups=2)),
+    Case("tiny_tri_audio_as_transformer", "ViT-tiny-16", "tri", 4, "audio",
+         dict(_TINY_LENS, perceiver_as_transformer=True, perceiver_num_latents=8, audio_mel_bins=32, audio_target_length=48), dict(unlock_cls=True)),
+    Case("tiny_tri_depth_frames", "ViT-tiny-16", "tri", 3, "depth", dict(perceiver_num_latents=16), dict(unlock_cls=True), image_frames=2),
     # BASELINE.json configs[0]: ViT-B/32 image-text ClipLoss, batch 8
     Case("vitb32_clip_bs8", "ViT-B-32", "clip", 8, full_grads=False),
     # reduced-batch versions of configs[2..4] (full-size weights, reference runs them in seconds)
@@ -109,7 +119,7 @@ def build_inputs(case: Case, args=None) -> Dict[str, torch.Tensor]:
     ctx, vocab = cfg["text_cfg"]["context_length"], cfg["text_cfg"]["vocab_size"]
     B = case.batch
     out = {
-        "image": s.synth_normal("image", (B, 3, img, img), seed=case.seed + 1),
+        "image": s.synth_normal("image", (B, case.image_frames, 3, img, img) if case.image_frames else (B, 3, img, img), seed=case.seed + 1),
         "text": s.synth_text(B, ctx, vocab, seed=case.seed + 1),
     }
     ov = case.overrides
@@ -121,6 +131,10 @@ def build_inputs(case: Case, args=None) -> Dict[str, torch.Tensor]:
         out["visual"] = s.synth_normal("audio", (B, g("audio_target_length", 512), g("audio_mel_bins", 128)), seed=case.seed + 1)
     elif case.modality == "depth":
         out["visual"] = s.synth_normal("depth", (B, 1, img, img), seed=case.seed + 1)
+    elif case.modality == "tactile":
+        out["visual"] = s.synth_normal("tactile", (B, 3, img, img), seed=case.seed + 1)
+    elif case.modality == "eeg":
+        out["visual"] = s.synth_normal("eeg", (B, g("eeg_chans", 128), g("eeg_time_len", 512)), seed=case.seed + 1)
     elif case.modality == "pc":
         pts, start = (s.synth_shapes if case.shapes else s.synth_points)(B, g("pc_npoints", 8192), seed=case.seed + 1)
         out["visual"] = pts

@@ -145,6 +145,16 @@ def depth_adapter(sd: SD, pre: str, x):
     return tok, sd[pre + "pos_emb"]
 
 
+def eeg_adapter(sd: SD, pre: str, x, stride: int):
+    """PatchEmbed1D.forward modal_eeg/models/EEG_tokenizer.py:35-42: Conv1d(in_chans, width, k=window, stride) WITH bias over
+    time as an explicit window gather + GEMM, transposed to [B, L, width]; returns (x, pos)."""
+    w, b = sd[pre + "proj.weight"], sd[pre + "proj.bias"]  # [O, C, k], [O]
+    O, C, k = w.shape
+    win = x.unfold(2, k, stride)  # [B, C, L, k]
+    cols = win.permute(0, 2, 1, 3).reshape(x.shape[0], win.shape[2], C * k)
+    return cols @ w.reshape(O, C * k).t() + b, sd[pre + "pos_emb"]
+
+
 def fps_indices(xyz, npoint: int, start: torch.Tensor):
     """misc.fps modal_3d/models/pointbert/misc.py:48-68 with the random start index
     (misc.py:60) passed in so the result is comparable."""
@@ -287,11 +297,15 @@ def image_tower(sd: SD, pre: str, image, heads: int, act=gelu, taps: Optional[di
 
 def lens_tower(sd: SD, pre: str, x, modality: str, heads: int, act=gelu,
                perceiver_as_identity: bool = False, latent_heads: int = 16, cross_heads: int = 1,
-               fps_start=None, taps: Optional[dict] = None, **adapter_kw):
-    """VisionTransformer.forward for audio / depth / pc (transformer.py:724-753): adapter ->
-    x + pos -> Lens (or Identity) -> ViT trunk."""
+               fps_start=None, taps: Optional[dict] = None, perceiver_as_transformer: bool = False, **adapter_kw):
+    """VisionTransformer.forward for audio / depth / pc / eeg (transformer.py:724-753): adapter ->
+    x + pos -> Lens (or Identity, or a plain Transformer) -> ViT trunk; tactile takes the image path (transformer.py:715-718)."""
     ap = pre + "visual_adapter."
-    if modality == "audio":
+    if modality == "tactile":
+        return image_tower(sd, pre, x, heads, act, taps)
+    if modality == "eeg":
+        tok, pos = eeg_adapter(sd, ap, x, **adapter_kw)
+    elif modality == "audio":
         tok, pos = audio_adapter(sd, ap, x, **adapter_kw)
     elif modality == "depth":
         tok, pos = depth_adapter(sd, ap, x)
@@ -302,7 +316,12 @@ def lens_tower(sd: SD, pre: str, x, modality: str, heads: int, act=gelu,
     t = tok + pos
     if taps is not None:
         taps[pre + "adapter"] = t
-    if not perceiver_as_identity:
+    if perceiver_as_transformer and not perceiver_as_identity:
+        # perceiver.py:372-381 builds transformer.Transformer and transformer.py:751 calls it on the BATCH-FIRST tokens
+        # [B, M, C]; nn.MultiheadAttention (batch_first=False) therefore attends over dim 0 -- across the samples of the batch,
+        # separately for every token position.  Restated as is: swap the two leading dims around a batch-first transformer.
+        t = transformer(sd, pre + "perceiver.", t.transpose(0, 1), heads, act).transpose(0, 1)
+    elif not perceiver_as_identity:
         t = perceiver(sd, pre + "perceiver.", t, cross_heads, latent_heads)
         if taps is not None:
             taps[pre + "perceiver"] = t
@@ -383,7 +402,12 @@ def clip_forward(sd: SD, image, text, vision_heads: int, text_heads: int, act=ge
 def triclip_forward(sd: SD, image, text, visual_x, modality: str, vision_heads: int, text_heads: int,
                     act=gelu, **lens_kw):
     """TriCLIP.forward model.py:542-621 ('original impl' branch)."""
-    fi = l2_normalize(image_tower(sd, "image.", image, vision_heads, act))
+    if image.ndim == 5:  # model.py:591-604: normalise every frame's features, average over frames, normalise again
+        b, t = image.shape[:2]
+        fi = l2_normalize(image_tower(sd, "image.", image.reshape((b * t,) + tuple(image.shape[2:])), vision_heads, act))
+        fi = l2_normalize(fi.reshape(b, t, -1).mean(1))
+    else:
+        fi = l2_normalize(image_tower(sd, "image.", image, vision_heads, act))
     ft = l2_normalize(text_tower(sd, text, text_heads, act))
     fv = l2_normalize(lens_tower(sd, "visual.", visual_x, modality, vision_heads, act, **lens_kw))
     return fi, ft, fv, sd["logit_scale"].exp()

@@ -77,12 +77,14 @@ def run_oracle(case, sd, args, inp, grad_keys=(), new_stats=None):
         kw = {}
         if case.modality == "audio":
             kw = dict(fstride=args.audio_fstride, tstride=args.audio_tstride)
+        if case.modality == "eeg":
+            kw = dict(stride=args.eeg_stride)
         if case.modality == "pc":
             kw = dict(fps_start=inp["fps_start"], num_group=args.pc_num_group, group_size=args.pc_group_size)
             if case.bn_train:
                 kw.update(bn_train=True, new_stats=new_stats if new_stats is not None else {})
         fi, ft, fv, ls = O.triclip_forward(sd, inp["image"], inp["text"], inp["visual"], case.modality, vh, th,
-                                           perceiver_as_identity=bool(args.perceiver_as_identity),
+                                           perceiver_as_identity=bool(args.perceiver_as_identity), perceiver_as_transformer=bool(args.perceiver_as_transformer),
                                            latent_heads=args.perceiver_latent_heads, cross_heads=args.perceiver_cross_heads, **kw)
         loss = O.tri_clip_loss(fi, ft, fv, ls)
         feats = {"image_features": fi, "text_features": ft, "visual_features": fv}

@@ -224,3 +224,66 @@ def test_point_tokenizer_sync_batchnorm(tmp_path):
         cos = float(torch.nn.functional.cosine_similarity(tot.flatten(), g.flatten(), dim=0))
         assert err < 8e-2 * float(g.abs().max()) + 1e-4 and cos > 0.998, (k, err, float(g.abs().max()), cos)  # bf16 activations
 
+
+
+# ----------------------------------------------------------------------------- TrainStep(accum_freq > 1) + GradReducer
+def _accum_worker(rank, port, out):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=W)
+    from tests import emu_ops
+    from tests.common import C, build_model
+    from vitlens_b200 import engine
+    from vitlens_b200.grad_sync import GradReducer
+    from vitlens_b200.train_step import TrainStep
+
+    engine._ops = emu_ops
+    import open_clip
+
+    class Recorder(torch.optim.SGD):
+        def __init__(self, params):
+            super().__init__(params, lr=0.0)
+            self.seen = None
+
+        def step(self):
+            self.seen = [p.grad.detach().clone() for g in self.param_groups for p in g["params"]]
+
+    case = C.CASES["tiny_tri_audio"]
+    model, sd, args = build_model(case)
+    model.output_dict = True
+    inp = C.build_inputs(case, args)
+    params = [p for p in model.parameters() if p.requires_grad]
+    B = case.batch
+    half = B // 2
+    sl = [slice(0, half), slice(half, B)]
+    mine = [(inp["image"][s][rank::W], inp["text"][s][rank::W], inp["visual"][s][rank::W]) for s in sl]  # two micro-batches of this rank
+    # (a) local gradients of the accumulated step, no reducer
+    opt = Recorder(params)
+    step = TrainStep(model, open_clip.TriClipLoss(), opt, accum_freq=2)
+    assert not step(*mine[0])
+    assert step(*mine[1])
+    local = opt.seen
+    # (b) the same with the bucketed reducer attached: it must fire once, after the LAST micro-batch, on the accumulated values
+    opt2 = Recorder(params)
+    red = GradReducer(params, bucket_bytes=1 << 14)
+    step2 = TrainStep(model, open_clip.TriClipLoss(), opt2, accum_freq=2, reducer=red, world_size=W)
+    for _ in range(2):  # two optimizer steps: buckets must re-arm
+        assert not step2(*mine[0])
+        assert step2(*mine[1])
+    torch.save(dict(local=local, reduced=opt2.seen, n_buckets=len(red.buckets)), out.format(rank))
+    dist.destroy_process_group()
+
+
+def test_train_step_accumulation_with_gradient_reducer(tmp_path):
+    """TrainStep(accum_freq=2) with a GradReducer attached (the multi-GPU audio recipe).  Micro-batch backward passes
+    before the last one run under reducer.no_sync(); the reduced gradients equal the cross-rank mean of the accumulated
+    local gradients (TrainStep scales the summing all-reduce by 1 / world for optimizers that do not take grad_scale)."""
+    out = str(tmp_path / "a{}.pt")
+    mp.spawn(_accum_worker, args=(_free_port(), out), nprocs=W, join=True)
+    r = [torch.load(out.format(i)) for i in range(W)]
+    assert r[0]["n_buckets"] > 1
+    for k in range(len(r[0]["local"])):
+        want = (r[0]["local"][k] + r[1]["local"][k]) / W
+        for rank in range(W):
+            assert torch.allclose(r[rank]["reduced"][k], want, rtol=1e-5, atol=1e-7), k

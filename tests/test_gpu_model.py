@@ -80,7 +80,8 @@ def _check(name, grad_cos=0.97, norm_tol=0.1):
     assert not bad, bad[:10]
 
 
-@pytest.mark.parametrize("name", ["tiny_clip", "tiny_tri_audio", "tiny_tri_depth", "tiny_tri_pc", "tiny_tri_pc_bntrain"])
+@pytest.mark.parametrize("name", ["tiny_clip", "tiny_tri_audio", "tiny_tri_depth", "tiny_tri_pc", "tiny_tri_pc_bntrain",
+                                  "tiny_tri_eeg", "tiny_tri_tactile", "tiny_tri_audio_as_transformer", "tiny_tri_depth_frames"])
 def test_tiny_models_vs_reference_fixture(name):
     _check(name)
 
@@ -135,14 +136,14 @@ def test_full_batch_properties_vitl14():
 
 
 def test_vitlens_encode_api():
-    from mm_vit_lens import ViTLens
-    from open_clip import ModalityType
+    """mm_vit_lens.ViTLens.encode (vitlens.py:170-189) against the REFERENCE's own ViTLens class run on the same synthetic
+    weights and tensors (tests/golden/vitlens_encode.pt, oracle/make_golden_api.py): image tower, the text closure
+    (vitlens.py:75-97), audio with the mean over clips (vitlens.py:175-183), depth; normalised and raw features.  The weights
+    are loaded through the release checkpoint's wire format (`vitlens.<modality>.*` keys, strict)."""
+    from tests.api_common import check_vitlens_encode
 
-    m = ViTLens(modality_loaded=[ModalityType.IMAGE, ModalityType.DEPTH], device="cuda")
-    with torch.no_grad():
-        out = m.encode({ModalityType.IMAGE: torch.randn(2, 3, 224, 224), ModalityType.DEPTH: torch.randn(2, 1, 224, 224)})
-    assert out["image"].shape == (2, 768) and out["depth"].shape == (2, 768)
-    assert float((out["depth"].norm(dim=-1) - 1).abs().max()) < 1e-4
+    rows = check_vitlens_encode("cuda")
+    _report(case="vitlens_encode", vs="reference ViTLens.encode", **rows)
 
 
 @pytest.mark.parametrize("name", ["tiny_tri_pc", "vitl14_pc_bs2"])

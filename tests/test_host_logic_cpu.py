@@ -5,7 +5,8 @@ import torch
 
 from tests.common import C, build_model, cosine, relerr, run_model
 
-CASES = ["tiny_clip", "tiny_tri_audio", "tiny_tri_depth", "tiny_tri_pc", "tiny_tri_pc_bntrain"]
+CASES = ["tiny_clip", "tiny_tri_audio", "tiny_tri_depth", "tiny_tri_pc", "tiny_tri_pc_bntrain",
+         "tiny_tri_eeg", "tiny_tri_tactile", "tiny_tri_audio_as_transformer", "tiny_tri_depth_frames"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -85,3 +86,11 @@ def test_weight_cache_entries_die_with_their_parameter(emu):
     gc.collect()
     assert all(all(r() is not None for r in hit[2]) for hit in engine.WEIGHTS._c.values())  # no entry points at a dead parameter
     assert len(engine.WEIGHTS._c) < n_before
+
+
+def test_vitlens_encode_vs_reference_class(emu):
+    """ViTLens.encode host logic (text closure, audio clip mean, checkpoint wire-format keys) with emulated kernels against
+    the reference's own ViTLens run (tests/golden/vitlens_encode.pt)."""
+    from tests.api_common import check_vitlens_encode
+
+    check_vitlens_encode("cpu")

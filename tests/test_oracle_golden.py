@@ -7,7 +7,8 @@ import torch
 
 from tests.common import C, build_model, relerr, run_oracle
 
-FAST = ["tiny_clip", "tiny_tri_audio", "tiny_tri_depth", "tiny_tri_pc", "tiny_tri_pc_bntrain", "vitb32_clip_bs8"]
+FAST = ["tiny_clip", "tiny_tri_audio", "tiny_tri_depth", "tiny_tri_pc", "tiny_tri_pc_bntrain", "vitb32_clip_bs8",
+        "tiny_tri_eeg", "tiny_tri_tactile", "tiny_tri_audio_as_transformer", "tiny_tri_depth_frames"]
 SLOW = ["vitl14_audio128_bs2", "vitl14_depth_bs2", "vitl14_pc_bs2", "vitl14_pc_bs8_bntrain"]
 
 

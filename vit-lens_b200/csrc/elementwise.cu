@@ -780,7 +780,8 @@ constexpr int kAdamChunk = 16384;
 // update: with *sumsq = sum over ALL gradients of g^2 (vl_multi_sqnorm), every gradient is scaled by
 // min(1, max_norm / (grad_scale * sqrt(*sumsq) + 1e-6)) on its way into the moments -- no extra pass over the gradients.
 __global__ void __launch_bounds__(256) adamw_multi_kernel(const long long* __restrict__ ptrs, const long long* __restrict__ sizes,
-                                                          const float* __restrict__ wds, const int2* __restrict__ chunk_tab, float lr, float b1,
+                                                          const float* __restrict__ wds, const float* __restrict__ lrs,
+                                                          const int2* __restrict__ chunk_tab, float lr, float b1,
                                                           float b2, float eps, float bc1, float bc2, float grad_scale,
                                                           const float* __restrict__ sumsq, float max_norm) {
   if (sumsq != nullptr) grad_scale *= fminf(1.0f, max_norm / (grad_scale * sqrtf(__ldg(sumsq)) + 1e-6f));
@@ -788,6 +789,8 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const long long* __res
   const long long* pr = ptrs + 5ll * ct.x;
   float* p = reinterpret_cast<float*>(pr[0]);
   const float* g = reinterpret_cast<const float*>(pr[1]);
+  if (g == nullptr) return;  // no gradient this step: the parameter (and its moments) stay untouched, as in torch.optim
+  if (lrs != nullptr) lr = lrs[ct.x];  // per-tensor learning rate (param_groups)
   float* m = reinterpret_cast<float*>(pr[2]);
   float* v = reinterpret_cast<float*>(pr[3]);
   __nv_bfloat16* p16 = reinterpret_cast<__nv_bfloat16*>(pr[4]);
@@ -815,7 +818,7 @@ __global__ void __launch_bounds__(256) multi_sqnorm_kernel(const long long* __re
   const float* g = reinterpret_cast<const float*>(ptrs[5ll * ct.x + 1]);
   const long long n = sizes[ct.x];
   const long long base = static_cast<long long>(ct.y) * kAdamChunk;
-  const long long end = min(n, base + kAdamChunk);
+  const long long end = g != nullptr ? min(n, base + kAdamChunk) : base;  // a tensor without a gradient contributes 0
   float acc = 0.f;
   for (long long i = base + threadIdx.x; i < end; i += 256) acc = fmaf(g[i], g[i], acc);
   __shared__ float red[8];
@@ -1085,13 +1088,13 @@ int vl_lse_combine(const float* part_max, const float* part_sum, const float* di
   return scratch_free(part, s);
 }
 
-int vl_adamw_multi(const int64_t* ptrs, const int64_t* sizes, const float* wds, const int32_t* chunk_tab, int32_t n_chunks, float lr,
-                   float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream) {
+int vl_adamw_multi(const int64_t* ptrs, const int64_t* sizes, const float* wds, const float* lrs, const int32_t* chunk_tab, int32_t n_chunks,
+                   float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream) {
   VL_CHECK_ARG(ptrs && sizes && wds && chunk_tab && n_chunks > 0 && step >= 1, "vl_adamw_multi: bad arguments");
   const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
   adamw_multi_kernel<<<n_chunks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const long long*)ptrs, (const long long*)sizes, wds,
-                                                                                     reinterpret_cast<const int2*>(chunk_tab), lr, beta1, beta2, eps,
-                                                                                     bc1, bc2, grad_scale, nullptr, 0.f);
+                                                                                     lrs, reinterpret_cast<const int2*>(chunk_tab), lr, beta1, beta2,
+                                                                                     eps, bc1, bc2, grad_scale, nullptr, 0.f);
   return launch_check("adamw_multi");
 }
 
@@ -1106,14 +1109,14 @@ int vl_multi_sqnorm(const int64_t* ptrs, const int64_t* sizes, const int32_t* ch
   return scratch_free(part, s);
 }
 
-int vl_adamw_multi_clip(const int64_t* ptrs, const int64_t* sizes, const float* wds, const int32_t* chunk_tab, int32_t n_chunks, float lr,
-                        float beta1, float beta2, float eps, int32_t step, float grad_scale, const float* sumsq, float max_norm,
-                        void* stream) {
+int vl_adamw_multi_clip(const int64_t* ptrs, const int64_t* sizes, const float* wds, const float* lrs, const int32_t* chunk_tab,
+                        int32_t n_chunks, float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale, const float* sumsq,
+                        float max_norm, void* stream) {
   VL_CHECK_ARG(ptrs && sizes && wds && chunk_tab && sumsq && n_chunks > 0 && step >= 1 && max_norm > 0.f, "vl_adamw_multi_clip: bad arguments");
   const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
   adamw_multi_kernel<<<n_chunks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const long long*)ptrs, (const long long*)sizes, wds,
-                                                                                     reinterpret_cast<const int2*>(chunk_tab), lr, beta1, beta2, eps,
-                                                                                     bc1, bc2, grad_scale, sumsq, max_norm);
+                                                                                     lrs, reinterpret_cast<const int2*>(chunk_tab), lr, beta1, beta2,
+                                                                                     eps, bc1, bc2, grad_scale, sumsq, max_norm);
   return launch_check("adamw_multi_clip");
 }
 }

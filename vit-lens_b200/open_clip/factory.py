@@ -20,7 +20,7 @@ import torch
 
 from .constants import CKPT_CACHE_DIR, OPENAI_DATASET_MEAN, OPENAI_DATASET_STD
 from .loss import ClipLoss, ClipLossGeneral, TriClipLoss
-from .model import CLIP, TriCLIP, get_cast_dtype
+from .model import CLIP, TriCLIP, get_cast_dtype, resize_pos_embed
 from .module_cfg import get_input_adapter_cfg, get_perceiver_cfg
 
 HF_HUB_PREFIX = "hf-hub:"
@@ -91,6 +91,7 @@ def load_checkpoint(model, checkpoint_path, strict=True, args=None):
                 state_dict[k.replace("visual.", "image.")] = v
                 if do_pop:
                     state_dict.pop(k)
+    resize_pos_embed(state_dict, model)
     incompatible_keys = model.load_state_dict(state_dict, strict=strict)
     if len(incompatible_keys.missing_keys) or len(incompatible_keys.unexpected_keys):
         logging.info(msg=incompatible_keys)
@@ -175,8 +176,9 @@ def tri_create_model(model_name: str, pretrained: Optional[str] = None, precisio
     if model_cfg.pop("custom_text", False) or force_custom_text or "hf_model_name" in model_cfg.get("text_cfg", {}):
         raise NotImplementedError("TriCustomTextCLIP / HF text towers are outside the ViT-Lens hot path")
     model = TriCLIP(**model_cfg, cast_dtype=get_cast_dtype(precision))
-    model = _finish(model, model_name, pretrained if pretrained and os.path.exists(str(pretrained)) else None, precision, device,
-                    strict, args, output_dict, require_pretrained)
+    # `pretrained` goes through unchanged: a path that does not exist raises (factory.py:318-337 does the same for unknown
+    # tags) instead of silently leaving a randomly initialised frozen ViT under the Lens
+    model = _finish(model, model_name, pretrained, precision, device, strict, args, output_dict, require_pretrained)
     skip = getattr(args, "skip_trans_first_n_layers", None)
     if skip is not None:
         n_blocks = len(model.visual.transformer.resblocks)

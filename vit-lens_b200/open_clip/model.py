@@ -214,15 +214,52 @@ class TriCLIP(nn.Module, _TextMixin):
     def forward(self, image: Optional[torch.Tensor] = None, text: Optional[torch.Tensor] = None, visual_x: Optional[torch.Tensor] = None):
         if self.exp_args is not None and getattr(self.exp_args, "visual_modality_type", None) == "video" and getattr(self.exp_args, "vid_distill_tokens", False):
             raise NotImplementedError("video token distillation is outside the ViT-Lens hot path")
-        image_features = self.encode_image(image, normalize=True) if image is not None else None
+        # 5-D image input [b, t, c, h, w] (model.py:591-604): every frame is encoded AND L2-normalised on its own, the
+        # normalised frame features are averaged over t, and the mean is normalised again
+        n_img = None
         if image is not None and image.ndim == 5:
-            image_features = _normalize(image_features)
+            n_img = image.size(1)
+            image = image.reshape((-1,) + tuple(image.shape[2:]))
+        image_features = self.encode_image(image, normalize=True) if image is not None else None
+        if n_img is not None:
+            image_features = _normalize(image_features.reshape(-1, n_img, image_features.shape[-1]).mean(1))
         text_features = self.encode_text(text, normalize=True) if text is not None else None
         visual_features = self.encode_visual(visual_x, normalize=True) if visual_x is not None else None
         if self.output_dict:
             return {"image_features": image_features, "text_features": text_features, "visual_features": visual_features,
                     "logit_scale": self.logit_scale.exp()}
         return image_features, text_features, visual_features, self.logit_scale.exp()
+
+
+def resize_pos_embed(state_dict, model, interpolation: str = "bicubic", antialias: bool = True):
+    """model.py:1079-1146: when a checkpoint's `visual.positional_embedding` has another token count than the model, the
+    grid part (everything after the class token) is resampled as a 2-D image to the model's grid -- for a Lens tower to
+    the floor(sqrt(num_latents))^2 grid and then nearest-neighbour stretched to num_latents rows -- and written back into
+    `state_dict`.  Host-side, runs once at load time."""
+    import math
+
+    import torch.nn.functional as F
+
+    old = state_dict.get("visual.positional_embedding", None)
+    visual = getattr(model, "visual", None)
+    if old is None or visual is None or not hasattr(visual, "grid_size"):
+        return
+    gh, gw = visual.grid_size if isinstance(visual.grid_size, (tuple, list)) else (visual.grid_size, visual.grid_size)
+    extra = 1  # the class token
+    lens = bool(getattr(visual, "use_perceiver", False))
+    n_lat = visual.vision_cfg.exp_args.perceiver_num_latents if lens else None
+    new_len = (n_lat if lens else gh * gw) + extra
+    if new_len == old.shape[0]:
+        return
+    tok, img = old[:extra], old[extra:]
+    og = int(math.sqrt(len(img)))
+    target = (int(math.sqrt(n_lat)),) * 2 if lens else (gh, gw)
+    img = img.reshape(1, og, og, -1).permute(0, 3, 1, 2)
+    img = F.interpolate(img, size=target, mode=interpolation, antialias=antialias, align_corners=False)
+    img = img.permute(0, 2, 3, 1).reshape(target[0] * target[1], -1)
+    if lens and target[0] * target[1] != n_lat:
+        img = F.interpolate(img.unsqueeze(0).transpose(1, 2), size=n_lat, mode="nearest").transpose(1, 2).squeeze(0)
+    state_dict["visual.positional_embedding"] = torch.cat([tok, img], dim=0)
 
 
 def convert_weights_to_lp(model: nn.Module, dtype=torch.float16):

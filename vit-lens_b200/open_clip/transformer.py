@@ -302,8 +302,15 @@ class VisionTransformer(nn.Module):
         t = self._adapter_tokens(x, **kwargs)
         if self.use_perceiver:
             exp = self.vision_cfg.exp_args
-            if exp.perceiver_as_identity or exp.perceiver_as_transformer:
+            if exp.perceiver_as_identity:
                 t = self.perceiver(t)
+            elif exp.perceiver_as_transformer:
+                # The reference hands its BATCH-FIRST tokens [B, M, C] to transformer.Transformer (transformer.py:751), whose
+                # nn.MultiheadAttention is sequence-first: attention runs over dim 0, i.e. across the samples of the batch,
+                # separately per token position.  Same arithmetic here: M "samples" of B "tokens" each.
+                sw = t.to_bnd().transpose(0, 1).contiguous()
+                sw = self.perceiver(TokenMat(sw.reshape(t.N * t.B, t.D), t.N, t.B))
+                t = TokenMat(sw.to_bnd().transpose(0, 1).contiguous().reshape(t.B * t.N, t.D), t.B, t.N)
             else:
                 t = self.perceiver(t, return_embeddings=True)
         B, L = t.B, t.N

@@ -37,6 +37,9 @@ class GradReducer:
     """Overlapped, bucketed SUM all-reduce of the gradients of `params` (divide by world size in the optimizer).
 
     Usage per step:  loss.backward()  ->  reducer.finish()  ->  optimizer.step(grad_scale=1/world)  ->  zero_grad().
+    Gradient accumulation (several backward passes per optimizer step, training/train.py:154-210): run every backward except
+    the last under `with reducer.no_sync():` -- like DDP's no_sync the hooks then leave the buckets alone, gradients pile up in
+    p.grad, and the last backward reduces the accumulated values.
     """
 
     def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 96 << 20, group=None):
@@ -59,10 +62,27 @@ class GradReducer:
             for p in b.params:
                 self._of[p] = b
         self.stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self._armed = True
         self._handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in plist]
+
+    def no_sync(self):
+        """Context manager: backward passes inside it only accumulate into p.grad (no bucket is counted down or reduced)."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            old, self._armed = self._armed, False
+            try:
+                yield
+            finally:
+                self._armed = old
+
+        return ctx()
 
     # ------------------------------------------------------------------ hooks
     def _on_grad(self, p):
+        if not self._armed:
+            return
         b = self._of[p]
         b.pending -= 1
         if b.pending == 0:

@@ -165,9 +165,9 @@ _PROTOS = {
     "vl_cast_f32_bf16": [_P, _P, _L, _P],
     "vl_add_bf16": [_P, _P, _P, _L, _P],
     "vl_adamw_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
-    "vl_adamw_multi": [_P, _P, _P, _P, _I, _F, _F, _F, _F, _I, _F, _P],
+    "vl_adamw_multi": [_P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _I, _F, _P],
     "vl_multi_sqnorm": [_P, _P, _P, _I, _P, _P],
-    "vl_adamw_multi_clip": [_P, _P, _P, _P, _I, _F, _F, _F, _F, _I, _F, _P, _F, _P],
+    "vl_adamw_multi_clip": [_P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _I, _F, _P, _F, _P],
     "vl_lse_combine": [_P, _P, _P, _I, _I, _P, _P, _P],
     "vl_fps": [_P, _P, _I, _I, _I, _P, _P, _P],
     "vl_knn_group": [_P, _P, _I, _I, _I, _I, _P, _P, _P],
@@ -341,11 +341,11 @@ def group_max(x, out, arg, *, groups, G, C):
 ADAM_CHUNK = 16384
 
 
-def adamw_multi(ptrs, sizes, wds, chunk_tab, *, n_chunks, lr, beta1, beta2, eps, step, grad_scale=1.0, sumsq=None, max_norm=None):
+def adamw_multi(ptrs, sizes, wds, chunk_tab, *, n_chunks, lr, beta1, beta2, eps, step, grad_scale=1.0, sumsq=None, max_norm=None, lrs=None):
     if sumsq is None:
-        _call("vl_adamw_multi", _p(ptrs), _p(sizes), _p(wds), _p(chunk_tab), n_chunks, lr, beta1, beta2, eps, step, grad_scale)
+        _call("vl_adamw_multi", _p(ptrs), _p(sizes), _p(wds), _p(lrs), _p(chunk_tab), n_chunks, lr, beta1, beta2, eps, step, grad_scale)
     else:
-        _call("vl_adamw_multi_clip", _p(ptrs), _p(sizes), _p(wds), _p(chunk_tab), n_chunks, lr, beta1, beta2, eps, step, grad_scale,
+        _call("vl_adamw_multi_clip", _p(ptrs), _p(sizes), _p(wds), _p(lrs), _p(chunk_tab), n_chunks, lr, beta1, beta2, eps, step, grad_scale,
               _p(sumsq), float(max_norm))
 
 

@@ -85,11 +85,16 @@ class TrainStep:
             return False
         # re-forward every micro-batch with gradients; the others' cached features are the negatives (train.py:176-210)
         self.optimizer.zero_grad()
+        import contextlib
+
         for j, inp in enumerate(self._inputs):
             out = dict(self.model(*inp))
             logit_scale = out.pop("logit_scale")
             feats = {k: torch.cat(acc[:j] + [out[k]] + acc[j + 1:]) for k, acc in self._feats.items()}
-            self._loss(feats, logit_scale).backward()
+            # only the LAST micro-batch's backward may hand the (by then fully accumulated) gradients to the reducer
+            last = j == len(self._inputs) - 1
+            with (contextlib.nullcontext() if (last or self.reducer is None) else self.reducer.no_sync()):
+                self._loss(feats, logit_scale).backward()
         self._finish()
         self._inputs, self._feats = [], {}
         return True
