@@ -482,3 +482,52 @@ def test_row_reductions_are_bit_deterministic(ops):
     close(runs[0]["ln_db"], dy.float().sum(0), tol=1e-3, atol=0.05)
     close(runs[0]["dcls"], dy[: 6 * 257].float().reshape(6, 257, D)[:, 0].sum(0), tol=1e-3, atol=0.02)
     close(runs[0]["mom"][:3], pts.sum(0), tol=1e-3, atol=0.05)
+
+
+def test_adamw_param_groups_state_dict_and_missing_grads(ops):
+    """torch.optim.AdamW drop-in behaviour the reference's loop relies on: per-group learning rates rewritten by the scheduler
+    (assign_learning_rate writes param_group["lr"]), parameters whose grad is None are skipped, state_dict() / load_state_dict()
+    round-trip in torch's layout (a torch.optim.AdamW state dict loads into this optimizer and vice versa), and the plan follows
+    a parameter whose storage moved."""
+    from vitlens_b200 import optim
+
+    torch.manual_seed(4)
+    shapes = {"w": (130, 72), "b": (130,), "unused": (17, 8), "big": (40000, 3)}
+    ours = {k: torch.nn.Parameter(torch.randn(s, device="cuda")) for k, s in shapes.items()}
+    ref = {k: torch.nn.Parameter(v.detach().clone()) for k, v in ours.items()}
+
+    def groups(d):
+        return [dict(params=[d["b"]], weight_decay=0.0, lr=3e-3), dict(params=[d["w"], d["unused"], d["big"]], weight_decay=0.2)]
+
+    ropt = torch.optim.AdamW(groups(ref), lr=1e-3, betas=(0.9, 0.98), eps=1e-6)
+    opt = optim.AdamW(groups(ours), lr=1e-3, betas=(0.9, 0.98), eps=1e-6)
+
+    def run(o_ours, o_ref, steps, lr_mul=1.0):
+        for step in range(steps):
+            for k in ours:
+                if k == "unused":
+                    continue  # never receives a gradient
+                g = torch.randn(shapes[k], device="cuda")
+                ours[k].grad, ref[k].grad = g.clone(), g.clone()
+            for o in (o_ours, o_ref):  # the scheduler's assign_learning_rate
+                for grp in o.param_groups:
+                    grp["lr"] = grp["lr"] * lr_mul
+            o_ours.step()
+            o_ref.step()
+
+    run(opt, ropt, 3, lr_mul=0.9)
+    for k in ours:
+        close(ours[k].detach(), ref[k].detach(), tol=1e-5, atol=1e-6)
+    assert torch.equal(ours["unused"].detach(), ref["unused"].detach())
+    # checkpoint / resume through each other's state dicts
+    sd_ours, sd_ref = opt.state_dict(), ropt.state_dict()
+    assert sd_ours["param_groups"][0]["params"] == sd_ref["param_groups"][0]["params"]
+    opt2 = optim.AdamW(groups(ours), lr=1e-3, betas=(0.9, 0.98), eps=1e-6)
+    opt2.load_state_dict(sd_ref)  # torch -> ours
+    ropt2 = torch.optim.AdamW(groups(ref), lr=1e-3, betas=(0.9, 0.98), eps=1e-6)
+    ropt2.load_state_dict(sd_ours)  # ours -> torch
+    with torch.no_grad():  # move one parameter's storage: the fused plan must notice
+        ours["w"].data = ours["w"].data.clone()
+    run(opt2, ropt2, 2)
+    for k in ours:
+        close(ours[k].detach(), ref[k].detach(), tol=1e-5, atol=1e-6)

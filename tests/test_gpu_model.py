@@ -158,6 +158,51 @@ def test_point_cloud_tower_forward_vs_reference_fixture(name):
     assert cosine(fv.cpu(), gold["visual_features"]) > 0.999
 
 
+def test_train_step_accumulation_on_device():
+    """vitlens_b200.train_step.TrainStep with accum_freq=2 (training/train.py:154-210: cached no-grad features, per-micro-batch
+    re-forward) on the CUDA kernels with the fused AdamW + in-kernel clip: the accumulated gradients equal one step on the whole
+    batch (logit_scale accumulates accum_freq times, as in the reference loop), the parameters move, logit_scale stays clamped."""
+    import open_clip
+    from vitlens_b200 import optim
+    from vitlens_b200.train_step import TrainStep
+
+    case = C.CASES["tiny_tri_audio"]
+    seen = {}
+
+    class Spy(optim.AdamW):
+        def step(self, **kw):
+            seen["g"] = {id(p): p.grad.detach().clone() for p in self._all_params() if p.grad is not None}
+            return super().step(**kw)
+
+    def run(accum):
+        model, sd, args = build_model(case, device="cuda")
+        model.output_dict = True
+        inp = {k: v.cuda() for k, v in C.build_inputs(case, args).items()}
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        before = {n: p.detach().clone() for n, p in named}
+        step = TrainStep(model, open_clip.TriClipLoss(), Spy(named, lr=1e-3), accum_freq=accum, grad_clip_norm=1.0)
+        B = case.batch
+        if accum == 1:
+            assert step(inp["image"], inp["text"], inp["visual"])
+        else:
+            h = B // 2
+            assert not step(inp["image"][:h], inp["text"][:h], inp["visual"][:h])
+            assert step(inp["image"][h:], inp["text"][h:], inp["visual"][h:])
+        torch.cuda.synchronize()
+        moved = sum(int(not torch.equal(before[n], p.detach())) for n, p in named)
+        assert moved >= len(named) - 2, (moved, len(named))
+        assert 0.0 <= float(model.logit_scale) <= 4.6053
+        return {n: seen["g"][id(p)] for n, p in named}
+
+    whole, acc = run(1), run(2)
+    for n, g in whole.items():
+        if float(g.abs().max()) < 1e-6:
+            continue
+        mult = 2.0 if n == "logit_scale" else 1.0
+        assert cosine(acc[n], g) > 0.98 or g.numel() == 1, (n, cosine(acc[n], g))
+        assert abs(float(acc[n].norm()) - mult * float(g.norm())) < 0.08 * mult * float(g.norm()) + 1e-5, n
+
+
 def _grads_once(case_name):
     case = C.CASES[case_name]
     gold = C.load_golden(case_name)

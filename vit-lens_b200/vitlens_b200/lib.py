@@ -20,7 +20,9 @@ launch_count = 0  # number of vl_* kernel-launching calls issued (bench.py repor
 # the launching stream and (start, end, algorithmic flops | kind, bytes) is appended.
 GEMM_TIMING = None
 ATTN_TIMING = None
-CALL_TIMING = None  # bench.py's per-kernel breakdown pass: list of (entry point, start event, end event)
+# bench.py's per-kernel breakdown pass: list of (entry point, start event, end event, bound, algorithmic amount) with bound
+# "tensor" (amount = FLOPs) / "hbm" (amount = bytes) / None
+CALL_TIMING = None
 
 
 def _timed(store, payload, fn):
@@ -138,7 +140,7 @@ def gemm(a, b, d, *, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, epilogue=EP
         e0.record()
         _check(_fn("vl_gemm_bf16")(C.cast(C.pointer(args), C.c_void_p), _stream()), "vl_gemm_bf16")
         e1.record()
-        CALL_TIMING.append((f"vl_gemm_bf16/{kind}/epi{int(epilogue)}", e0, e1))
+        CALL_TIMING.append((f"vl_gemm_bf16/{kind}/epi{int(epilogue)}", e0, e1, "tensor", 2.0 * M * N * K))
         return
     _timed(GEMM_TIMING, (2.0 * M * N * K, (M, N, K, int(epilogue), int(a_mn), int(b_mn))),
            lambda: _check(_fn("vl_gemm_bf16")(C.cast(C.pointer(args), C.c_void_p), _stream()), "vl_gemm_bf16"))
@@ -192,14 +194,14 @@ def _fn(name):
     return f
 
 
-def _call(name, *args):
+def _call(name, *args, work=None):
     _count()
     if CALL_TIMING is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = _fn(name)(*args, _stream())
         e1.record()
-        CALL_TIMING.append((name, e0, e1))
+        CALL_TIMING.append((name, e0, e1) + (work if work is not None else (None, 0.0)))
     else:
         rc = _fn(name)(*args, _stream())
     if rc != 0:
@@ -216,23 +218,26 @@ BF16, F32 = torch.bfloat16, torch.float32
 def attention_fwd(q, k, v, o, lse, *, B, H, nq, nk, ldq, ldk, ldv, ldo, scale, causal=False):
     byts = 2.0 * B * H * 64 * (2 * nq + 2 * nk)  # read Q,K,V + write O (bf16)
     _timed(ATTN_TIMING, ("fwd", byts),
-           lambda: _call("vl_attention_fwd", _p(q), _p(k), _p(v), _p(o), _p(lse), B, H, nq, nk, ldq, ldk, ldv, ldo, float(scale), int(causal)))
+           lambda: _call("vl_attention_fwd", _p(q), _p(k), _p(v), _p(o), _p(lse), B, H, nq, nk, ldq, ldk, ldv, ldo, float(scale), int(causal),
+                         work=("hbm", byts)))
 
 
 def attention_bwd(q, k, v, o, dout, lse, dq, dk, dv, *, B, H, nq, nk, ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, scale, causal=False):
     byts = 2.0 * B * H * 64 * (4 * nq + 4 * nk)  # read Q,K,V,O,dO + write dQ,dK,dV (bf16)
     _timed(ATTN_TIMING, ("bwd", byts),
            lambda: _call("vl_attention_bwd", _p(q), _p(k), _p(v), _p(o), _p(dout), _p(lse), _p(dq), _p(dk), _p(dv), B, H, nq, nk,
-                         ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, float(scale), int(causal)))
+                         ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, float(scale), int(causal), work=("hbm", byts)))
 
 
 def layernorm_fwd(x, w, b, y, mean, rstd, *, T, D, ldx, ldy, row_index=None, eps=1e-5):
-    _call("vl_layernorm_fwd", _p(x), ldx, _p(row_index), _p(w), _p(b), _p(y), ldy, _p(mean), _p(rstd), T, D, float(eps))
+    _call("vl_layernorm_fwd", _p(x), ldx, _p(row_index), _p(w), _p(b), _p(y), ldy, _p(mean), _p(rstd), T, D, float(eps),
+          work=("hbm", 2.0 * T * D * 2))  # read x, write y (bf16)
 
 
 def layernorm_bwd(dy, x, w, mean, rstd, dx, dw, db, *, T, D, lddy, ldx, lddx, dres=None, lddres=0, row_index=None, dres_sum=None):
     _call("vl_layernorm_bwd", _p(dy), lddy, _p(x), ldx, _p(row_index), _p(w), _p(mean), _p(rstd), _p(dres), lddres,
-          _p(dx), lddx, _p(dw), _p(db), _p(dres_sum), T, D)
+          _p(dx), lddx, _p(dw), _p(db), _p(dres_sum), T, D,
+          work=("hbm", (3.0 + (dres is not None)) * T * D * 2))  # read dy, x (+ dres), write dx (bf16)
 
 
 def colsum(dy, db, *, T, N, ld):
@@ -269,11 +274,11 @@ def l2norm_bwd(dy, y, inv_norm, dx, *, B, E):
 
 
 def geglu_fwd(h, out, *, M, F):
-    _call("vl_geglu_fwd", _p(h), _p(out), M, F)
+    _call("vl_geglu_fwd", _p(h), _p(out), M, F, work=("hbm", 3.0 * M * F * 2))
 
 
 def geglu_bwd(h, dout, dh, *, M, F):
-    _call("vl_geglu_bwd", _p(h), _p(dout), _p(dh), M, F)
+    _call("vl_geglu_bwd", _p(h), _p(dout), _p(dh), M, F, work=("hbm", 5.0 * M * F * 2))
 
 
 def cast_f32_bf16(inp, out):
