@@ -213,6 +213,22 @@ int vl_moments3(const float* x, float* out12, int64_t R, void* stream);
 int vl_col_affine_bf16(const void* a, const void* b, const float* p0, const float* p1, const float* p2, void* out, int64_t R, int32_t C,
                        int32_t act, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Zero-shot evaluation on the device (reference training/zero_shot.py:36-60,155-257,572-789, open_clip/zero_shot_classifier.py:
+ * 27-88, open_clip/metrics/{accuracy,map,recall}.py).  Similarities come from vl_gemm_bf16 (fp32 output); these finish the job.
+ */
+/* out[g] = normalize(mean_t normalize(x[g*T + t])) over the T templates of class g (fp32 rows of E <= 1024); transpose_out
+ * writes the [E, G] classifier layout of build_zero_shot_classifier (ldo = row stride of out). */
+int vl_template_mean(const float* x, float* out, int32_t G, int32_t T, int32_t E, int64_t ldo, int32_t transpose_out, void* stream);
+/* Row-wise top-k (k <= 16) of fp32 scores[rows, cols]: idx_out[rows, k] int32 (descending score, ties -> smaller column, -1 when
+ * cols < k), val_out optional.  torch.topk in accuracy()/acc()/Recall.retrieval_eval. */
+int vl_topk_rows(const float* scores, int64_t ld, int32_t rows, int32_t cols, int32_t k, int32_t* idx_out, float* val_out, void* stream);
+/* Per-class average precision over N samples (sklearn.metrics.average_precision_score(average=None), metrics/map.py:50), ties
+ * share a threshold; apply_sigmoid mirrors map.py:36.  ap_out[C] (0 for a class without positives), npos_out[C] optional.
+ * N <= 25600 (one class column lives in shared memory). */
+int vl_average_precision(const float* scores, int64_t lds, const float* targets, int64_t ldt, int32_t N, int32_t C, int32_t apply_sigmoid,
+                         float* ap_out, int32_t* npos_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

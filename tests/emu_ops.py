@@ -350,3 +350,44 @@ def gemm_grouped_residual_relu(a, b, gp, group, *, bias=None, relu=True):
         acc = acc + bias
     acc = acc + gp.float().repeat_interleave(group, dim=0)
     return (torch.relu(acc) if relu else acc).to(BF16)
+
+
+# ----------------------------------------------------------------------------- zero-shot evaluation
+def template_mean(x, n_templates, transpose_out=False):
+    _n()
+    G, E = x.shape[0] // n_templates, x.shape[1]
+    v = x / x.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    m = v.reshape(G, n_templates, E).mean(1)
+    m = m / m.norm(dim=-1, keepdim=True)
+    return m.t().contiguous() if transpose_out else m
+
+
+def topk_rows(scores, k, want_values=False):
+    _n()
+    # descending value, ties -> smaller column: a stable sort of the negated scores
+    order = torch.sort(-scores, dim=1, stable=True)[1][:, :k].to(torch.int32)
+    if order.shape[1] < k:
+        order = torch.cat([order, torch.full((scores.shape[0], k - order.shape[1]), -1, dtype=torch.int32)], 1)
+    return (order, torch.gather(scores, 1, order.long().clamp_min(0))) if want_values else order
+
+
+def average_precision(scores, targets, apply_sigmoid=True):
+    _n()
+    s = torch.sigmoid(scores) if apply_sigmoid else scores
+    N, C = s.shape
+    ap = torch.zeros(C)
+    npos = (targets > 0.5).sum(0).to(torch.int32)
+    for c in range(C):
+        pos = (targets[:, c] > 0.5).nonzero().flatten()
+        if pos.numel() == 0:
+            continue
+        ge = s[:, c][None, :] >= s[pos, c][:, None]
+        ap[c] = (((ge & (targets[:, c] > 0.5)[None, :]).sum(1).double() / ge.sum(1).double()).sum() / pos.numel()).float()
+    return ap, npos
+
+
+def similarity(feats, gallery_t=None, gallery=None):
+    _n()
+    a = feats.to(BF16).float()
+    g = gallery.to(BF16).float().t() if gallery is not None else gallery_t.to(BF16).float()
+    return a @ g

@@ -146,6 +146,15 @@ def test_vitlens_encode_api():
     _report(case="vitlens_encode", vs="reference ViTLens.encode", **rows)
 
 
+def test_zero_shot_eval_on_device():
+    """classifier from text templates, similarity GEMM, vl_topk_rows / vl_average_precision, retrieval recall --
+    against the reference's own functions (tests/golden/zero_shot.pt, oracle/make_golden_zeroshot.py).  Rankings and counts are
+    exact (integer work), AP to 1e-6."""
+    from tests.zeroshot_common import check_zero_shot
+
+    _report(case="zero_shot_eval", vs="reference functions", **check_zero_shot("cuda"))
+
+
 @pytest.mark.parametrize("name", ["tiny_tri_pc", "vitl14_pc_bs2"])
 def test_point_cloud_tower_forward_vs_reference_fixture(name):
     """FPS + kNN + grouped PointNet + point Lens + ViT, frozen tokenizer, against the reference's features."""

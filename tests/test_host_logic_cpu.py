@@ -94,3 +94,19 @@ def test_vitlens_encode_vs_reference_class(emu):
     from tests.api_common import check_vitlens_encode
 
     check_vitlens_encode("cpu")
+
+
+def test_zero_shot_eval_vs_reference_functions(emu, monkeypatch):
+    """Zero-shot evaluation host logic (classifier from templates, top-k accuracy, mAP, retrieval recall; training/zero_shot.py,
+    open_clip/metrics/*) with emulated kernels against the reference's own functions (tests/golden/zero_shot.pt)."""
+    import open_clip.metrics.accuracy as A
+    import open_clip.metrics.map as M
+    import open_clip.metrics.recall as R
+    import open_clip.zero_shot_classifier as ZC
+    import training.zero_shot as Z
+
+    for mod in (A, M, R, ZC, Z):
+        monkeypatch.setattr(mod, "_ops", emu)
+    from tests.zeroshot_common import check_zero_shot
+
+    check_zero_shot("cpu")

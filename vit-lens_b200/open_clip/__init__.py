@@ -9,5 +9,6 @@ from .model import (CLIP, CLIPTextCfg, CLIPVisionCfg, TriCLIP, convert_weights_t
                     trace_model)
 from .tokenizer import tokenize
 from .transform import AugmentationCfg, image_transform
+from .zero_shot_classifier import build_zero_shot_classifier, build_zero_shot_classifier_legacy
 
 __version__ = "2.20.0+vitlens_b200"

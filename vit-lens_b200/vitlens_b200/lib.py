@@ -181,6 +181,9 @@ _PROTOS = {
     "vl_moments3": [_P, _P, _L, _P],
     "vl_col_affine_bf16": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _P],
     "vl_group_max": [_P, _P, _P, _L, _I, _I, _P],
+    "vl_template_mean": [_P, _P, _I, _I, _I, _L, _I, _P],
+    "vl_topk_rows": [_P, _L, _I, _I, _I, _P, _P, _P],
+    "vl_average_precision": [_P, _L, _P, _L, _I, _I, _I, _P, _P, _P],
 }
 
 
@@ -341,6 +344,18 @@ def col_affine(a, b, p0, p1, p2, out, *, R, C, act):
 
 def group_max(x, out, arg, *, groups, G, C):
     _call("vl_group_max", _p(x), _p(out), _p(arg), groups, G, C)
+
+
+def template_mean(x, out, *, G, T, E, ldo, transpose_out):
+    _call("vl_template_mean", _p(x), _p(out), G, T, E, ldo, int(transpose_out))
+
+
+def topk_rows(scores, idx_out, val_out, *, ld, rows, cols, k):
+    _call("vl_topk_rows", _p(scores), ld, rows, cols, k, _p(idx_out), _p(val_out))
+
+
+def average_precision(scores, targets, ap_out, npos_out, *, lds, ldt, N, C, apply_sigmoid):
+    _call("vl_average_precision", _p(scores), lds, _p(targets), ldt, N, C, int(apply_sigmoid), _p(ap_out), _p(npos_out))
 
 
 ADAM_CHUNK = 16384

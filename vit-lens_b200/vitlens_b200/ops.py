@@ -365,3 +365,42 @@ def gemm_grouped_residual_relu(a, b, gp, group, *, bias=None, relu=True):
     L.gemm(a, b, out, M=M, N=N, K=K, lda=_ld(a), ldb=_ld(b), ldd=N, epilogue=L.EPI_RESIDUAL, bias=bias, aux_in=gp, ldaux=_ld(gp),
            aux_row_div=group, relu=relu)
     return out
+
+
+# ----------------------------------------------------------------------------- zero-shot evaluation
+def template_mean(x, n_templates, transpose_out=False):
+    """normalize(mean over templates of normalize(x)) per class: x fp32 [G*T, E] -> [G, E] (or [E, G] with transpose_out)."""
+    assert x.is_cuda and x.dtype == F32 and x.dim() == 2 and x.shape[0] % n_templates == 0
+    G, E = x.shape[0] // n_templates, x.shape[1]
+    out = torch.empty((E, G) if transpose_out else (G, E), device=x.device, dtype=F32)
+    L.template_mean(x.contiguous(), out, G=G, T=n_templates, E=E, ldo=out.shape[1], transpose_out=transpose_out)
+    return out
+
+
+def topk_rows(scores, k, want_values=False):
+    """Row-wise top-k of fp32 scores [R, C] -> int32 indices [R, k] (ties -> smaller column) and optionally the values."""
+    assert scores.is_cuda and scores.dtype == F32 and scores.dim() == 2 and scores.stride(1) == 1
+    R, Cn = scores.shape
+    idx = torch.empty((R, k), device=scores.device, dtype=torch.int32)
+    val = torch.empty((R, k), device=scores.device, dtype=F32) if want_values else None
+    L.topk_rows(scores, idx, val, ld=scores.stride(0), rows=R, cols=Cn, k=k)
+    return (idx, val) if want_values else idx
+
+
+def average_precision(scores, targets, apply_sigmoid=True):
+    """Per-class average precision (sklearn definition): scores, targets fp32 [N, C] -> (ap [C] fp32, positives [C] int32)."""
+    assert scores.is_cuda and scores.dtype == F32 and targets.dtype == F32 and scores.shape == targets.shape
+    N, Cn = scores.shape
+    ap = torch.empty((Cn,), device=scores.device, dtype=F32)
+    npos = torch.empty((Cn,), device=scores.device, dtype=torch.int32)
+    L.average_precision(scores.contiguous(), targets.contiguous(), ap, npos, lds=Cn, ldt=Cn, N=N, C=Cn, apply_sigmoid=apply_sigmoid)
+    return ap, npos
+
+
+def similarity(feats, gallery_t=None, gallery=None):
+    """fp32 [B, C] similarities of fp32 features [B, E] with a gallery given as [E, C] (classifier layout) or [C, E] -- the
+    tcgen05 GEMM with bf16-rounded operands and fp32 accumulation / output."""
+    a = cast_bf16(feats)
+    if gallery is not None:
+        return gemm(a, cast_bf16(gallery), out_dtype=F32)
+    return gemm(a, cast_bf16(gallery_t), b_t=True, out_dtype=F32)
