@@ -229,6 +229,21 @@ int vl_topk_rows(const float* scores, int64_t ld, int32_t rows, int32_t cols, in
 int vl_average_precision(const float* scores, int64_t lds, const float* targets, int64_t ldt, int32_t N, int32_t C, int32_t apply_sigmoid,
                          float* ap_out, int32_t* npos_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Input pipelines on the device.
+ */
+/* Kaldi-compatible log-mel filterbank + pad/crop + normalisation (reference modal_audio/processors/at_processor.py:845-872, i.e.
+ * torchaudio.compliance.kaldi.fbank(htk_compat, hanning, 25/10 ms, dither 0, power, log) -> ZeroPad/crop to target_len ->
+ * (x - mean) / std).  wav: fp32 [n_clips] clips of n_samples, clip_stride apart; window fp32 [frame_len]; mel fp32 [n_mel, 257]
+ * (get_mel_banks' matrix padded with a zero column); out fp32 [n_clips, target_len, n_mel].  frame_len <= 512 (FFT size 512). */
+int vl_fbank(const float* wav, int64_t clip_stride, int32_t n_clips, int32_t n_samples, int32_t frame_len, int32_t frame_shift, const float* window,
+             const float* mel, int32_t n_mel, float preemph, int32_t target_len, float mean, float std, float* out, void* stream);
+/* pc_norm (modal_3d/processors/pc_processor.py:32-38): per cloud, xyz -= centroid, xyz /= max distance; in/out fp32 [B, N, C >= 3]. */
+int vl_pc_norm(const float* in, float* out, int32_t B, int32_t N, int32_t C, void* stream);
+/* DepthNorm + Normalize of the depth (disparity) channel (modal_depth/processors/transforms_rgbd.py:393-413, vt_processor.py:
+ * 311-322): out = (clamp(d, min_depth[, max_depth]) / max_depth - mean) / std. */
+int vl_depth_norm(const float* in, float* out, int64_t n, float min_depth, float max_depth, int32_t clamp_max, float mean, float std, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -411,3 +411,62 @@ def triclip_forward(sd: SD, image, text, visual_x, modality: str, vision_heads: 
     ft = l2_normalize(text_tower(sd, text, text_heads, act))
     fv = l2_normalize(lens_tower(sd, "visual.", visual_x, modality, vision_heads, act, **lens_kw))
     return fi, ft, fv, sd["logit_scale"].exp()
+
+
+# --------------------------------------------------------------------------- input pipelines
+def kaldi_fbank(waveform, sample_rate: float = 16000.0, n_mel: int = 128, frame_length_ms: float = 25.0, frame_shift_ms: float = 10.0,
+                preemphasis: float = 0.97, low_freq: float = 20.0):
+    """The arithmetic lives in a THIRD-PARTY dependency: torchaudio.compliance.kaldi.fbank (reference requirements: torchaudio,
+    unpinned), called at modal_audio/processors/at_processor.py:854-863 with htk_compat=True, use_energy=False,
+    window_type="hanning", dither=0.0, frame_shift=10.  Restated from the published Kaldi algorithm (feature-window.cc,
+    mel-computations.cc): snip_edges framing, per-frame DC removal, pre-emphasis with the first sample against itself, Hann window
+    (symmetric), zero-pad to 512, power spectrum, triangular filters on the HTK mel scale over [20 Hz, Nyquist], log(max(., eps)).
+    waveform [samples] -> [frames, n_mel].  tests/ pin this against torchaudio itself wherever torchaudio is importable."""
+    x = waveform.double()
+    flen, shift = int(sample_rate * frame_length_ms * 0.001), int(sample_rate * frame_shift_ms * 0.001)
+    n_frames = 1 + (x.numel() - flen) // shift
+    fr = x.unfold(0, flen, shift)[:n_frames]
+    fr = fr - fr.mean(dim=1, keepdim=True)
+    prev = torch.cat([fr[:, :1], fr[:, :-1]], dim=1)
+    fr = fr - preemphasis * prev
+    n = torch.arange(flen, dtype=torch.float64)
+    fr = fr * (0.5 - 0.5 * torch.cos(2 * math.pi * n / (flen - 1)))
+    nfft = 512
+    fr = torch.nn.functional.pad(fr, (0, nfft - flen))
+    k = torch.arange(nfft // 2 + 1, dtype=torch.float64)
+    ang = -2 * math.pi * k[:, None] * torch.arange(nfft, dtype=torch.float64)[None, :] / nfft
+    power = (fr @ torch.cos(ang).t()) ** 2 + (fr @ torch.sin(ang).t()) ** 2  # explicit DFT
+    mel = lambda f: 1127.0 * torch.log(1.0 + f / 700.0)  # noqa: E731
+    lo, hi = mel(torch.tensor(low_freq, dtype=torch.float64)), mel(torch.tensor(0.5 * sample_rate, dtype=torch.float64))
+    delta = (hi - lo) / (n_mel + 1)
+    b = torch.arange(n_mel, dtype=torch.float64)[:, None]
+    left, center, right = lo + b * delta, lo + (b + 1) * delta, lo + (b + 2) * delta
+    m = mel(sample_rate / nfft * torch.arange(nfft // 2, dtype=torch.float64))[None, :]
+    bins = torch.clamp(torch.minimum((m - left) / (center - left), (right - m) / (right - center)), min=0)
+    bins = torch.nn.functional.pad(bins, (0, 1))
+    return torch.log(torch.clamp(power @ bins.t(), min=1.1920929e-07)).float()
+
+
+def ast_clip(waveform, target_length: int = 512, mean: float = -4.2677393, std: float = 4.5689974, **kw):
+    """convert2fbank + transform of AudioASTProcessorEval (at_processor.py:845-872): fbank, zero-pad / crop to target_length
+    frames, (x - mean) / std."""
+    fb = kaldi_fbank(waveform, **kw)
+    p = target_length - fb.shape[0]
+    fb = torch.nn.functional.pad(fb, (0, 0, 0, p)) if p > 0 else fb[:target_length]
+    return (fb - mean) / std
+
+
+def pc_norm(pc):
+    """modal_3d/processors/pc_processor.py:32-38 (xyz in the first three channels)."""
+    xyz = pc[:, :3] - pc[:, :3].mean(dim=0)
+    xyz = xyz / xyz.pow(2).sum(dim=1).sqrt().max()
+    return torch.cat([xyz, pc[:, 3:]], dim=1)
+
+
+def depth_norm(depth, max_depth: float = 75.0, min_depth: float = 0.01, clamp_max_before_scale: bool = True, mean: float = 0.0418, std: float = 0.0295):
+    """modal_depth/processors/transforms_rgbd.py:393-413 (DepthNorm) followed by transforms.Normalize on the depth channel
+    (vt_processor.py:311-322,170-171)."""
+    d = depth.clamp(min=min_depth)
+    if clamp_max_before_scale:
+        d = d.clamp(max=max_depth)
+    return (d / max_depth - mean) / std

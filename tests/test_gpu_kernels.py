@@ -453,6 +453,7 @@ def test_row_reductions_are_bit_deterministic(ops):
     dy = torch.randn(T, D, device="cuda").to(BF)
     w = torch.randn(D, device="cuda")
     y, mean, rstd = ops.layernorm_fwd(x, w, torch.zeros_like(w))
+    pts = torch.randn(5000, 3, device="cuda")
     runs = []
     for _ in range(3):
         torch.empty(1 << 22, device="cuda").fill_(float("nan"))  # poison the allocator's free blocks
@@ -469,7 +470,6 @@ def test_row_reductions_are_bit_deterministic(ops):
         lse, r["loss_sum"] = ops.rowlse(p16, q16, alpha=alpha)
         _, r["dscale"] = ops.clipgrad(p16, q16, alpha=alpha, row_lse=lse, col_lse=lse, label_off=0, gscale=1.0 / 1024)
         r["cs2a"], r["cs2b"] = ops.colsum2(dy, x)
-        pts = torch.randn(5000, 3, device="cuda")
         r["mom"] = ops.moments3(pts)
         r["wg3"] = ops.wgrad3(dy[:5000, :128].contiguous(), pts)
         torch.cuda.synchronize()
@@ -531,3 +531,23 @@ def test_adamw_param_groups_state_dict_and_missing_grads(ops):
     run(opt2, ropt2, 2)
     for k in ours:
         close(ours[k].detach(), ref[k].detach(), tol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,H,n", [(3, 16, 257), (2, 4, 600), (2, 2, 77)])
+def test_attention_backward_is_bit_deterministic(ops, B, H, n):
+    """The attention backward (incl. the CUDA-core tail rows of N = 128k + t, whose mat-vec partial sums meet in a fixed warp
+    order) returns bit-identical dQ / dK / dV on repeated launches."""
+    torch.manual_seed(5)
+    D = H * 64
+    qkv = torch.randn(B * n, 3 * D, device="cuda").to(BF)
+    do = torch.randn(B * n, D, device="cuda").to(BF)
+    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    o, lse = ops.attention_fwd(q, k, v, B=B, H=H, nq=n, nk=n)
+    outs = []
+    for _ in range(4):
+        d = torch.empty_like(qkv)
+        ops.attention_bwd(q, k, v, o, do, lse, d[:, :D], d[:, D:2 * D], d[:, 2 * D:], B=B, H=H, nq=n, nk=n)
+        torch.cuda.synchronize()
+        outs.append(d)
+    for other in outs[1:]:
+        assert torch.equal(outs[0], other)

@@ -41,10 +41,11 @@ constexpr int kFTq = 0;                               // [kMaxTail][2][64]  q_t 
 constexpr int kFTk = kFTq + kMaxTail * 2 * kHD;       // [kMaxTail][2][64]  k_t | v_t
 constexpr int kFStat = kFTk + kMaxTail * 2 * kHD;     // [kMaxTail][2]      lse2_t, D_t
 constexpr int kFDq = kFStat + kMaxTail * 2;           // [kMaxTail][64]     dQ of the tail queries
-constexpr int kFDk = kFDq + kMaxTail * kHD;           // [kMaxTail][64]     dK of the tail keys
-constexpr int kFDv = kFDk + kMaxTail * kHD;           // [kMaxTail][64]     dV of the tail keys
-constexpr int kFCoef = kFDv + kMaxTail * kHD;         // [2 groups][2][128] per-row coefficients for the mat-vecs
-constexpr int kFEnd = kFCoef + 2 * 2 * kT;
+constexpr int kFDk = kFDq + kMaxTail * kHD;           // [2 groups][kMaxTail][64] dK of the tail keys (one copy per compute group: no
+constexpr int kFDv = kFDk + 2 * kMaxTail * kHD;       // [2 groups][kMaxTail][64] dV   cross-group accumulation order to depend on)
+constexpr int kFCoef = kFDv + 2 * kMaxTail * kHD;     // [2 groups][2][128] per-row coefficients for the mat-vecs
+constexpr int kFPart = kFCoef + 2 * 2 * kT;           // [2 groups][4 warps][64] per-warp partial sums of a mat-vec
+constexpr int kFEnd = kFPart + 2 * 4 * kHD;
 constexpr int kOffBar = kOffF + kFEnd * 4;
 constexpr int kSmem = kOffBar + 256 + 1024;
 
@@ -92,8 +93,10 @@ __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 1
 __device__ __forceinline__ void both_groups_sync() { asm volatile("bar.sync 3, 256;" ::: "memory"); }
 
 // out[d] += sum_r coef[r] * tile[r][d] over the 128 rows of a swizzled [128 x 64] bf16 tile; executed by the 128 threads
-// of one compute group (x = thread index in the group): thread x covers dims (2*(x&31), +1) of rows [32*(x>>5), +32).
-__device__ __forceinline__ void matvec_rows(const float* coef, const uint8_t* tile, float* out, int x) {
+// of one compute group g (x = thread index in the group): thread x covers dims (2*(x&31), +1) of rows [32*(x>>5), +32).
+// The four warps' partial sums meet in `part` ([4][64] floats of this group) and are added in warp order by the first 64
+// threads -- a fixed order, no floating-point atomics, so the kernel is bit-reproducible.  Ends with a group barrier.
+__device__ __forceinline__ void matvec_rows(const float* coef, const uint8_t* tile, float* out, int x, float* part, int g) {
   const int dp = x & 31, r0 = (x >> 5) * 32;
   float a0 = 0.f, a1 = 0.f;
 #pragma unroll 8
@@ -104,8 +107,11 @@ __device__ __forceinline__ void matvec_rows(const float* coef, const uint8_t* ti
     a0 = fmaf(c, bf16_lo(w), a0);
     a1 = fmaf(c, bf16_hi(w), a1);
   }
-  atomicAdd(out + 2 * dp, a0);
-  atomicAdd(out + 2 * dp + 1, a1);
+  part[(x >> 5) * kHD + 2 * dp] = a0;
+  part[(x >> 5) * kHD + 2 * dp + 1] = a1;
+  group_sync(g);
+  if (x < kHD) out[x] += ((part[x] + part[kHD + x]) + part[2 * kHD + x]) + part[3 * kHD + x];
+  group_sync(g);
 }
 
 __device__ __forceinline__ void store_row32(__nv_bfloat16* dst, const uint32_t (&v)[32], bool accum) {
@@ -197,7 +203,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tmem_relinquish();
   }
   // zero the tail accumulators
-  for (int i = threadIdx.x; i < 3 * kMaxTail * kHD; i += kThreads) sf[kFDq + i] = 0.f;
+  for (int i = threadIdx.x; i < 5 * kMaxTail * kHD; i += kThreads) sf[kFDq + i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -341,6 +347,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     uint8_t* sPDg = bp + kOffPD + g * 32768;
     float* coef0 = sf + kFCoef + g * 2 * kT;
     float* coef1 = coef0 + kT;
+    float* mvpart = sf + kFPart + g * 4 * kHD;
+    float* sDkg = sf + kFDk + g * kMaxTail * kHD;  // this group's share of the tail keys' dK / dV
+    float* sDvg = sf + kFDv + g * kMaxTail * kHD;
     const int dbg_cta = static_cast<int>(blockIdx.x) - 4 * static_cast<int>(gridDim.x) / 7;  // a CTA of a later wave (warm caches)
     const bool dbg_on = p.dbg != nullptr && dbg_cta >= 0 && dbg_cta < 8 && x == 0;
     int dbg_n = 0;
@@ -415,9 +424,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         coef0[r] = ptk[t];
         coef1[r] = dsk[t];
         group_sync(g);
-        matvec_rows(coef0, sDOg, sf + kFDv + t * kHD, x);
-        matvec_rows(coef1, sQg, sf + kFDk + t * kHD, x);
-        group_sync(g);
+        matvec_rows(coef0, sDOg, sDvg + t * kHD, x, mvpart, g);
+        matvec_rows(coef1, sQg, sDkg + t * kHD, x, mvpart, g);
       }
     };
 
@@ -586,8 +594,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int t = 0; t < p.tq; ++t) {
             coef0[r] = cf[t];
             group_sync(g);
-            matvec_rows(coef0, sKs, sf + kFDq + t * kHD, x);
-            group_sync(g);
+            matvec_rows(coef0, sKs, sf + kFDq + t * kHD, x, mvpart, g);
           }
         }
       }
@@ -658,7 +665,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             const float ds = pv * (dp - s_stat[2 * t + 1]) * p.scale;
             dq0 = fmaf(ds, kv[d0], dq0);
             dq1 = fmaf(ds, kv[d0 + 1], dq1);
-            sf[kFDk + u * kHD + d0] += ds * qv[d0];
+            sf[kFDk + u * kHD + d0] += ds * qv[d0];  // (group 0's copy collects the tail x tail terms)
             sf[kFDk + u * kHD + d0 + 1] += ds * qv[d0 + 1];
             sf[kFDv + u * kHD + d0] += pv * gv[d0];
             sf[kFDv + u * kHD + d0 + 1] += pv * gv[d0 + 1];
@@ -671,8 +678,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const long long grow = krow0 + p.nk_main + u;
           __nv_bfloat16* dkp = p.dk + grow * p.lddk + h * kHD + d0;
           __nv_bfloat16* dvp = p.dv + grow * p.lddv + h * kHD + d0;
-          float k0 = sf[kFDk + u * kHD + d0], k1 = sf[kFDk + u * kHD + d0 + 1];
-          float v0 = sf[kFDv + u * kHD + d0], v1 = sf[kFDv + u * kHD + d0 + 1];
+          constexpr int kG1 = kMaxTail * kHD;  // offset of group 1's copy
+          float k0 = sf[kFDk + u * kHD + d0] + sf[kFDk + kG1 + u * kHD + d0], k1 = sf[kFDk + u * kHD + d0 + 1] + sf[kFDk + kG1 + u * kHD + d0 + 1];
+          float v0 = sf[kFDv + u * kHD + d0] + sf[kFDv + kG1 + u * kHD + d0], v1 = sf[kFDv + u * kHD + d0 + 1] + sf[kFDv + kG1 + u * kHD + d0 + 1];
           if (p.accum_kv) {
             const uint32_t ok_ = *reinterpret_cast<const uint32_t*>(dkp), ov_ = *reinterpret_cast<const uint32_t*>(dvp);
             k0 += bf16_lo(ok_); k1 += bf16_hi(ok_); v0 += bf16_lo(ov_); v1 += bf16_hi(ov_);

@@ -181,6 +181,9 @@ _PROTOS = {
     "vl_moments3": [_P, _P, _L, _P],
     "vl_col_affine_bf16": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _P],
     "vl_group_max": [_P, _P, _P, _L, _I, _I, _P],
+    "vl_fbank": [_P, _L, _I, _I, _I, _I, _P, _P, _I, _F, _I, _F, _F, _P, _P],
+    "vl_pc_norm": [_P, _P, _I, _I, _I, _P],
+    "vl_depth_norm": [_P, _P, _L, _F, _F, _I, _F, _F, _P],
     "vl_template_mean": [_P, _P, _I, _I, _I, _L, _I, _P],
     "vl_topk_rows": [_P, _L, _I, _I, _I, _P, _P, _P],
     "vl_average_precision": [_P, _L, _P, _L, _I, _I, _I, _P, _P, _P],
@@ -344,6 +347,19 @@ def col_affine(a, b, p0, p1, p2, out, *, R, C, act):
 
 def group_max(x, out, arg, *, groups, G, C):
     _call("vl_group_max", _p(x), _p(out), _p(arg), groups, G, C)
+
+
+def fbank(wav, window, mel, out, *, clip_stride, n_clips, n_samples, frame_len, frame_shift, n_mel, preemph, target_len, mean, std):
+    _call("vl_fbank", _p(wav), clip_stride, n_clips, n_samples, frame_len, frame_shift, _p(window), _p(mel), n_mel, float(preemph), target_len,
+          float(mean), float(std), _p(out))
+
+
+def pc_norm(inp, out, *, B, N, C):
+    _call("vl_pc_norm", _p(inp), _p(out), B, N, C)
+
+
+def depth_norm(inp, out, *, n, min_depth, max_depth, clamp_max, mean, std):
+    _call("vl_depth_norm", _p(inp), _p(out), n, float(min_depth), float(max_depth), int(clamp_max), float(mean), float(std))
 
 
 def template_mean(x, out, *, G, T, E, ldo, transpose_out):
