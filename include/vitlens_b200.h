@@ -101,6 +101,15 @@ typedef struct {
    * M >= 512, N > 128, LINEAR epilogue, fp32 output; rejected (VL_ENOTSUP) otherwise. */
   float* rowsum_out;
   int32_t loss_flags; /* VL_EPI_CLIPGRAD only, see above */
+  /* B sharded by rows over the ranks of the box (the all-gathered features of the contrastive loss, loss.py:55-76): when
+   * b_peers != NULL, B's global row r lives at b_peers[r / b_peer_rows] + (r % b_peer_rows) * ldb -- device pointers into the
+   * peers' arenas (vl_comm_peer_ptr) -- and `b` is ignored.  The kernel loads every tile from its owner over NVLink; if
+   * peer_flags != NULL (device int32 [b_npeers] in THIS rank's arena) the first touch of peer q waits for
+   * peer_flags[q] >= peer_flag_value.  b_peer_rows % 256 == 0 (B K-major) or % 64 == 0 (b_mn) when b_npeers > 1. */
+  const void* const* b_peers; /* HOST array of b_npeers device pointers */
+  int32_t b_npeers, b_peer_rows;
+  const int32_t* peer_flags;
+  int32_t peer_flag_value;
 } VlGemmArgs;
 
 int vl_gemm_bf16(const VlGemmArgs* args, void* stream);
@@ -109,6 +118,34 @@ int vl_gemm_rowlse_parts(int32_t N);
 /* lse[i] = log sum_p out_vec1[i,p]*exp(out_vec0[i,p] - max_p) + max_p;  *loss_sum = sum_i (lse[i] - diag[i]) (written) */
 int vl_lse_combine(const float* part_max, const float* part_sum, const float* diag, int32_t M, int32_t nparts,
                    float* lse, float* loss_sum, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Symmetric peer memory over NVLink / NVSwitch for the data-parallel step (reference gather_features
+ * loss.py:20-78 and the DDP gradient all-reduce pc_tri_main.py:378-380).  One arena per rank (cudaMalloc here, CUDA IPC), mapped
+ * into every rank of the box.  The first 2 KiB of each arena are int32 flags[64][8]: flags[idx][src] is written by rank src and
+ * polled by the owner; values are monotonically increasing tickets ("ready" = flag >= ticket).
+ *   vl_comm_init      allocate + zero this rank's arena, return its 64-byte IPC handle (exchange them out of band, e.g. with
+ *                     torch.distributed.all_gather_object) and its address
+ *   vl_comm_connect   all_handles = world x 64 bytes in rank order: map the peers' arenas
+ *   vl_comm_peer_ptr  base address of rank `peer`'s arena in this process
+ *   vl_comm_signal    after all prior work on `stream`: flags[flag_idx][my rank] = value in every arena (system-scope release)
+ *   vl_comm_wait      `stream` waits until flags[flag_idx][p] >= value for every p (traps after ~20 s instead of hanging)
+ *   vl_comm_peer_reduce_f32 / _gather_f32   out[i] = sum_p arena_p[offset + 4 i]  (rank order, deterministic) / out[p*n + i] = ...
+ *   vl_allgather_features   publish the packed bf16 feature block at `offset` of the own arena (no copy: vl_gemm_bf16 with
+ *                     b_peers reads the blocks in place)
+ *   vl_allreduce_grads      copy-engine push of [offset, offset + bytes) of the own arena to the same range of every peer's
+ *                     arena + ticket; vl_adamw_multi_src sums the world copies in rank order
+ */
+int vl_comm_init(int32_t rank, int32_t world, int64_t arena_bytes, void* handle_out, void** arena_out);
+int vl_comm_connect(const void* all_handles);
+int vl_comm_peer_ptr(int32_t peer, void** ptr_out);
+int vl_comm_destroy(void);
+int vl_comm_signal(int32_t flag_idx, int32_t value, void* stream);
+int vl_comm_wait(int32_t flag_idx, int32_t value, void* stream);
+int vl_comm_peer_reduce_f32(int64_t offset, int64_t n, float* out, void* stream);
+int vl_comm_peer_gather_f32(int64_t offset, int64_t n, float* out, void* stream);
+int vl_allgather_features(int64_t offset, int64_t bytes, int32_t flag_idx, int32_t ticket, void* stream);
+int vl_allreduce_grads(int64_t offset, int64_t bytes, int32_t flag_idx, int32_t ticket, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-head attention core, head_dim = 64 (ViT-L/14, ViT-B/32, CLIP text, Lens self/cross).
@@ -177,16 +214,19 @@ int vl_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float
  * or 0); sizes / wds: per tensor element count / weight decay; lrs: per tensor learning rate (optimizer param_groups; the
  * scheduler's assign_learning_rate, training/scheduler.py) or NULL = `lr` for all; chunk_tab: [n_chunks][2] int32 (tensor id,
  * chunk index), chunks of 16384 elements.  A tensor whose gradient pointer is 0 is skipped (torch.optim semantics for
- * grad None).  The bf16 copy (the tensor-core operand cache) is refreshed in the same pass. */
+ * grad None).  The bf16 copy (the tensor-core operand cache) is refreshed in the same pass.  n_src > 1: every gradient is the
+ * sum, in source order, of n_src copies src_stride ELEMENTS apart (the ranks' slots of vl_allreduce_grads; the DDP reduction
+ * of pc_tri_main.py:378-380 folded into the update) -- n_src = 1, src_stride = 0 for plain gradients. */
 int vl_adamw_multi(const int64_t* ptrs, const int64_t* sizes, const float* wds, const float* lrs, const int32_t* chunk_tab, int32_t n_chunks,
-                   float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream);
+                   float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale, int32_t n_src, int64_t src_stride, void* stream);
 /* Gradient-norm clipping (torch.nn.utils.clip_grad_norm_, reference training/train.py:212-240) without an extra pass over the
  * gradients: vl_multi_sqnorm writes sum(g^2) over every tensor of the same tables to *sumsq (deterministic); vl_adamw_multi_clip is
  * vl_adamw_multi with every gradient scaled by min(1, max_norm / (grad_scale * sqrt(*sumsq) + 1e-6)). */
-int vl_multi_sqnorm(const int64_t* ptrs, const int64_t* sizes, const int32_t* chunk_tab, int32_t n_chunks, float* sumsq, void* stream);
+int vl_multi_sqnorm(const int64_t* ptrs, const int64_t* sizes, const int32_t* chunk_tab, int32_t n_chunks, float* sumsq, int32_t n_src,
+                    int64_t src_stride, void* stream);
 int vl_adamw_multi_clip(const int64_t* ptrs, const int64_t* sizes, const float* wds, const float* lrs, const int32_t* chunk_tab,
                         int32_t n_chunks, float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale, const float* sumsq,
-                        float max_norm, void* stream);
+                        float max_norm, int32_t n_src, int64_t src_stride, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Point-cloud tokenizer (reference modal_3d/models/pointbert): farthest point sampling with explicit start indices

@@ -551,3 +551,31 @@ def test_attention_backward_is_bit_deterministic(ops, B, H, n):
         outs.append(d)
     for other in outs[1:]:
         assert torch.equal(outs[0], other)
+
+
+@pytest.mark.parametrize("W,rows", [(1, 300), (2, 256), (4, 512)])
+def test_peer_sharded_gemm_matches_gathered_operand(ops, W, rows):
+    """vl_gemm_bf16 with b_peers (the feature all-gather fused into the loss GEMMs): B's row blocks live in separate buffers --
+    here W local buffers standing in for W ranks' arenas; over NVLink only the addresses differ -- with a ticket flag per block.
+    Row-LSE, gradient epilogue and the dX GEMM must equal the same calls on the concatenated matrix bit for bit."""
+    torch.manual_seed(6)
+    E, Bl = 768, rows
+    blocks = [torch.nn.functional.normalize(torch.randn(rows, E, device="cuda"), dim=-1).to(BF).contiguous() for _ in range(W)]
+    cat = torch.cat(blocks).contiguous()
+    x = torch.nn.functional.normalize(torch.randn(Bl, E, device="cuda"), dim=-1).to(BF).contiguous()
+    flags = torch.full((8,), 7, device="cuda", dtype=torch.int32)
+    peer = ops.PeerRows(addrs=[b.data_ptr() for b in blocks], rows=rows, E=E, flags=flags.data_ptr(), ticket=7, local=blocks[0])
+    alpha = torch.tensor([14.3], device="cuda")
+    off = rows * (W - 1)
+    lse_a, sum_a = ops.rowlse(x, cat, alpha=alpha, label_off=off)
+    lse_b, sum_b = ops.rowlse(x, peer, alpha=alpha, label_off=off)
+    assert torch.equal(lse_a, lse_b) and torch.equal(sum_a, sum_b)
+    col = torch.randn(W * rows, device="cuda") * 0.1 + float(lse_a.mean())
+    ga, dsa = ops.clipgrad(x, cat, alpha=alpha, row_lse=lse_a, col_lse=col, label_off=off, gscale=0.5 / Bl)
+    gb, dsb = ops.clipgrad(x, peer, alpha=alpha, row_lse=lse_a, col_lse=col, label_off=off, gscale=0.5 / Bl)
+    assert torch.equal(ga, gb) and torch.equal(dsa, dsb)
+    if rows % 64 == 0:
+        dxa = ops.gemm(ga, cat, b_t=True, out_dtype=torch.float32, alpha_dev=alpha)
+        dxb = ops.gemm(ga, peer, b_t=True, out_dtype=torch.float32, alpha_dev=alpha)
+        close(dxb, dxa, tol=1e-5, atol=1e-7)  # (pair kernel vs single-CTA kernel: same products, different accumulation grouping)
+        close(dxb, alpha * (ga.float() @ cat.float()), tol=2e-3)

@@ -783,7 +783,9 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const long long* __res
                                                           const float* __restrict__ wds, const float* __restrict__ lrs,
                                                           const int2* __restrict__ chunk_tab, float lr, float b1,
                                                           float b2, float eps, float bc1, float bc2, float grad_scale,
-                                                          const float* __restrict__ sumsq, float max_norm) {
+                                                          const float* __restrict__ sumsq, float max_norm, int n_src, long long src_stride) {
+  // n_src > 1: the gradient is the sum, in source order, of n_src copies src_stride elements apart (the ranks' slots of the
+  // peer-memory gradient exchange, vl_allreduce_grads): every rank adds the same values in the same order
   if (sumsq != nullptr) grad_scale *= fminf(1.0f, max_norm / (grad_scale * sqrtf(__ldg(sumsq)) + 1e-6f));
   const int2 ct = chunk_tab[blockIdx.x];
   const long long* pr = ptrs + 5ll * ct.x;
@@ -799,7 +801,9 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const long long* __res
   const long long base = static_cast<long long>(ct.y) * kAdamChunk;
   const long long end = min(n, base + kAdamChunk);
   for (long long i = base + threadIdx.x; i < end; i += 256) {
-    const float gi = g[i] * grad_scale;
+    float gsum = g[i];
+    for (int q = 1; q < n_src; ++q) gsum += g[i + q * src_stride];
+    const float gi = gsum * grad_scale;
     float pi = p[i] * (1.0f - lr * wd);
     const float mi = b1 * m[i] + (1.0f - b1) * gi;
     const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
@@ -813,14 +817,19 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const long long* __res
 
 // out[blockIdx.x] = sum of g^2 over one 16384-element chunk of one gradient tensor (same tables as adamw_multi_kernel)
 __global__ void __launch_bounds__(256) multi_sqnorm_kernel(const long long* __restrict__ ptrs, const long long* __restrict__ sizes,
-                                                           const int2* __restrict__ chunk_tab, float* __restrict__ out) {
+                                                           const int2* __restrict__ chunk_tab, float* __restrict__ out, int n_src,
+                                                           long long src_stride) {
   const int2 ct = chunk_tab[blockIdx.x];
   const float* g = reinterpret_cast<const float*>(ptrs[5ll * ct.x + 1]);
   const long long n = sizes[ct.x];
   const long long base = static_cast<long long>(ct.y) * kAdamChunk;
   const long long end = g != nullptr ? min(n, base + kAdamChunk) : base;  // a tensor without a gradient contributes 0
   float acc = 0.f;
-  for (long long i = base + threadIdx.x; i < end; i += 256) acc = fmaf(g[i], g[i], acc);
+  for (long long i = base + threadIdx.x; i < end; i += 256) {
+    float gs = g[i];
+    for (int q = 1; q < n_src; ++q) gs += g[i + q * src_stride];
+    acc = fmaf(gs, gs, acc);
+  }
   __shared__ float red[8];
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -1089,21 +1098,23 @@ int vl_lse_combine(const float* part_max, const float* part_sum, const float* di
 }
 
 int vl_adamw_multi(const int64_t* ptrs, const int64_t* sizes, const float* wds, const float* lrs, const int32_t* chunk_tab, int32_t n_chunks,
-                   float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream) {
-  VL_CHECK_ARG(ptrs && sizes && wds && chunk_tab && n_chunks > 0 && step >= 1, "vl_adamw_multi: bad arguments");
+                   float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale, int32_t n_src, int64_t src_stride, void* stream) {
+  VL_CHECK_ARG(ptrs && sizes && wds && chunk_tab && n_chunks > 0 && step >= 1 && n_src >= 1, "vl_adamw_multi: bad arguments");
   const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
   adamw_multi_kernel<<<n_chunks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const long long*)ptrs, (const long long*)sizes, wds,
                                                                                      lrs, reinterpret_cast<const int2*>(chunk_tab), lr, beta1, beta2,
-                                                                                     eps, bc1, bc2, grad_scale, nullptr, 0.f);
+                                                                                     eps, bc1, bc2, grad_scale, nullptr, 0.f, n_src, src_stride);
   return launch_check("adamw_multi");
 }
 
-int vl_multi_sqnorm(const int64_t* ptrs, const int64_t* sizes, const int32_t* chunk_tab, int32_t n_chunks, float* sumsq, void* stream) {
-  VL_CHECK_ARG(ptrs && sizes && chunk_tab && sumsq && n_chunks > 0, "vl_multi_sqnorm: bad arguments");
+int vl_multi_sqnorm(const int64_t* ptrs, const int64_t* sizes, const int32_t* chunk_tab, int32_t n_chunks, float* sumsq, int32_t n_src,
+                    int64_t src_stride, void* stream) {
+  VL_CHECK_ARG(ptrs && sizes && chunk_tab && sumsq && n_chunks > 0 && n_src >= 1, "vl_multi_sqnorm: bad arguments");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   float* part = nullptr;
   if (int rc = scratch_alloc(reinterpret_cast<void**>(&part), (size_t)n_chunks * sizeof(float), s)) return rc;
-  multi_sqnorm_kernel<<<n_chunks, 256, 0, s>>>((const long long*)ptrs, (const long long*)sizes, reinterpret_cast<const int2*>(chunk_tab), part);
+  multi_sqnorm_kernel<<<n_chunks, 256, 0, s>>>((const long long*)ptrs, (const long long*)sizes, reinterpret_cast<const int2*>(chunk_tab), part, n_src,
+                                               src_stride);
   if (int rc = launch_check("multi_sqnorm")) return rc;
   if (int rc = launch_colreduce(part, n_chunks, 1, sumsq, nullptr, nullptr, s)) return rc;
   return scratch_free(part, s);
@@ -1111,12 +1122,12 @@ int vl_multi_sqnorm(const int64_t* ptrs, const int64_t* sizes, const int32_t* ch
 
 int vl_adamw_multi_clip(const int64_t* ptrs, const int64_t* sizes, const float* wds, const float* lrs, const int32_t* chunk_tab,
                         int32_t n_chunks, float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale, const float* sumsq,
-                        float max_norm, void* stream) {
-  VL_CHECK_ARG(ptrs && sizes && wds && chunk_tab && sumsq && n_chunks > 0 && step >= 1 && max_norm > 0.f, "vl_adamw_multi_clip: bad arguments");
+                        float max_norm, int32_t n_src, int64_t src_stride, void* stream) {
+  VL_CHECK_ARG(ptrs && sizes && wds && chunk_tab && sumsq && n_chunks > 0 && step >= 1 && max_norm > 0.f && n_src >= 1, "vl_adamw_multi_clip: bad arguments");
   const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
   adamw_multi_kernel<<<n_chunks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const long long*)ptrs, (const long long*)sizes, wds,
                                                                                      lrs, reinterpret_cast<const int2*>(chunk_tab), lr, beta1, beta2,
-                                                                                     eps, bc1, bc2, grad_scale, sumsq, max_norm);
+                                                                                     eps, bc1, bc2, grad_scale, sumsq, max_norm, n_src, src_stride);
   return launch_check("adamw_multi_clip");
 }
 }

@@ -10,6 +10,8 @@
 // TMEM holds two accumulator buffers (2 x BN columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1.  Operands may be K-major ([rows, K] row-major) or MN-major ([K, rows]
 // row-major, used by the weight-gradient GEMMs where K is the token dimension).
+#include <type_traits>
+
 #include "vl_host.h"
 #include "vl_sm100.cuh"
 
@@ -43,6 +45,9 @@ struct GemmParams {
   const float* fparam_dev;
   int aux_row_div, relu;
   int loss_flags;
+  int b_peer_rows;               // PEER kernels: B's global row r lives in peer r / b_peer_rows at local row r % b_peer_rows
+  const int* peer_flags;         // PEER kernels: int32 [n peers] tickets in THIS rank's arena, or null
+  int peer_flag_value;
   float* rowsum_out;  // fp32 [tiles_n * split_k][M] partial row sums of A (one row per (n-tile, split); launch_colreduce adds them in
                       // order -> the bias gradient of a weight-gradient GEMM), or null
   int dbg;  // bring-up knob 9: 1 skip epilogue, 2 no global traffic in the epilogue, 4 sleeping epilogue waits, 8 MMA ignores full barriers
@@ -444,10 +449,26 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
   }
 }
 
-template <int BN, int EW, int EPI = -1>
+// PEER = true: the B operand is sharded by rows over the ranks of the box (the all-gathered feature matrix of the contrastive
+// loss, reference loss.py:55-76): one tensor map per peer arena, and the producer loads each tile straight from its owner's
+// memory over NVLink after seeing that peer's ticket -- the all-gather happens inside the GEMM, tile by tile.
+struct PeerMaps {
+  CUtensorMap m[8];
+};
+struct NoPeerMaps {
+  int unused;
+};
+__device__ __forceinline__ int ld_acquire_sys_s32(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <int BN, int EW, int EPI = -1, bool PEER = false>
 __global__ void __launch_bounds__((KernelCfg<BN, EW>::kThreads), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
-                 const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmX, const GemmParams p,
+                 const __grid_constant__ typename std::conditional<PEER, PeerMaps, NoPeerMaps>::type pmB) {
   constexpr bool TE = EW > 0;
   constexpr int kEpiWarps = KernelCfg<BN, EW>::kEpiWarps;
   using Cfg = GemmCfg<BN, TE>;
@@ -500,6 +521,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      [[maybe_unused]] uint32_t peers_seen = 0;
+      // PEER: the tensor map and local row of B's global row `row`; the first touch of a peer waits for its ticket
+      [[maybe_unused]] auto peer_map = [&](int row, int& local_row) -> const CUtensorMap* {
+        if constexpr (PEER) {
+          const int pr = row / p.b_peer_rows;
+          local_row = row - pr * p.b_peer_rows;
+          if (p.peer_flags != nullptr && !((peers_seen >> pr) & 1u)) {
+            const long long t0 = clock64();
+            unsigned spins = 0;
+            while (ld_acquire_sys_s32(p.peer_flags + pr) < p.peer_flag_value) {
+              __nanosleep(100);
+              if ((++spins & 1023u) == 0 && clock64() - t0 > 40000000000ll) __trap();  // a peer that never publishes fails the launch
+            }
+            asm volatile("fence.proxy.async.global;" ::: "memory");  // the TMA (async proxy) reads that follow see the payload
+            peers_seen |= 1u << pr;
+          }
+          return &pmB.m[pr];
+        } else {
+          local_row = row;
+          return &tmB;
+        }
+      };
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         int m_blk, n_blk, ks;
         tile_coords(p, t, m_blk, n_blk, ks);
@@ -518,11 +561,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               tma_load_2d(sa + c * (kBK * 128), &tmA, full_bar(stage), m_blk * kBM + c * 64, kb * kBK);
           }
           if (!p.b_mn) {
-            tma_load_2d(sb, &tmB, full_bar(stage), kb * kBK, n_blk * BN);
+            int lrow;
+            const CUtensorMap* mb = peer_map(n_blk * BN, lrow);  // (host: b_peer_rows % BN == 0, a tile never straddles two peers)
+            tma_load_2d(sb, mb, full_bar(stage), kb * kBK, lrow);
           } else {
+            int lrow;
+            const CUtensorMap* mb = peer_map(kb * kBK, lrow);    // rows of an MN-major B are K indices (host: b_peer_rows % 64 == 0)
 #pragma unroll
             for (int c = 0; c < BN / 64; ++c)
-              tma_load_2d(sb + c * (kBK * 128), &tmB, full_bar(stage), n_blk * BN + c * 64, kb * kBK);
+              tma_load_2d(sb + c * (kBK * 128), mb, full_bar(stage), n_blk * BN + c * 64, lrow);
           }
           if (++stage == Cfg::kStages) {
             stage = 0;
@@ -730,6 +777,9 @@ static int launch_gemm(const VlGemmArgs& a, cudaStream_t stream) {
   p.relu = a.relu;
   p.rowsum_out = a.rowsum_out;
   p.loss_flags = a.loss_flags;
+  p.b_peer_rows = a.b_peer_rows;
+  p.peer_flags = a.peer_flags;
+  p.peer_flag_value = a.peer_flag_value;
   p.dbg = debug_get(9);
   // K-major: 8-row groups 1024 B apart, +32 B per UMMA_K inside the swizzle row.
   // MN-major: 64-wide chunks kBK*128 B apart (LBO), 8-K groups 1024 B apart (SBO), +2048 B per UMMA_K.
@@ -749,7 +799,7 @@ static int launch_gemm(const VlGemmArgs& a, cudaStream_t stream) {
   {
     const int mode = debug_get(8);
     const bool pair_ok = a.M >= 4 * kBM && BN == 256;
-    const bool pair_default = a.epilogue != VL_EPI_ROWLSE && a.epilogue != VL_EPI_CLIPGRAD;
+    const bool pair_default = a.epilogue != VL_EPI_ROWLSE && a.epilogue != VL_EPI_CLIPGRAD && a.b_peers == nullptr;
     if (mode == 2 || (mode == 0 && pair_default && pair_ok)) return launch_gemm2<BN>(a, p, stream);
   }
   CUtensorMap tmA, tmB, tmD, tmX;
@@ -759,13 +809,27 @@ static int launch_gemm(const VlGemmArgs& a, cudaStream_t stream) {
   else
     rc = make_tmap_bf16_2d(&tmA, a.a, a.M, a.K, a.lda, 64, kBK);
   if (rc) return rc;
-  if (!p.b_mn)
-    rc = make_tmap_bf16_2d(&tmB, a.b, a.K, a.N, a.ldb, kBK, BN);
-  else
-    rc = make_tmap_bf16_2d(&tmB, a.b, a.N, a.K, a.ldb, 64, kBK);
-  if (rc) return rc;
+  PeerMaps pm;
+  if (a.b_peers == nullptr) {
+    if (!p.b_mn)
+      rc = make_tmap_bf16_2d(&tmB, a.b, a.K, a.N, a.ldb, kBK, BN);
+    else
+      rc = make_tmap_bf16_2d(&tmB, a.b, a.N, a.K, a.ldb, 64, kBK);
+    if (rc) return rc;
+  } else {
+    // one map per peer over ITS rows only: out-of-range rows of a ragged last tile read as zero, never the next allocation
+    for (int q = 0; q < a.b_npeers; ++q) {
+      if (!p.b_mn)
+        rc = make_tmap_bf16_2d(&pm.m[q], a.b_peers[q], a.K, a.b_peer_rows, a.ldb, kBK, BN);
+      else
+        rc = make_tmap_bf16_2d(&pm.m[q], a.b_peers[q], a.N, a.b_peer_rows, a.ldb, 64, kBK);
+      if (rc) return rc;
+    }
+    for (int q = a.b_npeers; q < 8; ++q) pm.m[q] = pm.m[0];
+    tmB = pm.m[0];
+  }
 
-  const bool te = tma_epilogue_ok<BN>(a, p);
+  const bool te = tma_epilogue_ok<BN>(a, p) && a.b_peers == nullptr;
   const int total = p.tiles_m * p.tiles_n * p.split_k;
   int grid = total < num_sms() ? total : num_sms();
   if (debug_get(7) > 0 && debug_get(7) < grid) grid = debug_get(7);
@@ -782,7 +846,7 @@ static int launch_gemm(const VlGemmArgs& a, cudaStream_t stream) {
       VL_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, 8, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgT::kSmemBytes));   \
       attr_ = true;                                                                                                                 \
     }                                                                                                                               \
-    gemm_bf16_kernel<BN, 8, EPI_><<<grid, KernelCfg<BN, 8>::kThreads, CfgT::kSmemBytes, stream>>>(tmA, tmB, tmD, tmX, p);           \
+    gemm_bf16_kernel<BN, 8, EPI_><<<grid, KernelCfg<BN, 8>::kThreads, CfgT::kSmemBytes, stream>>>(tmA, tmB, tmD, tmX, p, NoPeerMaps{0}); \
   } while (0)
       switch (a.epilogue) {
         case VL_EPI_LINEAR: VL_LAUNCH_TE1(VL_EPI_LINEAR); break;
@@ -806,7 +870,16 @@ static int launch_gemm(const VlGemmArgs& a, cudaStream_t stream) {
     if ((rc = scratch_alloc(reinterpret_cast<void**>(&ds_part), (size_t)ds_n * sizeof(float), stream))) return rc;
     p.scalar_out = ds_part;
   }
-  gemm_bf16_kernel<BN, 0><<<grid, KernelCfg<BN, 0>::kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmA, tmA, p);
+  if (a.b_peers != nullptr) {
+    static bool attr_peer = false;
+    if (!attr_peer) {
+      VL_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, 0, -1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+      attr_peer = true;
+    }
+    gemm_bf16_kernel<BN, 0, -1, true><<<grid, KernelCfg<BN, 0>::kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmA, tmA, p, pm);
+  } else {
+    gemm_bf16_kernel<BN, 0><<<grid, KernelCfg<BN, 0>::kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmA, tmA, p, NoPeerMaps{0});
+  }
   if ((rc = launch_check("gemm_bf16_kernel"))) return rc;
   if (ds_part != nullptr) {
     if ((rc = launch_colreduce(ds_part, ds_n, 1, a.scalar_out, nullptr, nullptr, stream))) return rc;
@@ -1191,7 +1264,7 @@ static int launch_gemm2(const VlGemmArgs& a, GemmParams p, cudaStream_t stream) 
 
 extern "C" int vl_gemm_bf16(const VlGemmArgs* a, void* stream) {
   using namespace vl;
-  VL_CHECK_ARG(a != nullptr && a->a && a->b && (a->d || a->epilogue == VL_EPI_ROWLSE), "vl_gemm_bf16: null pointer");
+  VL_CHECK_ARG(a != nullptr && a->a && (a->b || a->b_peers) && (a->d || a->epilogue == VL_EPI_ROWLSE), "vl_gemm_bf16: null pointer");
   VL_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "vl_gemm_bf16: non-positive dims M=%d N=%d K=%d", a->M, a->N, a->K);
   const bool loss_epi = a->epilogue == VL_EPI_ROWLSE || a->epilogue == VL_EPI_CLIPGRAD;
   VL_CHECK_ARG(a->N % 8 == 0 || loss_epi, "vl_gemm_bf16: N=%d must be a multiple of 8", a->N);
@@ -1221,7 +1294,20 @@ extern "C" int vl_gemm_bf16(const VlGemmArgs* a, void* stream) {
     set_error("vl_gemm_bf16: rowsum_out needs the CTA-pair kernel (M >= 512, N > 128), the LINEAR epilogue and fp32 output");
     return VL_ENOTSUP;
   }
+  if (a->b_peers != nullptr) {
+    VL_CHECK_ARG(a->b_npeers >= 1 && a->b_npeers <= 8 && a->b_peer_rows > 0, "vl_gemm_bf16: b_npeers / b_peer_rows invalid");
+    VL_CHECK_ARG(a->split_k <= 1 && a->rowsum_out == nullptr, "vl_gemm_bf16: b_peers excludes split_k and rowsum_out");
+    const long long rows = static_cast<long long>(a->b_npeers) * a->b_peer_rows;
+    VL_CHECK_ARG(rows == (a->b_mn ? a->K : a->N), "vl_gemm_bf16: b_npeers * b_peer_rows must equal B's row count (%lld)", rows);
+    if (a->b_npeers > 1 && a->b_peer_rows % (a->b_mn ? 64 : 256) != 0) {
+      set_error("vl_gemm_bf16: b_peer_rows=%d must be a multiple of %d (a tile must not straddle two peers); gather into one buffer instead",
+                a->b_peer_rows, a->b_mn ? 64 : 256);
+      return VL_ENOTSUP;
+    }
+    for (int q = 0; q < a->b_npeers; ++q) VL_CHECK_ARG(a->b_peers[q] != nullptr, "vl_gemm_bf16: null peer pointer");
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (a->b_peers != nullptr) return launch_gemm<256>(*a, s);
   if (a->epilogue == VL_EPI_ROWLSE || a->epilogue == VL_EPI_CLIPGRAD) return launch_gemm<256>(*a, s);  // fixed part geometry
   if (a->N <= 128) return launch_gemm<128>(*a, s);
   return launch_gemm<256>(*a, s);

@@ -59,6 +59,7 @@ class _ContrastiveBase(nn.Module):
         self.use_horovod = use_horovod
         self.prev_num_logits = 0
         self.labels = {}
+        self._arena_in_use = None
 
     def get_ground_truth(self, device, num_logits) -> torch.Tensor:
         labels = torch.arange(num_logits, device=device, dtype=torch.long)
@@ -67,9 +68,23 @@ class _ContrastiveBase(nn.Module):
         return labels
 
     # ---- distributed plumbing
+    def _arena(self, Bl):
+        """The peer-memory arena when this exchange can run over it (vitlens_b200.comm; all ranks on one NVLink box, row blocks
+        the peer GEMMs can address in place), else None -> NCCL collectives."""
+        from vitlens_b200 import comm, ops
+
+        if not (has_distributed and dist.is_initialized()) or not ops.peer_rows_ok(Bl):
+            return None
+        return comm.init_arena()
+
     def _gather_packed(self, feats):
-        """One all-gather of the packed [k, B_loc, E] block -> list of k tensors [Bg, E] (rank-major rows)."""
+        """The packed [k, B_loc, E] feature block of every rank -> k matrices [Bg, E] (rank-major rows).  Over the peer arena
+        nothing is gathered: each matrix is an ops.PeerRows whose row blocks the loss GEMMs read in place over NVLink; otherwise
+        ONE all_gather_into_tensor of the packed block (the reference issues one all-gather per tensor, loss.py:55-76)."""
         W = self.world_size
+        A = self._arena(feats[0].shape[0])
+        if A is not None:
+            return A.publish_features(feats)
         packed = torch.stack([f.detach().float() for f in feats], 0).contiguous()  # [k, B_loc, E]
         k, Bl, Ed = packed.shape
         out = torch.empty((W * k, Bl, Ed), device=packed.device, dtype=packed.dtype)
@@ -78,16 +93,31 @@ class _ContrastiveBase(nn.Module):
         return [out[:, i].reshape(W * Bl, Ed) for i in range(k)]
 
     def _gather_vec(self, v):
+        A = self._arena_in_use
+        if A is not None:
+            return A.all_gather_vec(v)
         out = torch.empty((self.world_size * v.numel(),), device=v.device, dtype=v.dtype)
         dist.all_gather_into_tensor(out, v.contiguous())
         return out
 
+    def _sum_ranks(self, t):
+        """Cross-rank sum of a small tensor (loss value / d(scale) partial sums)."""
+        A = self._arena_in_use
+        if A is not None:
+            return A.all_reduce_sum(t)
+        t = t.clone()
+        dist.all_reduce(t)
+        return t
+
     def _pair(self, x, y, all_x, all_y, logit_scale):
         """Loss of one (x, y) feature pair for this rank's rows; value follows the reference's definition."""
+        from vitlens_b200 import ops
+
         W = self.world_size
         Bl = x.shape[0]
         if W == 1:
             return E.ContrastiveFn.apply(x, y, None, None, logit_scale, 0, Bl, Bl, True, None, None)
+        self._arena_in_use = all_x.arena if isinstance(all_x, ops.PeerRows) else None
         Bg = W * Bl
         off = self.rank * Bl
         if self.local_loss:
@@ -97,13 +127,11 @@ class _ContrastiveBase(nn.Module):
         grad_rows = Bl if self.gather_with_grad else Bg
 
         def ds_post(ds):
-            ds = ds.clone()
-            dist.all_reduce(ds)
+            ds = self._sum_ranks(ds)
             return ds / W if self.gather_with_grad else ds
 
         part = E.ContrastiveFn.apply(x, y, all_x, all_y, logit_scale, off, Bg, grad_rows, True, self._gather_vec, ds_post)
-        total = part.detach().clone()
-        dist.all_reduce(total)
+        total = self._sum_ranks(part.detach())
         return part + (total - part.detach())
 
 

@@ -18,6 +18,7 @@ import weakref
 import torch
 
 from . import ops as _ops
+from .ops import PeerRows as _PeerRows
 
 BF16, F32 = torch.bfloat16, torch.float32
 
@@ -472,8 +473,11 @@ class ContrastiveFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, y, all_x, all_y, scale, label_off, val_rows, grad_rows, col_term, gather_lse, ds_post, ds_rows_only=False):
         x16, y16 = _ops.cast_bf16(x.detach()), _ops.cast_bf16(y.detach())
-        ax16 = x16 if all_x is None else _ops.cast_bf16(all_x.detach())
-        ay16 = y16 if all_y is None else _ops.cast_bf16(all_y.detach())
+        # all_x / all_y: None (single process), a gathered [B_all, E] tensor, or ops.PeerRows -- the rows of rank p read in place
+        # from p's peer arena inside the GEMMs (the all-gather of loss.py:55-76 fused into the logits kernel)
+        peer = isinstance(all_x, _PeerRows)
+        ax16 = all_x if peer else (x16 if all_x is None else _ops.cast_bf16(all_x.detach()))
+        ay16 = all_y if peer else (y16 if all_y is None else _ops.cast_bf16(all_y.detach()))
         s = scale.detach().float().reshape(1).contiguous()  # stays on the device: no host sync in the step
         lse_x, sum_x = _ops.rowlse(x16, ay16, alpha=s, label_off=label_off)
         lse_y, sum_y = _ops.rowlse(y16, ax16, alpha=s, label_off=label_off)
@@ -483,7 +487,8 @@ class ContrastiveFn(torch.autograd.Function):
         if col_term:
             col_x = gather_lse(lse_y) if gather_lse is not None else lse_y  # columns of the x-direction = rows of the y-direction
             col_y = gather_lse(lse_x) if gather_lse is not None else lse_x
-        ctx.save_for_backward(x16, y16, ax16, ay16, lse_x, lse_y, col_x, col_y, s)
+        ctx.peer = (ax16, ay16) if peer else None
+        ctx.save_for_backward(x16, y16, empty if peer else ax16, empty if peer else ay16, lse_x, lse_y, col_x, col_y, s)
         ctx.cfg = (label_off, grad_rows, col_term, ds_post, ds_rows_only)
         return loss.reshape(())
 
@@ -491,6 +496,11 @@ class ContrastiveFn(torch.autograd.Function):
     def backward(ctx, dloss):
         x16, y16, ax16, ay16, lse_x, lse_y, col_x, col_y, s = ctx.saved_tensors
         label_off, grad_rows, col_term, ds_post, ds_rows_only = ctx.cfg
+        if ctx.peer is not None:
+            ax16, ay16 = ctx.peer
+            if ax16.arena is not None and not ax16.arena.features_alive(ax16.ticket):
+                raise RuntimeError("contrastive backward: the peer arena's feature ring has been overwritten since this loss's forward "
+                                   "(more than two later loss forwards); run backward earlier or set VL_COMM=nccl")
         gs = 1.0 / (2.0 * grad_rows)
         dl = dloss.detach().float().reshape(1).contiguous()  # upstream gradient stays on the device too
         gx, ds_x = _ops.clipgrad(x16, ay16, alpha=s, row_lse=lse_x, col_lse=col_x if col_term else None, label_off=label_off, gscale=gs, gscale_dev=dl,

@@ -52,6 +52,7 @@ class GemmArgs(C.Structure):
         ("out_vec2", C.c_void_p), ("scalar_out", C.c_void_p), ("iparam", C.c_int32), ("fparam", C.c_float),
         ("alpha_dev", C.c_void_p), ("fparam_dev", C.c_void_p), ("aux_row_div", C.c_int32), ("relu", C.c_int32), ("rowsum_out", C.c_void_p),
         ("loss_flags", C.c_int32),
+        ("b_peers", C.c_void_p), ("b_npeers", C.c_int32), ("b_peer_rows", C.c_int32), ("peer_flags", C.c_void_p), ("peer_flag_value", C.c_int32),
     ]
 
 
@@ -122,17 +123,23 @@ def _count():
 def gemm(a, b, d, *, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, epilogue=EPI_LINEAR, bias=None,
          aux_in=None, aux_out=None, ldaux=0, alpha=1.0, accumulate=False, split_k=1, act_quick=False,
          row_vec=None, col_vec=None, out_vec0=None, out_vec1=None, out_vec2=None, scalar_out=None, iparam=0, fparam=0.0,
-         alpha_dev=None, fparam_dev=None, aux_row_div=0, relu=False, rowsum_out=None, loss_flags=0):
+         alpha_dev=None, fparam_dev=None, aux_row_div=0, relu=False, rowsum_out=None, loss_flags=0,
+         b_peers=None, b_peer_rows=0, peer_flags=0, peer_flag_value=0):
     """Raw GEMM call; see include/vitlens_b200.h.  a, b bf16; d bf16 or fp32; bias fp32."""
-    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    assert a.dtype == torch.bfloat16 and (b is None or b.dtype == torch.bfloat16)
     assert d is None or d.dtype in (torch.bfloat16, torch.float32)
+    peer_arr = None
+    if b_peers is not None:  # raw device addresses of B's row blocks in the peers' arenas
+        peer_arr = (C.c_void_p * len(b_peers))(*[int(q) for q in b_peers])
     assert bias is None or bias.dtype == torch.float32
     args = GemmArgs(
         _ptr(a), _ptr(b), _ptr(d), M, N, K, lda, ldb, ldd, int(a_mn), int(b_mn),
         int(d is not None and d.dtype == torch.float32), int(accumulate), int(split_k), int(epilogue), int(act_quick), float(alpha),
         _ptr(bias), _ptr(aux_in), _ptr(aux_out), ldaux,
         _ptr(row_vec), _ptr(col_vec), _ptr(out_vec0), _ptr(out_vec1), _ptr(out_vec2), _ptr(scalar_out), int(iparam), float(fparam),
-        _ptr(alpha_dev), _ptr(fparam_dev), int(aux_row_div), int(relu), _ptr(rowsum_out), int(loss_flags))
+        _ptr(alpha_dev), _ptr(fparam_dev), int(aux_row_div), int(relu), _ptr(rowsum_out), int(loss_flags),
+        C.cast(peer_arr, C.c_void_p) if peer_arr is not None else C.c_void_p(0), len(b_peers) if b_peers is not None else 0, int(b_peer_rows),
+        C.c_void_p(int(peer_flags)), int(peer_flag_value))
     _count()
     if CALL_TIMING is not None:
         kind = "wgrad" if (a_mn and b_mn) else ("dgrad" if b_mn else "fwd")
@@ -167,9 +174,15 @@ _PROTOS = {
     "vl_cast_f32_bf16": [_P, _P, _L, _P],
     "vl_add_bf16": [_P, _P, _P, _L, _P],
     "vl_adamw_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
-    "vl_adamw_multi": [_P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _I, _F, _P],
-    "vl_multi_sqnorm": [_P, _P, _P, _I, _P, _P],
-    "vl_adamw_multi_clip": [_P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _I, _F, _P, _F, _P],
+    "vl_adamw_multi": [_P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _I, _F, _I, _L, _P],
+    "vl_multi_sqnorm": [_P, _P, _P, _I, _P, _I, _L, _P],
+    "vl_adamw_multi_clip": [_P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _I, _F, _P, _F, _I, _L, _P],
+    "vl_comm_signal": [_I, _I, _P],
+    "vl_comm_wait": [_I, _I, _P],
+    "vl_comm_peer_reduce_f32": [_L, _L, _P, _P],
+    "vl_comm_peer_gather_f32": [_L, _L, _P, _P],
+    "vl_allgather_features": [_L, _L, _I, _I, _P],
+    "vl_allreduce_grads": [_L, _L, _I, _I, _P],
     "vl_lse_combine": [_P, _P, _P, _I, _I, _P, _P, _P],
     "vl_fps": [_P, _P, _I, _I, _I, _P, _P, _P],
     "vl_knn_group": [_P, _P, _I, _I, _I, _I, _P, _P, _P],
@@ -377,13 +390,73 @@ def average_precision(scores, targets, ap_out, npos_out, *, lds, ldt, N, C, appl
 ADAM_CHUNK = 16384
 
 
-def adamw_multi(ptrs, sizes, wds, chunk_tab, *, n_chunks, lr, beta1, beta2, eps, step, grad_scale=1.0, sumsq=None, max_norm=None, lrs=None):
+def adamw_multi(ptrs, sizes, wds, chunk_tab, *, n_chunks, lr, beta1, beta2, eps, step, grad_scale=1.0, sumsq=None, max_norm=None, lrs=None,
+                n_src=1, src_stride=0):
     if sumsq is None:
-        _call("vl_adamw_multi", _p(ptrs), _p(sizes), _p(wds), _p(lrs), _p(chunk_tab), n_chunks, lr, beta1, beta2, eps, step, grad_scale)
+        _call("vl_adamw_multi", _p(ptrs), _p(sizes), _p(wds), _p(lrs), _p(chunk_tab), n_chunks, lr, beta1, beta2, eps, step, grad_scale,
+              int(n_src), int(src_stride))
     else:
         _call("vl_adamw_multi_clip", _p(ptrs), _p(sizes), _p(wds), _p(lrs), _p(chunk_tab), n_chunks, lr, beta1, beta2, eps, step, grad_scale,
-              _p(sumsq), float(max_norm))
+              _p(sumsq), float(max_norm), int(n_src), int(src_stride))
 
 
-def multi_sqnorm(ptrs, sizes, chunk_tab, sumsq, *, n_chunks):
-    _call("vl_multi_sqnorm", _p(ptrs), _p(sizes), _p(chunk_tab), n_chunks, _p(sumsq))
+def multi_sqnorm(ptrs, sizes, chunk_tab, sumsq, *, n_chunks, n_src=1, src_stride=0):
+    _call("vl_multi_sqnorm", _p(ptrs), _p(sizes), _p(chunk_tab), n_chunks, _p(sumsq), int(n_src), int(src_stride))
+
+
+# ----------------------------------------------------------------------------- peer memory (csrc/comm.cu)
+def comm_init(rank: int, world: int, arena_bytes: int):
+    """-> (64-byte IPC handle, address of this rank's arena)"""
+    lib = load()
+    handle = C.create_string_buffer(64)
+    arena = C.c_void_p()
+    lib.vl_comm_init.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.vl_comm_init.restype = C.c_int
+    _check(lib.vl_comm_init(rank, world, arena_bytes, handle, C.byref(arena)), "vl_comm_init")
+    return handle.raw, arena.value
+
+
+def comm_connect(all_handles: bytes):
+    lib = load()
+    lib.vl_comm_connect.argtypes = [C.c_char_p]
+    lib.vl_comm_connect.restype = C.c_int
+    _check(lib.vl_comm_connect(all_handles), "vl_comm_connect")
+
+
+def comm_peer_ptr(peer: int) -> int:
+    lib = load()
+    out = C.c_void_p()
+    lib.vl_comm_peer_ptr.argtypes = [C.c_int32, C.POINTER(C.c_void_p)]
+    lib.vl_comm_peer_ptr.restype = C.c_int
+    _check(lib.vl_comm_peer_ptr(peer, C.byref(out)), "vl_comm_peer_ptr")
+    return out.value
+
+
+def comm_destroy():
+    lib = load()
+    lib.vl_comm_destroy.restype = C.c_int
+    _check(lib.vl_comm_destroy(), "vl_comm_destroy")
+
+
+def comm_signal(flag_idx, value):
+    _call("vl_comm_signal", int(flag_idx), int(value))
+
+
+def comm_wait(flag_idx, value):
+    _call("vl_comm_wait", int(flag_idx), int(value))
+
+
+def comm_peer_reduce(offset, n, out):
+    _call("vl_comm_peer_reduce_f32", int(offset), int(n), _p(out))
+
+
+def comm_peer_gather(offset, n, out):
+    _call("vl_comm_peer_gather_f32", int(offset), int(n), _p(out))
+
+
+def allgather_features(offset, nbytes, flag_idx, ticket):
+    _call("vl_allgather_features", int(offset), int(nbytes), int(flag_idx), int(ticket))
+
+
+def allreduce_grads(offset, nbytes, flag_idx, ticket):
+    _call("vl_allreduce_grads", int(offset), int(nbytes), int(flag_idx), int(ticket))

@@ -30,6 +30,32 @@ def _ld(t: torch.Tensor) -> int:
     return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
 
 
+class PeerRows:
+    """A bf16 matrix [world * rows, E] whose row block p lives in rank p's peer arena (vitlens_b200.comm): the all-gathered
+    features of the contrastive loss, never materialised -- the GEMMs load each tile from its owner over NVLink."""
+
+    __slots__ = ("addrs", "rows", "E", "flags", "ticket", "local", "arena")
+
+    def __init__(self, addrs, rows, E, flags, ticket, local, arena=None):
+        self.addrs, self.rows, self.E, self.flags, self.ticket, self.local, self.arena = list(addrs), rows, E, flags, ticket, local, arena
+
+    @property
+    def shape(self):
+        return (len(self.addrs) * self.rows, self.E)
+
+    @property
+    def device(self):
+        return self.local.device
+
+    def kw(self, wait=True):
+        return dict(b_peers=self.addrs, b_peer_rows=self.rows, peer_flags=self.flags if wait else 0, peer_flag_value=self.ticket)
+
+
+def peer_rows_ok(rows: int) -> bool:
+    """Row blocks the peer GEMMs can address in place (a 256-column logits tile must not straddle two ranks)."""
+    return rows % 256 == 0
+
+
 def pick_split_k(M: int, N: int, K: int) -> int:
     """Split the reduction of a weight-gradient GEMM when its (M, N) grid alone cannot fill the GPU.
 
@@ -60,7 +86,10 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, epilogue=EPI_LINEAR, aux_in=N
          out_dtype=BF16, alpha=1.0, accumulate=False, split_k=None, act_quick=False, alpha_dev=None, want_rowsum=False):
     """out[M,N] = epilogue(alpha * A @ B^T); A = a ([M,K]) or a^T when a_t (a is [K,M]); B = b ([N,K]) or b^T when b_t.
     want_rowsum (fp32 LINEAR outputs, rowsum_fusable shapes): also returns sum_k A[m, k] as fp32 [M]."""
-    _v2(a, BF16), _v2(b, BF16)
+    _v2(a, BF16)
+    peer = b if isinstance(b, PeerRows) else None
+    if peer is None:
+        _v2(b, BF16)
     M, K = (a.shape[1], a.shape[0]) if a_t else (a.shape[0], a.shape[1])
     N, Kb = (b.shape[1], b.shape[0]) if b_t else (b.shape[0], b.shape[1])
     assert K == Kb, f"K mismatch {K} vs {Kb}"
@@ -82,9 +111,14 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, epilogue=EPI_LINEAR, aux_in=N
     if want_rowsum:
         assert rowsum_fusable(M, N) and out.dtype == F32 and epilogue == EPI_LINEAR and not want_aux_out
         rowsum = torch.empty((M,), device=a.device, dtype=F32)
-    L.gemm(a, b, out, M=M, N=N, K=K, lda=_ld(a), ldb=_ld(b), ldd=_ld(out), a_mn=a_t, b_mn=b_t, epilogue=epilogue, bias=bias,
-           aux_in=aux_in, aux_out=aux_out, ldaux=ldaux, alpha=alpha, accumulate=accumulate, split_k=split_k, act_quick=act_quick,
-           alpha_dev=alpha_dev, rowsum_out=rowsum)
+    if peer is not None:
+        assert not accumulate and not want_rowsum and split_k == 1
+        L.gemm(a, None, out, M=M, N=N, K=K, lda=_ld(a), ldb=peer.E, ldd=_ld(out), a_mn=a_t, b_mn=b_t, epilogue=epilogue, bias=bias,
+               aux_in=aux_in, aux_out=aux_out, ldaux=ldaux, alpha=alpha, act_quick=act_quick, alpha_dev=alpha_dev, **peer.kw())
+    else:
+        L.gemm(a, b, out, M=M, N=N, K=K, lda=_ld(a), ldb=_ld(b), ldd=_ld(out), a_mn=a_t, b_mn=b_t, epilogue=epilogue, bias=bias,
+               aux_in=aux_in, aux_out=aux_out, ldaux=ldaux, alpha=alpha, accumulate=accumulate, split_k=split_k, act_quick=act_quick,
+               alpha_dev=alpha_dev, rowsum_out=rowsum)
     if want_rowsum:
         return out, rowsum
     return (out, aux_out) if want_aux_out else out
@@ -212,10 +246,13 @@ def geglu_bwd(h, dout):
     return dh
 
 
-def cast_bf16(x):
-    """fp32 -> bf16 copy (weights for the tensor cores, dfeatures for the head GEMMs)."""
+def cast_bf16(x, out=None):
+    """fp32 -> bf16 copy (weights for the tensor cores, dfeatures for the head GEMMs); `out`: a contiguous bf16 destination
+    (e.g. a slot of the peer arena)."""
     x = x.contiguous()
-    out = torch.empty(x.shape, device=x.device, dtype=BF16)
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=BF16)
+    assert out.dtype == BF16 and out.is_contiguous() and out.numel() == x.numel()
     L.cast_f32_bf16(x, out)
     return out
 
@@ -229,7 +266,10 @@ def add_bf16(a, b):
 def rowlse(p16, q16, *, alpha, label_off=0):
     """Row-wise log-sum-exp of alpha * P @ Q^T without materialising the logits (alpha: 1-element fp32 device tensor).
     Returns (lse [M] fp32, sum_i(lse_i - z[i, i + label_off]) as a 1-element fp32 tensor)."""
-    _v2(p16, BF16), _v2(q16, BF16)
+    _v2(p16, BF16)
+    peer = q16 if isinstance(q16, PeerRows) else None
+    if peer is None:
+        _v2(q16, BF16)
     M, E = p16.shape
     N = q16.shape[0]
     nparts = L.rowlse_parts(N)
@@ -237,8 +277,8 @@ def rowlse(p16, q16, *, alpha, label_off=0):
     pm = torch.full((M, nparts), float("-inf"), device=dev, dtype=F32)
     ps = torch.zeros((M, nparts), device=dev, dtype=F32)
     diag = torch.zeros((M,), device=dev, dtype=F32)
-    L.gemm(p16, q16, None, M=M, N=N, K=E, lda=_ld(p16), ldb=_ld(q16), ldd=0, epilogue=L.EPI_ROWLSE, alpha=1.0, alpha_dev=alpha,
-           out_vec0=pm, out_vec1=ps, out_vec2=diag, iparam=label_off)
+    L.gemm(p16, None if peer else q16, None, M=M, N=N, K=E, lda=_ld(p16), ldb=peer.E if peer else _ld(q16), ldd=0, epilogue=L.EPI_ROWLSE,
+           alpha=1.0, alpha_dev=alpha, out_vec0=pm, out_vec1=ps, out_vec2=diag, iparam=label_off, **(peer.kw() if peer else {}))
     lse = torch.empty((M,), device=dev, dtype=F32)
     loss_sum = torch.empty((1,), device=dev, dtype=F32)
     L.lse_combine(pm, ps, diag, lse, loss_sum, M=M, nparts=nparts)
@@ -249,15 +289,18 @@ def clipgrad(p16, q16, *, alpha, row_lse, col_lse, label_off, gscale, gscale_dev
     """g[M,N] (bf16) = gscale * (exp(z - row_lse_i) + [col_lse] exp(z - col_lse_j) - k * onehot(j == i + label_off)),
     z = alpha * P @ Q^T;  also returns sum(g * P@Q^T) (d loss / d alpha) as a 1-element fp32 tensor -- with ds_row_only the sum
     runs over the row term gscale * (exp(z - row_lse_i) - onehot) alone."""
-    _v2(p16, BF16), _v2(q16, BF16)
+    _v2(p16, BF16)
+    peer = q16 if isinstance(q16, PeerRows) else None
+    if peer is None:
+        _v2(q16, BF16)
     M, E = p16.shape
     N = q16.shape[0]
     N8 = (N + 7) // 8 * 8
     g = torch.zeros((M, N8), device=p16.device, dtype=BF16)
     ds = torch.empty((1,), device=p16.device, dtype=F32)
-    L.gemm(p16, q16, g, M=M, N=N, K=E, lda=_ld(p16), ldb=_ld(q16), ldd=N8, epilogue=L.EPI_CLIPGRAD, alpha=1.0, alpha_dev=alpha,
-           row_vec=row_lse, col_vec=col_lse, iparam=label_off, fparam=gscale, fparam_dev=gscale_dev, scalar_out=ds,
-           loss_flags=1 if ds_row_only else 0)
+    L.gemm(p16, None if peer else q16, g, M=M, N=N, K=E, lda=_ld(p16), ldb=peer.E if peer else _ld(q16), ldd=N8, epilogue=L.EPI_CLIPGRAD,
+           alpha=1.0, alpha_dev=alpha, row_vec=row_lse, col_vec=col_lse, iparam=label_off, fparam=gscale, fparam_dev=gscale_dev, scalar_out=ds,
+           loss_flags=1 if ds_row_only else 0, **(peer.kw(wait=False) if peer else {}))
     return g[:, :N], ds
 
 

@@ -148,8 +148,10 @@ class AdamW:
         return self.wds, self.lrs
 
     @torch.no_grad()
-    def step(self, grad_scale: float = 1.0, clip_norm: float = None):
-        """One update.  grad_scale multiplies every gradient (1 / world_size after a summing all-reduce).  clip_norm: the
+    def step(self, grad_scale: float = 1.0, clip_norm: float = None, n_src: int = 1, src_stride: int = 0):
+        """One update.  grad_scale multiplies every gradient (1 / world_size after a summing all-reduce).  n_src / src_stride:
+        every p.grad is the first of n_src copies src_stride elements apart that the kernel adds up in order (the peer-memory
+        gradient exchange, grad_sync.GradReducer.n_src / .src_stride).  clip_norm: the
         reference's --grad-clip-norm (torch.nn.utils.clip_grad_norm_ over all parameters, train.py:212-240), applied to the
         scaled gradients inside the fused kernel; the total norm lands in self.grad_norm (a device scalar, no host sync)."""
         params = self._all_params()
@@ -189,10 +191,11 @@ class AdamW:
         sumsq = None
         if clip_norm is not None:
             sumsq = torch.empty((1,), dtype=torch.float32, device=self.ptr_dev.device)
-            L.multi_sqnorm(self.ptr_dev, self.sizes, self.chunk_tab, sumsq, n_chunks=self.chunk_tab.shape[0])
+            L.multi_sqnorm(self.ptr_dev, self.sizes, self.chunk_tab, sumsq, n_chunks=self.chunk_tab.shape[0], n_src=n_src, src_stride=src_stride)
             self.grad_norm = sumsq.sqrt() * grad_scale
         L.adamw_multi(self.ptr_dev, self.sizes, wds, self.chunk_tab, n_chunks=self.chunk_tab.shape[0], lr=g0["lr"], beta1=g0["betas"][0],
-                      beta2=g0["betas"][1], eps=g0["eps"], step=self.t, grad_scale=grad_scale, sumsq=sumsq, max_norm=clip_norm, lrs=lrs)
+                      beta2=g0["betas"][1], eps=g0["eps"], step=self.t, grad_scale=grad_scale, sumsq=sumsq, max_norm=clip_norm, lrs=lrs,
+                      n_src=n_src, src_stride=src_stride)
         engine.WEIGHTS.clear_derived()  # concatenated / padded / folded copies are rebuilt lazily; plain copies were refreshed above
 
 

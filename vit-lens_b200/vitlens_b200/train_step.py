@@ -48,10 +48,11 @@ class TrainStep:
         from . import optim as _optim
 
         if self.reducer is not None:
-            self.reducer.finish()
+            self.reducer.finish(materialize=not isinstance(self.optimizer, _optim.AdamW))
         scale = 1.0 / self.world_size if self.reducer is not None else 1.0
         if isinstance(self.optimizer, _optim.AdamW):
-            self.optimizer.step(grad_scale=scale, clip_norm=self.grad_clip_norm)
+            src = dict(n_src=self.reducer.n_src, src_stride=self.reducer.src_stride) if self.reducer is not None else {}
+            self.optimizer.step(grad_scale=scale, clip_norm=self.grad_clip_norm, **src)
         else:
             params = [p for p in self.model.parameters() if p.grad is not None]
             if scale != 1.0:
