@@ -2,10 +2,14 @@
 (a) the REFERENCE's golden outputs and (b) the CPU oracle on the same seeded weights + inputs, plus
 size-independent properties at the full BASELINE batch.
 
-Stated bf16 tolerances (activations / residual stream bf16, fp32 accumulate): feature cosine >= 0.999 vs the fp32
-reference, |loss - ref| <= 2e-2 * |ref|, gradient cosine >= 0.97 (tiny models) / 0.95 (full size), gradient norms within
-10 %.  Every comparison's ACHIEVED numbers are appended to gpurun_out/parity_report.jsonl (one JSON line per case; the
-committed copy of a B200 run lives under profiles/).
+Stated bf16 tolerances (activations / residual stream bf16, fp32 accumulate), set to <= 2x the worst value MEASURED on a B200
+over all cases (profiles/r02_parity_report.jsonl): feature cosine >= 0.9998 vs the fp32 reference (worst measured 0.99992),
+|loss - ref| <= 6e-3 * |ref| (2.7e-3), gradient cosine >= 0.985 for the tiny models (0.9931) / 0.975 at full size (0.9894),
+gradient norms within 7 % (3.3 %).  For scale: the REFERENCE's own mixed-precision path -- the oracle under
+torch.autocast(bfloat16), profiles/r02_autocast_deviation.jsonl -- sits at feature cosine 0.99993-0.99998, loss 1e-3-5e-3 and
+gradient cosine 0.9983-0.9997 on the same fixtures (0.90 on tiny_tri_pc_bntrain), i.e. this contract is as tight as the
+reference's AMP.  Every comparison's ACHIEVED numbers are appended to gpurun_out/parity_report.jsonl (one JSON line per case).
+
 
 Order: cheap and wide first (tiny models, the BASELINE-size batch, the public encode API), the long full-size fixtures last,
 so `-x` never hides the broad checks behind one slow case."""
@@ -16,6 +20,8 @@ import pytest
 import torch
 
 from tests.common import C, ROOT, build_model, cosine, relerr, run_model, run_oracle
+
+FEATURE_COS, LOSS_REL, GRAD_COS_TINY, GRAD_COS_FULL, NORM_TOL = 0.9998, 6e-3, 0.985, 0.975, 0.07
 
 pytestmark = pytest.mark.gpu
 
@@ -31,7 +37,7 @@ def _report(**row):
     print("parity", json.dumps(row))
 
 
-def _check(name, grad_cos=0.97, norm_tol=0.1):
+def _check(name, grad_cos=GRAD_COS_TINY, norm_tol=NORM_TOL):
     case = C.CASES[name]
     gold = C.load_golden(name)
     model, sd, args = build_model(case, device="cuda")
@@ -44,10 +50,10 @@ def _check(name, grad_cos=0.97, norm_tol=0.1):
         c = cosine(v.detach().cpu(), gold[k])
         row["cos_" + k] = round(c, 6)
         row["relerr_" + k] = round(relerr(v.detach().cpu(), gold[k]), 5)
-        assert c > 0.999, (name, k, c)
+        assert c > FEATURE_COS, (name, k, c)
         assert abs(float(v.detach().norm(dim=-1).mean()) - 1.0) < 1e-3
     row["loss"], row["loss_ref"] = float(loss.detach()), float(gold["loss"])
-    assert abs(float(loss.detach()) - float(gold["loss"])) < 2e-2 * abs(float(gold["loss"])), (float(loss.detach()), float(gold["loss"]))
+    assert abs(float(loss.detach()) - float(gold["loss"])) < LOSS_REL * abs(float(gold["loss"])), (float(loss.detach()), float(gold["loss"]))
     if case.bn_train:  # running statistics after one training-mode forward (bf16 activations: 1 % of the largest entry)
         assert relerr(C.bn_running(model.state_dict()), gold["bn_running"]) < 1e-2
     loss.backward()
@@ -254,4 +260,4 @@ def test_full_size_models_vs_reference_fixture(name):
     """Full-size weights (ViT-B/32 = BASELINE configs[0]; ViT-L/14 + audio / depth / point Lens = reduced-batch configs[2..4]).
     vitl14_pc_bs8_bntrain: training-mode BatchNorm over eight clouds of distinct shapes (a well-conditioned contrastive batch,
     oracle/cases.py) -- same tolerances as every other case."""
-    _check(name, grad_cos=0.95)
+    _check(name, grad_cos=GRAD_COS_FULL)

@@ -3,7 +3,9 @@ skipped on a single-GPU box, where bench.py's N > 1 parity leg is the on-hardwar
 NCCL, the real CUDA kernels:
   * ClipLoss / TriClipLoss for all four (local_loss, gather_with_grad) combinations against the per-rank results of the REAL
     reference run under gloo (tests/golden/dist_loss_w2.pt): loss, d/d(local features), d/d(logit_scale);
-  * GradReducer (bucketed all-reduce overlapped with backward on a side stream) against the explicit cross-rank sum."""
+  * GradReducer (bucketed all-reduce overlapped with backward on a side stream) against the explicit cross-rank sum;
+  * the peer-memory transport (CUDA IPC arena over NVLink: feature gather fused into the loss GEMMs, rank-ordered small
+    exchanges, copy-engine gradient push + in-optimizer sum) against the NCCL transport in the same processes."""
 import os
 import socket
 
@@ -69,7 +71,76 @@ def _worker(rank, port, out):
         steps.append(max(float((p.grad.double() - w).abs().max() / w.abs().max().clamp_min(1e-30)) for p, w in zip(params, want)))
         for p in params:
             p.grad = None
-    torch.save(dict(res=res, reducer_err=steps, n_buckets=len(red.buckets)), out.format(rank))
+    # ---- the peer-memory transport (vitlens_b200.comm): same losses with the feature gather fused into the GEMMs and the small
+    # exchanges over the arena, against the NCCL transport of this very process; then the copy-engine gradient exchange
+    from vitlens_b200 import comm, optim
+
+    Bl, E = 256, 768
+    g = torch.Generator().manual_seed(100 + rank)
+    fx, fy, fv = (torch.nn.functional.normalize(torch.randn(Bl, E, generator=g), dim=-1).to(dev) for _ in range(3))
+
+    def run_losses():
+        out = {}
+        for tri, ll, gwg in DC.COMBOS:
+            x, y, v = (t.clone().requires_grad_(True) for t in (fx, fy, fv))
+            s = torch.tensor(2.659, device=dev, requires_grad=True)
+            kw = dict(local_loss=ll, gather_with_grad=gwg, rank=rank, world_size=W)
+            loss = open_clip.TriClipLoss(**kw)(x, y, v, s.exp()) if tri else open_clip.ClipLoss(**kw)(x, y, s.exp())
+            loss.backward()
+            out[(tri, ll, gwg)] = dict(loss=loss.detach().cpu(), dx=x.grad.cpu(), dy=y.grad.cpu(), dv=v.grad.cpu() if tri else None, ds=s.grad.cpu())
+        return out
+
+    os.environ["VL_COMM"] = "nccl"
+    via_nccl = run_losses()
+    assert comm.arena() is None
+    del os.environ["VL_COMM"]
+    total = sum(p.numel() for p in params)
+    arena = comm.init_arena(nbytes=(64 << 20) + W * (total + 64) * 4)
+    assert arena is not None
+    via_peer = run_losses()
+    via_peer2 = run_losses()  # ring slots / tickets advance: a second round must agree bit for bit
+    peer_err = 0.0
+    for key in via_nccl:
+        for k, vref in via_nccl[key].items():
+            if vref is None:
+                continue
+            assert torch.equal(via_peer[key][k], via_peer2[key][k]), (key, k)
+            peer_err = max(peer_err, float((via_peer[key][k] - vref).abs().max() / vref.abs().max().clamp_min(1e-30)))
+    # gradient exchange over the copy engines + in-optimizer sum vs the NCCL all-reduce + plain optimizer
+    torch.manual_seed(0)
+    net2 = torch.nn.Sequential(torch.nn.Linear(64, 512), torch.nn.GELU(), torch.nn.Linear(512, 512), torch.nn.GELU(), torch.nn.Linear(512, 8)).to(dev)
+    net2.load_state_dict(net.state_dict())
+    p2 = list(net2.parameters())
+    red2 = GradReducer(p2, bucket_bytes=1 << 18, arena=arena)
+    o1 = optim.AdamW([dict(params=params)], lr=1e-2, weight_decay=0.1)
+    o2 = optim.AdamW([dict(params=p2)], lr=1e-2, weight_decay=0.1)
+    mat_err = []
+    for step in range(3):
+        gg = torch.Generator().manual_seed(50 * step + rank)
+        xin = torch.randn(32, 64, generator=gg).to(dev)
+        net(xin).square().sum().backward()
+        red.finish()
+        net2(xin).square().sum().backward()
+        if step == 0:  # materialised sums equal the NCCL all-reduce
+            red2.finish(materialize=True)
+            mat_err.append(max(float((a.grad - b.grad).abs().max() / b.grad.abs().max().clamp_min(1e-30)) for a, b in zip(p2, params)))
+            o2.step(grad_scale=1.0 / W)
+        else:          # the sum folded into the optimizer
+            red2.finish()
+            o2.step(grad_scale=1.0 / W, n_src=red2.n_src, src_stride=red2.src_stride)
+        o1.step(grad_scale=1.0 / W)
+        o1.zero_grad()
+        o2.zero_grad()
+    torch.cuda.synchronize()
+    w_err = max(float((a.detach() - b.detach()).abs().max() / b.detach().abs().max()) for a, b in zip(p2, params))
+    # every rank must hold bit-identical weights after the rank-ordered sums
+    chk = torch.stack([p.detach().double().sum() for p in p2])
+    both = [torch.empty_like(chk) for _ in range(W)]
+    dist.all_gather(both, chk)
+    same_weights = bool(torch.equal(both[0], both[1]))
+    torch.save(dict(res=res, reducer_err=steps, n_buckets=len(red.buckets), peer_err=peer_err, mat_err=mat_err, w_err=w_err, same_weights=same_weights,
+                    n_buckets_peer=len(red2.buckets)), out.format(rank))
+    comm.destroy_arena()
     dist.destroy_process_group()
 
 
@@ -96,5 +167,9 @@ def test_two_rank_loss_and_gradient_exchange_on_hardware(tmp_path):
                 assert err <= tol, (name, r, k, err)
     print("two-rank parity vs the reference run (max relative error):", worst)
     for r in range(W):
-        assert got[r]["n_buckets"] > 1
+        assert got[r]["n_buckets"] > 1 and got[r]["n_buckets_peer"] > 1
         assert max(got[r]["reducer_err"]) < 1e-6, got[r]["reducer_err"]
+        # peer-memory transport == NCCL transport (same kernels; only the order of the tiny cross-rank sums differs)
+        assert got[r]["peer_err"] < 1e-5, got[r]["peer_err"]
+        assert max(got[r]["mat_err"]) < 1e-6 and got[r]["w_err"] < 1e-5 and got[r]["same_weights"], (got[r]["mat_err"], got[r]["w_err"], got[r]["same_weights"])
+    print("peer-memory vs NCCL transport:", {k: got[0][k] for k in ("peer_err", "mat_err", "w_err", "same_weights")})

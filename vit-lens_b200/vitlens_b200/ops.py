@@ -442,8 +442,12 @@ def average_precision(scores, targets, apply_sigmoid=True):
 
 def similarity(feats, gallery_t=None, gallery=None):
     """fp32 [B, C] similarities of fp32 features [B, E] with a gallery given as [E, C] (classifier layout) or [C, E] -- the
-    tcgen05 GEMM with bf16-rounded operands and fp32 accumulation / output."""
+    tcgen05 GEMM with bf16-rounded operands and fp32 accumulation / output.  (The gallery is zero-padded to a multiple of 8
+    entries for the GEMM; the result is the [B, C] view of the padded output.)"""
     a = cast_bf16(feats)
-    if gallery is not None:
-        return gemm(a, cast_bf16(gallery), out_dtype=F32)
-    return gemm(a, cast_bf16(gallery_t), b_t=True, out_dtype=F32)
+    g = cast_bf16(gallery if gallery is not None else gallery_t.t().contiguous())  # [C, E]
+    Cn = g.shape[0]
+    C8 = (Cn + 7) // 8 * 8
+    if C8 != Cn:
+        g = torch.cat([g, g.new_zeros((C8 - Cn, g.shape[1]))]).contiguous()
+    return gemm(a, g, out_dtype=F32)[:, :Cn]
