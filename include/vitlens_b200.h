@@ -47,7 +47,11 @@ enum {
   VL_EPI_GELU = 1,     /* u = alpha*acc + bias; aux_out(bf16) = u if given; d = act(u)           */
   VL_EPI_RESIDUAL = 2, /* d = alpha*acc + bias + aux_in                                          */
   VL_EPI_GELU_BWD = 3, /* d = alpha*acc * act'(aux_in)     (dgrad of c_proj fused with GELU bwd) */
-  VL_EPI_GEGLU = 4,    /* reserved (fused GEGLU); returns VL_ENOTSUP today                         */
+  VL_EPI_GEGLU = 4,    /* Lens FeedForward (perceiver.py:85-102): B = the [2F, K] weight with rows PERMUTED so that rows
+                          [n*256, n*256+128) are value rows n*128.. and rows [n*256+128, (n+1)*256) the gate rows
+                          F + n*128.. (bias permuted alike); u = alpha*acc + bias; aux_out[M, 2F] = u in the ORIGINAL
+                          column order (value | gate, needed by the backward); d[M, F] = value * gelu(gate).
+                          M >= 512, N = 2F with N % 256 == 0 (VL_ENOTSUP otherwise: use vl_geglu_fwd)          */
   /* Contrastive-loss epilogues (replace `logit_scale * x @ y.T` + F.cross_entropy, loss.py:116-163,
    * 346-385) -- the [rows x cols] logits never reach HBM:                                         */
   VL_EPI_ROWLSE = 5,   /* z = alpha*acc. Per row and per 128/64-column part p: out_vec0[row*nparts+p] = max z,

@@ -391,3 +391,28 @@ def similarity(feats, gallery_t=None, gallery=None):
     a = feats.to(BF16).float()
     g = gallery.to(BF16).float().t() if gallery is not None else gallery_t.to(BF16).float()
     return a @ g
+
+
+def geglu_fusable(M, F):
+    return M >= 512 and F % 128 == 0
+
+
+def geglu_permute_rows(w):
+    F = w.shape[0] // 2
+    idx = torch.arange(F).view(F // 128, 128)
+    return w.index_select(0, torch.cat([idx, idx + F], dim=1).reshape(-1)).contiguous()
+
+
+def gemm_geglu(a, w_perm16, bias_perm):
+    _n()
+    F = w_perm16.shape[0] // 2
+    inv = torch.empty(2 * F, dtype=torch.long)
+    idx = torch.arange(F).view(F // 128, 128)
+    inv[torch.cat([idx, idx + F], dim=1).reshape(-1)] = torch.arange(2 * F)
+    acc = a.float() @ w_perm16.float().t() + bias_perm
+    h = acc[:, inv]  # back to the original (value | gate) column order
+    return (h[:, :F] * F_gelu(h[:, F:])).to(BF16), h.to(BF16)
+
+
+def F_gelu(x):
+    return F.gelu(x)

@@ -449,6 +449,80 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
   }
 }
 
+// Fused GEGLU epilogue (Lens FeedForward, reference perceiver.py:85-102: Linear(d, 2F) -> chunk -> value * gelu(gate)).  The
+// weight rows are PERMUTED on the host so that every 256-column tile holds the value columns [n*128, n*128 + 128) in its first
+// half and the matching gate columns in its second half; the warp that owns value slice s (64 columns) also owns gate slice
+// s + 2.  It writes three 32 x 64 blocks: the two pre-activation blocks back to h (the [M, 2F] tensor the backward needs, in
+// the ORIGINAL column order: value at column c, gate at F + c) and value * gelu(gate) to the [M, F] output.
+template <int BN, typename Release>
+__device__ __forceinline__ void epilogue_tile_geglu(const GemmParams& p, const CUtensorMap* tmD, const CUtensorMap* tmX, uint32_t tmem_base,
+                                                    uint32_t acc_col, int row_w, int n_blk, int s, int quarter, int lane, uint32_t bufA,
+                                                    uint32_t bufB, Release release) {
+  const int F = p.N / 2;
+  const int out_col = n_blk * (BN / 2) + s * 64;  // column in the output and in the value half of h
+  const int gcol = n_blk * BN + s * 64;           // GEMM column of the value slice (gate slice: + BN / 2)
+  const float alpha_eff = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f);
+  const uint32_t sw = lane & 7;
+  const uint32_t rowA = bufA + lane * 128, rowB = bufB + lane * 128;
+  const uint32_t tval = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc_col + s * 64;
+  const uint32_t tgate = tval + BN / 2;
+  uint32_t outp[32];  // value * gelu(gate) of the 64 columns, packed bf16
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[16], g[16];
+    tmem_ld16(tval + c * 16, v);
+    tmem_ld16(tgate + c * 16, g);
+    float bv[16], bg[16];
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 x4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + gcol + c * 16 + j)) : make_float4(0, 0, 0, 0);
+      const float4 y4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + gcol + BN / 2 + c * 16 + j)) : make_float4(0, 0, 0, 0);
+      bv[j] = x4.x; bv[j + 1] = x4.y; bv[j + 2] = x4.z; bv[j + 3] = x4.w;
+      bg[j] = y4.x; bg[j + 1] = y4.y; bg[j + 2] = y4.z; bg[j + 3] = y4.w;
+    }
+    tc_wait_ld();
+    if (c == 3) release();
+    float fv[16], fg[16];
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      const float2 a2 = make_float2(alpha_eff, alpha_eff);
+      const float2 r = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), a2, make_float2(bv[j], bv[j + 1]));
+      const float2 q = __ffma2_rn(make_float2(__uint_as_float(g[j]), __uint_as_float(g[j + 1])), a2, make_float2(bg[j], bg[j + 1]));
+      fv[j] = r.x; fv[j + 1] = r.y;
+      fg[j] = q.x; fg[j + 1] = q.y;
+    }
+    const uint32_t o0 = ((2 * c) ^ sw) << 4, o1 = ((2 * c + 1) ^ sw) << 4;
+    st_shared_v4(rowA + o0, pack_bf16(fv[0], fv[1]), pack_bf16(fv[2], fv[3]), pack_bf16(fv[4], fv[5]), pack_bf16(fv[6], fv[7]));
+    st_shared_v4(rowA + o1, pack_bf16(fv[8], fv[9]), pack_bf16(fv[10], fv[11]), pack_bf16(fv[12], fv[13]), pack_bf16(fv[14], fv[15]));
+    st_shared_v4(rowB + o0, pack_bf16(fg[0], fg[1]), pack_bf16(fg[2], fg[3]), pack_bf16(fg[4], fg[5]), pack_bf16(fg[6], fg[7]));
+    st_shared_v4(rowB + o1, pack_bf16(fg[8], fg[9]), pack_bf16(fg[10], fg[11]), pack_bf16(fg[12], fg[13]), pack_bf16(fg[14], fg[15]));
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {  // value * gelu(gate), two elements per FMA-pipe instruction
+      const float2 act = gelu_erf_fwd2(make_float2(fg[j], fg[j + 1]));
+      const float2 o = __fmul2_rn(make_float2(fv[j], fv[j + 1]), act);
+      outp[8 * c + (j >> 1)] = pack_bf16(o.x, o.y);
+    }
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0 && !(p.dbg & 2)) {
+    tma_store_2d(tmX, bufA, out_col, row_w);      // value pre-activations  -> h[:, c]
+    tma_store_commit();
+    tma_store_2d(tmX, bufB, F + out_col, row_w);  // gate pre-activations   -> h[:, F + c]
+    tma_store_commit();
+    tma_store_wait_read<1>();                     // the first store has finished reading block A: reuse it for the output
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) st_shared_v4(rowA + ((j ^ sw) << 4), outp[4 * j], outp[4 * j + 1], outp[4 * j + 2], outp[4 * j + 3]);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0 && !(p.dbg & 2)) {
+    tma_store_2d(tmD, bufA, out_col, row_w);
+    tma_store_commit();
+  }
+}
+
 // PEER = true: the B operand is sharded by rows over the ranks of the box (the all-gathered feature matrix of the contrastive
 // loss, reference loss.py:55-76): one tensor map per peer arena, and the producer loads each tile straight from its owner's
 // memory over NVLink after seeing that peer's ticket -- the all-gather happens inside the GEMM, tile by tile.
@@ -715,11 +789,18 @@ static int launch_gemm2(const VlGemmArgs& a, GemmParams p, cudaStream_t stream);
 template <int BN>
 static bool tma_epilogue_ok(const VlGemmArgs& a, const GemmParams& p) {
   return BN == 256 && !a.d_f32 && !a.accumulate && p.split_k == 1 && p.aux_row_div == 1 &&
-         (a.epilogue == VL_EPI_LINEAR || a.epilogue == VL_EPI_GELU || a.epilogue == VL_EPI_RESIDUAL || a.epilogue == VL_EPI_GELU_BWD) &&
+         (a.epilogue == VL_EPI_LINEAR || a.epilogue == VL_EPI_GELU || a.epilogue == VL_EPI_RESIDUAL || a.epilogue == VL_EPI_GELU_BWD ||
+          a.epilogue == VL_EPI_GEGLU) &&
          (reinterpret_cast<uintptr_t>(a.d) & 15) == 0 && debug_get(10) != 1;
 }
 
 static int make_epilogue_maps(const VlGemmArgs& a, CUtensorMap* tmD, CUtensorMap* tmX) {
+  if (a.epilogue == VL_EPI_GEGLU) {  // output [M, N / 2]; the pre-activations go to aux_out [M, N]
+    int rc = make_tmap_bf16_2d(tmD, a.d, a.N / 2, a.M, a.ldd, 64, 32);
+    if (rc) return rc;
+    VL_CHECK_ARG((reinterpret_cast<uintptr_t>(a.aux_out) & 15) == 0, "vl_gemm_bf16: aux pointer must be 16-byte aligned");
+    return make_tmap_bf16_2d(tmX, a.aux_out, a.N, a.M, a.ldaux, 64, 32);
+  }
   int rc = make_tmap_bf16_2d(tmD, a.d, a.N, a.M, a.ldd, 64, 32);
   if (rc) return rc;
   const void* xptr = (a.epilogue == VL_EPI_GELU) ? a.aux_out : a.aux_in;
@@ -1138,7 +1219,17 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(tempty_bar(acc), 0));
       };
-      if constexpr (TE) {
+      if constexpr (TE && EPI == VL_EPI_GEGLU) {
+        static_assert(!TE || (kSlicesPerWarp == 2 && kGroups == 2), "GEGLU epilogue: 8 warps, value slice s and gate slice s + 2 per warp");
+        bool released = false;
+        if (row_w < p.M && !(p.dbg & 1)) {
+          const int s = e >> 2;
+          epilogue_tile_geglu<BN>(p, &tmD, &tmX, tmem_base, acc * BN, row_w, n_blk, s, quarter, lane, stg_base + (s * 4 + quarter) * kEpiBufBytes,
+                                  stg_base + ((s + kGroups) * 4 + quarter) * kEpiBufBytes, release);
+          released = true;
+        }
+        if (!released) release();
+      } else if constexpr (TE) {
         bool released = false;
         if (row_w < p.M && !(p.dbg & 1)) {
 #pragma unroll
@@ -1233,6 +1324,7 @@ static int launch_gemm2(const VlGemmArgs& a, GemmParams p, cudaStream_t stream) 
         case VL_EPI_LINEAR: VL_LAUNCH_TE2(VL_EPI_LINEAR); break;
         case VL_EPI_GELU: VL_LAUNCH_TE2(VL_EPI_GELU); break;
         case VL_EPI_RESIDUAL: VL_LAUNCH_TE2(VL_EPI_RESIDUAL); break;
+        case VL_EPI_GEGLU: VL_LAUNCH_TE2(VL_EPI_GEGLU); break;
         default: VL_LAUNCH_TE2(VL_EPI_GELU_BWD); break;
       }
 #undef VL_LAUNCH_TE2
@@ -1280,9 +1372,18 @@ extern "C" int vl_gemm_bf16(const VlGemmArgs* a, void* stream) {
     VL_CHECK_ARG(a->aux_in != nullptr && a->ldaux % 8 == 0 && a->ldaux >= a->N, "vl_gemm_bf16: aux_in / ldaux invalid");
   if (a->epilogue == VL_EPI_GELU && a->aux_out)
     VL_CHECK_ARG(a->ldaux % 8 == 0 && a->ldaux >= a->N, "vl_gemm_bf16: ldaux invalid");
-  if (a->epilogue < 0 || a->epilogue > VL_EPI_CLIPGRAD || a->epilogue == VL_EPI_GEGLU) {
+  if (a->epilogue < 0 || a->epilogue > VL_EPI_CLIPGRAD) {
     set_error("vl_gemm_bf16: epilogue %d not supported", a->epilogue);
     return VL_ENOTSUP;
+  }
+  if (a->epilogue == VL_EPI_GEGLU) {
+    VL_CHECK_ARG(a->aux_out != nullptr && a->ldaux % 8 == 0 && a->ldaux >= a->N && !a->d_f32 && !a->accumulate && a->split_k <= 1 && a->ldd >= a->N / 2,
+                 "vl_gemm_bf16: GEGLU needs a bf16 output [M, N/2], aux_out [M, N] (ldaux >= N) and no split_k");
+    if (!(a->M >= 4 * kBM && a->N % 256 == 0 && a->b_peers == nullptr && (reinterpret_cast<uintptr_t>(a->d) & 15) == 0 && debug_get(8) != 1 &&
+          debug_get(10) != 1)) {
+      set_error("vl_gemm_bf16: the fused GEGLU epilogue runs on the CTA-pair kernel: M >= 512 and N %% 256 == 0 (use vl_geglu_fwd otherwise)");
+      return VL_ENOTSUP;
+    }
   }
   VL_CHECK_ARG(!((a->relu || a->aux_row_div > 1) && (a->d_f32 || (a->epilogue != VL_EPI_LINEAR && a->epilogue != VL_EPI_RESIDUAL))),
                "vl_gemm_bf16: relu / aux_row_div need a bf16 LINEAR or RESIDUAL epilogue");

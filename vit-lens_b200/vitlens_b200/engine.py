@@ -424,8 +424,14 @@ class LensFFFn(torch.autograd.Function):
     def forward(ctx, x, nw, nb, w0, b0, w2, b2):
         need = any(ctx.needs_input_grad)
         xn, m, r = _ops.layernorm_fwd(x, nw, nb, want_stats=need)
-        h = _ops.gemm(xn, w16(w0), bias=b0)
-        gg = _ops.geglu_fwd(h)
+        if _ops.geglu_fusable(xn.shape[0], w0.shape[0] // 2):
+            # one GEMM: the epilogue pairs every value column with its gate column (weight rows permuted once per weight version)
+            wp = WEIGHTS.get(w0, "geglu", lambda w: _ops.cast_bf16(_ops.geglu_permute_rows(w.detach())))
+            bp = WEIGHTS.get(b0, "geglu", lambda b: _ops.geglu_permute_rows(b.detach().float()))
+            gg, h = _ops.gemm_geglu(xn, wp, bp)
+        else:
+            h = _ops.gemm(xn, w16(w0), bias=b0)
+            gg = _ops.geglu_fwd(h)
         y = _ops.gemm(gg, w16(w2), bias=b2, epilogue=_ops.EPI_RESIDUAL, aux_in=x)
         if need:
             ctx.save_for_backward(x, xn, m, r, h, gg, nw, w0, w2)

@@ -233,6 +233,34 @@ def l2norm_bwd(dy, y, inv):
     return dx
 
 
+def geglu_fusable(M: int, F: int) -> bool:
+    """True when Linear(d, 2F) + GEGLU can run as ONE GEMM with the VL_EPI_GEGLU epilogue (CTA-pair kernel, whole tiles)."""
+    return M >= 512 and F % 128 == 0
+
+
+def geglu_permute_rows(w):
+    """Row permutation of the FeedForward's first Linear for the fused epilogue: every 256-row tile = 128 value rows followed by
+    the 128 gate rows of the same output columns.  w: [2F, ...] (weight) or [2F] (bias)."""
+    F2 = w.shape[0]
+    F = F2 // 2
+    idx = torch.arange(F, device=w.device).view(F // 128, 128)
+    perm = torch.cat([idx, idx + F], dim=1).reshape(-1)
+    return w.index_select(0, perm).contiguous()
+
+
+def gemm_geglu(a, w_perm16, bias_perm):
+    """(value * gelu(gate) [M, F], h [M, 2F] pre-activations in the ORIGINAL column order) of a @ W^T + b with W / b given in the
+    geglu_permute_rows layout -- reference perceiver.py:85-102 in one launch."""
+    _v2(a, BF16), _v2(w_perm16, BF16)
+    M, K = a.shape
+    N = w_perm16.shape[0]
+    assert geglu_fusable(M, N // 2) and w_perm16.shape[1] == K
+    out = torch.empty((M, N // 2), device=a.device, dtype=BF16)
+    h = torch.empty((M, N), device=a.device, dtype=BF16)
+    L.gemm(a, w_perm16, out, M=M, N=N, K=K, lda=_ld(a), ldb=_ld(w_perm16), ldd=N // 2, epilogue=L.EPI_GEGLU, bias=bias_perm, aux_out=h, ldaux=N)
+    return out, h
+
+
 def geglu_fwd(h):
     M, F2 = h.shape
     out = torch.empty((M, F2 // 2), device=h.device, dtype=BF16)
