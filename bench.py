@@ -285,7 +285,7 @@ def run_cuda(args):
     if world > 1:  # peer-memory arena: fused feature gather in the loss + copy-engine gradient exchange (VL_COMM=nccl switches it off)
         from vitlens_b200 import comm
 
-        arena = comm.init_arena(nbytes=(96 << 20) + world * (wl.n_params + 64) * 4)
+        arena = comm.init_arena(nbytes=world * (wl.n_params + 64) * 4 + (1 << 20))
     reducer = grad_sync.GradReducer(params, arena=arena) if world > 1 else None
 
     def train_step(inputs):

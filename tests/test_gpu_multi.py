@@ -95,7 +95,7 @@ def _worker(rank, port, out):
     assert comm.arena() is None
     del os.environ["VL_COMM"]
     total = sum(p.numel() for p in params)
-    arena = comm.init_arena(nbytes=(64 << 20) + W * (total + 64) * 4)
+    arena = comm.init_arena(nbytes=W * (total + 64) * 4 + (1 << 20))
     assert arena is not None
     via_peer = run_losses()
     via_peer2 = run_losses()  # ring slots / tickets advance: a second round must agree bit for bit

@@ -48,7 +48,7 @@ class PeerArena:
         self.small_off = FLAG_BYTES
         self.feat_off = self.small_off + SMALL_SLOTS * SMALL_BYTES
         self.cursor = self.feat_off + FEAT_SLOTS * self.feat_bytes
-        self.nbytes = max(int(nbytes), self.cursor)
+        self.nbytes = self.cursor + int(nbytes) + 4096  # `nbytes`: room for alloc() (gradient regions) on top of the fixed rings
         handle, self.base = L.comm_init(rank, world, self.nbytes)
         handles: List[bytes] = [b""] * world
         if world > 1:
@@ -139,8 +139,9 @@ def arena() -> Optional[PeerArena]:
 
 
 def init_arena(nbytes: int = 0, feat_bytes: int = 16 << 20, group=None) -> Optional[PeerArena]:
-    """Create the process-wide arena (idempotent).  Returns None when peer memory is switched off (VL_COMM=nccl) or
-    torch.distributed is not initialised with more than one rank."""
+    """Create the process-wide arena (idempotent): the flag block, the small-exchange and feature rings plus `nbytes` of
+    bump-allocated space (GradReducer needs world x 4 bytes x trainable parameters).  Returns None when peer memory is switched
+    off (VL_COMM=nccl) or torch.distributed is not initialised with more than one rank."""
     global _ARENA
     import torch.distributed as dist
 
