@@ -1363,7 +1363,7 @@ extern "C" int vl_gemm_bf16(const VlGemmArgs* a, void* stream) {
   VL_CHECK_ARG(a->lda % 8 == 0 && a->ldb % 8 == 0, "vl_gemm_bf16: lda/ldb must be multiples of 8 elements");
   VL_CHECK_ARG(a->ldd % (a->d_f32 ? 4 : 8) == 0, "vl_gemm_bf16: ldd misaligned");
   VL_CHECK_ARG(a->lda >= (a->a_mn ? a->M : a->K) && a->ldb >= (a->b_mn ? a->N : a->K) &&
-                   (a->epilogue == VL_EPI_ROWLSE || a->ldd >= ((a->N + 7) / 8) * 8),
+                   (a->epilogue == VL_EPI_ROWLSE || a->ldd >= (((a->epilogue == VL_EPI_GEGLU ? a->N / 2 : a->N) + 7) / 8) * 8),
                "vl_gemm_bf16: leading dimension smaller than the (8-padded) row length");
   VL_CHECK_ARG(!(a->accumulate && !a->d_f32), "vl_gemm_bf16: accumulate needs fp32 output");
   VL_CHECK_ARG(!(a->split_k > 1 && !(a->accumulate && a->d_f32)), "vl_gemm_bf16: split_k needs accumulate fp32 output");
