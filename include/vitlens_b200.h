@@ -114,6 +114,10 @@ typedef struct {
   int32_t b_npeers, b_peer_rows;
   const int32_t* peer_flags;
   int32_t peer_flag_value;
+  /* loss epilogues: optional byte mask [M, N] (row stride ldmask); where it is 0 the logit is replaced by the constant 0 and
+   * carries no gradient -- `logits * mask` of ClipLossSimMask / ClipLossLabelMask / TriClipLossLabelMask (loss.py:485-903) */
+  const uint8_t* mask;
+  int64_t ldmask;
 } VlGemmArgs;
 
 int vl_gemm_bf16(const VlGemmArgs* args, void* stream);

@@ -364,12 +364,27 @@ def tri_clip_loss(image, text, visual, logit_scale):
     return clip_loss(image, visual, logit_scale) + clip_loss(text, visual, logit_scale)
 
 
+def sim_mask(all_x, sim_thres: float):
+    """ClipLossSimMask.get_logits loss.py:535-542 / 566-573: pairs whose teacher features are at least `sim_thres` similar are
+    masked out, the diagonal is always kept."""
+    sim = all_x.detach() @ all_x.detach().t()
+    return torch.logical_or(torch.logical_not(sim >= sim_thres), torch.eye(all_x.shape[0], dtype=torch.bool))
+
+
+def label_mask(all_x_labels, all_y_labels):
+    """ClipLossLabelMask.get_logits loss.py:667-679 / 706-717: same-class pairs are masked out, the diagonal is kept."""
+    if all_x_labels.ndim == 1:
+        all_x_labels, all_y_labels = all_x_labels.unsqueeze(0), all_y_labels.unsqueeze(0)
+    return torch.logical_or(torch.logical_not(all_x_labels.t() == all_y_labels), torch.eye(all_x_labels.shape[1], dtype=torch.bool))
+
+
 def clip_loss_sharded(xs: Sequence[torch.Tensor], ys: Sequence[torch.Tensor], logit_scale, rank: int,
-                      local_loss: bool, gather_with_grad: bool):
+                      local_loss: bool, gather_with_grad: bool, mask=None):
     """What rank `rank` computes in ClipLoss / gather_features (loss.py:20-78, 346-385) at
     world_size == len(xs); xs[r], ys[r] are rank r's local feature blocks.  Non-grad gather:
     remote blocks are detached; the local block keeps grad only when not local_loss
-    (loss.py:63-76)."""
+    (loss.py:63-76).  `mask` (bool [B_all, B_all]): the mask variants' `logits * mask` (loss.py:544-575, 681-722) -- the
+    x-direction logits take mask rows, the y-direction logits mask.T rows."""
     W = len(xs)
     if gather_with_grad:
         ax = torch.cat(list(xs), 0)
@@ -381,9 +396,15 @@ def clip_loss_sharded(xs: Sequence[torch.Tensor], ys: Sequence[torch.Tensor], lo
     if local_loss:
         lx = (logit_scale * xs[rank]) @ ay.t()
         ly = (logit_scale * ys[rank]) @ ax.t()
-        off = xs[rank].shape[0] * rank
+        bl = xs[rank].shape[0]
+        off = bl * rank
+        if mask is not None:
+            lx = lx * mask[off:off + bl]
+            ly = ly * mask.t()[off:off + bl]
         return (cross_entropy_arange(lx, off) + cross_entropy_arange(ly, off)) / 2
     lx = (logit_scale * ax) @ ay.t()
+    if mask is not None:
+        lx = lx * mask
     return (cross_entropy_arange(lx) + cross_entropy_arange(lx.t())) / 2
 
 

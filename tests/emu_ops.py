@@ -230,23 +230,28 @@ def add_bf16(a, b):
     return (a.float() + b.float()).to(BF16)
 
 
-def rowlse(p16, q16, *, alpha, label_off=0):
+def rowlse(p16, q16, *, alpha, label_off=0, mask=None):
     _n()
     alpha = float(alpha)
     z = alpha * (p16.float() @ q16.float().t())
+    if mask is not None:
+        z = z * (mask != 0)
     lse = torch.logsumexp(z, -1)
     M = z.shape[0]
     diag = z[torch.arange(M), torch.arange(M) + label_off]
     return lse, (lse - diag).sum().reshape(1)
 
 
-def clipgrad(p16, q16, *, alpha, row_lse, col_lse, label_off, gscale, gscale_dev=None, ds_row_only=False):
+def clipgrad(p16, q16, *, alpha, row_lse, col_lse, label_off, gscale, gscale_dev=None, ds_row_only=False, mask=None):
     _n()
     alpha = float(alpha)
     if gscale_dev is not None:
         gscale = gscale * float(gscale_dev)
     acc = p16.float() @ q16.float().t()
     z = alpha * acc
+    keep = None if mask is None else (mask != 0).float()
+    if keep is not None:
+        z = z * keep
     M, N = z.shape
     g = torch.exp(z - row_lse[:, None])
     grow = g
@@ -257,7 +262,10 @@ def clipgrad(p16, q16, *, alpha, row_lse, col_lse, label_off, gscale, gscale_dev
     onehot = torch.zeros(M, N)
     onehot[torch.arange(M), torch.arange(M) + label_off] = 1.0
     g = gscale * (g - k * onehot)
-    ds = (gscale * (grow - onehot) * acc).sum() if ds_row_only else (g * acc).sum()
+    grow = gscale * (grow - onehot)
+    if keep is not None:
+        g, grow = g * keep, grow * keep
+    ds = (grow * acc).sum() if ds_row_only else (g * acc).sum()
     return g.to(BF16), ds.reshape(1)
 
 

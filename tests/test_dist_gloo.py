@@ -84,6 +84,44 @@ def test_sharded_contrastive_loss_matches_reference_run(tri, tmp_path):
                     assert err <= tol * float(ref.abs().max()) + 1e-5, (name, r, k, err, float(ref.abs().max()))
 
 
+def _mask_loss_worker(rank, port, out):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=W)
+    from tests import emu_ops
+    from tests import maskloss_common as MC
+    from vitlens_b200 import engine
+
+    engine._ops = emu_ops
+    import open_clip
+
+    gold = MC.load_golden()
+    X, Y, V, LX, LY, LV = MC.inputs(gold)
+    res = {}
+    for kind in MC.KINDS:
+        for ll, gwg in MC.FLAGS:
+            kw = dict(local_loss=ll, gather_with_grad=gwg, rank=rank, world_size=W)
+            res[(kind, ll, gwg)] = MC.run_ours(open_clip, gold, kind, kw, X[rank], Y[rank], V[rank], LX[rank], LY[rank], LV[rank])
+    torch.save(res, out.format(rank))
+    dist.destroy_process_group()
+
+
+def test_sharded_mask_losses_match_reference_run(tmp_path):
+    """ClipLossSimMask / ClipLossLabelMask / TriClipLossLabelMask at world size 2 against the REAL reference's per-rank results
+    under gloo (tests/golden/mask_loss.pt), all four (local_loss, gather_with_grad) combinations."""
+    from tests import maskloss_common as MC
+
+    out = str(tmp_path / "m{}.pt")
+    mp.spawn(_mask_loss_worker, args=(_free_port(), out), nprocs=W, join=True)
+    got = [torch.load(out.format(r), weights_only=False) for r in range(W)]
+    gold = MC.load_golden()
+    for kind in MC.KINDS:
+        for ll, gwg in MC.FLAGS:
+            for r in range(W):
+                MC.compare(got[r][(kind, ll, gwg)], gold, f"{kind}_local{int(ll)}_gwg{int(gwg)}/rank{r}")
+
+
 def _reducer_worker(rank, port, out):
     import torch.distributed as dist
 

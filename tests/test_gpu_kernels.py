@@ -581,14 +581,14 @@ def test_peer_sharded_gemm_matches_gathered_operand(ops, W, rows):
         close(dxb, alpha * (ga.float() @ cat.float()), tol=2e-3)
 
 
-@pytest.mark.parametrize("M,K,F", [(1024, 1024, 4096), (640, 256, 512), (65 * 128 + 40, 1024, 4096)])
-def test_fused_geglu_epilogue_equals_unfused(ops, M, K, F):
+@pytest.mark.parametrize("M,K,Fd", [(1024, 1024, 4096), (640, 256, 512), (65 * 128 + 40, 1024, 4096)])
+def test_fused_geglu_epilogue_equals_unfused(ops, M, K, Fd):
     """VL_EPI_GEGLU (Lens FeedForward, perceiver.py:85-102, one launch) against Linear + the stand-alone GEGLU kernel and against
     fp32 torch: the saved pre-activations h come back in the original (value | gate) column order."""
     torch.manual_seed(7)
     a = torch.randn(M, K, device="cuda").to(BF)
-    w = (torch.randn(2 * F, K, device="cuda") * K ** -0.5)
-    b = torch.randn(2 * F, device="cuda") * 0.1
+    w = (torch.randn(2 * Fd, K, device="cuda") * K ** -0.5)
+    b = torch.randn(2 * Fd, device="cuda") * 0.1
     w16 = w.to(BF)
     h_ref = ops.gemm(a, w16, bias=b)
     gg_ref = ops.geglu_fwd(h_ref)
@@ -596,4 +596,4 @@ def test_fused_geglu_epilogue_equals_unfused(ops, M, K, F):
     assert torch.equal(h, h_ref)                       # same accumulators, same bias, same rounding
     close(gg, gg_ref, tol=1e-2)                        # the fused product is taken from the fp32 pre-activations, the unfused from bf16
     full = a.float() @ w16.float().t() + b
-    close(gg, full[:, :F] * F.gelu(full[:, F:]), tol=2e-2)
+    close(gg, full[:, :Fd] * F.gelu(full[:, Fd:]), tol=2e-2)

@@ -218,6 +218,47 @@ def test_train_step_accumulation_on_device():
         assert abs(float(acc[n].norm()) - mult * float(g.norm())) < 0.08 * mult * float(g.norm()) + 1e-5, n
 
 
+def test_mask_losses_on_device_vs_reference_run():
+    """ClipLossSimMask / ClipLossLabelMask / TriClipLossLabelMask (loss.py:485-903) through the CUDA loss epilogues (`mask` of
+    VlGemmArgs) against the REAL reference's results (tests/golden/mask_loss.pt), world size 1."""
+    import open_clip
+    from tests import maskloss_common as MC
+
+    gold = MC.load_golden()
+    X, Y, V, LX, LY, LV = (MC.flat(t) for t in MC.inputs(gold))
+    for kind in MC.KINDS:
+        got = MC.run_ours(open_clip, gold, kind, dict(world_size=1), X, Y, V, LX, LY, LV, device="cuda")
+        worst = MC.compare(got, gold, f"{kind}_w1")
+        _report(case=f"mask_loss {kind} world 1", max_rel_err=worst)
+
+
+def test_grad_checkpointing_on_device():
+    """set_grad_checkpointing(True) on the CUDA path: bit-identical loss / gradients, and a smaller activation footprint
+    (vitl14_depth_bs2 trains four ViT blocks and back-propagates through all 24)."""
+    case = C.CASES["vitl14_depth_bs2"]
+
+    def run(ckpt):
+        model, sd, args = build_model(case, device="cuda")
+        model.set_grad_checkpointing(ckpt)
+        inp = C.build_inputs(case, args)
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        feats, ls, loss = run_model(case, model, inp)
+        peak_fwd = torch.cuda.max_memory_allocated() - base
+        loss.backward()
+        torch.cuda.synchronize()
+        return float(loss.detach()), {k: p.grad.clone() for k, p in model.named_parameters() if p.requires_grad}, peak_fwd
+
+    l0, g0, m0 = run(False)
+    l1, g1, m1 = run(True)
+    assert l0 == l1
+    for k in g0:
+        assert torch.equal(g0[k], g1[k]), k
+    _report(case="grad_checkpointing vitl14_depth_bs2", forward_peak_bytes_plain=m0, forward_peak_bytes_checkpointed=m1)
+    assert m1 < 0.6 * m0, (m0, m1)
+
+
 def _grads_once(case_name):
     case = C.CASES[case_name]
     gold = C.load_golden(case_name)

@@ -51,6 +51,16 @@ def _worker(rank, port, out):
         loss = open_clip.TriClipLoss(**kw)(x, y, v, s.exp()) if tri else open_clip.ClipLoss(**kw)(x, y, s.exp())
         loss.backward()
         res[(tri, ll, gwg)] = dict(loss=loss.detach().cpu(), dx=x.grad.cpu(), dy=y.grad.cpu(), dv=v.grad.cpu() if tri else None, ds=s.grad.cpu())
+    # the mask variants (loss.py:485-903) on both transports' default path
+    from tests import maskloss_common as MC
+
+    mgold = MC.load_golden()
+    mX, mY, mV, mLX, mLY, mLV = MC.inputs(mgold)
+    mres = {}
+    for kind in MC.KINDS:
+        for ll, gwg in MC.FLAGS:
+            kw = dict(local_loss=ll, gather_with_grad=gwg, rank=rank, world_size=W)
+            mres[(kind, ll, gwg)] = MC.run_ours(open_clip, mgold, kind, kw, mX[rank], mY[rank], mV[rank], mLX[rank], mLY[rank], mLV[rank], device=dev)
     # bucketed gradient exchange on the device
     torch.manual_seed(0)
     net = torch.nn.Sequential(torch.nn.Linear(64, 512), torch.nn.GELU(), torch.nn.Linear(512, 512), torch.nn.GELU(), torch.nn.Linear(512, 8)).to(dev)
@@ -138,7 +148,7 @@ def _worker(rank, port, out):
     both = [torch.empty_like(chk) for _ in range(W)]
     dist.all_gather(both, chk)
     same_weights = bool(torch.equal(both[0], both[1]))
-    torch.save(dict(res=res, reducer_err=steps, n_buckets=len(red.buckets), peer_err=peer_err, mat_err=mat_err, w_err=w_err, same_weights=same_weights,
+    torch.save(dict(res=res, mres=mres, reducer_err=steps, n_buckets=len(red.buckets), peer_err=peer_err, mat_err=mat_err, w_err=w_err, same_weights=same_weights,
                     n_buckets_peer=len(red2.buckets)), out.format(rank))
     comm.destroy_arena()
     dist.destroy_process_group()
@@ -166,6 +176,16 @@ def test_two_rank_loss_and_gradient_exchange_on_hardware(tmp_path):
                 tol = 1e-2 if k == "loss" else 3e-2  # bf16-rounded operands in the logits GEMMs
                 assert err <= tol, (name, r, k, err)
     print("two-rank parity vs the reference run (max relative error):", worst)
+    from tests import maskloss_common as MC
+
+    mgold = MC.load_golden()
+    mworst = {}
+    for kind in MC.KINDS:
+        for ll, gwg in MC.FLAGS:
+            for r in range(W):
+                for k, e in MC.compare(got[r]["mres"][(kind, ll, gwg)], mgold, f"{kind}_local{int(ll)}_gwg{int(gwg)}/rank{r}").items():
+                    mworst[k] = max(mworst.get(k, 0.0), e)
+    print("two-rank mask-loss parity vs the reference run (max relative error):", mworst)
     for r in range(W):
         assert got[r]["n_buckets"] > 1 and got[r]["n_buckets_peer"] > 1
         assert max(got[r]["reducer_err"]) < 1e-6, got[r]["reducer_err"]

@@ -110,3 +110,55 @@ def test_zero_shot_eval_vs_reference_functions(emu, monkeypatch):
     from tests.zeroshot_common import check_zero_shot
 
     check_zero_shot("cpu")
+
+
+def test_grad_checkpointing_reproduces_gradients(emu):
+    """set_grad_checkpointing (transformer.py:366-368): every block keeps only its input and is re-run inside backward; loss and
+    gradients are those of the plain run (the kernels are deterministic, so exactly)."""
+    case = C.CASES["tiny_tri_depth"]
+
+    def run(ckpt):
+        model, sd, args = build_model(case)
+        model.set_grad_checkpointing(ckpt)
+        assert model.visual.transformer.grad_checkpointing is ckpt
+        inp = C.build_inputs(case, args)
+        feats, ls, loss = run_model(case, model, inp)
+        loss.backward()
+        return float(loss.detach()), {k: p.grad.clone() for k, p in model.named_parameters() if p.requires_grad}
+
+    l0, g0 = run(False)
+    l1, g1 = run(True)
+    assert l0 == l1 and g0.keys() == g1.keys()
+    for k in g0:
+        assert torch.equal(g0[k], g1[k]), k
+
+
+def test_mask_losses_vs_reference_run(emu):
+    """ClipLossSimMask / ClipLossLabelMask / TriClipLossLabelMask (loss.py:485-903) at world size 1 against the REAL reference's
+    results (tests/golden/mask_loss.pt): the masks are built on the host side of the kernels, `logits * mask` is applied inside
+    the loss epilogues."""
+    import open_clip
+    from tests import maskloss_common as MC
+
+    gold = MC.load_golden()
+    X, Y, V, LX, LY, LV = (MC.flat(t) for t in MC.inputs(gold))
+    for kind in MC.KINDS:
+        got = MC.run_ours(open_clip, gold, kind, dict(world_size=1), X, Y, V, LX, LY, LV)
+        MC.compare(got, gold, f"{kind}_w1")
+
+
+def test_create_loss_selects_the_reference_classes():
+    """factory.create_loss (factory.py:420-470): contra_loss_type / use_dual_loss pick the same classes as the reference."""
+    from types import SimpleNamespace
+
+    import open_clip
+
+    base = dict(local_loss=False, gather_with_grad=False, rank=0, world_size=1, horovod=False, distill=False, model="ViT-L-14", n_tower=3,
+                sim_thres=0.9)
+    pick = lambda **kw: type(open_clip.create_loss(SimpleNamespace(**{**base, **kw}))).__name__  # noqa: E731
+    assert pick(contra_loss_type="general", use_dual_loss=False) == "TriClipLoss"
+    assert pick(contra_loss_type="general", use_dual_loss=True) == "ClipLossGeneral"
+    assert pick(contra_loss_type="label_mask", use_dual_loss=False) == "TriClipLossLabelMask"
+    assert pick(contra_loss_type="label_mask", use_dual_loss=True) == "ClipLossLabelMask"
+    assert pick(contra_loss_type="sim_mask", use_dual_loss=True) == "ClipLossSimMask"
+    assert pick(n_tower=2) == "ClipLoss"

@@ -72,3 +72,20 @@ def test_oracle_sharded_loss_matches_reference_run_under_gloo():
                 ref = gold[f"{name}/rank{r}/{k}"]
                 err = float((v.detach() - ref).abs().max())
                 assert err <= 2e-5 * float(ref.abs().max()) + 1e-7, (name, r, k, err)
+
+
+def test_oracle_mask_losses_match_reference_run():
+    """oracle.sim_mask / label_mask / clip_loss_sharded(mask=) against the REAL reference's ClipLossSimMask, ClipLossLabelMask and
+    TriClipLossLabelMask (loss.py:485-903; oracle/make_golden_maskloss.py): world size 1 and per rank under two gloo processes."""
+    from tests import maskloss_common as MC
+
+    gold = MC.load_golden()
+    W = int(gold["world"])
+    for kind in MC.KINDS:
+        ours = MC.oracle_per_rank(gold, kind, False, False, 1)[0]
+        MC.compare({k: (v.detach() if v is not None else None) for k, v in ours.items()}, gold, f"{kind}_w1", 2e-5, 2e-5)
+        for ll, gwg in MC.FLAGS:
+            per = MC.oracle_per_rank(gold, kind, ll, gwg, W)
+            for r in range(W):
+                MC.compare({k: (v.detach() if v is not None else None) for k, v in per[r].items()}, gold,
+                           f"{kind}_local{int(ll)}_gwg{int(gwg)}/rank{r}", 2e-5, 2e-5)

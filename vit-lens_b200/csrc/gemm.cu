@@ -45,6 +45,8 @@ struct GemmParams {
   const float* fparam_dev;
   int aux_row_div, relu;
   int loss_flags;
+  const uint8_t* mask;           // loss epilogues: optional [M, N] bytes (ld = ldmask); 0 -> the logit is replaced by 0 (loss.py:540-575)
+  long long ldmask;
   int b_peer_rows;               // PEER kernels: B's global row r lives in peer r / b_peer_rows at local row r % b_peer_rows
   const int* peer_flags;         // PEER kernels: int32 [n peers] tickets in THIS rank's arena, or null
   int peer_flag_value;
@@ -145,9 +147,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
     }
     tc_wait_ld();
     float f[CW];
+    // mask variants of the contrastive loss (ClipLossSimMask / ClipLossLabelMask, loss.py:485-748): `logits * mask` -- a masked
+    // logit is the constant 0 (it keeps its softmax mass exp(0 - lse) but carries no gradient)
+    uint32_t mbits = 0xffffffffu;
+    if (p.mask != nullptr && row_ok && (p.epi == VL_EPI_ROWLSE || p.epi == VL_EPI_CLIPGRAD)) {
+      mbits = 0u;
+      const uint8_t* mr = p.mask + static_cast<long long>(row) * p.ldmask + col0;
+#pragma unroll
+      for (int j = 0; j < CW; ++j)
+        if (col0 + j < p.N && mr[j] != 0) mbits |= 1u << j;
+    }
     if (p.epi == VL_EPI_ROWLSE) {
 #pragma unroll
-      for (int j = 0; j < CW; ++j) f[j] = __uint_as_float(v[j]) * alpha_eff;
+      for (int j = 0; j < CW; ++j) f[j] = ((mbits >> j) & 1u) ? __uint_as_float(v[j]) * alpha_eff : 0.f;
       if (c == 0) {
         lse_m = -INFINITY;
         lse_s = 0.f;
@@ -186,7 +198,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
 #pragma unroll
       for (int j = 0; j < CW; ++j) {
         const float accv = __uint_as_float(v[j]);
-        const float z = accv * alpha_eff;
+        const bool keep = (mbits >> j) & 1u;
+        const float z = keep ? accv * alpha_eff : 0.f;
         float gval = 0.f;
         if (row_ok && col0 + j < p.N) {
           gval = __expf(z - rl);
@@ -195,7 +208,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
           if (p.col_vec) gval += __expf(z - __ldg(p.col_vec + col0 + j));
           if (on_diag) gval -= p.col_vec ? 2.f : 1.f;
           gval *= fparam_eff;
-          dsum += ((p.loss_flags & 1) ? grow * fparam_eff : gval) * accv;
+          if (!keep) gval = 0.f;  // d(logit * mask) / d(logit) = mask
+          else dsum += ((p.loss_flags & 1) ? grow * fparam_eff : gval) * accv;
         }
         f[j] = gval;
       }
@@ -858,6 +872,8 @@ static int launch_gemm(const VlGemmArgs& a, cudaStream_t stream) {
   p.relu = a.relu;
   p.rowsum_out = a.rowsum_out;
   p.loss_flags = a.loss_flags;
+  p.mask = a.mask;
+  p.ldmask = a.ldmask;
   p.b_peer_rows = a.b_peer_rows;
   p.peer_flags = a.peer_flags;
   p.peer_flag_value = a.peer_flag_value;

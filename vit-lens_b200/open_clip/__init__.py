@@ -4,7 +4,7 @@ for the in-scope symbols."""
 from .constants import OPENAI_DATASET_MEAN, OPENAI_DATASET_STD, ModalityType
 from .factory import (add_model_config, create_loss, create_model, create_model_and_transforms, get_model_config,
                       get_tokenizer, list_models, load_checkpoint, tri_create_model, tri_create_model_and_transforms)
-from .loss import ClipLoss, ClipLossGeneral, TriClipLoss, gather_features
+from .loss import ClipLoss, ClipLossGeneral, ClipLossLabelMask, ClipLossSimMask, TriClipLoss, TriClipLossLabelMask, gather_features
 from .model import (CLIP, CLIPTextCfg, CLIPVisionCfg, TriCLIP, convert_weights_to_lp, get_cast_dtype, get_input_dtype,
                     trace_model)
 from .tokenizer import tokenize

@@ -19,7 +19,7 @@ from typing import Optional, Tuple, Union
 import torch
 
 from .constants import CKPT_CACHE_DIR, OPENAI_DATASET_MEAN, OPENAI_DATASET_STD
-from .loss import ClipLoss, ClipLossGeneral, TriClipLoss
+from .loss import ClipLoss, ClipLossGeneral, ClipLossLabelMask, ClipLossSimMask, TriClipLoss, TriClipLossLabelMask
 from .model import CLIP, TriCLIP, get_cast_dtype, resize_pos_embed
 from .module_cfg import get_input_adapter_cfg, get_perceiver_cfg
 
@@ -225,15 +225,24 @@ def tri_create_model_and_transforms(model_name: str, pretrained: Optional[str] =
 
 
 def create_loss(args):
-    """factory.py:750-851 for the loss classes on the covered path; research variants (distill, CoCa, label/sim masks)
-    raise NotImplementedError."""
+    """factory.py:750-851: the contrastive loss classes incl. the label / similarity mask variants; distillation, CoCa and
+    video-token distillation (other model families) raise NotImplementedError."""
     kw = dict(local_loss=args.local_loss, gather_with_grad=args.gather_with_grad, cache_labels=True, rank=args.rank,
               world_size=args.world_size, use_horovod=getattr(args, "horovod", False))
     if getattr(args, "distill", False) or "coca" in str(getattr(args, "model", "")).lower() or getattr(args, "vid_distill_tokens", False):
         raise NotImplementedError("distillation / CoCa / video-token losses are outside the ViT-Lens hot path")
     if getattr(args, "n_tower", 2) == 3:
         loss_type = getattr(args, "contra_loss_type", "general")
-        if loss_type != "general":
-            raise NotImplementedError(f"contra_loss_type={loss_type!r}: mask variants are outside the covered path")
-        return ClipLossGeneral(**kw) if getattr(args, "use_dual_loss", False) else TriClipLoss(**kw)
+        if getattr(args, "use_dual_loss", False):
+            if loss_type == "general":
+                return ClipLossGeneral(**kw)
+            if loss_type == "label_mask":
+                return ClipLossLabelMask(use_mask=True, **kw)
+            if loss_type == "sim_mask":
+                return ClipLossSimMask(sim_thres=args.sim_thres, **kw)
+            raise NotImplementedError(loss_type)
+        if loss_type == "general":
+            return TriClipLoss(**kw)
+        if loss_type == "label_mask":
+            return TriClipLossLabelMask(**kw)
     return ClipLoss(**kw)

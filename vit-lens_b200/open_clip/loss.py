@@ -77,6 +77,17 @@ class _ContrastiveBase(nn.Module):
             return None
         return comm.init_arena()
 
+    def _gather_tensors(self, feats):
+        """NCCL / gloo gather of the packed block as plain tensors (the mask variants also need the gathered rows on the host side
+        of the kernels to build their masks)."""
+        W = self.world_size
+        packed = torch.stack([f.detach().float() for f in feats], 0).contiguous()
+        k, Bl, Ed = packed.shape
+        out = torch.empty((W * k, Bl, Ed), device=packed.device, dtype=packed.dtype)
+        dist.all_gather_into_tensor(out, packed)
+        out = out.view(W, k, Bl, Ed)
+        return [out[:, i].reshape(W * Bl, Ed) for i in range(k)]
+
     def _gather_packed(self, feats):
         """The packed [k, B_loc, E] feature block of every rank -> k matrices [Bg, E] (rank-major rows).  Over the peer arena
         nothing is gathered: each matrix is an ops.PeerRows whose row blocks the loss GEMMs read in place over NVLink; otherwise
@@ -109,20 +120,25 @@ class _ContrastiveBase(nn.Module):
         dist.all_reduce(t)
         return t
 
-    def _pair(self, x, y, all_x, all_y, logit_scale):
-        """Loss of one (x, y) feature pair for this rank's rows; value follows the reference's definition."""
+    def _pair(self, x, y, all_x, all_y, logit_scale, mask=None):
+        """Loss of one (x, y) feature pair for this rank's rows; value follows the reference's definition.  `mask`: the full
+        bool [B_all, B_all] keep-matrix of the mask variants (`logits * mask`), sliced here to this rank's rows."""
         from vitlens_b200 import ops
 
         W = self.world_size
         Bl = x.shape[0]
+        masks = None
+        if mask is not None:
+            r0 = self.rank * Bl if W > 1 else 0
+            masks = (mask[r0:r0 + Bl].to(torch.uint8).contiguous(), mask.t()[r0:r0 + Bl].to(torch.uint8).contiguous())
         if W == 1:
-            return E.ContrastiveFn.apply(x, y, None, None, logit_scale, 0, Bl, Bl, True, None, None)
+            return E.ContrastiveFn.apply(x, y, None, None, logit_scale, 0, Bl, Bl, True, None, None, False, masks)
         self._arena_in_use = all_x.arena if isinstance(all_x, ops.PeerRows) else None
         Bg = W * Bl
         off = self.rank * Bl
         if self.local_loss:
             col = bool(self.gather_with_grad)
-            return E.ContrastiveFn.apply(x, y, all_x, all_y, logit_scale, off, Bl, Bl, col, self._gather_vec if col else None, None, col)
+            return E.ContrastiveFn.apply(x, y, all_x, all_y, logit_scale, off, Bl, Bl, col, self._gather_vec if col else None, None, col, masks)
         # full-matrix loss on every rank in the reference: value / d(scale) need cross-rank sums
         grad_rows = Bl if self.gather_with_grad else Bg
 
@@ -130,7 +146,7 @@ class _ContrastiveBase(nn.Module):
             ds = self._sum_ranks(ds)
             return ds / W if self.gather_with_grad else ds
 
-        part = E.ContrastiveFn.apply(x, y, all_x, all_y, logit_scale, off, Bg, grad_rows, True, self._gather_vec, ds_post)
+        part = E.ContrastiveFn.apply(x, y, all_x, all_y, logit_scale, off, Bg, grad_rows, True, self._gather_vec, ds_post, False, masks)
         total = self._sum_ranks(part.detach())
         return part + (total - part.detach())
 
@@ -167,3 +183,79 @@ class TriClipLoss(_ContrastiveBase):
         total_loss = self._pair(image_features, visual_features, all_i, all_v, logit_scale) + \
             self._pair(text_features, visual_features, all_t, all_v, logit_scale)
         return {"contrastive_loss": total_loss} if output_dict else total_loss
+
+
+# ----------------------------------------------------------------------------- mask variants (loss.py:485-903)
+def _eye(n, device):
+    return torch.eye(n, device=device, dtype=torch.bool)
+
+
+class ClipLossSimMask(_ContrastiveBase):
+    """loss.py:485-598: pairs whose TEACHER features x are more similar than `sim_thres` are taken out of the contrast --
+    `logits * mask` with mask = not (x x^T >= sim_thres) or I.  The similarity matrix comes from the tcgen05 GEMM, the masking
+    itself is applied inside the loss epilogues."""
+
+    def __init__(self, local_loss=False, gather_with_grad=False, cache_labels=False, rank=0, world_size=1, sim_thres=0.9, use_horovod=False):
+        super().__init__(local_loss, gather_with_grad, cache_labels, rank, world_size, use_horovod)
+        self.sim_thres = sim_thres
+
+    def forward(self, x_features, y_features, logit_scale, output_dict=False, key="contrastive loss[with sim mask]"):
+        all_x = all_y = None
+        teacher = x_features
+        if self.world_size > 1:
+            all_x, all_y = self._gather_tensors([x_features, y_features])
+            teacher = all_x
+        t = teacher.detach().float().contiguous()
+        sim = E._ops.similarity(t, gallery=t)
+        mask = torch.logical_or(torch.logical_not(sim >= self.sim_thres), _eye(t.shape[0], t.device))
+        total_loss = self._pair(x_features, y_features, all_x, all_y, logit_scale, mask)
+        return {key: total_loss} if output_dict else total_loss
+
+
+def _label_mask(x_labels, y_labels, n, device):
+    if x_labels.ndim == 1:
+        x_labels, y_labels = x_labels.unsqueeze(0), y_labels.unsqueeze(0)
+    return torch.logical_or(torch.logical_not(x_labels.T == y_labels), _eye(n, device))
+
+
+class ClipLossLabelMask(_ContrastiveBase):
+    """loss.py:601-746: samples of the same class are not each other's negatives -- mask = (label_x != label_y^T) or I."""
+
+    def __init__(self, local_loss=False, gather_with_grad=False, cache_labels=False, rank=0, world_size=1, use_mask=False, use_horovod=False):
+        super().__init__(local_loss, gather_with_grad, cache_labels, rank, world_size, use_horovod)
+        self.use_mask = use_mask
+
+    def _all_labels(self, lab):
+        if self.world_size == 1:
+            return lab
+        out = [torch.zeros_like(lab) for _ in range(self.world_size)]
+        dist.all_gather(out, lab.contiguous())
+        return torch.cat(out, dim=0)
+
+    def _masked_pair(self, x, y, logit_scale, x_labels, y_labels):
+        all_x = all_y = None
+        if self.world_size > 1:
+            all_x, all_y = self._gather_tensors([x, y])
+        mask = None
+        if x_labels is not None and y_labels is not None and self.use_mask:
+            assert x_labels.shape == y_labels.shape
+            ax, ay = self._all_labels(x_labels), self._all_labels(y_labels)
+            mask = _label_mask(ax, ay, ax.shape[0], x.device)
+        return self._pair(x, y, all_x, all_y, logit_scale, mask)
+
+    def forward(self, x_features, y_features, logit_scale, x_labels=None, y_labels=None, output_dict=False, key="image-text"):
+        total_loss = self._masked_pair(x_features, y_features, logit_scale, x_labels, y_labels)
+        return {key: total_loss} if output_dict else total_loss
+
+
+class TriClipLossLabelMask(ClipLossLabelMask):
+    """loss.py:749-903: the (image, visual) and (text, visual) pairs of TriClipLoss, each with its label mask."""
+
+    def __init__(self, local_loss=False, gather_with_grad=False, cache_labels=False, rank=0, world_size=1, use_horovod=False):
+        super().__init__(local_loss, gather_with_grad, cache_labels, rank, world_size, True, use_horovod)
+
+    def forward(self, image_features, text_features, visual_features, logit_scale, image_labels=None, text_labels=None, visual_labels=None,
+                output_dict=False):
+        total_loss = self._masked_pair(image_features, visual_features, logit_scale, image_labels, visual_labels) + \
+            self._masked_pair(text_features, visual_features, logit_scale, text_labels, visual_labels)
+        return {"tri_contrastive_loss": total_loss} if output_dict else total_loss

@@ -136,7 +136,15 @@ class Transformer(nn.Module):
         public = not isinstance(x, TokenMat)
         t = TokenMat.from_bnd(x.permute(1, 0, 2)) if public else x
         for r in self.resblocks:
-            t = r(t, attn_mask=attn_mask)
+            if self.grad_checkpointing and torch.is_grad_enabled() and (t.t.requires_grad or any(p.requires_grad for p in r.parameters())):
+                # transformer.py:366-368: `x = checkpoint(r, x, None, None, attn_mask)` -- keep only the block's input (one
+                # [T, D] bf16 matrix instead of ~17 T D bytes of saved activations) and re-run its kernels inside backward
+                B, N = t.B, t.N
+                y = torch.utils.checkpoint.checkpoint(lambda tt, r=r, B=B, N=N: r(TokenMat(tt, B, N), attn_mask=attn_mask).t, t.t,
+                                                      use_reentrant=False)
+                t = TokenMat(y, B, N)
+            else:
+                t = r(t, attn_mask=attn_mask)
         return t.to_bnd().permute(1, 0, 2).to(x.dtype) if public else t
 
     def lock(self, *args, **kwargs):
@@ -263,7 +271,7 @@ class VisionTransformer(nn.Module):
 
     @torch.jit.ignore
     def set_grad_checkpointing(self, enable=True):
-        self.transformer.grad_checkpointing = enable  # activations are already minimal; flag kept for API parity
+        self.transformer.grad_checkpointing = enable  # Transformer.forward re-runs each block's kernels in backward
 
     # ------------------------------------------------------------------ forward pieces
     def img_adapter_forawrd(self, x: torch.Tensor) -> TokenMat:  # (sic) name kept from transformer.py:659

@@ -477,7 +477,7 @@ class ContrastiveFn(torch.autograd.Function):
     ranks' losses (it is what all_gather's backward sends home), so d(this rank's loss)/d(scale) sums the row term alone."""
 
     @staticmethod
-    def forward(ctx, x, y, all_x, all_y, scale, label_off, val_rows, grad_rows, col_term, gather_lse, ds_post, ds_rows_only=False):
+    def forward(ctx, x, y, all_x, all_y, scale, label_off, val_rows, grad_rows, col_term, gather_lse, ds_post, ds_rows_only=False, masks=None):
         x16, y16 = _ops.cast_bf16(x.detach()), _ops.cast_bf16(y.detach())
         # all_x / all_y: None (single process), a gathered [B_all, E] tensor, or ops.PeerRows -- the rows of rank p read in place
         # from p's peer arena inside the GEMMs (the all-gather of loss.py:55-76 fused into the logits kernel)
@@ -485,8 +485,11 @@ class ContrastiveFn(torch.autograd.Function):
         ax16 = all_x if peer else (x16 if all_x is None else _ops.cast_bf16(all_x.detach()))
         ay16 = all_y if peer else (y16 if all_y is None else _ops.cast_bf16(all_y.detach()))
         s = scale.detach().float().reshape(1).contiguous()  # stays on the device: no host sync in the step
-        lse_x, sum_x = _ops.rowlse(x16, ay16, alpha=s, label_off=label_off)
-        lse_y, sum_y = _ops.rowlse(y16, ax16, alpha=s, label_off=label_off)
+        # masks = (mask_x [B_loc, B_all], mask_y [B_loc, B_all]) uint8 or None: `logits * mask` of the mask loss variants
+        mkw_x = {} if masks is None else dict(mask=masks[0])
+        mkw_y = {} if masks is None else dict(mask=masks[1])
+        lse_x, sum_x = _ops.rowlse(x16, ay16, alpha=s, label_off=label_off, **mkw_x)
+        lse_y, sum_y = _ops.rowlse(y16, ax16, alpha=s, label_off=label_off, **mkw_y)
         loss = (sum_x + sum_y) / (2.0 * val_rows)
         empty = torch.empty(0, device=x.device)
         col_x = col_y = empty
@@ -496,6 +499,7 @@ class ContrastiveFn(torch.autograd.Function):
         ctx.peer = (ax16, ay16) if peer else None
         ctx.save_for_backward(x16, y16, empty if peer else ax16, empty if peer else ay16, lse_x, lse_y, col_x, col_y, s)
         ctx.cfg = (label_off, grad_rows, col_term, ds_post, ds_rows_only)
+        ctx.masks = masks
         return loss.reshape(())
 
     @staticmethod
@@ -509,10 +513,12 @@ class ContrastiveFn(torch.autograd.Function):
                                    "(more than two later loss forwards); run backward earlier or set VL_COMM=nccl")
         gs = 1.0 / (2.0 * grad_rows)
         dl = dloss.detach().float().reshape(1).contiguous()  # upstream gradient stays on the device too
+        mkw_x = {} if ctx.masks is None else dict(mask=ctx.masks[0])
+        mkw_y = {} if ctx.masks is None else dict(mask=ctx.masks[1])
         gx, ds_x = _ops.clipgrad(x16, ay16, alpha=s, row_lse=lse_x, col_lse=col_x if col_term else None, label_off=label_off, gscale=gs, gscale_dev=dl,
-                                 ds_row_only=ds_rows_only)
+                                 ds_row_only=ds_rows_only, **mkw_x)
         gy, ds_y = _ops.clipgrad(y16, ax16, alpha=s, row_lse=lse_y, col_lse=col_y if col_term else None, label_off=label_off, gscale=gs, gscale_dev=dl,
-                                 ds_row_only=ds_rows_only)
+                                 ds_row_only=ds_rows_only, **mkw_y)
         dx = _ops.gemm(gx, ay16, b_t=True, out_dtype=F32, alpha_dev=s) if _need(ctx, 0) else None
         dy = _ops.gemm(gy, ax16, b_t=True, out_dtype=F32, alpha_dev=s) if _need(ctx, 1) else None
         dscale = None
@@ -522,7 +528,7 @@ class ContrastiveFn(torch.autograd.Function):
             if ds_post is not None:
                 dscale = ds_post(dscale)
             dscale = dscale.reshape(())
-        return dx, dy, None, None, dscale, None, None, None, None, None, None, None
+        return dx, dy, None, None, dscale, None, None, None, None, None, None, None, None
 
 
 class AddFn(torch.autograd.Function):

@@ -53,6 +53,7 @@ class GemmArgs(C.Structure):
         ("alpha_dev", C.c_void_p), ("fparam_dev", C.c_void_p), ("aux_row_div", C.c_int32), ("relu", C.c_int32), ("rowsum_out", C.c_void_p),
         ("loss_flags", C.c_int32),
         ("b_peers", C.c_void_p), ("b_npeers", C.c_int32), ("b_peer_rows", C.c_int32), ("peer_flags", C.c_void_p), ("peer_flag_value", C.c_int32),
+        ("mask", C.c_void_p), ("ldmask", C.c_int64),
     ]
 
 
@@ -124,7 +125,7 @@ def gemm(a, b, d, *, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, epilogue=EP
          aux_in=None, aux_out=None, ldaux=0, alpha=1.0, accumulate=False, split_k=1, act_quick=False,
          row_vec=None, col_vec=None, out_vec0=None, out_vec1=None, out_vec2=None, scalar_out=None, iparam=0, fparam=0.0,
          alpha_dev=None, fparam_dev=None, aux_row_div=0, relu=False, rowsum_out=None, loss_flags=0,
-         b_peers=None, b_peer_rows=0, peer_flags=0, peer_flag_value=0):
+         b_peers=None, b_peer_rows=0, peer_flags=0, peer_flag_value=0, mask=None):
     """Raw GEMM call; see include/vitlens_b200.h.  a, b bf16; d bf16 or fp32; bias fp32."""
     assert a.dtype == torch.bfloat16 and (b is None or b.dtype == torch.bfloat16)
     assert d is None or d.dtype in (torch.bfloat16, torch.float32)
@@ -139,7 +140,7 @@ def gemm(a, b, d, *, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, epilogue=EP
         _ptr(row_vec), _ptr(col_vec), _ptr(out_vec0), _ptr(out_vec1), _ptr(out_vec2), _ptr(scalar_out), int(iparam), float(fparam),
         _ptr(alpha_dev), _ptr(fparam_dev), int(aux_row_div), int(relu), _ptr(rowsum_out), int(loss_flags),
         C.cast(peer_arr, C.c_void_p) if peer_arr is not None else C.c_void_p(0), len(b_peers) if b_peers is not None else 0, int(b_peer_rows),
-        C.c_void_p(int(peer_flags)), int(peer_flag_value))
+        C.c_void_p(int(peer_flags)), int(peer_flag_value), _ptr(mask), 0 if mask is None else mask.stride(0))
     _count()
     if CALL_TIMING is not None:
         kind = "wgrad" if (a_mn and b_mn) else ("dgrad" if b_mn else "fwd")

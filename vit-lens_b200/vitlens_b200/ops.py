@@ -291,8 +291,16 @@ def add_bf16(a, b):
     return out
 
 
-def rowlse(p16, q16, *, alpha, label_off=0):
-    """Row-wise log-sum-exp of alpha * P @ Q^T without materialising the logits (alpha: 1-element fp32 device tensor).
+def _mask8(mask, M, N):
+    if mask is None:
+        return None
+    assert mask.dtype == torch.uint8 and tuple(mask.shape) == (M, N) and mask.stride(1) == 1 and mask.is_cuda
+    return mask
+
+
+def rowlse(p16, q16, *, alpha, label_off=0, mask=None):
+    """Row-wise log-sum-exp of alpha * P @ Q^T without materialising the logits (alpha: 1-element fp32 device tensor); `mask`
+    (uint8 [M, N]): logits where it is 0 are replaced by 0 (`logits * mask`, loss.py:540-575).
     Returns (lse [M] fp32, sum_i(lse_i - z[i, i + label_off]) as a 1-element fp32 tensor)."""
     _v2(p16, BF16)
     peer = q16 if isinstance(q16, PeerRows) else None
@@ -306,14 +314,15 @@ def rowlse(p16, q16, *, alpha, label_off=0):
     ps = torch.zeros((M, nparts), device=dev, dtype=F32)
     diag = torch.zeros((M,), device=dev, dtype=F32)
     L.gemm(p16, None if peer else q16, None, M=M, N=N, K=E, lda=_ld(p16), ldb=peer.E if peer else _ld(q16), ldd=0, epilogue=L.EPI_ROWLSE,
-           alpha=1.0, alpha_dev=alpha, out_vec0=pm, out_vec1=ps, out_vec2=diag, iparam=label_off, **(peer.kw() if peer else {}))
+           alpha=1.0, alpha_dev=alpha, out_vec0=pm, out_vec1=ps, out_vec2=diag, iparam=label_off, mask=_mask8(mask, M, N),
+           **(peer.kw() if peer else {}))
     lse = torch.empty((M,), device=dev, dtype=F32)
     loss_sum = torch.empty((1,), device=dev, dtype=F32)
     L.lse_combine(pm, ps, diag, lse, loss_sum, M=M, nparts=nparts)
     return lse, loss_sum
 
 
-def clipgrad(p16, q16, *, alpha, row_lse, col_lse, label_off, gscale, gscale_dev=None, ds_row_only=False):
+def clipgrad(p16, q16, *, alpha, row_lse, col_lse, label_off, gscale, gscale_dev=None, ds_row_only=False, mask=None):
     """g[M,N] (bf16) = gscale * (exp(z - row_lse_i) + [col_lse] exp(z - col_lse_j) - k * onehot(j == i + label_off)),
     z = alpha * P @ Q^T;  also returns sum(g * P@Q^T) (d loss / d alpha) as a 1-element fp32 tensor -- with ds_row_only the sum
     runs over the row term gscale * (exp(z - row_lse_i) - onehot) alone."""
@@ -328,7 +337,7 @@ def clipgrad(p16, q16, *, alpha, row_lse, col_lse, label_off, gscale, gscale_dev
     ds = torch.empty((1,), device=p16.device, dtype=F32)
     L.gemm(p16, None if peer else q16, g, M=M, N=N, K=E, lda=_ld(p16), ldb=peer.E if peer else _ld(q16), ldd=N8, epilogue=L.EPI_CLIPGRAD,
            alpha=1.0, alpha_dev=alpha, row_vec=row_lse, col_vec=col_lse, iparam=label_off, fparam=gscale, fparam_dev=gscale_dev, scalar_out=ds,
-           loss_flags=1 if ds_row_only else 0, **(peer.kw(wait=False) if peer else {}))
+           loss_flags=1 if ds_row_only else 0, mask=_mask8(mask, M, N), **(peer.kw(wait=False) if peer else {}))
     return g[:, :N], ds
 
 
