@@ -110,8 +110,14 @@ def timing():
         f()
         L.debug_set(13, 0)
 
+    def g_old():
+        L.debug_set(12, 2)
+        g()
+        L.debug_set(12, 0)
+
     for name, fn, byts, flops in (("fwd", f, 4 * B * N * D * 2, 4.0 * B * H * N * N * 64), ("fwd(one-tile kernel)", f_old, 4 * B * N * D * 2, 4.0 * B * H * N * N * 64),
-                                  ("bwd", g, 8 * B * N * D * 2, 10.0 * B * H * N * N * 64)):
+                                  ("bwd", g, 8 * B * N * D * 2, 10.0 * B * H * N * N * 64),
+                                  ("bwd(gen-2 kernel)", g_old, 8 * B * N * D * 2, 10.0 * B * H * N * N * 64)):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()

@@ -964,7 +964,11 @@ int vl_attention_bwd(const void* q, const void* k, const void* v, const void* o,
   if (int rc = check_common("vl_attention_bwd", B, H, nq, nk, ldq, ldk, ldv)) return rc;
   VL_CHECK_ARG(ldo % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0, "vl_attention_bwd: bad leading dims");
   VL_CHECK_ARG(!causal || nq == nk, "vl_attention_bwd: causal requires nq == nk");
-  // debug knob 12: 1 = the first-generation kernel (one compute group + separate tail kernel, nq <= 384)
+  // debug knob 12: 0 = default (non-causal: third-generation kernel, keys on the TMEM lanes; causal: second generation),
+  // 2 = second generation for everything, 1 = the first-generation kernel (one compute group + separate tail kernel, nq <= 384)
+  if (debug_get(12) == 0 && !causal)
+    return launch_attn_bwd3(q, k, v, o, dout, lse, dq, dk, dv, B, H, nq, nk, ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, scale,
+                            reinterpret_cast<cudaStream_t>(stream));
   if (debug_get(12) != 1)
     return launch_attn_bwd2(q, k, v, o, dout, lse, dq, dk, dv, B, H, nq, nk, ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, scale, causal,
                             reinterpret_cast<cudaStream_t>(stream));

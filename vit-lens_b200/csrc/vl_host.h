@@ -63,6 +63,11 @@ int launch_attn_bwd2(const void* q, const void* k, const void* v, const void* o,
                      int B, int H, int nq, int nk, long long ldq, long long ldk, long long ldv, long long ldo, long long lddo, long long lddq,
                      long long lddk, long long lddv, float scale, int causal, cudaStream_t stream);
 
+// attention_bwd3.cu (non-causal)
+int launch_attn_bwd3(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, void* dq, void* dk, void* dv,
+                     int B, int H, int nq, int nk, long long ldq, long long ldk, long long ldv, long long ldo, long long lddo, long long lddq,
+                     long long lddk, long long lddv, float scale, cudaStream_t stream);
+
 // attention_fwd2.cu
 int launch_attn_fwd2(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int nq, int nk, long long ldq, long long ldk,
                      long long ldv, long long ldo, float scale, cudaStream_t stream);
