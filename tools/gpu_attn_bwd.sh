@@ -9,4 +9,4 @@ grep -B4 BAD gpurun_out/probe_bwd_$tag.log | head -40
 timeout 120 python tools/probe_attn.py time > gpurun_out/probe_time_$tag.log 2>&1; echo "time rc=$?"
 grep bwd gpurun_out/probe_time_$tag.log
 timeout 90 python tools/probe_attn_bwd3_timeline.py > gpurun_out/bwd3_timeline_$tag.log 2>&1; echo "timeline rc=$?"
-head -46 gpurun_out/bwd3_timeline_$tag.log; grep -A70 issuer gpurun_out/bwd3_timeline_$tag.log
+head -46 gpurun_out/bwd3_timeline_$tag.log; grep -A24 issuer gpurun_out/bwd3_timeline_$tag.log; grep prologue: gpurun_out/bwd3_timeline_$tag.log

@@ -115,9 +115,17 @@ def timing():
         g()
         L.debug_set(12, 0)
 
-    for name, fn, byts, flops in (("fwd", f, 4 * B * N * D * 2, 4.0 * B * H * N * N * 64), ("fwd(one-tile kernel)", f_old, 4 * B * N * D * 2, 4.0 * B * H * N * N * 64),
+    def g_knob(c):
+        def fn():
+            L.debug_set(14, c)
+            g()
+            L.debug_set(14, 0)
+        return fn
+
+    extra = [(f"bwd(L2 prefetch distance {c})", g_knob(c), 8 * B * N * D * 2, 10.0 * B * H * N * N * 64) for c in (-1, 74, 296)]
+    for name, fn, byts, flops in extra + [("fwd", f, 4 * B * N * D * 2, 4.0 * B * H * N * N * 64), ("fwd(one-tile kernel)", f_old, 4 * B * N * D * 2, 4.0 * B * H * N * N * 64),
                                   ("bwd", g, 8 * B * N * D * 2, 10.0 * B * H * N * N * 64),
-                                  ("bwd(gen-2 kernel)", g_old, 8 * B * N * D * 2, 10.0 * B * H * N * N * 64)):
+                                  ("bwd(gen-2 kernel)", g_old, 8 * B * N * D * 2, 10.0 * B * H * N * N * 64)]:
         for _ in range(3):
             fn()
         torch.cuda.synchronize()

@@ -19,12 +19,12 @@ def bwd():
                     ldv=3 * D, ldo=D, lddo=D, lddq=3 * D, lddk=3 * D, lddv=3 * D, scale=0.125)
 for _ in range(3):
     bwd()
-buf = torch.zeros(16 * 64, device="cuda", dtype=torch.int64)
+buf = torch.zeros(17 * 64, device="cuda", dtype=torch.int64)
 h.vl_debug_buffer(ctypes.c_void_p(buf.data_ptr()))
 bwd()
 torch.cuda.synchronize()
 h.vl_debug_buffer(ctypes.c_void_p(0))
-t = buf.cpu().reshape(16, 64)
+t = buf.cpu().reshape(17, 64)
 nqt = min(2, ((N - (N % 128 if 0 < N % 128 <= 4 and N > 128 else 0)) + 127) // 128)
 tail = N % 128 if 0 < N % 128 <= 4 and N > 128 else 0
 nkb = (N - tail + 127) // 128
@@ -67,3 +67,9 @@ for c in range(1):
         val = int(row[n])
         print(f"   {nm:32s} +{val - prev:7d}   (t={val - base})")
         prev = val
+
+for c in range(4):
+    row = t[16][c * 8:(c + 1) * 8]
+    base = int(row[0])
+    print(f"--- CTA {c} prologue: entry=0 (group start stamp at {int(t[c][0]) - base}), producer starts {int(row[1]) - base}, loads issued {int(row[2]) - base}, "
+          f"Q0 landed {int(row[3]) - base}, dO0/O0 landed {int(row[4]) - base}, K0/V0 landed {int(row[5]) - base}")

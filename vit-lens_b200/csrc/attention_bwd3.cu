@@ -53,7 +53,8 @@ constexpr int kFNl = 0;                          // [kNStat]  -lse * log2(e)   (
 constexpr int kFNd = kFNl + kNStat;              // [kNStat]  -D * scale
 constexpr int kFCoef = kFNd + kNStat;            // [2][kMaxTail][128]  dS of the tail queries per key (helpers' mat-vec input)
 constexpr int kFTk = kFCoef + 2 * kMaxTail * kT;  // [2][kMaxTail][256]  P | dS of the tail keys per query of the range (helpers' mat-vec input)
-constexpr int kFEnd = kFTk + 2 * kMaxTail * 2 * kT;
+constexpr int kFXch = kFTk + 2 * kMaxTail * 2 * kT;  // [3][kMaxTail][32] float2: helper warp 1's partial sums
+constexpr int kFEnd = kFXch + 3 * kMaxTail * 64;
 constexpr int kOffBar = kOffF + kFEnd * 4;
 constexpr int kSmem = kOffBar + 256 + 1024;
 static_assert(kSmem <= 227 * 1024, "shared memory budget");
@@ -63,6 +64,7 @@ struct Params {
   int q0, nq_main, tq;  // this launch: query rows [q0, q0 + nq_main) as tiles, [q0 + nq_main, +tq) as the tail unit
   int nk_main, tk;      // keys [0, nk_main) in 128-key blocks on the TMEM lanes, tail keys [nk_main, nk_main + tk) as N = 16 columns
   int accum_kv;
+  int pf_dist;          // L2 prefetch distance in CTAs (0 = off): the inputs of CTA blockIdx + pf_dist are prefetched by this one
   float scale;
   const __nv_bfloat16 *q, *k, *v, *o, *dout;
   long long ldq, ldk, ldv, ldo, lddo;
@@ -126,7 +128,10 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   float* sf = reinterpret_cast<float*>(bp + kOffF);
   const uint32_t bars = base + kOffBar;
   // barrier slots (8 bytes each)
-  const uint32_t bar_q = bars, bar_do = bars + 8;
+  // inputs per query tile, so the first tile's units start while the second tile is still on its way: bar_q(i): Q_i (+ the tail
+  // keys with tile 0, the tail queries with the last tile); bar_do(i): dO_i, O_i (+ the tail queries' dO with the last tile)
+  auto bar_q = [&](int i) { return bars + (i ? 8u * 26 : 0u); };
+  auto bar_do = [&](int i) { return bars + (i ? 8u * 27 : 8u); };
   auto bar_kvfull = [&](int s) { return bars + 8u * (2 + s); };
   auto bar_kvempty = [&](int s) { return bars + 8u * (4 + s); };
   auto bar_sfull = [&](int g, uint32_t bsel) { return bars + 8u * (6 + 2 * g + bsel); };  // S^T and dP^T of a unit are in TMEM buffer bsel
@@ -137,7 +142,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   auto bar_cfull = [&](int b) { return bars + 8u * (16 + b); };   // tail-query dS coefficients of a key block written
   auto bar_cfree = [&](int b) { return bars + 8u * (18 + b); };   // ... and consumed by the helper warps
   const uint32_t bar_dkvfull = bars + 8u * 20, bar_dkvfree = bars + 8u * 21, bar_dqfull = bars + 8u * 22, tmem_slot = bars + 8u * 23;
-  const uint32_t bar_tks = bars + 8u * 24;  // scores of the tail keys (Q K_t^T, dO V_t^T) are in TMEM
+  auto bar_tks = [&](int i) { return bars + 8u * (i ? 28 : 24); };  // scores of tile i against the tail keys (Q K_t^T, dO V_t^T) are in TMEM
   const uint32_t bar_tkc = bars + 8u * 25;  // ... and their P / dS coefficients in shared memory (eight compute warps)
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(bp + kOffBar + 8 * 23);
 
@@ -150,14 +155,20 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const bool has_tail = p.tq > 0;
   const bool has_tk = p.tk > 0;
 
+  const int dbg_cta0 = static_cast<int>(blockIdx.x) - 4 * static_cast<int>(gridDim.x) / 7;
+  const bool dbg0 = p.dbg != nullptr && dbg_cta0 >= 0 && dbg_cta0 < 8;
+  if (dbg0 && threadIdx.x == 0) p.dbg[1024 + dbg_cta0 * 8 + 0] = clock64();  // kernel entry
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmDO);
     tma_prefetch_desc(&tmO);
-    mbar_init(bar_q, 1);
-    mbar_init(bar_do, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_q(i), 1);
+      mbar_init(bar_do(i), 1);
+      mbar_init(bar_tks(i), 1);
+    }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_kvfull(s), 1);
       mbar_init(bar_kvempty(s), has_tail ? 3 : 1);  // MMA commit (+ the two helper warps, which read K rows)
@@ -172,7 +183,6 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     mbar_init(bar_dkvfull, 1);
     mbar_init(bar_dkvfree, 8);
     mbar_init(bar_dqfull, 1);
-    mbar_init(bar_tks, 1);
     mbar_init(bar_tkc, 8);
     fence_mbar_init();
     tma_prefetch_desc(&tmDQ);
@@ -194,31 +204,75 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   auto tDQ = [&](int i) { return tmem + 384u + 64u * i; };
 
   // Register budget: setmaxnreg moves registers inside the CTA's own allocation (384 threads x 168 at launch = 64512), so
-  // 128 x 56 + 256 x 224 = 64512 is the most the compute groups can get; asking for more blocks forever.
+  // 128 x R0 + 256 x R1 must not exceed 64512 (asking for more blocks forever): 128 x 88 + 256 x 208 = 64512.
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     if (warp == 0) {
       // ================================================================== TMA producer
       if (elect_one()) {
-        // issue order = need order: Q and the first K / V block feed S^T; dO feeds dP^T; O is only needed for D
-        mbar_expect_tx(bar_q, nqt * 16384 + (has_tail ? 2048 : 0) + (has_tk ? 4096 : 0));
-        for (int i = 0; i < nqt; ++i) tma_load_2d(sQ + i * 16384, &tmQ, bar_q, h * kHD, static_cast<int>(qrow0) + i * kT);
-        if (has_tail) tma_load_2d(sQt, &tmQt, bar_q, h * kHD, static_cast<int>(qrow0) + p.nq_main);
-        if (has_tk) {
-          tma_load_2d(sKt, &tmKt, bar_q, h * kHD, static_cast<int>(krow0) + p.nk_main);
-          tma_load_2d(sVt, &tmVt, bar_q, h * kHD, static_cast<int>(krow0) + p.nk_main);
-        }
+        // issue order = need order: tile 0's Q, the first K / V block, tile 0's dO and O (for D); then the second tile; then
+        // the remaining K / V blocks through the ring.  O_0 lands in staging buffer 0 (chunk 0), O_1 in staging buffer 1 (chunk 1):
+        // both are consumed before the first dS^T is written there.
+        const int qr = static_cast<int>(qrow0), kr = static_cast<int>(krow0);
+        auto load_tile = [&](int i) {
+          const bool last = i == nqt - 1;
+          mbar_expect_tx(bar_q(i), 16384 + ((last && has_tail) ? 2048 : 0) + ((i == 0 && has_tk) ? 4096 : 0));
+          tma_load_2d(sQ + i * 16384, &tmQ, bar_q(i), h * kHD, qr + i * kT);
+          if (i == 0 && has_tk) {
+            tma_load_2d(sKt, &tmKt, bar_q(0), h * kHD, kr + p.nk_main);
+            tma_load_2d(sVt, &tmVt, bar_q(0), h * kHD, kr + p.nk_main);
+          }
+          if (last && has_tail) tma_load_2d(sQt, &tmQt, bar_q(i), h * kHD, qr + p.nq_main);
+        };
+        auto load_do = [&](int i) {
+          const bool last = i == nqt - 1;
+          mbar_expect_tx(bar_do(i), 2 * 16384 + ((last && has_tail) ? 2048 : 0));
+          tma_load_2d(sDO + i * 16384, &tmDO, bar_do(i), h * kHD, qr + i * kT);
+          tma_load_2d(sST + i * (32768 + 16384), &tmO, bar_do(i), h * kHD, qr + i * kT);
+          if (last && has_tail) tma_load_2d(sDOt, &tmDOt, bar_do(i), h * kHD, qr + p.nq_main);
+        };
+        if (dbg0) p.dbg[1024 + dbg_cta0 * 8 + 1] = clock64();  // producer starts issuing
+        load_tile(0);
         for (int j = 0; j < nkblk; ++j) {
           const int s = j & 1;
           mbar_wait(bar_kvempty(s), ((j >> 1) & 1) ^ 1);
           mbar_expect_tx(bar_kvfull(s), 32768);
-          tma_load_2d(sK + s * 16384, &tmK, bar_kvfull(s), h * kHD, static_cast<int>(krow0) + j * kT);
-          tma_load_2d(sV + s * 16384, &tmV, bar_kvfull(s), h * kHD, static_cast<int>(krow0) + j * kT);
+          tma_load_2d(sK + s * 16384, &tmK, bar_kvfull(s), h * kHD, kr + j * kT);
+          tma_load_2d(sV + s * 16384, &tmV, bar_kvfull(s), h * kHD, kr + j * kT);
           if (j == 0) {
-            mbar_expect_tx(bar_do, nqt * 2 * 16384 + (has_tail ? 2048 : 0));
-            for (int i = 0; i < nqt; ++i) tma_load_2d(sDO + i * 16384, &tmDO, bar_do, h * kHD, static_cast<int>(qrow0) + i * kT);
-            if (has_tail) tma_load_2d(sDOt, &tmDOt, bar_do, h * kHD, static_cast<int>(qrow0) + p.nq_main);
-            for (int i = 0; i < nqt; ++i) tma_load_2d(sST + i * 16384, &tmO, bar_do, h * kHD, static_cast<int>(qrow0) + i * kT);
+            load_do(0);
+            if (nqt > 1) {
+              load_tile(1);
+              load_do(1);
+            }
+            if (dbg0) p.dbg[1024 + dbg_cta0 * 8 + 2] = clock64();  // first batch of loads issued
+          }
+          if (j == min(1, nkblk - 1)) {
+            // Measured: the first bytes of a CTA's loads arrive ~4.6 k cycles after they are issued (more than 1 GB of tensors behind
+            // one CTA per SM: every new CTA starts on cold TLB entries and cold DRAM pages), 15 % of the CTA's life with nothing to
+            // overlap it.  So every CTA pulls the inputs of the CTA one wave ahead of it into L2 while it computes itself.
+            const int nb = static_cast<int>(blockIdx.x) + p.pf_dist;
+            if (p.pf_dist > 0 && nb < static_cast<int>(gridDim.x)) {
+              const int h2 = nb % p.H, b2 = nb / p.H;
+              const int qr2 = b2 * p.nq + p.q0, kr2 = b2 * p.nk;
+              for (int i = 0; i < nqt; ++i) {
+                tma_prefetch_2d(&tmQ, h2 * kHD, qr2 + i * kT);
+                tma_prefetch_2d(&tmDO, h2 * kHD, qr2 + i * kT);
+                tma_prefetch_2d(&tmO, h2 * kHD, qr2 + i * kT);
+              }
+              for (int jj = 0; jj < nkblk; ++jj) {
+                tma_prefetch_2d(&tmK, h2 * kHD, kr2 + jj * kT);
+                tma_prefetch_2d(&tmV, h2 * kHD, kr2 + jj * kT);
+              }
+              if (has_tail) {
+                tma_prefetch_2d(&tmQt, h2 * kHD, qr2 + p.nq_main);
+                tma_prefetch_2d(&tmDOt, h2 * kHD, qr2 + p.nq_main);
+              }
+              if (has_tk) {
+                tma_prefetch_2d(&tmKt, h2 * kHD, kr2 + p.nk_main);
+                tma_prefetch_2d(&tmVt, h2 * kHD, kr2 + p.nk_main);
+              }
+            }
           }
         }
       }
@@ -243,6 +297,24 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         // ahead of the group's compute, so a group finds its next scores waiting when it hands a unit over.
         int sblk0 = 0, sblk1 = 0, sidx0 = 0, sidx1 = 0;
         uint32_t ns0 = 0, ns1 = 0;
+        // Inputs of query tile i have landed.  Tail keys (the cls key of
+        // 257 = 2 x 128 + 1) ride as N = 16 COLUMNS with the queries on the lanes: S = Q_i K_t^T, dP = dO_i V_t^T go into the still
+        // unused dQ accumulator of the tile (read by the tile's compute group before the first dQ MMA can be issued).
+        auto tile_ready = [&](int i) {
+          mbar_wait(bar_q(i), 0);
+          if (dbg0 && i == 0) p.dbg[1024 + dbg_cta0 * 8 + 3] = clock64();  // Q_0 (+ tail keys) landed
+          mbar_wait(bar_do(i), 0);
+          if (dbg0 && i == 0) p.dbg[1024 + dbg_cta0 * 8 + 4] = clock64();  // dO_0, O_0 landed
+          tc_fence_after();
+          if (has_tk) {
+            const uint32_t kt_k = (sKt >> 4) | kLoK, vt_k = (sVt >> 4) | kLoK;
+#pragma unroll
+            for (int k = 0; k < kHD / 16; ++k) umma_ss_lohi(tDQ(i), q_k + i * 1024u + 2 * k, kt_k + 2 * k, kHi, idesc_st, k > 0);
+#pragma unroll
+            for (int k = 0; k < kHD / 16; ++k) umma_ss_lohi(tDQ(i) + 16u, do_k + i * 1024u + 2 * k, vt_k + 2 * k, kHi, idesc_st, k > 0);
+            umma_commit(bar_tks(i));
+          }
+        };
         auto issue_next = [&](int g) {
           int& sblk = g ? sblk1 : sblk0;
           int& sidx = g ? sidx1 : sidx0;
@@ -253,6 +325,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (sidx == 0) {  // first unit of a key block for this group: K / V must have landed
             mbar_wait(bar_kvfull(s), (sblk >> 1) & 1);
             tc_fence_after();
+            if (dbg0 && sblk == 0 && g == 0) p.dbg[1024 + dbg_cta0 * 8 + 5] = clock64();  // K_0, V_0 landed
           }
           const bool tail = sidx == kUPT * nqt;
           const uint32_t rows = static_cast<uint32_t>(sidx / kUPT) * 1024u + static_cast<uint32_t>(g) * 512u + static_cast<uint32_t>(sidx % kUPT) * (kQU * 8u);
@@ -279,21 +352,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (dbg_on && dbg_n < 63) p.dbg[512 + dbg_cta * 64 + (dbg_n++)] = clock64();           \
   } while (0)
         VL_ISTAMP();
-        mbar_wait(bar_q, 0);
-        mbar_wait(bar_do, 0);
-        if (has_tk) {
-          // tail keys (the cls key of 257 = 2 x 128 + 1) ride as N = 16 COLUMNS, queries on the lanes: S = Q_i K_t^T, dP = dO_i V_t^T
-          // into the still unused dQ accumulators (read by the compute groups before their first hand-over)
-          const uint32_t kt_k = (sKt >> 4) | kLoK, vt_k = (sVt >> 4) | kLoK;
-          tc_fence_after();
-          for (int i = 0; i < nqt; ++i) {
-#pragma unroll
-            for (int k = 0; k < kHD / 16; ++k) umma_ss_lohi(tDQ(i), q_k + i * 1024u + 2 * k, kt_k + 2 * k, kHi, idesc_st, k > 0);
-#pragma unroll
-            for (int k = 0; k < kHD / 16; ++k) umma_ss_lohi(tDQ(i) + 16u, do_k + i * 1024u + 2 * k, vt_k + 2 * k, kHi, idesc_st, k > 0);
-          }
-          umma_commit(bar_tks);
-        }
+        for (int i = 0; i < nqt; ++i) tile_ready(i);
 #pragma unroll 1
         for (int n = 0; n < 2 * kUPT; ++n) issue_next(n & 1);  // kUPT units ahead for both groups
         VL_ISTAMP();
@@ -348,72 +407,70 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #undef VL_ISTAMP
       }
     } else if (has_tail || has_tk) {
-      // ================================================================== helper warps (64 threads, thread = head dim d)
+      // ================================================================== helper warps (2 warps; lane = head dims 2 lane, 2 lane + 1)
       // What is left on CUDA cores, off the compute groups' critical path:
       //  * tail keys: dV_u[d] = sum_q P[q, u] dO[q, d], dK_u[d] = sum_q dS[q, u] Q[q, d] over the range's queries (coefficients from the
       //    compute groups' prologue), plus the tail-query x tail-key corner;
-      //  * tail queries: dQ_t[d] = sum over keys dS[t, key] K[key, d], accumulated over the key blocks in key order (coefficients from
-      //    compute group 0's tail unit).  Fixed summation orders: deterministic.
-      const int d = (warp - 2) * 32 + lane;
+      //  * tail queries: dQ_t[d] = sum over keys dS[t, key] K[key, d] (coefficients from compute group 0's tail unit).
+      // The two warps split the rows of every mat-vec in halves and meet once at the end (partials through shared memory, added
+      // in a fixed order: deterministic).
+      const int hw = warp - 2;
+      const int d0 = 2 * lane;
       const float sl2 = p.scale * kLog2e;
-      float acc[kMaxTail] = {0.f, 0.f, 0.f, 0.f};  // dQ of the tail queries
+      float2 acc[kMaxTail], ak[kMaxTail], av[kMaxTail];  // dQ of the tail queries; dK / dV of the tail keys (this warp's share)
+#pragma unroll
+      for (int t = 0; t < kMaxTail; ++t) acc[t] = ak[t] = av[t] = make_float2(0.f, 0.f);
       if (has_tk) {
-        float ak[kMaxTail] = {0.f, 0.f, 0.f, 0.f}, av[kMaxTail] = {0.f, 0.f, 0.f, 0.f};
-        mbar_wait(bar_q, 0);
-        mbar_wait(bar_do, 0);
+        for (int i = 0; i < nqt; ++i) {
+          mbar_wait(bar_q(i), 0);
+          mbar_wait(bar_do(i), 0);
+        }
         mbar_wait(bar_tkc, 0);
-        const float* cp = sf + kFTk;                      // [t][q] P
-        const float* cd = sf + kFTk + kMaxTail * 2 * kT;  // [t][q] dS
-        const int nq_rows = nqt * kT;                     // rows past nq_main carry zero coefficients
-#pragma unroll 2
-        for (int q = 0; q < nq_rows; ++q) {
-          const uint32_t off = static_cast<uint32_t>(q >> 7) * 16384u + sw128_off(q & 127, d);
-          const float gv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(bp + kOffDO + off));
-          const float qv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(bp + kOffQ + off));
+        const float* cp = sf + kFTk;                      // [u][q] P
+        const float* cd = sf + kFTk + kMaxTail * 2 * kT;  // [u][q] dS
+        if (hw < nqt) {  // warp hw takes query tile hw (rows past nq_main carry zero coefficients)
+          const uint8_t* gt = bp + kOffDO + hw * 16384;
+          const uint8_t* qt = bp + kOffQ + hw * 16384;
+#pragma unroll 4
+          for (int q = 0; q < kT; ++q) {
+            const uint32_t off = sw128_off(q, d0);
+            const uint32_t gw = *reinterpret_cast<const uint32_t*>(gt + off), qw = *reinterpret_cast<const uint32_t*>(qt + off);
+            const float2 gv = make_float2(bf16_lo(gw), bf16_hi(gw)), qv = make_float2(bf16_lo(qw), bf16_hi(qw));
 #pragma unroll
-          for (int u = 0; u < kMaxTail; ++u) {
-            av[u] = fmaf(cp[u * 2 * kT + q], gv, av[u]);
-            ak[u] = fmaf(cd[u * 2 * kT + q], qv, ak[u]);
+            for (int u = 0; u < kMaxTail; ++u) {
+              if (u < p.tk) {
+                const float cpv = cp[u * 2 * kT + hw * kT + q], cdv = cd[u * 2 * kT + hw * kT + q];
+                av[u] = __ffma2_rn(make_float2(cpv, cpv), gv, av[u]);
+                ak[u] = __ffma2_rn(make_float2(cdv, cdv), qv, ak[u]);
+              }
+            }
           }
         }
-        // tail query x tail key: every thread evaluates the few scalar scores itself (64-term dots from shared memory) and
-        // updates its own dim
-        for (int t = 0; t < p.tq; ++t) {
-          const float qtd = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(bp + kOffQt + sw128_off(t, d)));
-          const float gtd = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(bp + kOffDOt + sw128_off(t, d)));
+        if (hw == 0) {
+          // tail query x tail key: the few scalar scores by warp reduction, then every lane updates its two dims
+          for (int t = 0; t < p.tq; ++t) {
+            const uint32_t qtw = *reinterpret_cast<const uint32_t*>(bp + kOffQt + sw128_off(t, d0));
+            const uint32_t gtw = *reinterpret_cast<const uint32_t*>(bp + kOffDOt + sw128_off(t, d0));
 #pragma unroll
-          for (int u = 0; u < kMaxTail; ++u) {
-            if (u >= p.tk) break;
-            float sd = 0.f, dp = 0.f;
-#pragma unroll 8
-            for (int e = 0; e < kHD; ++e) {
-              sd = fmaf(__bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(bp + kOffQt + sw128_off(t, e))),
-                        __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(bp + kOffKt + sw128_off(u, e))), sd);
-              dp = fmaf(__bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(bp + kOffDOt + sw128_off(t, e))),
-                        __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(bp + kOffVt + sw128_off(u, e))), dp);
+            for (int u = 0; u < kMaxTail; ++u) {
+              if (u >= p.tk) break;
+              const uint32_t kuw = *reinterpret_cast<const uint32_t*>(bp + kOffKt + sw128_off(u, d0));
+              const uint32_t vuw = *reinterpret_cast<const uint32_t*>(bp + kOffVt + sw128_off(u, d0));
+              float sd = bf16_lo(qtw) * bf16_lo(kuw) + bf16_hi(qtw) * bf16_hi(kuw);
+              float dp = bf16_lo(gtw) * bf16_lo(vuw) + bf16_hi(gtw) * bf16_hi(vuw);
+#pragma unroll
+              for (int o2 = 16; o2 > 0; o2 >>= 1) {
+                sd += __shfl_xor_sync(0xffffffffu, sd, o2);
+                dp += __shfl_xor_sync(0xffffffffu, dp, o2);
+              }
+              const float pv = ex2_approx(fmaf(sd, sl2, sf[kFNl + 2 * kT + t]));
+              const float ds = pv * fmaf(dp, p.scale, sf[kFNd + 2 * kT + t]);
+              av[u] = __ffma2_rn(make_float2(pv, pv), make_float2(bf16_lo(gtw), bf16_hi(gtw)), av[u]);
+              ak[u] = __ffma2_rn(make_float2(ds, ds), make_float2(bf16_lo(qtw), bf16_hi(qtw)), ak[u]);
+#pragma unroll
+              for (int t2 = 0; t2 < kMaxTail; ++t2)
+                if (t2 == t) acc[t2] = __ffma2_rn(make_float2(ds, ds), make_float2(bf16_lo(kuw), bf16_hi(kuw)), acc[t2]);
             }
-            const float pv = ex2_approx(fmaf(sd, sl2, sf[kFNl + 2 * kT + t]));
-            const float ds = pv * fmaf(dp, p.scale, sf[kFNd + 2 * kT + t]);
-            av[u] = fmaf(pv, gtd, av[u]);
-            ak[u] = fmaf(ds, qtd, ak[u]);
-            const float kud = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(bp + kOffKt + sw128_off(u, d)));
-#pragma unroll
-            for (int t2 = 0; t2 < kMaxTail; ++t2)
-              if (t2 == t) acc[t2] = fmaf(ds, kud, acc[t2]);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < kMaxTail; ++u) {
-          if (u < p.tk) {
-            __nv_bfloat16* dkp = p.dk + (krow0 + p.nk_main + u) * p.lddk + h * kHD + d;
-            __nv_bfloat16* dvp = p.dv + (krow0 + p.nk_main + u) * p.lddv + h * kHD + d;
-            float k0 = ak[u], v0 = av[u];
-            if (p.accum_kv) {
-              k0 += __bfloat162float(*dkp);
-              v0 += __bfloat162float(*dvp);
-            }
-            *dkp = __float2bfloat16(k0);
-            *dvp = __float2bfloat16(v0);
           }
         }
       }
@@ -424,12 +481,18 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           mbar_wait(bar_cfull(cb), (j >> 1) & 1);
           const uint8_t* kt = bp + kOffK + s * 16384;
           const float* cf = sf + kFCoef + cb * kMaxTail * kT;
-          const int nrow = min(kT, p.nk_main - j * kT);
+          const int r1 = min(kT / 2 * (hw + 1), p.nk_main - j * kT);  // warp hw takes key rows [64 hw, 64 hw + 64) of the block
 #pragma unroll 4
-          for (int r = 0; r < nrow; ++r) {
-            const float kv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(kt + sw128_off(r, d)));
+          for (int r = kT / 2 * hw; r < r1; ++r) {
+            const uint32_t kw = *reinterpret_cast<const uint32_t*>(kt + sw128_off(r, d0));
+            const float2 kv = make_float2(bf16_lo(kw), bf16_hi(kw));
 #pragma unroll
-            for (int t = 0; t < kMaxTail; ++t) acc[t] = fmaf(cf[t * kT + r], kv, acc[t]);
+            for (int t = 0; t < kMaxTail; ++t) {
+              if (t < p.tq) {
+                const float c = cf[t * kT + r];
+                acc[t] = __ffma2_rn(make_float2(c, c), kv, acc[t]);
+              }
+            }
           }
           __syncwarp();
           if (lane == 0) {
@@ -437,14 +500,44 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             mbar_arrive(bar_kvempty(s));
           }
         }
+      }
+      // the two warps' partial sums meet: warp 1 hands its registers over through shared memory (the coefficient area of the tail
+      // unit is dead by now for the tail keys' part; a private slice is used to stay clear of it)
+      float2* xch = reinterpret_cast<float2*>(sf + kFXch);  // [3][kMaxTail][32] float2
+      if (hw == 1) {
 #pragma unroll
-        for (int t = 0; t < kMaxTail; ++t)
-          if (t < p.tq) p.dq[(qrow0 + p.nq_main + t) * p.lddq + h * kHD + d] = __float2bfloat16(acc[t]);
+        for (int t = 0; t < kMaxTail; ++t) {
+          xch[(0 * kMaxTail + t) * 32 + lane] = acc[t];
+          xch[(1 * kMaxTail + t) * 32 + lane] = ak[t];
+          xch[(2 * kMaxTail + t) * 32 + lane] = av[t];
+        }
+      }
+      asm volatile("bar.sync 4, 64;" ::: "memory");
+      if (hw == 0) {
+#pragma unroll
+        for (int t = 0; t < kMaxTail; ++t) {
+          if (t < p.tq) {
+            const float2 o = xch[(0 * kMaxTail + t) * 32 + lane];
+            *reinterpret_cast<uint32_t*>(p.dq + (qrow0 + p.nq_main + t) * p.lddq + h * kHD + d0) = pack_bf16(acc[t].x + o.x, acc[t].y + o.y);
+          }
+          if (t < p.tk) {
+            const float2 ok_ = xch[(1 * kMaxTail + t) * 32 + lane], ov_ = xch[(2 * kMaxTail + t) * 32 + lane];
+            __nv_bfloat16* dkp = p.dk + (krow0 + p.nk_main + t) * p.lddk + h * kHD + d0;
+            __nv_bfloat16* dvp = p.dv + (krow0 + p.nk_main + t) * p.lddv + h * kHD + d0;
+            float k0 = ak[t].x + ok_.x, k1 = ak[t].y + ok_.y, v0 = av[t].x + ov_.x, v1 = av[t].y + ov_.y;
+            if (p.accum_kv) {
+              const uint32_t okw = *reinterpret_cast<const uint32_t*>(dkp), ovw = *reinterpret_cast<const uint32_t*>(dvp);
+              k0 += bf16_lo(okw); k1 += bf16_hi(okw); v0 += bf16_lo(ovw); v1 += bf16_hi(ovw);
+            }
+            *reinterpret_cast<uint32_t*>(dkp) = pack_bf16(k0, k1);
+            *reinterpret_cast<uint32_t*>(dvp) = pack_bf16(v0, v1);
+          }
+        }
       }
     }
   } else {
     // ================================================================== compute groups
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     const int g = (warp - 4) >> 2;      // 0 or 1: query half [64 g, 64 g + 64) of every tile
     const int quarter = warp & 3;       // TMEM lane quarter of this warp
     const int r = quarter * 32 + lane;  // key row inside the block = TMEM lane
@@ -462,11 +555,14 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   } while (0)
     VL_STAMP();
 
-    // ---- prologue: per-query statistics  nl = -lse log2 e,  nd = -D scale  with D = rowsum(dO * O)   (thread = query row here)
+    // ---- per-query statistics  nl = -lse log2 e,  nd = -D scale  with D = rowsum(dO * O): group g's threads own the rows of query
+    // tile g (group 0 also the tail queries).  (Tried: group 1 computing tile 1's statistics after its first unit, so that the first
+    // tile's units start before the second tile has landed -- measured slower, 0.49 vs 0.46 ms: the extra two-group barrier and
+    // the delayed first hand-over of group 1 cost more than the ~1 k cycles the earlier start saves.)
     float dsk[kMaxTail] = {0.f, 0.f, 0.f, 0.f};  // dS of this thread's query row against the tail keys (for its dQ row)
-    {
+    auto tile_stats = [&]() {
       const int qrow = g * kT + x;  // row inside this launch's main range
-      const bool ok = g < nqt && qrow < p.nq_main;
+      const bool ok = qrow < p.nq_main;
       float lse = 0.f;
       if (ok) lse = p.lse[(static_cast<long long>(b) * p.H + h) * p.nq + p.q0 + qrow];
       if (warp == 4) {  // tail queries: one warp, two dims per lane, coalesced 128-byte rows
@@ -488,40 +584,38 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
         }
       }
-      float D = 0.f;
-      if (g < nqt) {
-        mbar_wait(bar_do, 0);
-        if (ok) D = dot_rows_sw128(bp + kOffDO + g * 16384, bp + kOffST + g * 16384, x);
-      }
+      mbar_wait(bar_do(g), 0);
+      const float D = ok ? dot_rows_sw128(bp + kOffDO + g * 16384, bp + kOffST + g * (32768 + 16384), x) : 0.f;
       sNl[qrow] = ok ? -lse * kLog2e : -INFINITY;  // rows that do not exist: exp2(s - inf) = 0 -> P = dS = 0
       sNd[qrow] = -D * p.scale;
       if (has_tk) {
-        // tail keys: this thread's query row against the tq' <= 4 tail keys (scores sit in the still unused dQ accumulator of the
+        // tail keys: this thread's query row against the <= 4 tail keys (scores sit in the still unused dQ accumulator of the
         // row's tile).  P / dS go to the helper warps (dV / dK of the tail keys); dS stays here for this row's dQ.
         float* cp = sf + kFTk;
         float* cd = sf + kFTk + kMaxTail * 2 * kT;
-        if (g < nqt) {
-          mbar_wait(bar_tks, 0);
-          tc_fence_after();
-          uint32_t sv[16], dpv[16];
-          tmem_ld16(tDQ(g) + lane_off, sv);
-          tmem_ld16(tDQ(g) + 16u + lane_off, dpv);
-          tc_wait_ld();
+        mbar_wait(bar_tks(g), 0);
+        tc_fence_after();
+        uint32_t sv[16], dpv[16];
+        tmem_ld16(tDQ(g) + lane_off, sv);
+        tmem_ld16(tDQ(g) + 16u + lane_off, dpv);
+        tc_wait_ld();
 #pragma unroll
-          for (int u = 0; u < kMaxTail; ++u) {
-            const float pv = (ok && u < p.tk) ? ex2_approx(fmaf(__uint_as_float(sv[u]), sl2, -lse * kLog2e)) : 0.f;
-            const float ds = pv * fmaf(__uint_as_float(dpv[u]), p.scale, -D * p.scale);
-            dsk[u] = ds;
-            cp[u * 2 * kT + qrow] = pv;
-            cd[u * 2 * kT + qrow] = ds;
-          }
-          tc_fence_before();
+        for (int u = 0; u < kMaxTail; ++u) {
+          const float pv = (ok && u < p.tk) ? ex2_approx(fmaf(__uint_as_float(sv[u]), sl2, -lse * kLog2e)) : 0.f;
+          const float ds = pv * fmaf(__uint_as_float(dpv[u]), p.scale, -D * p.scale);
+          dsk[u] = ds;
+          cp[u * 2 * kT + qrow] = pv;
+          cd[u * 2 * kT + qrow] = ds;
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tkc);
+        tc_fence_before();
       }
+    };
+    if (g < nqt) tile_stats();
+    if (has_tk) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tkc);
     }
-    both_groups_sync();  // statistics visible; the O tiles (staging buffer 0) are dead from here on
+    both_groups_sync();  // statistics visible; the O tiles (staging buffers) are dead from here on
     VL_STAMP();
 
     uint32_t cs = 0;        // units received (TMEM buffer = cs & 1, sfull phase = (cs >> 1) & 1)
@@ -720,7 +814,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tma_store_commit();
       }
     }
-    if (x == 0) tma_store_wait<0>();  // bulk stores complete before the CTA retires
+    if (x == 0) tma_store_wait_read<0>();  // the bulk stores have read their staging tiles before the CTA (and its shared memory) retires
     VL_STAMP();
 #undef VL_STAMP
   }
@@ -787,6 +881,9 @@ int launch_attn_bwd3(const void* q, const void* k, const void* v, const void* o,
   p.dq = reinterpret_cast<__nv_bfloat16*>(dq); p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.dv = reinterpret_cast<__nv_bfloat16*>(dv);
   p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
   p.dbg = debug_buffer();
+  // debug knob 14: L2 prefetch distance in CTAs (0 = default: one wave = the number of SMs, -1 = off)
+  const int knob = debug_get(14);
+  p.pf_dist = knob < 0 ? 0 : (knob > 0 ? knob : num_sms());
   for (int q0 = 0; q0 < nq_main_all; q0 += 2 * kT) {
     p.q0 = q0;
     p.nq_main = nq_main_all - q0 < 2 * kT ? nq_main_all - q0 : 2 * kT;

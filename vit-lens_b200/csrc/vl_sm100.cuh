@@ -72,6 +72,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* map, uint3
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 prefetch of a tile (no shared-memory destination, no barrier): used to pull the inputs of the CTA that will run one wave later
+// into L2 -- and its pages into the TLB hierarchy -- while this CTA computes
+__device__ __forceinline__ void tma_prefetch_2d(const void* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
