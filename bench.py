@@ -471,6 +471,11 @@ def run_cuda(args):
             # output is still in L2 when the kernel ends): no re-reads of Q / K / V
             mhsa["fwd"]["traffic"] = int((405338112 + 113060864) * B / 256)
             mhsa["fwd"]["kernel"] = "attn_fwd2_kernel (persistent, P in TMEM), per launch; algorithmic %d B" % (4 * B * 257 * 1024 * 2)
+        if "bwd" in mhsa and args.config == 1:
+            # attn_bwd3_kernel at batch 256 (profiles/r02_ncu_attn_bwd3.txt: 679.6 MB read + 368.2 MB written; algorithmic 1078 MB):
+            # Q / K / V / O / dO are read once (the L2 prefetch of the next wave's tiles adds no DRAM traffic)
+            mhsa["bwd"]["traffic"] = int((679634944 + 368246784) * B / 256)
+            mhsa["bwd"]["kernel"] = "attn_bwd3_kernel (keys on the TMEM lanes), per launch; algorithmic %d B" % (8 * B * 257 * 1024 * 2)
     cpu = None
     if not args.no_cpu_baseline and world == 1 and args.config == 1:
         sps, cores, sec = time_cpu(2, 1)
