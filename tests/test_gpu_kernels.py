@@ -105,7 +105,11 @@ def _ref_attn(q, k, v, causal):
     (2, 2, 17, 17, False, True), (4, 12, 50, 50, False, True), (2, 1, 128, 512, False, False), (1, 1, 1, 1, False, True),
     (2, 2, 513, 513, False, True), (2, 1, 229, 229, False, True), (1, 2, 130, 259, False, False), (2, 1, 300, 300, True, True),
     (1, 1, 640, 132, False, False), (2, 2, 16, 48, False, False), (2, 1, 8, 16, False, False), (1, 2, 40, 208, False, False),
-    (2, 1, 80, 80, True, True)])
+    (2, 1, 80, 80, True, True),
+    # the third-generation backward's special paths: tail queries / tail keys of N = 128 k + t (t <= 4) alone and together, several
+    # query ranges with accumulation into dK / dV, the ViT-Lens latent lengths 129 = 128 + cls and 260 = 2 x 128 + 4
+    (3, 2, 129, 129, False, True), (2, 2, 128, 129, False, False), (2, 2, 129, 128, False, False), (2, 3, 260, 260, False, True),
+    (1, 2, 516, 258, False, False), (2, 1, 64, 131, False, False)])
 def test_attention_fwd_bwd(ops, B, H, nq, nk, causal, packed):
     D = H * 64
     if packed:
@@ -551,6 +555,33 @@ def test_attention_backward_is_bit_deterministic(ops, B, H, n):
         outs.append(d)
     for other in outs[1:]:
         assert torch.equal(outs[0], other)
+
+
+@pytest.mark.parametrize("B,H,nq,nk", [(2, 4, 257, 257), (2, 2, 256, 600), (2, 2, 129, 129)])
+def test_attention_backward_generations_agree(ops, B, H, nq, nk):
+    """attn_bwd3 (keys on the TMEM lanes; default for non-causal attention) against attn_bwd2 (queries on the lanes; still the causal
+    text-tower kernel, `vl_debug_set(12, 2)` forces it): same math, different summation orders -> agreement to bf16 rounding."""
+    from vitlens_b200 import lib as L
+
+    torch.manual_seed(11)
+    D = H * 64
+    q = torch.randn(B * nq, D, device="cuda").to(BF)
+    kv = torch.randn(B * nk, 2 * D, device="cuda").to(BF)
+    k, v = kv[:, :D], kv[:, D:]
+    do = torch.randn(B * nq, D, device="cuda").to(BF)
+    o, lse = ops.attention_fwd(q, k, v, B=B, H=H, nq=nq, nk=nk)
+    res = []
+    for knob in (0, 2):
+        L.debug_set(12, knob)
+        try:
+            dq, dkv = torch.zeros_like(q), torch.zeros_like(kv)
+            ops.attention_bwd(q, k, v, o, do, lse, dq, dkv[:, :D], dkv[:, D:], B=B, H=H, nq=nq, nk=nk)
+            torch.cuda.synchronize()
+        finally:
+            L.debug_set(12, 0)
+        res.append((dq, dkv))
+    close(res[0][0], res[1][0].float(), tol=1e-2)
+    close(res[0][1], res[1][1].float(), tol=1e-2)
 
 
 @pytest.mark.parametrize("W,rows", [(1, 300), (2, 256), (4, 512)])

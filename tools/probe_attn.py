@@ -117,9 +117,9 @@ def timing():
 
     def g_knob(c):
         def fn():
-            L.debug_set(14, c)
+            L.debug_set(15, c)
             g()
-            L.debug_set(14, 0)
+            L.debug_set(15, 0)
         return fn
 
     extra = [(f"bwd(L2 prefetch distance {c})", g_knob(c), 8 * B * N * D * 2, 10.0 * B * H * N * N * 64) for c in (-1, 74, 296)]

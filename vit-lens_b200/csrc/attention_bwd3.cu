@@ -881,8 +881,8 @@ int launch_attn_bwd3(const void* q, const void* k, const void* v, const void* o,
   p.dq = reinterpret_cast<__nv_bfloat16*>(dq); p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.dv = reinterpret_cast<__nv_bfloat16*>(dv);
   p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
   p.dbg = debug_buffer();
-  // debug knob 14: L2 prefetch distance in CTAs (0 = default: one wave = the number of SMs, -1 = off)
-  const int knob = debug_get(14);
+  // debug knob 15: L2 prefetch distance in CTAs (0 = default: one wave = the number of SMs, -1 = off)
+  const int knob = debug_get(15);
   p.pf_dist = knob < 0 ? 0 : (knob > 0 ? knob : num_sms());
   for (int q0 = 0; q0 < nq_main_all; q0 += 2 * kT) {
     p.q0 = q0;
