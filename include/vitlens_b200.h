@@ -127,6 +127,34 @@ int vl_gemm_rowlse_parts(int32_t N);
 int vl_lse_combine(const float* part_max, const float* part_sum, const float* diag, int32_t M, int32_t nparts,
                    float* lse, float* loss_sum, void* stream);
 
+/* Fused backward of one direction of the gathered InfoNCE loss (reference: gather_features + ClipLoss / TriClipLoss backward,
+ * open_clip/loss.py:55-76, 116-138, 158-163; `logits * mask` of the mask variants loss.py:485-903):
+ *   dx[i, :] = s * sum_j g[i, j] * y[j, :],   g = gscale * (exp(z - row_lse_i) + [col_lse] exp(z - col_lse_j) - k * onehot(j == i + label_off)),
+ *   z = s * x y^T (masked entries: z = 0, g = 0);  *ds_out = sum g * (x y^T)  (with ds_row_only: the row term of g alone).
+ * One launch: logits and g stay in TMEM; y is either one bf16 matrix [N, E] or y_npeers row blocks of y_peer_rows rows living in
+ * the ranks' peer arenas (read in place over NVLink -- the all-gather fused into the kernel).  E % 64 == 0. */
+typedef struct {
+  const void* x;            /* bf16 [M, E], row stride ldx */
+  const void* y;            /* bf16 [N, E], row stride ldy (or null with y_peers) */
+  const void* const* y_peers;
+  int32_t y_npeers, y_peer_rows;
+  int32_t M, N, E;
+  int64_t ldx, ldy;
+  float* dx;                /* fp32 [M, E], row stride lddx */
+  int64_t lddx;
+  const float* row_lse;     /* [M] */
+  const float* col_lse;     /* [N] or null */
+  int32_t label_off;
+  const float* alpha_dev;   /* device scalar: logit scale s */
+  float gscale;
+  const float* gscale_dev;  /* optional device scalar multiplied into gscale (upstream gradient) */
+  float* ds_out;            /* device scalar (written) or null */
+  int32_t ds_row_only;
+  const uint8_t* mask;      /* [M, N] bytes, row stride ldmask, or null */
+  int64_t ldmask;
+} VlClipBwdArgs;
+int vl_clip_backward(const VlClipBwdArgs* args, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Symmetric peer memory over NVLink / NVSwitch for the data-parallel step (reference gather_features
  * loss.py:20-78 and the DDP gradient all-reduce pc_tri_main.py:378-380).  One arena per rank (cudaMalloc here, CUDA IPC), mapped

@@ -286,6 +286,17 @@ def fps(pts, start, npoint):
     return idx, centers
 
 
+def clip_backward_fusable(E, q16):
+    return E % 64 == 0
+
+
+def clip_backward(p16, q16, *, alpha, row_lse, col_lse, label_off, gscale, gscale_dev=None, ds_row_only=False, mask=None, want_ds=True):
+    """The fused one-launch backward (vl_clip_backward): g rounded to bf16 as the kernel does, then dX = alpha * g @ Q."""
+    g, ds = clipgrad(p16, q16, alpha=alpha, row_lse=row_lse, col_lse=col_lse, label_off=label_off, gscale=gscale, gscale_dev=gscale_dev,
+                     ds_row_only=ds_row_only, mask=mask)
+    return float(alpha) * (g.float() @ q16.float()), ds
+
+
 def knn_group(pts, centers, G, k, want_idx=False):
     _n()
     B, N, _ = pts.shape

@@ -292,6 +292,52 @@ def test_contrastive_epilogues(ops, Bl, Ball, off):
         assert abs(float(ds) - float((gr * (z / s)).sum())) < 2e-2 * float((gr * (z / s)).abs().sum()) + 1e-4
 
 
+@pytest.mark.parametrize("Bl,Ball,off,E,masked", [(8, 8, 0, 768, False), (512, 512, 0, 768, False), (64, 256, 128, 768, True), (100, 300, 100, 512, True),
+                                                  (256, 2048, 512, 1024, False), (130, 130, 0, 64, False), (256, 1024, 256, 640, False)])
+def test_fused_contrastive_backward(ops, Bl, Ball, off, E, masked):
+    """vl_clip_backward (one launch per direction: logits and their gradient stay in TMEM) against the two-GEMM path (VL_EPI_CLIPGRAD
+    writes g to HBM, a plain GEMM reads it back) and against fp32 torch: dX = s * g @ Y, d(loss)/d(scale) sum, with and without the
+    column term, the row-only d(scale) of the local-loss variants, and the byte mask of the mask losses."""
+    torch.manual_seed(3)
+    x = F.normalize(torch.randn(Bl, E, device="cuda"), dim=-1).to(BF)
+    y = F.normalize(torch.randn(Ball, E, device="cuda"), dim=-1).to(BF)
+    s = 14.3
+    s_dev = torch.tensor([s], device="cuda")
+    mask = (torch.rand(Bl, Ball, device="cuda") > 0.2).to(torch.uint8) if masked else None
+    if masked:
+        mask[torch.arange(Bl), torch.arange(Bl) + off] = 1
+    lse, _ = ops.rowlse(x, y, alpha=s_dev, label_off=off, **({} if mask is None else dict(mask=mask)))
+    col = torch.randn(Ball, device="cuda") + 3
+    assert ops.clip_backward_fusable(E, y)
+    for cl in (None, col):
+        for row_only in (False, True):
+            kw = dict(alpha=s_dev, row_lse=lse, col_lse=cl, label_off=off, gscale=0.02, gscale_dev=torch.tensor([0.5], device="cuda"),
+                      ds_row_only=row_only, **({} if mask is None else dict(mask=mask)))
+            dx, ds = ops.clip_backward(x, y, **kw)
+            g, ds_ref = ops.clipgrad(x, y, **kw)
+            dx_ref = ops.gemm(g.contiguous() if g.stride(0) % 8 else g, y, b_t=True, out_dtype=torch.float32, alpha_dev=s_dev)
+            close(dx, dx_ref, tol=2e-3, atol=1e-6)   # same bf16-rounded g, fp32 accumulation in a different grouping
+            assert abs(float(ds) - float(ds_ref)) <= 1e-4 * abs(float(ds_ref)) + 1e-6, (float(ds), float(ds_ref))
+            # fp32 torch
+            acc = x.float() @ y.float().t()
+            z = s * acc
+            keep = torch.ones_like(z) if mask is None else (mask != 0).float()
+            z = z * keep
+            gr = torch.exp(z - lse[:, None])
+            k = 1.0
+            if cl is not None:
+                gr = gr + torch.exp(z - cl[None, :])
+                k = 2.0
+            oh = torch.zeros_like(z)
+            oh[torch.arange(Bl), torch.arange(Bl) + off] = 1
+            gr = 0.01 * (gr - k * oh) * keep
+            close(dx, s * (gr @ y.float()), tol=1e-2, atol=1e-6)
+    torch.cuda.synchronize()
+    d1, _ = ops.clip_backward(x, y, **kw)
+    d2, _ = ops.clip_backward(x, y, **kw)
+    assert torch.equal(d1, d2)  # deterministic
+
+
 def test_adamw(ops):
     from vitlens_b200 import lib as L
 

@@ -515,12 +515,18 @@ class ContrastiveFn(torch.autograd.Function):
         dl = dloss.detach().float().reshape(1).contiguous()  # upstream gradient stays on the device too
         mkw_x = {} if ctx.masks is None else dict(mask=ctx.masks[0])
         mkw_y = {} if ctx.masks is None else dict(mask=ctx.masks[1])
-        gx, ds_x = _ops.clipgrad(x16, ay16, alpha=s, row_lse=lse_x, col_lse=col_x if col_term else None, label_off=label_off, gscale=gs, gscale_dev=dl,
-                                 ds_row_only=ds_rows_only, **mkw_x)
-        gy, ds_y = _ops.clipgrad(y16, ax16, alpha=s, row_lse=lse_y, col_lse=col_y if col_term else None, label_off=label_off, gscale=gs, gscale_dev=dl,
-                                 ds_row_only=ds_rows_only, **mkw_y)
-        dx = _ops.gemm(gx, ay16, b_t=True, out_dtype=F32, alpha_dev=s) if _need(ctx, 0) else None
-        dy = _ops.gemm(gy, ax16, b_t=True, out_dtype=F32, alpha_dev=s) if _need(ctx, 1) else None
+        kw = dict(alpha=s, label_off=label_off, gscale=gs, gscale_dev=dl, ds_row_only=ds_rows_only)
+        if _ops.clip_backward_fusable(x16.shape[1], ay16) and _ops.clip_backward_fusable(x16.shape[1], ax16):
+            # one launch per direction: the gradient tile g = d loss / d logits never leaves the SM (vl_clip_backward)
+            dx, ds_x = _ops.clip_backward(x16, ay16, row_lse=lse_x, col_lse=col_x if col_term else None, **kw, **mkw_x)
+            dy, ds_y = _ops.clip_backward(y16, ax16, row_lse=lse_y, col_lse=col_y if col_term else None, **kw, **mkw_y)
+            dx = dx if _need(ctx, 0) else None
+            dy = dy if _need(ctx, 1) else None
+        else:
+            gx, ds_x = _ops.clipgrad(x16, ay16, row_lse=lse_x, col_lse=col_x if col_term else None, **kw, **mkw_x)
+            gy, ds_y = _ops.clipgrad(y16, ax16, row_lse=lse_y, col_lse=col_y if col_term else None, **kw, **mkw_y)
+            dx = _ops.gemm(gx, ay16, b_t=True, out_dtype=F32, alpha_dev=s) if _need(ctx, 0) else None
+            dy = _ops.gemm(gy, ax16, b_t=True, out_dtype=F32, alpha_dev=s) if _need(ctx, 1) else None
         dscale = None
         if _need(ctx, 4):
             # with the column term every logit's gradient appears in both directions

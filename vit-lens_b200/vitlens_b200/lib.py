@@ -158,6 +158,7 @@ def gemm(a, b, d, *, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, epilogue=EP
 _P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 _PROTOS = {
     "vl_gemm_bf16": [_P, _P],
+    "vl_clip_backward": [_P, _P],
     "vl_attention_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _L, _F, _I, _P],
     "vl_attention_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _L, _L, _F, _I, _P],
     "vl_layernorm_fwd": [_P, _L, _P, _P, _P, _P, _L, _P, _P, _I, _I, _F, _P],
@@ -317,6 +318,29 @@ def rowlse_parts(N: int) -> int:
     f = load().vl_gemm_rowlse_parts
     f.argtypes, f.restype = [C.c_int32], C.c_int
     return f(N)
+
+
+class ClipBwdArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("y", C.c_void_p), ("y_peers", C.c_void_p), ("y_npeers", C.c_int32), ("y_peer_rows", C.c_int32),
+        ("M", C.c_int32), ("N", C.c_int32), ("E", C.c_int32), ("ldx", C.c_int64), ("ldy", C.c_int64),
+        ("dx", C.c_void_p), ("lddx", C.c_int64), ("row_lse", C.c_void_p), ("col_lse", C.c_void_p), ("label_off", C.c_int32),
+        ("alpha_dev", C.c_void_p), ("gscale", C.c_float), ("gscale_dev", C.c_void_p), ("ds_out", C.c_void_p), ("ds_row_only", C.c_int32),
+        ("mask", C.c_void_p), ("ldmask", C.c_int64),
+    ]
+
+
+def clip_backward(x, y, dx, *, M, N, E, ldx, ldy, row_lse, col_lse, label_off, alpha_dev, gscale, gscale_dev=None, ds_out=None,
+                  ds_row_only=False, mask=None, y_peers=None, y_peer_rows=0):
+    """vl_clip_backward; see include/vitlens_b200.h.  y: bf16 [N, E] or None with y_peers (device addresses of the ranks' row blocks)."""
+    peer_arr = None
+    if y_peers is not None:
+        peer_arr = (C.c_void_p * len(y_peers))(*[int(a) for a in y_peers])
+    args = ClipBwdArgs(
+        _ptr(x), _ptr(y), C.cast(peer_arr, C.c_void_p) if peer_arr is not None else C.c_void_p(0), len(y_peers) if y_peers is not None else 0,
+        int(y_peer_rows), int(M), int(N), int(E), int(ldx), int(ldy), _ptr(dx), int(dx.stride(0)), _ptr(row_lse), _ptr(col_lse), int(label_off),
+        _ptr(alpha_dev), float(gscale), _ptr(gscale_dev), _ptr(ds_out), int(ds_row_only), _ptr(mask), 0 if mask is None else mask.stride(0))
+    _call("vl_clip_backward", C.cast(C.pointer(args), C.c_void_p), work=("tensor", 2.0 * M * N * E * 2))
 
 
 def lse_combine(part_max, part_sum, diag, lse, loss_sum, *, M, nparts):

@@ -11,6 +11,8 @@ from __future__ import annotations
 
 from typing import Optional, Tuple
 
+import os
+
 import torch
 
 from . import lib as L
@@ -339,6 +341,36 @@ def clipgrad(p16, q16, *, alpha, row_lse, col_lse, label_off, gscale, gscale_dev
            alpha=1.0, alpha_dev=alpha, row_vec=row_lse, col_vec=col_lse, iparam=label_off, fparam=gscale, fparam_dev=gscale_dev, scalar_out=ds,
            loss_flags=1 if ds_row_only else 0, mask=_mask8(mask, M, N), **(peer.kw(wait=False) if peer else {}))
     return g[:, :N], ds
+
+
+def clip_backward_fusable(E: int, q16) -> bool:
+    """True when vl_clip_backward can take this direction of the loss in one launch: embed dim a multiple of 64 and, with the
+    features sharded over peer arenas, row blocks that a 128-row block never straddles.  VL_LOSS_BWD=unfused forces the two-GEMM
+    path (g through HBM) for A/B checks."""
+    if os.environ.get("VL_LOSS_BWD", "") == "unfused" or E % 64 != 0:
+        return False
+    if isinstance(q16, PeerRows):
+        return len(q16.addrs) == 1 or q16.rows % 128 == 0
+    return True
+
+
+def clip_backward(p16, q16, *, alpha, row_lse, col_lse, label_off, gscale, gscale_dev=None, ds_row_only=False, mask=None, want_ds=True):
+    """One direction of the contrastive backward in ONE launch: dX [M, E] fp32 = alpha * g @ Q with
+    g = gscale * (exp(z - row_lse_i) + [col_lse] exp(z - col_lse_j) - k * onehot(j == i + label_off)), z = alpha * P @ Q^T (masked
+    entries carry no gradient), and sum(g * P@Q^T) as a 1-element tensor -- what clipgrad() + gemm() compute through an HBM copy of
+    g.  q16: bf16 [N, E] or PeerRows (every rank's rows read in place over NVLink)."""
+    _v2(p16, BF16)
+    peer = q16 if isinstance(q16, PeerRows) else None
+    if peer is None:
+        _v2(q16, BF16)
+    M, E = p16.shape
+    N = q16.shape[0]
+    dx = torch.empty((M, E), device=p16.device, dtype=F32)
+    ds = torch.empty((1,), device=p16.device, dtype=F32) if want_ds else None
+    L.clip_backward(p16, None if peer else q16, dx, M=M, N=N, E=E, ldx=_ld(p16), ldy=peer.E if peer else _ld(q16), row_lse=row_lse, col_lse=col_lse,
+                    label_off=label_off, alpha_dev=alpha, gscale=gscale, gscale_dev=gscale_dev, ds_out=ds, ds_row_only=ds_row_only,
+                    mask=_mask8(mask, M, N), y_peers=peer.addrs if peer else None, y_peer_rows=peer.rows if peer else 0)
+    return dx, ds
 
 
 # ----------------------------------------------------------------------------- point-cloud tokenizer
