@@ -342,44 +342,51 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-// Standard normal CDF as a logistic of an odd polynomial:  Phi(x) ~ 1 / (1 + 2^(x * P(x^2))),  P of degree 4 in x^2 fitted
-// (minimax over |x| <= 7, coefficients pre-multiplied by -2 log2 e) to atanh(erf(x / sqrt 2)).  Measured in fp32 against
-// the double-precision erf: |Phi err| < 3.1e-6, |x Phi(x) - GELU(x)| < 6.4e-6, |GELU' err| < 3.1e-6 over [-9, 9] -- two
-// orders below the bf16 rounding of the value being produced -- for 1 FMUL + 4 FFMA + FMUL + EX2 + FADD + RCP.
-// Saturates correctly: x -> +inf gives 1, x -> -inf gives 0 (2^+inf = inf, rcp(inf) = 0).
+// Standard normal CDF as a logistic of an odd polynomial,  Phi(x) ~ 1 / (1 + 2^(x * P(x^2))),  P of degree 4 in x^2 fitted (minimax
+// over |x| <= 7) to atanh(erf(x / sqrt 2)) -- written as  0.5 + 0.5 * tanh(x * Q(x^2)),  Q = -P ln2 / 2,  so that it costs ONE
+// special-function op (MUFU.TANH) instead of two (EX2 + RCP): the activation epilogues of the GEMMs are bound by the MUFU pipe
+// (16 results / clk / SM against a 128 x 256 tile every ~8 k cycles) and by the latency of the dependent MUFU pair.  The
+// polynomial alone is within 3.1e-6 of Phi (measured in fp32 against double-precision erf over [-9, 9]); tanh.approx adds
+// <= 2^-11 relative on tanh, i.e. <= 2.5e-4 absolute on Phi -- a factor 16 below the bf16 rounding (2^-9 relative) of the
+// GELU value it multiplies.  Saturates correctly: x -> +inf gives 1, x -> -inf gives 0.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float norm_cdf_fast(float x, float x2) {
-  float g = fmaf(x2, -3.133493464702042e-06f, 8.992205403046682e-05f);
-  g = fmaf(g, x2, 3.281688259448856e-04f);
-  g = fmaf(g, x2, -0.10511893779039383f);
-  g = fmaf(g, x2, -2.3021240234375f);
-  return rcp_approx(1.0f + ex2_approx(x * g));
+  float g = fmaf(x2, 1.0859860e-06f, -3.1164609e-05f);
+  g = fmaf(g, x2, -1.1373465e-04f);
+  g = fmaf(g, x2, 3.6431447e-02f);
+  g = fmaf(g, x2, 7.9785539e-01f);
+  return fmaf(0.5f, tanh_approx(x * g), 0.5f);
 }
 
 // Branch-free activation bodies (callers pick the variant once per loop, never per element, so the
 // unrolled element streams interleave for ILP).
 __device__ __forceinline__ float gelu_erf_fwd(float x) { return x * norm_cdf_fast(x, x * x); }
-__device__ __forceinline__ float gelu_quick_fwd(float x) { return x * rcp_approx(1.0f + __expf(-1.702f * x)); }
+// QuickGELU x * sigmoid(1.702 x), sigmoid(u) = 0.5 + 0.5 tanh(u / 2): one MUFU op as well
+__device__ __forceinline__ float sigmoid_fast(float u) { return fmaf(0.5f, tanh_approx(0.5f * u), 0.5f); }
+__device__ __forceinline__ float gelu_quick_fwd(float x) { return x * sigmoid_fast(1.702f * x); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float x2 = x * x;
   const float cdf = norm_cdf_fast(x, x2);
   return fmaf(0.3989422804014327f * x, ex2_approx(-0.72134752044448170f * x2), cdf);
 }
 __device__ __forceinline__ float gelu_quick_grad(float x) {
-  const float s = rcp_approx(1.0f + __expf(-1.702f * x));
+  const float s = sigmoid_fast(1.702f * x);
   return s * fmaf(1.702f * x, 1.0f - s, 1.0f);
 }
 // Two elements per instruction: sm_100 executes fp32 FMA / ADD / MUL on register pairs (FFMA2 / FADD2 / FMUL2), which halves
-// the FMA-pipe instruction count of the activation epilogues (they are issue- and latency-bound next to the MMA main loop);
-// the two MUFU ops per element stay scalar.  Same polynomial and the same results as the scalar bodies above up to the
-// rounding of individual operations.
+// the FMA-pipe instruction count of the activation epilogues; the MUFU ops stay scalar.  Same polynomial and the same results
+// as the scalar bodies above up to the rounding of individual operations.
 __device__ __forceinline__ float2 norm_cdf_fast2(float2 x, float2 x2) {
-  float2 g = __ffma2_rn(x2, make_float2(-3.133493464702042e-06f, -3.133493464702042e-06f), make_float2(8.992205403046682e-05f, 8.992205403046682e-05f));
-  g = __ffma2_rn(g, x2, make_float2(3.281688259448856e-04f, 3.281688259448856e-04f));
-  g = __ffma2_rn(g, x2, make_float2(-0.10511893779039383f, -0.10511893779039383f));
-  g = __ffma2_rn(g, x2, make_float2(-2.3021240234375f, -2.3021240234375f));
+  float2 g = __ffma2_rn(x2, make_float2(1.0859860e-06f, 1.0859860e-06f), make_float2(-3.1164609e-05f, -3.1164609e-05f));
+  g = __ffma2_rn(g, x2, make_float2(-1.1373465e-04f, -1.1373465e-04f));
+  g = __ffma2_rn(g, x2, make_float2(3.6431447e-02f, 3.6431447e-02f));
+  g = __ffma2_rn(g, x2, make_float2(7.9785539e-01f, 7.9785539e-01f));
   const float2 t = __fmul2_rn(x, g);
-  const float2 d = __fadd2_rn(make_float2(ex2_approx(t.x), ex2_approx(t.y)), make_float2(1.0f, 1.0f));
-  return make_float2(rcp_approx(d.x), rcp_approx(d.y));
+  return __ffma2_rn(make_float2(0.5f, 0.5f), make_float2(tanh_approx(t.x), tanh_approx(t.y)), make_float2(0.5f, 0.5f));
 }
 __device__ __forceinline__ float2 gelu_erf_fwd2(float2 x) { return __fmul2_rn(x, norm_cdf_fast2(x, __fmul2_rn(x, x))); }
 __device__ __forceinline__ float2 gelu_erf_grad2(float2 x) {
