@@ -30,9 +30,19 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // y[i,:] = (x[r,:] - mean) * rstd * w + b with r = row_index ? row_index[i] : i.
 // Warp per row; lane l owns the 16-byte vectors l, l + 32, ... of every row, so its slice of w / b is loop-invariant and lives
 // in registers (re-reading it per row made the kernel L1-bound: 8 KB of weight traffic per 2 KB row, l1tex 80 % busy in ncu).
-// The row itself stays packed (bf16) in registers and is unpacked in each of the three passes; the next row is in flight
-// while the current one is normalised.
-template <int CH>
+// The row itself stays packed (bf16) in registers and is unpacked in each of the three passes.  The next kLnPF rows of the warp
+// are in flight as cp.async copies into a private shared-memory ring (each lane copies and later reads only its own 16-byte
+// chunks: no barrier at all): with 16 warps per SM and one register-held row ahead the kernel had ~32 KB in flight per SM and
+// sat at 0.6 of the HBM peak (latency-bound by Little's law: 6.5 TB/s x ~1 us needs ~44 KB per SM); the ring holds 4x that.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+template <int CH, int kLnPF>
 __global__ void __launch_bounds__(256, 2) layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
                                                                const long long* __restrict__ row_index,
                                                                const float* __restrict__ w, const float* __restrict__ b,
@@ -60,30 +70,38 @@ __global__ void __launch_bounds__(256, 2) layernorm_fwd_kernel(const __nv_bfloat
       for (int j = 0; j < 8; ++j) wr[c][j] = br[c][j] = 0.f;
     }
   }
-  uint4 nxt[CH];  // the next row of this warp is already in flight while the current one is normalised
-  auto fetch = [&](long long r) {
-    const long long src = row_index ? row_index[r] : r;
-    const uint4* xr = reinterpret_cast<const uint4*>(x + src * ldx);
+  extern __shared__ uint4 ln_ring[];  // [warps per CTA][kLnPF][CH * 32] 16-byte chunks
+  uint4* my = ln_ring + static_cast<size_t>(threadIdx.x >> 5) * kLnPF * CH * 32 + lane;
+  auto fetch = [&](long long r, int slot) {  // (always commits a group, possibly empty: the wait below counts groups)
+    if (r < T) {
+      const long long src = row_index ? row_index[r] : r;
+      const uint4* xr = reinterpret_cast<const uint4*>(x + src * ldx);
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int i = lane + c * 32;
-      nxt[c] = (i < nvec) ? xr[i] : make_uint4(0u, 0u, 0u, 0u);
+      for (int c = 0; c < CH; ++c) {
+        const int i = lane + c * 32;
+        if (i < nvec) cp_async16(smem_u32(my + (slot * CH + c) * 32), xr + i);
+      }
     }
+    cp_async_commit();
   };
-  if (row < T) fetch(row);
+#pragma unroll
+  for (int k = 0; k < kLnPF; ++k) fetch(row + k * stride, k);
   const float invD = 1.0f / D;
+  int slot = 0;
   for (; row < T; row += stride) {
+    cp_async_wait<kLnPF - 1>();  // this row's copies (the oldest group) have landed
     uint4 cur[CH];
     float s = 0.f;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
-      cur[c] = nxt[c];
+      cur[c] = (lane + c * 32 < nvec) ? my[(slot * CH + c) * 32] : make_uint4(0u, 0u, 0u, 0u);
       float v[8];
       unpack8(cur[c], v);  // vectors past the row are zero
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += v[j];
     }
-    if (row + stride < T) fetch(row + stride);
+    fetch(row + kLnPF * stride, slot);  // refill the slot just read (the sum above depends on every chunk of it)
+    slot = slot + 1 == kLnPF ? 0 : slot + 1;
     const float mu = warp_sum(s) * invD;
     float q = 0.f;
 #pragma unroll
@@ -372,18 +390,42 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_d1024_v2_kernel(const __
 #pragma unroll
   for (int j = 0; j < 4; ++j) aw[j] = ab[j] = make_float2(0.f, 0.f);
   const long long step = (long long)gridDim.x * (2 * R);
-  for (long long r0 = (long long)blockIdx.x * (2 * R) + slot * R; r0 - slot * R < T; r0 += step) {
+  // The rows of the NEXT step are in flight (cp.async into a two-stage ring; every thread copies and later reads only its own
+  // 16-byte chunks, so no barrier is involved) while this step is reduced and written: without it the kernel alternated between
+  // a load phase and a compute phase with nothing in flight (0.59 of the HBM peak inside the step).
+  extern __shared__ uint4 lnb_ring[];  // [2 stages][x | dy | dres][R][256 threads]
+  auto fetch = [&](long long r0n, int st) {  // always commits a group (possibly empty)
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const long long row = r0n + i;
+      if (row < T) {
+        cp_async16(smem_u32(lnb_ring + ((st * 3 + 0) * R + i) * 256 + t), x + row * ldx + c0);
+        cp_async16(smem_u32(lnb_ring + ((st * 3 + 1) * R + i) * 256 + t), dy + row * lddy + c0);
+        if (HAS_RES) cp_async16(smem_u32(lnb_ring + ((st * 3 + 2) * R + i) * 256 + t), dres + row * lddres + c0);
+      }
+    }
+    cp_async_commit();
+  };
+  int st = 0;
+  fetch((long long)blockIdx.x * (2 * R) + slot * R, 0);
+  for (long long r0 = (long long)blockIdx.x * (2 * R) + slot * R; r0 - slot * R < T; r0 += step, st ^= 1) {
+    fetch(r0 + step, st ^ 1);
     uint4 xr[R], gr[R], rr[R];
     float mu[R], rs[R];
 #pragma unroll
     for (int i = 0; i < R; ++i) {
       const long long row = r0 + i;
       const bool ok = row < T;
-      xr[i] = ok ? *reinterpret_cast<const uint4*>(x + row * ldx + c0) : make_uint4(0u, 0u, 0u, 0u);
-      gr[i] = ok ? *reinterpret_cast<const uint4*>(dy + row * lddy + c0) : make_uint4(0u, 0u, 0u, 0u);
-      if (HAS_RES) rr[i] = ok ? *reinterpret_cast<const uint4*>(dres + row * lddres + c0) : make_uint4(0u, 0u, 0u, 0u);
       mu[i] = ok ? mean[row] : 0.f;
       rs[i] = ok ? rstd[row] : 0.f;
+    }
+    cp_async_wait<1>();  // this step's copies have landed (the next step's may still be in flight)
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const bool ok = r0 + i < T;
+      xr[i] = ok ? lnb_ring[((st * 3 + 0) * R + i) * 256 + t] : make_uint4(0u, 0u, 0u, 0u);
+      gr[i] = ok ? lnb_ring[((st * 3 + 1) * R + i) * 256 + t] : make_uint4(0u, 0u, 0u, 0u);
+      if (HAS_RES) rr[i] = ok ? lnb_ring[((st * 3 + 2) * R + i) * 256 + t] : make_uint4(0u, 0u, 0u, 0u);
     }
     float2 xh[R][4], g[R][4];
     float s[2 * R];
@@ -862,12 +904,22 @@ int vl_layernorm_fwd(const void* x, int64_t ldx, const int64_t* row_index, const
   VL_CHECK_ARG(T > 0 && D > 0 && D % 8 == 0 && D <= 256 * kMaxLnChunks, "vl_layernorm_fwd: D=%d must be a multiple of 8 and <= 2048", D);
   VL_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0, "vl_layernorm_fwd: ld must be a multiple of 8");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const int grid = grid_for((long long)T * 32, 256);
+  int grid = grid_for((long long)T * 32, 256);
+  if (grid > 2 * num_sms()) grid = 2 * num_sms();  // persistent: two resident CTAs per SM, each warp walks its rows through the ring
   const int ch = (D / 8 + 31) / 32;
-#define VL_LN_FWD(CH)                                                                                                          \
-  layernorm_fwd_kernel<CH><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, (const long long*)row_index, w, b, \
-                                                reinterpret_cast<__nv_bfloat16*>(y), ldy, mean, rstd, T, D, eps)
-  if (ch <= 1) VL_LN_FWD(1); else if (ch <= 2) VL_LN_FWD(2); else if (ch <= 4) VL_LN_FWD(4); else VL_LN_FWD(8);
+  // rows in flight per warp (cp.async ring): 4 (6 measured the same: 52.1 vs 50.7 us at 65792 x 1024), 3 for 4 KB rows
+#define VL_LN_FWD(CH, PF)                                                                                                      \
+  do {                                                                                                                         \
+    constexpr int smem_ = 8 * PF * CH * 32 * 16;                                                                               \
+    static bool attr_ = false;                                                                                                 \
+    if (!attr_) {                                                                                                              \
+      VL_CUDA(cudaFuncSetAttribute(layernorm_fwd_kernel<CH, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_));         \
+      attr_ = true;                                                                                                            \
+    }                                                                                                                          \
+    layernorm_fwd_kernel<CH, PF><<<grid, 256, smem_, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, (const long long*)row_index, w, b, \
+                                                          reinterpret_cast<__nv_bfloat16*>(y), ldy, mean, rstd, T, D, eps);    \
+  } while (0)
+  if (ch <= 1) VL_LN_FWD(1, 4); else if (ch <= 2) VL_LN_FWD(2, 4); else if (ch <= 4) VL_LN_FWD(4, 4); else VL_LN_FWD(8, 3);
 #undef VL_LN_FWD
   return launch_check("layernorm_fwd");
 }
@@ -898,12 +950,19 @@ int vl_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, c
     }
     const bool al16 = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dres)) & 15) == 0;
     if (al16 && debug_get(14) != 1) {  // knob 14: 1 = first-generation D = 1024 kernel (four columns per thread)
+      constexpr int kRing = 2 * 3 * 4 * 256 * 16;  // two stages of (x | dy | dres) x 4 rows x 256 threads x 16 bytes
+      static bool attr_ = false;
+      if (!attr_) {
+        VL_CUDA(cudaFuncSetAttribute(layernorm_bwd_d1024_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRing));
+        VL_CUDA(cudaFuncSetAttribute(layernorm_bwd_d1024_v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRing));
+        attr_ = true;
+      }
       if (dres)
-        layernorm_bwd_d1024_v2_kernel<true><<<g2, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(x), ldx, w,
+        layernorm_bwd_d1024_v2_kernel<true><<<g2, 256, kRing, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(x), ldx, w,
                                                                mean, rstd, reinterpret_cast<const __nv_bfloat16*>(dres), lddres,
                                                                reinterpret_cast<__nv_bfloat16*>(dx), lddx, part, T);
       else
-        layernorm_bwd_d1024_v2_kernel<false><<<g2, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(x), ldx,
+        layernorm_bwd_d1024_v2_kernel<false><<<g2, 256, kRing, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(x), ldx,
                                                                 w, mean, rstd, nullptr, 0, reinterpret_cast<__nv_bfloat16*>(dx), lddx, part, T);
       if (int rc = launch_check("layernorm_bwd_d1024_v2")) return rc;
       return finish(g2);

@@ -50,6 +50,14 @@ static EncodeTiledFn encode_fn() {
 
 int make_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const void* base, const uint64_t* dims,
               const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+  // cuTensorMapEncodeTiled is a DRIVER entry point: it needs a current context on the calling thread.  Autograd runs backward on
+  // its own threads, and the first call of a backward pass may be this one (seen: CUDA_ERROR_INVALID_CONTEXT when the loss
+  // backward was the first kernel of the thread) -- a runtime call binds the device's primary context.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
