@@ -916,11 +916,14 @@ int vl_attention_fwd(const void* q, const void* k, const void* v, void* o, float
   VL_CHECK_ARG(ldo % 8 == 0 && ldo >= (int64_t)H * kHD, "vl_attention_fwd: bad ldo");
   VL_CHECK_ARG(!causal || nq == nk, "vl_attention_fwd: causal requires nq == nk");
   {
-    // two or more full query tiles, non-causal: the persistent two-group kernel (attention_fwd2.cu).
+    // two or more full query tiles, non-causal: the persistent two-group kernel (attention_fwd2.cu) ...
     // debug knob 13: 1 = keep the one-tile-per-CTA kernel below for every shape
     const int t2 = nq % kTQ;
     const int tq2 = (nq > kTQ && t2 == 1) ? 1 : 0;  // the kernel folds one tail row (N = 128 k + 1) in on CUDA cores
-    if (!causal && nq - tq2 > kTQ && debug_get(13) != 1)
+    // ... and 128 + 1 rows (the 128-latent Lens + cls of the audio / depth / point recipes): one softmax group idles, but the tail row
+    // rides inside the kernel instead of a second launch (measured at batch 512 x 16 heads: 0.227 vs 0.292 ms; at exactly 128 rows
+    // the one-tile kernel is the faster one, 0.163 vs 0.202 ms).  knob 17: 1 = the persistent kernel for every single-tile length
+    if (!causal && (nq - tq2 > kTQ || tq2 == 1 || (debug_get(17) == 1 && nq - tq2 >= 16)) && debug_get(13) != 1)
       return launch_attn_fwd2(q, k, v, o, lse, B, H, nq, nk, ldq, ldk, ldv, ldo, scale, reinterpret_cast<cudaStream_t>(stream));
   }
   CUtensorMap tmQ, tmK, tmV;

@@ -9,6 +9,8 @@ def get_visual_adapter(cfg, **kwargs):
             from .modal_3d.models.pointbert.point_encoder import PointTokenizer
 
             return PointTokenizer(config=cfg)
+        # 'pnsa' (pointnet_util.py:345-368) is unreachable in the reference too: PointNSATokenizer.forward needs xyz=, which
+        # TriCLIP.encode_visual never passes (model.py:524-525)
         raise NotImplementedError(f"pc_tokenizer={cfg.pc_tokenizer!r}: only 'pointbert' (vitlensL) is on the covered path")
     if vtype == "3dpc_raw":
         return nn.Identity()
