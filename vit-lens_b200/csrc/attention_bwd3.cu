@@ -235,7 +235,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         load_tile(0);
         for (int j = 0; j < nkblk; ++j) {
           const int s = j & 1;
-          mbar_wait(bar_kvempty(s), ((j >> 1) & 1) ^ 1);
+          mbar_wait_trap(bar_kvempty(s), ((j >> 1) & 1) ^ 1);
           mbar_expect_tx(bar_kvfull(s), 32768);
           tma_load_2d(sK + s * 16384, &tmK, bar_kvfull(s), h * kHD, kr + j * kT);
           tma_load_2d(sV + s * 16384, &tmV, bar_kvfull(s), h * kHD, kr + j * kT);
@@ -301,9 +301,9 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         // 257 = 2 x 128 + 1) ride as N = 16 COLUMNS with the queries on the lanes: S = Q_i K_t^T, dP = dO_i V_t^T go into the still
         // unused dQ accumulator of the tile (read by the tile's compute group before the first dQ MMA can be issued).
         auto tile_ready = [&](int i) {
-          mbar_wait(bar_q(i), 0);
+          mbar_wait_trap(bar_q(i), 0);
           if (dbg0 && i == 0) p.dbg[1024 + dbg_cta0 * 8 + 3] = clock64();  // Q_0 (+ tail keys) landed
-          mbar_wait(bar_do(i), 0);
+          mbar_wait_trap(bar_do(i), 0);
           if (dbg0 && i == 0) p.dbg[1024 + dbg_cta0 * 8 + 4] = clock64();  // dO_0, O_0 landed
           tc_fence_after();
           if (has_tk) {
@@ -323,7 +323,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const int ng = kUPT * nqt + ((g == 0 && has_tail) ? 1 : 0);
           const int s = sblk & 1;
           if (sidx == 0) {  // first unit of a key block for this group: K / V must have landed
-            mbar_wait(bar_kvfull(s), (sblk >> 1) & 1);
+            mbar_wait_trap(bar_kvfull(s), (sblk >> 1) & 1);
             tc_fence_after();
             if (dbg0 && sblk == 0 && g == 0) p.dbg[1024 + dbg_cta0 * 8 + 5] = clock64();  // K_0, V_0 landed
           }
@@ -369,9 +369,9 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             const int i = tail ? 0 : u / (2 * kUPT), hq = tail ? 0 : (u >> 1) % kUPT, g = tail ? 0 : u & 1;
             uint32_t& np = g ? np1 : np0;
             const uint32_t bsel = np % kUPT;
-            mbar_wait(bar_pfull(g, bsel), (np / kUPT) & 1);
+            mbar_wait_trap(bar_pfull(g, bsel), (np / kUPT) & 1);
             ++np;
-            if (u == 0 && j > 0) mbar_wait(bar_dkvfree, (j - 1) & 1);  // dV / dK of the previous block drained
+            if (u == 0 && j > 0) mbar_wait_trap(bar_dkvfree, (j - 1) & 1);  // dV / dK of the previous block drained
             tc_fence_after();
             VL_ISTAMP();
             // dV_j += P^T dO, dK_j += dS^T Q over the unit's queries (A operands straight from TMEM); the first MMA of a key block
@@ -422,10 +422,10 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (int t = 0; t < kMaxTail; ++t) acc[t] = ak[t] = av[t] = make_float2(0.f, 0.f);
       if (has_tk) {
         for (int i = 0; i < nqt; ++i) {
-          mbar_wait(bar_q(i), 0);
-          mbar_wait(bar_do(i), 0);
+          mbar_wait_trap(bar_q(i), 0);
+          mbar_wait_trap(bar_do(i), 0);
         }
-        mbar_wait(bar_tkc, 0);
+        mbar_wait_trap(bar_tkc, 0);
         const float* cp = sf + kFTk;                      // [u][q] P
         const float* cd = sf + kFTk + kMaxTail * 2 * kT;  // [u][q] dS
         if (hw < nqt) {  // warp hw takes query tile hw (rows past nq_main carry zero coefficients)
@@ -477,8 +477,8 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (has_tail) {
         for (int j = 0; j < nkblk; ++j) {
           const int s = j & 1, cb = j & 1;
-          mbar_wait(bar_kvfull(s), (j >> 1) & 1);
-          mbar_wait(bar_cfull(cb), (j >> 1) & 1);
+          mbar_wait_trap(bar_kvfull(s), (j >> 1) & 1);
+          mbar_wait_trap(bar_cfull(cb), (j >> 1) & 1);
           const uint8_t* kt = bp + kOffK + s * 16384;
           const float* cf = sf + kFCoef + cb * kMaxTail * kT;
           const int r1 = min(kT / 2 * (hw + 1), p.nk_main - j * kT);  // warp hw takes key rows [64 hw, 64 hw + 64) of the block
@@ -584,7 +584,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
         }
       }
-      mbar_wait(bar_do(g), 0);
+      mbar_wait_trap(bar_do(g), 0);
       const float D = ok ? dot_rows_sw128(bp + kOffDO + g * 16384, bp + kOffST + g * (32768 + 16384), x) : 0.f;
       sNl[qrow] = ok ? -lse * kLog2e : -INFINITY;  // rows that do not exist: exp2(s - inf) = 0 -> P = dS = 0
       sNd[qrow] = -D * p.scale;
@@ -593,7 +593,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         // row's tile).  P / dS go to the helper warps (dV / dK of the tail keys); dS stays here for this row's dQ.
         float* cp = sf + kFTk;
         float* cd = sf + kFTk + kMaxTail * 2 * kT;
-        mbar_wait(bar_tks(g), 0);
+        mbar_wait_trap(bar_tks(g), 0);
         tc_fence_after();
         uint32_t sv[16], dpv[16];
         tmem_ld16(tDQ(g) + lane_off, sv);
@@ -631,11 +631,11 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll 1
         for (int hq = 0; hq < kUPT; ++hq) {
           const uint32_t tb = cs % kUPT;
-          mbar_wait(bar_sfull(g, tb), (cs / kUPT) & 1);
+          mbar_wait_trap(bar_sfull(g, tb), (cs / kUPT) & 1);
           ++cs;
           tc_fence_after();
           if (hq == 0) {
-            if (ntile >= 2) mbar_wait(bar_dsfree(sb), ((ntile >> 1) - 1) & 1);  // dQ MMAs of tile ntile - 2 have read the buffer
+            if (ntile >= 2) mbar_wait_trap(bar_dsfree(sb), ((ntile >> 1) - 1) & 1);  // dQ MMAs of tile ntile - 2 have read the buffer
             if (store_buf == static_cast<int>(sb)) {                          // ... and so has this group's last bulk store
               if (x == 0) tma_store_wait_read<0>();
               group_sync(g);
@@ -696,10 +696,10 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         // tail unit: N = 16 query columns, the first tq exist
         const int cb = j & 1;
         const uint32_t tb = cs % kUPT;
-        mbar_wait(bar_sfull(0, tb), (cs / kUPT) & 1);
+        mbar_wait_trap(bar_sfull(0, tb), (cs / kUPT) & 1);
         ++cs;
         tc_fence_after();
-        if (j >= 2) mbar_wait(bar_cfree(cb), ((j >> 1) - 1) & 1);
+        if (j >= 2) mbar_wait_trap(bar_cfree(cb), ((j >> 1) - 1) & 1);
         float* cf = sf + kFCoef + cb * kMaxTail * kT;
         if (warp_on) {
           const uint32_t tSg = tS(0, tb) + lane_off, tPg = tP(0, tb) + lane_off;
@@ -732,7 +732,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
       // ---- dV_j (group 0) / dK_j (group 1) -> global; thread r owns key row j * 128 + r
-      mbar_wait(bar_dkvfull, j & 1);
+      mbar_wait_trap(bar_dkvfull, j & 1);
       tc_fence_after();
       VL_STAMP();
       {
@@ -772,7 +772,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
     // ---- dQ tile g -> global (thread = query row of tile g)
     if (g < nqt) {
-      mbar_wait(bar_dqfull, 0);
+      mbar_wait_trap(bar_dqfull, 0);
       tc_fence_after();
       VL_STAMP();
       if (store_buf >= 0) {

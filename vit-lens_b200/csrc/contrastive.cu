@@ -112,7 +112,7 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const CUtensorMap* my = &pmY.m[pr];
         const int lrow = row - pr * p.peer_rows;
         for (int e = 0; e < ne; ++e) {
-          mbar_wait(bar_empty(stage), phase ^ 1);
+          mbar_wait_trap(bar_empty(stage), phase ^ 1);
           const uint32_t sx = base + kOffRing + stage * 32768;
           mbar_expect_tx(bar_full(stage), 32768);
           tma_load_2d(sx, &tmX, bar_full(stage), e * 64, m0);
@@ -122,7 +122,7 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             phase ^= 1;
           }
         }
-        mbar_wait(bar_ycempty, (j & 1) ^ 1);  // the dX MMAs of block j - 1 have read the slice tiles
+        mbar_wait_trap(bar_ycempty, (j & 1) ^ 1);  // the dX MMAs of block j - 1 have read the slice tiles
         mbar_expect_tx(bar_ycfull, nyc * 16384);
         for (int c = 0; c < nyc; ++c) tma_load_2d(base + kOffYc + c * 16384, my, bar_ycfull, c0 + c * 64, lrow);
       }
@@ -137,7 +137,7 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       for (int j = 0; j < nblk; ++j) {
         // S_j (overwrites g of block j - 1: its dX MMAs were issued before, same thread -> executed in order)
         for (int e = 0; e < ne; ++e) {
-          mbar_wait(bar_full(stage), phase);
+          mbar_wait_trap(bar_full(stage), phase);
           tc_fence_after();
           const uint32_t sx = base + kOffRing + stage * 32768;
 #pragma unroll
@@ -151,8 +151,8 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         }
         umma_commit(bar_sfull);
         // dX_slice += g_j Y_j[:, slice]
-        mbar_wait(bar_gfull, j & 1);
-        mbar_wait(bar_ycfull, j & 1);
+        mbar_wait_trap(bar_gfull, j & 1);
+        mbar_wait_trap(bar_ycfull, j & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < kT / 16; ++kk)
@@ -174,7 +174,7 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const float kdiag = p.col_lse ? 2.f : 1.f;
     float dsum = 0.f;
     for (int j = 0; j < nblk; ++j) {
-      mbar_wait(bar_sfull, j & 1);
+      mbar_wait_trap(bar_sfull, j & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < kT; c += 32) {
@@ -224,7 +224,7 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       if (lane == 0) mbar_arrive(bar_gfull);
     }
     // dX slice -> global (fp32), scaled by s
-    mbar_wait(bar_dxfull, 0);
+    mbar_wait_trap(bar_dxfull, 0);
     tc_fence_after();
     for (int c = 0; c < ncw; c += 32) {
       uint32_t v[32];

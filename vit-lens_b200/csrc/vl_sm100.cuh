@@ -62,6 +62,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Guarded wait for kernels whose hand-over protocol is young: a protocol bug must fail the launch (trap -> a CUDA error the caller
+// sees) instead of spinning forever and hanging the GPU.  The clock is only read every 2^16 spins.
+__device__ __forceinline__ void mbar_wait_trap(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xffffu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000ll) __trap();  // ~10 s
+    }
+  }
+}
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
