@@ -451,7 +451,8 @@ def run_cuda(args):
             # committed ncu --set full capture profiles/r01_ncu_gemm_fc_gelu_pair8.txt: 164.4 MB read + 1023.4 MB written, against
             # 143.1 MB + 1077.9 MB algorithmic (activations + weights in, activation + pre-activation out).  A capture constant
             # (ncu cannot run inside a timed bench); re-captured whenever the kernel changes.
-            roof["traffic"] = int((164438784 + 1023405000) * B / 256)  # captured at batch 256; the GEMM is linear in tokens
+            # profiles/r02_ncu_final_kernels.txt (ncu --set full, round-2 kernel): 155.5 MB read + 1022.0 MB written
+            roof["traffic"] = int((155527424 + 1021996000) * B / 256)  # captured at batch 256; the GEMM is linear in tokens
             roof["traffic_kernel"] = "gemm2_bf16_kernel<256,8> fc+GELU, per launch; algorithmic 1221036032 B; from the committed ncu capture"
         roof["launches_timed"] = len(gemm_t)
         roof["share_of_step"] = tot_ms / ms
@@ -467,9 +468,9 @@ def run_cuda(args):
                     "share_of_step": v[0] / ms} for k, v in by.items()}
         if "fwd" in mhsa and args.config == 1:
             # DRAM bytes of one attn_fwd2_kernel launch at batch 256 from the committed ncu --set full capture
-            # (profiles/r01_ncu_attn_fwd2_final.txt: 405.3 MB read + 113.1 MB written; algorithmic 539.0 MB, the last tiles'
+            # (profiles/r02_ncu_final_kernels.txt: 405.3 MB read + 113.0 MB written; algorithmic 539.0 MB, the last tiles'
             # output is still in L2 when the kernel ends): no re-reads of Q / K / V
-            mhsa["fwd"]["traffic"] = int((405338112 + 113060864) * B / 256)
+            mhsa["fwd"]["traffic"] = int((405348352 + 112985344) * B / 256)
             mhsa["fwd"]["kernel"] = "attn_fwd2_kernel (persistent, P in TMEM), per launch; algorithmic %d B" % (4 * B * 257 * 1024 * 2)
         if "bwd" in mhsa and args.config == 1:
             # attn_bwd3_kernel at batch 256 (profiles/r02_ncu_attn_bwd3.txt: 679.6 MB read + 368.2 MB written; algorithmic 1078 MB):
